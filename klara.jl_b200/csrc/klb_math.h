@@ -1,0 +1,316 @@
+/* klb_math.h -- deterministic arithmetic primitives shared by the sm_100a
+ * kernels and by the CPU oracle (which includes this file so that both sides
+ * run the SAME source for everything that is not IEEE-exact by itself).
+ *
+ * Contents
+ *   - bit casts, contraction-proof fp64 add/mul/fma/div/sqrt wrappers
+ *   - Philox4x32-10 counter-based generator (Salmon et al., SC'11) and the
+ *     counter layout that replaces the reference's unseeded global RNG
+ *     (reference draws: src/samplers/iterate/HMC.jl:135,165,
+ *      src/samplers/iterate/MALA.jl:84,94, src/samplers/iterate/MH.jl:79,97)
+ *   - uint64 -> uniform maps
+ *   - exp / log built only from IEEE add/mul/fma and table lookups, so that
+ *     gcc-on-x86 and nvcc-on-sm_100a return identical bits
+ *   - 256-layer ziggurat standard normal (the reference's randn(d) is Julia's
+ *     ziggurat; here it is keyed per (seed, chain, transition, element))
+ *
+ * Plain C99 / CUDA C++.  Compile host code with -ffp-contract=off.
+ */
+#ifndef KLB_MATH_H
+#define KLB_MATH_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define KLB_HD __host__ __device__ __forceinline__
+#else
+#include <math.h>
+#include <string.h>
+#define KLB_HD static inline
+#endif
+
+/* ---------------------------------------------------------------- bit casts */
+KLB_HD double klb_u2d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+KLB_HD uint64_t klb_d2u(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(d);
+#else
+  uint64_t u; memcpy(&u, &d, 8); return u;
+#endif
+}
+
+/* ------------------------------------------ contraction-proof fp64 operators */
+KLB_HD double klb_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+KLB_HD double klb_sub(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+KLB_HD double klb_mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+KLB_HD double klb_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return fma(a, b, c);
+#endif
+}
+KLB_HD double klb_div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+KLB_HD double klb_sqrt(double a) {
+#if defined(__CUDA_ARCH__)
+  return __dsqrt_rn(a);
+#else
+  return sqrt(a);
+#endif
+}
+/* exact for |v| < 2^53 */
+KLB_HD double klb_i2d(int64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ll2double_rn((long long)v);
+#else
+  return (double)v;
+#endif
+}
+
+/* ------------------------------------------------------------ Philox4x32-10 */
+#define KLB_PHILOX_M0 0xD2511F53u
+#define KLB_PHILOX_M1 0xCD9E8D57u
+#define KLB_PHILOX_W0 0x9E3779B9u
+#define KLB_PHILOX_W1 0xBB67AE85u
+
+KLB_HD uint32_t klb_mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+/* out[0..3] = Philox4x32-10(counter c0..c3, key k0,k1) */
+KLB_HD void klb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = klb_mulhi32(KLB_PHILOX_M0, c0), lo0 = KLB_PHILOX_M0 * c0;
+    uint32_t hi1 = klb_mulhi32(KLB_PHILOX_M1, c2), lo1 = KLB_PHILOX_M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += KLB_PHILOX_W0; k1 += KLB_PHILOX_W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* Counter layout (the RNG contract, DESIGN.md section "RNG"):
+ *   c0 = slot        pair index for TAG_NORMAL, element index for TAG_SLOW,
+ *                    0 for TAG_ACCEPT
+ *   c1 = low 32 bits of the job's global transition counter t (first
+ *        transition is t = 1; t = 0 is free for synthetic initial states)
+ *   c2 = global chain index
+ *   c3 = tag | attempt << 4 | (bits 32..47 of t) << 16
+ *   key = 64-bit seed
+ */
+#define KLB_TAG_NORMAL 0u
+#define KLB_TAG_SLOW   1u
+#define KLB_TAG_ACCEPT 2u
+
+typedef struct {
+  uint32_t k0, k1;   /* seed */
+  uint32_t t_lo;     /* c1 */
+  uint32_t chain;    /* c2 */
+  uint32_t t_hi16;   /* bits 32..47 of t, already shifted to bits 16..31 */
+} klb_stream;
+
+KLB_HD klb_stream klb_stream_make(uint64_t seed, uint64_t chain, uint64_t t) {
+  klb_stream s;
+  s.k0 = (uint32_t)seed; s.k1 = (uint32_t)(seed >> 32);
+  s.t_lo = (uint32_t)t; s.chain = (uint32_t)chain;
+  s.t_hi16 = (uint32_t)((t >> 32) & 0xFFFFu) << 16;
+  return s;
+}
+
+KLB_HD void klb_stream_draw(const klb_stream* s, uint32_t slot, uint32_t tag, uint32_t attempt,
+                            uint64_t* w0, uint64_t* w1) {
+  uint32_t o[4];
+  klb_philox4x32_10(slot, s->t_lo, s->chain, tag | (attempt << 4) | s->t_hi16, s->k0, s->k1, o);
+  *w0 = (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+  *w1 = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
+}
+
+/* --------------------------------------------------------- uniform variates */
+/* [0,1): same map and same edge behaviour as Julia's rand() (u = 0 => log u = -Inf => accept,
+ * src/samplers/iterate/MALA.jl:94) */
+KLB_HD double klb_u01(uint64_t w) { return klb_mul(klb_i2d((int64_t)(w >> 11)), 0x1p-53); }
+/* (0,1]: used where a logarithm must stay finite (ziggurat tail) */
+KLB_HD double klb_u01_open(uint64_t w) { return klb_mul(klb_i2d((int64_t)(w >> 11) + 1), 0x1p-53); }
+
+/* the accept/reject uniform of transition s->t for chain s->chain */
+KLB_HD double klb_accept_uniform(const klb_stream* s) {
+  uint64_t w0, w1;
+  klb_stream_draw(s, 0u, KLB_TAG_ACCEPT, 0u, &w0, &w1);
+  return klb_u01(w0);
+}
+
+/* ---------------------------------------------------------------- exp / log */
+#ifndef KLB_TABLES_H
+#include "klb_tables.h"
+#endif
+
+#define KLB_EXP_SHIFT 0x1.8p52
+
+/* exp(x); tab = pointer to a copy of KLB_TAB.  |error| < 0.51 ulp (tests/test_math.py). */
+KLB_HD double klb_exp(double x, const uint64_t* tab) {
+  if (!(x == x)) return x;
+  if (x > 709.782712893384) return klb_u2d(0x7FF0000000000000ULL);
+  if (x < -745.2) return 0.0;
+  const uint64_t* T = tab + KLB_TAB_EXP;
+  double z = klb_mul(x, klb_u2d(KLB_INVLN2N_BITS));
+  double kd = klb_add(z, KLB_EXP_SHIFT);
+  uint64_t ki = klb_d2u(kd);
+  kd = klb_sub(kd, KLB_EXP_SHIFT);
+  double r = klb_fma(kd, klb_u2d(KLB_NEGLN2HIN_BITS), x);
+  r = klb_fma(kd, klb_u2d(KLB_NEGLN2LON_BITS), r);
+  uint32_t j = (uint32_t)ki & 127u;
+  double tail = klb_u2d(T[2 * j]);
+  uint64_t sbits = T[2 * j + 1] + (ki << 45);
+  double r2 = klb_mul(r, r);
+  double p = klb_fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  double q = klb_fma(r, 1.0 / 6.0, 0.5);
+  double tmp = klb_fma(klb_mul(r2, r2), p, klb_fma(r2, q, klb_add(tail, r)));
+  /* k = j + 128 e ; the result is 2^e * H_j * (1 + tmp), H_j in [1,2) */
+  int32_t e = (int32_t)(((int64_t)(ki << 13)) >> 20); /* sign-extend the 51-bit integer, then >> 7 */
+  if (e >= -1021 && e <= 1022) {
+    double scale = klb_u2d(sbits);
+    return klb_fma(scale, tmp, scale);
+  }
+  if (e > 0) {              /* near overflow: evaluate at 2^-1009 and rescale */
+    double scale = klb_u2d(sbits - (1009ULL << 52));
+    return klb_mul(klb_fma(scale, tmp, scale), 0x1p1009);
+  }
+  {                         /* subnormal result: evaluate at 2^+1022 and rescale */
+    double scale = klb_u2d(sbits + (1022ULL << 52));
+    return klb_mul(klb_fma(scale, tmp, scale), 0x1p-1022);
+  }
+}
+
+/* log(x); error < 1 ulp, except < 2 ulp for x in (0.99, 1) (tests/test_math.py) */
+KLB_HD double klb_log(double x, const uint64_t* tab) {
+  uint64_t ix = klb_d2u(x);
+  int64_t kadj = 0;
+  if (ix - 0x0010000000000000ULL >= 0x7FE0000000000000ULL) {
+    /* x is 0, subnormal, negative, inf or nan */
+    if ((ix << 1) == 0) return klb_u2d(0xFFF0000000000000ULL);       /* log(+-0) = -inf */
+    if (ix == 0x7FF0000000000000ULL) return x;                          /* log(inf) = inf */
+    if ((ix >> 63) || (ix & 0x7FF0000000000000ULL) == 0x7FF0000000000000ULL)
+      return klb_u2d(0x7FF8000000000000ULL);                            /* nan */
+    ix = klb_d2u(klb_mul(x, 0x1p52));                                   /* subnormal */
+    kadj = -52;
+  }
+  const uint64_t* T = tab + KLB_TAB_LOG;
+  uint64_t tmp = ix - KLB_LOG_OFF_BITS;
+  uint32_t i = (uint32_t)(tmp >> 45) & 127u;
+  int64_t k = ((int64_t)tmp >> 52) + kadj;
+  uint64_t iz = ix - (tmp & (0xFFFULL << 52));
+  double invc = klb_u2d(T[2 * i]), logc = klb_u2d(T[2 * i + 1]);
+  double z = klb_u2d(iz);
+  double r = klb_fma(z, invc, -1.0);               /* z/c - 1, |r| <= 2^-8 */
+  double kd = klb_i2d(k);
+  double t1 = klb_mul(kd, klb_u2d(KLB_LN2HI_BITS)); /* exact: 21-bit x 11-bit */
+  double w = klb_add(t1, logc);
+  double e1 = klb_add(klb_sub(t1, w), logc);        /* fast two-sum (|t1| >= |logc| or t1 == 0) */
+  double hi = klb_add(w, r);
+  double bb = klb_sub(hi, w);
+  double e2 = klb_add(klb_sub(w, klb_sub(hi, bb)), klb_sub(r, bb));   /* two-sum */
+  double lo = klb_fma(kd, klb_u2d(KLB_LN2LO_BITS), klb_add(e1, e2));
+  double r2 = klb_mul(r, r);
+  double q = klb_fma(r2, 1.0 / 7.0, klb_fma(r, -1.0 / 6.0, 0.2));
+  double p = klb_fma(r2, q, klb_fma(r, -0.25, 1.0 / 3.0));
+  double y = klb_fma(klb_mul(r, r2), p, klb_fma(r2, -0.5, lo));
+  return klb_add(y, hi);
+}
+
+/* ------------------------------------------------- ziggurat standard normal */
+/* Layout of a 64-bit word w:  layer = w & 255, sign = bit 8, mantissa m = w >> 12. */
+
+/* Fast path: candidate x = +-(t-1)*X[layer], t = 1.m in [1,2).  Returns 1 when the
+ * candidate lies in the layer's rectangle below the density (accept, ~98.8 %). */
+KLB_HD int klb_zig_fast(uint64_t w, const uint64_t* tab, double* x) {
+  uint32_t idx = (uint32_t)w & 255u;
+  uint64_t m = w >> 12;
+  double X = klb_u2d(tab[KLB_TAB_ZXK + 2 * idx]);
+  uint64_t kk = tab[KLB_TAB_ZXK + 2 * idx + 1];
+  double t = klb_u2d(0x3FF0000000000000ULL | m);
+  double xx = klb_fma(t, X, -X);
+  *x = klb_u2d(klb_d2u(xx) ^ ((w & 256ULL) << 55));
+  return m < kk;
+}
+
+/* Complete draw for element `elem` given its first candidate word w (from
+ * klb_stream_draw(s, elem >> 1, KLB_TAG_NORMAL, 0), low word for even elem, high word for odd).
+ * Extra randomness comes from (slot = elem, TAG_SLOW, attempt = 1, 2, ...). */
+KLB_HD double klb_normal_from_word(uint64_t w, uint32_t elem, const klb_stream* s, const uint64_t* tab) {
+  uint32_t attempt = 0;
+  for (;;) {
+    double x;
+    if (klb_zig_fast(w, tab, &x)) return x;
+    uint32_t idx = (uint32_t)w & 255u;
+    uint64_t sign = (w & 256ULL) << 55;
+    uint64_t c0, c1;
+    if (attempt >= 4000u) return x;      /* unreachable in practice (p < 1e-1000); bounds the loop */
+    ++attempt;
+    klb_stream_draw(s, elem, KLB_TAG_SLOW, attempt, &c0, &c1);
+    if (idx == 0u) {
+      /* base strip beyond r: Marsaglia's exponential-majorant tail sampler */
+      for (;;) {
+        double xx = klb_mul(-klb_log(klb_u01_open(c0), tab), klb_u2d(KLB_ZIG_RINV_BITS));
+        double yy = -klb_log(klb_u01_open(c1), tab);
+        if (klb_add(yy, yy) > klb_mul(xx, xx) || attempt >= 4000u)
+          return klb_u2d(klb_d2u(klb_add(klb_u2d(KLB_ZIG_R_BITS), xx)) ^ sign);
+        ++attempt;
+        klb_stream_draw(s, elem, KLB_TAG_SLOW, attempt, &c0, &c1);
+      }
+    }
+    /* wedge of layer idx: y uniform on [f(x[idx]), f(x[idx+1])] against the density */
+    {
+      double f0 = klb_u2d(tab[KLB_TAB_ZF + idx]), f1 = klb_u2d(tab[KLB_TAB_ZF + idx + 1]);
+      double y = klb_fma(klb_u01(c0), klb_sub(f1, f0), f0);
+      if (y < klb_exp(klb_mul(klb_mul(-0.5, x), x), tab)) return x;
+    }
+    w = c1;                               /* rejected: next candidate */
+  }
+}
+
+/* Scalar reference draw of N(0,1) for (stream, element) -- what the oracle calls. */
+KLB_HD double klb_normal(const klb_stream* s, uint32_t elem, const uint64_t* tab) {
+  uint64_t w0, w1;
+  klb_stream_draw(s, elem >> 1, KLB_TAG_NORMAL, 0u, &w0, &w1);
+  return klb_normal_from_word((elem & 1u) ? w1 : w0, elem, s, tab);
+}
+
+#endif /* KLB_MATH_H */

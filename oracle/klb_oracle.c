@@ -1,0 +1,530 @@
+/* klb_oracle.c -- CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C restatement of Klara.jl's serial MCMC hot path, one C function per
+ * reference function, written to be read side by side with the Julia source
+ * (paths relative to the reference checkout, commit ffa4f6d0):
+ *
+ *   orc_run_chain      <- run(job::BasicMCJob)                 src/jobs/BasicMCJob.jl:212-244
+ *   orc_save           <- save / copy!(nstate, state, i)       src/jobs/BasicMCJob.jl:210,
+ *                         src/nstates/ParameterNStates/BasicContMuvParameterNState.jl:89-119
+ *   orc_hamiltonian    <- hamiltonian(logtarget, momentum)     src/samplers/samplers.jl:103
+ *   orc_leapfrog       <- leapfrog!(... Multivariate ...)      src/samplers/samplers.jl:122-134
+ *   orc_iterate_hmc    <- iterate!(job, HMC, Multivariate)     src/samplers/iterate/HMC.jl:124-224
+ *   orc_iterate_mala   <- iterate!(job, MALA, Multivariate)    src/samplers/iterate/MALA.jl:78-152
+ *   orc_iterate_mh     <- iterate!(job, MH, Multivariate)      src/samplers/iterate/MH.jl:72-141 (symmetric)
+ *   orc_rate / orc_reset_burnin                                src/tuners/tuners.jl:27-32
+ *   orc_tune           <- tune!(tune, ::AcceptanceRateMCTuner) src/tuners/AcceptanceRateMCTuner.jl:46
+ *   orc_logistic       <- logistic(x,l,k,x0,y0)                src/stats/logistic.jl:11
+ *   orc_logistic_rate_score / orc_erf_rate_score               src/tuners/AcceptanceRateMCTuner.jl:9,17
+ *   orc_tuner_state    <- tuner_state(...)                     src/samplers/samplers.jl:29-45
+ *   orc_upto / orc_logtarget / orc_gradlogtarget               src/variables/parameters/BasicContMuvParameter.jl:174-201,264-279
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library.  The product (klara.jl_b200/) never does.
+ *
+ * PARITY STATUS.  The reference cannot be executed (Julia 0.6, no julia binary) and it
+ * never seeds its RNG, so there is no golden chain to compare with: sampler-result
+ * parity is "parity unpinned" by the reference itself.  What IS pinned, bit-exactly,
+ * against the reference's own known-answer tests (tests/test_oracle_kat.py):
+ *   logistic(0.7,3,4,2.1,1.4)             test/common.jl:6
+ *   logistic_rate_score(0.25), (0.5,11)   test/AcceptanceRateMCTuner.jl:8-9
+ *   erf_rate_score(-0.1), (0.93,2)        test/AcceptanceRateMCTuner.jl:13-14
+ *   function-defined normal target values test/BasicContMuvParameter.jl:539-563
+ *   NState column layout                  test/ParameterNStates.jl:137-146
+ * and the random-number primitives against their published vectors (Philox4x32-10
+ * Random123 KAT) and against libm / theory.
+ *
+ * Deliberate replacement (documented in DESIGN.md): Julia's global MersenneTwister
+ * randn()/rand() are replaced by counter-based Philox streams keyed by
+ * (seed, chain, transition, element); the arithmetic of every other line follows the
+ * reference's un-fused evaluation order when cfg->arith == 0.
+ *
+ * Reductions (dot, sum) use the canonical order documented in DESIGN.md ("reduction
+ * order"), which is also what the device kernels execute; Julia's own dot/sum order is
+ * BLAS/SIMD dependent and not specified.
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../klara.jl_b200/csrc/klb_math.h"
+
+enum { ORC_MH = 0, ORC_MALA = 1, ORC_HMC = 2 };
+enum { ORC_ISO = 0, ORC_SHIFTED = 1, ORC_DENSE = 2, ORC_ROSEN = 3 };
+enum { ORC_VANILLA = 0, ORC_ACCRATE = 1 };
+
+typedef struct {
+  int32_t sampler, target, tuner, arith;      /* arith 0 = reference order (un-fused), 1 = fma-contracted */
+  int64_t nchains, dim, nsteps, burnin, thinning;
+  double step;                                /* leapstep / driftstep */
+  int32_t nleaps;
+  double target_rate, score_k;
+  int64_t period;
+  int32_t verbose;
+  uint32_t monitor;                           /* bit0 value, bit1 logtarget, bit2 gradlogtarget */
+  uint32_t diagnostics;                       /* bit0 accept */
+  uint64_t seed, chain_offset, t0;
+  int32_t nv;                                 /* reduction geometry: double2 units per lane (1,2,4,8,16) */
+  int32_t nthreads;                           /* OpenMP threads over chains; 1 = map(run, jobs) semantics */
+} orc_config;
+
+/* per-chain BasicMCTune (src/tuners/tuners.jl:5-25) */
+typedef struct { double step; int64_t accepted, proposed, totproposed; double rate; } orc_tune;
+
+/* one chain's BasicContMuvParameterState (src/states/ParameterStates/BasicContMuvParameterState.jl:62-97) */
+typedef struct { double* value; double logtarget; double* gradlogtarget; int accept; } orc_pstate;
+
+typedef struct {
+  const orc_config* cfg;
+  int64_t d, dp;              /* dim, padded dim = 64*nv */
+  const double* mu;           /* shifted-iso mean (padded with 0) */
+  const double* sigma;        /* MH proposal std-devs (padded with 0) */
+  const double* C;            /* dense precision, d x d row-major (symmetric) */
+  double ra, rb, rscale;      /* rosenbrock */
+} orc_model;
+
+/* ------------------------------------------------------------------ scalars */
+double orc_logistic(double x, double l, double k, double x0, double y0) {
+  /* l/(1+exp(-k*(x-x0)))+y0                                  src/stats/logistic.jl:11 */
+  return l / (1 + klb_exp(-k * (x - x0), KLB_TAB)) + y0;
+}
+double orc_logistic_rate_score(double x, double k) { return orc_logistic(x, 2., k, 0., 0.); }
+/* erf(k*x)+1 -- libm erf; host-only (the device library implements the logistic score) */
+double orc_erf_rate_score(double x, double k) { return erf(k * x) + 1; }
+
+double orc_exp(double x) { return klb_exp(x, KLB_TAB); }
+double orc_log(double x) { return klb_log(x, KLB_TAB); }
+void orc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
+  klb_philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1], out);
+}
+void orc_normals(uint64_t seed, uint64_t chain, uint64_t t, int64_t n, double* out) {
+  klb_stream s = klb_stream_make(seed, chain, t);
+  for (int64_t i = 0; i < n; ++i) out[i] = klb_normal(&s, (uint32_t)i, KLB_TAB);
+}
+double orc_uniform(uint64_t seed, uint64_t chain, uint64_t t) {
+  klb_stream s = klb_stream_make(seed, chain, t);
+  return klb_accept_uniform(&s);
+}
+int orc_plan_nv(int64_t dim) {
+  int nv = 1;
+  while (64 * (int64_t)nv < dim && nv < 16) nv *= 2;
+  return (64 * (int64_t)nv >= dim) ? nv : -1;
+}
+
+/* ------------------------------------------------- canonical reduction order
+ * Lane l (0..31) owns double2 units k = l + 32 m, m = 0..nv-1, i.e. elements 2k, 2k+1.
+ * Each lane keeps four accumulators; unit m adds its two addends, even element first,
+ * into accumulator m & 3; lane value = (acc0+acc1)+(acc2+acc3); lanes are combined by
+ * the xor butterfly 16, 8, 4, 2, 1.  `e` holds the addends (padded length 64*nv). */
+static double orc_reduce(const double* e, int nv) {
+  double lane[32], nxt[32];
+  for (int l = 0; l < 32; ++l) {
+    double acc[4] = {0., 0., 0., 0.};
+    for (int m = 0; m < nv; ++m) {
+      int k = l + 32 * m;
+      acc[m & 3] = acc[m & 3] + e[2 * k];
+      acc[m & 3] = acc[m & 3] + e[2 * k + 1];
+    }
+    lane[l] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+  for (int s = 16; s >= 1; s >>= 1) {
+    for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ s];
+    memcpy(lane, nxt, sizeof lane);
+  }
+  return lane[0];
+}
+/* same order with the products folded in by fma (arith == 1) */
+static double orc_reduce_fma(const double* a, const double* b, int nv) {
+  double lane[32], nxt[32];
+  for (int l = 0; l < 32; ++l) {
+    double acc[4] = {0., 0., 0., 0.};
+    for (int m = 0; m < nv; ++m) {
+      int k = l + 32 * m;
+      acc[m & 3] = fma(a[2 * k], b[2 * k], acc[m & 3]);
+      acc[m & 3] = fma(a[2 * k + 1], b[2 * k + 1], acc[m & 3]);
+    }
+    lane[l] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  }
+  for (int s = 16; s >= 1; s >>= 1) {
+    for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ s];
+    memcpy(lane, nxt, sizeof lane);
+  }
+  return lane[0];
+}
+
+/* dot(a, b) over padded vectors */
+static double orc_dot_m(const orc_model* M, const double* a, const double* b, double* scratch) {
+  if (M->cfg->arith == 1) return orc_reduce_fma(a, b, M->cfg->nv);
+  for (int64_t i = 0; i < M->dp; ++i) scratch[i] = a[i] * b[i];
+  return orc_reduce(scratch, M->cfg->nv);
+}
+/* exported for tests */
+double orc_dot(const double* a, const double* b, int64_t d, int nv, int arith) {
+  int64_t dp = 64 * (int64_t)nv;
+  double* pa = calloc(3 * dp, sizeof(double)); double* pb = pa + dp; double* sc = pb + dp;
+  memcpy(pa, a, d * sizeof(double)); memcpy(pb, b, d * sizeof(double));
+  double r;
+  if (arith == 1) r = orc_reduce_fma(pa, pb, nv);
+  else { for (int64_t i = 0; i < dp; ++i) sc[i] = pa[i] * pb[i]; r = orc_reduce(sc, nv); }
+  free(pa);
+  return r;
+}
+
+/* ------------------------------------------------------------ target library
+ * Device targets are descriptors, not closures (a Julia closure cannot run on the GPU);
+ * the definitions follow the reference's examples:
+ *   iso      plogtarget(z) = -dot(z, z), pgradlogtarget(z) = -2*z            README.md:153-155
+ *   shifted  -(x-mu).(x-mu), -2(x-mu)                    test/BasicContMuvParameter.jl:539-563
+ *   dense    -p.(C p), -2 C p        doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9
+ *   rosen    this repo's paired Rosenbrock; not in the reference
+ */
+static void orc_gradlogtarget(const orc_model* M, orc_pstate* s, double* scratch);
+
+static void orc_logtarget(const orc_model* M, orc_pstate* s, double* scratch) {
+  const double* x = s->value;
+  const int fm = M->cfg->arith == 1;
+  switch (M->cfg->target) {
+    case ORC_ISO:
+      s->logtarget = -orc_dot_m(M, x, x, scratch);
+      break;
+    case ORC_SHIFTED: {
+      double* df = scratch + M->dp;
+      for (int64_t i = 0; i < M->dp; ++i) df[i] = (i < M->d) ? x[i] - M->mu[i] : 0.;
+      s->logtarget = -orc_dot_m(M, df, df, scratch);
+      break;
+    }
+    case ORC_DENSE: {
+      /* (C x)_i accumulated by fma in increasing j (both arith modes: the reference's gemv order
+       * is BLAS-defined, i.e. unspecified), then -x.(Cx) in the canonical order */
+      double* cx = scratch + M->dp;
+      for (int64_t i = 0; i < M->dp; ++i) {
+        double acc = 0.;
+        if (i < M->d) for (int64_t j = 0; j < M->d; ++j) acc = fma(M->C[i * M->d + j], x[j], acc);
+        cx[i] = acc;
+      }
+      s->logtarget = -orc_dot_m(M, x, cx, scratch);
+      break;
+    }
+    case ORC_ROSEN: {
+      /* -(scale) * sum_k [ rb*(b - a^2)^2 + (ra - a)^2 ],  (a,b) = (x[2k], x[2k+1]) */
+      for (int64_t k = 0; 2 * k < M->dp; ++k) {
+        double a = x[2 * k], b = x[2 * k + 1], term = 0.;
+        if (2 * k + 1 < M->d) {
+          double u = fm ? fma(-a, a, b) : b - a * a;
+          double v = M->ra - a;
+          term = fm ? fma(M->rb * u, u, v * v) : M->rb * (u * u) + v * v;
+        }
+        scratch[2 * k] = term; scratch[2 * k + 1] = 0.;
+      }
+      s->logtarget = -(M->rscale * orc_reduce(scratch, M->cfg->nv));
+      break;
+    }
+  }
+}
+
+static void orc_gradlogtarget(const orc_model* M, orc_pstate* s, double* scratch) {
+  const double* x = s->value; double* g = s->gradlogtarget;
+  const int fm = M->cfg->arith == 1;
+  switch (M->cfg->target) {
+    case ORC_ISO:
+      for (int64_t i = 0; i < M->dp; ++i) g[i] = -2 * x[i];
+      break;
+    case ORC_SHIFTED:
+      for (int64_t i = 0; i < M->dp; ++i) g[i] = (i < M->d) ? -2 * (x[i] - M->mu[i]) : 0.;
+      break;
+    case ORC_DENSE:
+      for (int64_t i = 0; i < M->dp; ++i) {
+        double acc = 0.;
+        if (i < M->d) for (int64_t j = 0; j < M->d; ++j) acc = fma(M->C[i * M->d + j], x[j], acc);
+        g[i] = -2 * acc;
+      }
+      break;
+    case ORC_ROSEN:
+      for (int64_t k = 0; 2 * k < M->dp; ++k) {
+        double a = x[2 * k], b = x[2 * k + 1], ga = 0., gb = 0.;
+        if (2 * k + 1 < M->d) {
+          double u = fm ? fma(-a, a, b) : b - a * a;
+          double v = M->ra - a;
+          double t = ((4 * M->rb) * a) * u;
+          ga = M->rscale * (fm ? fma(2., v, t) : t + 2 * v);
+          gb = -(M->rscale * ((2 * M->rb) * u));
+        }
+        g[2 * k] = ga; g[2 * k + 1] = gb;
+      }
+      break;
+  }
+  (void)scratch;
+}
+
+/* uptogradlogtarget! = logtarget! then gradlogtarget!   BasicContMuvParameter.jl:264-279 */
+static void orc_upto(const orc_model* M, orc_pstate* s, double* scratch) {
+  orc_logtarget(M, s, scratch);
+  orc_gradlogtarget(M, s, scratch);
+}
+
+/* ------------------------------------------------------------------- tuners */
+static void orc_rate(orc_tune* t) { t->rate = (double)t->accepted / (double)t->proposed; }
+static void orc_reset_burnin(orc_tune* t) {
+  t->totproposed += t->proposed;
+  t->accepted = 0; t->proposed = 0; t->rate = NAN;
+}
+static void orc_tune_step(orc_tune* t, const orc_config* c) {
+  t->step *= orc_logistic_rate_score(t->rate - c->target_rate, c->score_k);
+}
+/* tuner_state: BasicMCTune(step, 0, 0, tuner.period); MH gets step 1.   samplers.jl:29-45 */
+void orc_tuner_state(const orc_config* c, orc_tune* t) {
+  t->step = (c->sampler == ORC_MH) ? 1. : c->step;
+  t->accepted = 0; t->proposed = 0; t->totproposed = c->period; t->rate = NAN;
+}
+static int orc_counters_on(const orc_config* c) {
+  if (c->sampler == ORC_MH) return c->verbose != 0;                    /* iterate/MH.jl:73-75 */
+  return (c->tuner == ORC_VANILLA && c->verbose) || c->tuner == ORC_ACCRATE; /* iterate/HMC.jl:129-133 */
+}
+/* the burn-in tuner block shared by HMC (:203-224) and MALA (:130-152); MH (:126-140) never tunes */
+static void orc_tuner_block(const orc_config* c, orc_tune* t) {
+  if (!orc_counters_on(c)) return;
+  if (t->totproposed <= c->burnin && t->proposed % c->period == 0) {
+    orc_rate(t);
+    if (c->tuner == ORC_ACCRATE && c->sampler != ORC_MH) orc_tune_step(t, c);
+    orc_reset_burnin(t);
+  }
+}
+
+/* ------------------------------------------------------------------ samplers */
+typedef struct {
+  orc_pstate sp;        /* sstate.pstate: the proposal */
+  double* momentum;     /* HMC momentum / MALA mu / MH scratch normals */
+  double* z;            /* normals */
+  double* scratch;      /* 3*dp */
+} orc_sstate;
+
+static double orc_hamiltonian(const orc_model* M, double logtarget, const double* p, double* scratch) {
+  return logtarget - 0.5 * orc_dot_m(M, p, p, scratch);
+}
+
+static void orc_leapfrog(const orc_model* M, orc_pstate* sp, double* mom, double step, double* scratch) {
+  const double h = 0.5 * step;                    /* Julia folds 0.5*step*g left to right */
+  if (M->cfg->arith == 1) {
+    for (int64_t i = 0; i < M->dp; ++i) mom[i] = fma(h, sp->gradlogtarget[i], mom[i]);
+    for (int64_t i = 0; i < M->dp; ++i) sp->value[i] = fma(step, mom[i], sp->value[i]);
+    orc_gradlogtarget(M, sp, scratch);
+    for (int64_t i = 0; i < M->dp; ++i) mom[i] = fma(h, sp->gradlogtarget[i], mom[i]);
+  } else {
+    for (int64_t i = 0; i < M->dp; ++i) mom[i] = mom[i] + h * sp->gradlogtarget[i];
+    for (int64_t i = 0; i < M->dp; ++i) sp->value[i] = sp->value[i] + step * mom[i];
+    orc_gradlogtarget(M, sp, scratch);
+    for (int64_t i = 0; i < M->dp; ++i) mom[i] = mom[i] + h * sp->gradlogtarget[i];
+  }
+}
+
+static void orc_randn(const orc_model* M, const klb_stream* st, double* z) {
+  for (int64_t i = 0; i < M->dp; ++i) z[i] = (i < M->d) ? klb_normal(st, (uint32_t)i, KLB_TAB) : 0.;
+}
+
+static void orc_iterate_hmc(const orc_model* M, orc_pstate* ps, orc_sstate* ss, orc_tune* tune,
+                            const klb_stream* st) {
+  const orc_config* c = M->cfg;
+  if (orc_counters_on(c)) tune->proposed += 1;
+  orc_randn(M, st, ss->momentum);
+  double oldh = orc_hamiltonian(M, ps->logtarget, ss->momentum, ss->scratch);
+  memcpy(ss->sp.value, ps->value, M->dp * sizeof(double));
+  memcpy(ss->sp.gradlogtarget, ps->gradlogtarget, M->dp * sizeof(double));
+  for (int i = 0; i < c->nleaps; ++i) orc_leapfrog(M, &ss->sp, ss->momentum, tune->step, ss->scratch);
+  orc_logtarget(M, &ss->sp, ss->scratch);
+  double newh = orc_hamiltonian(M, ss->sp.logtarget, ss->momentum, ss->scratch);
+  double ratio = newh - oldh;
+  double e = klb_exp(ratio, KLB_TAB);
+  double a = (e != e) ? e : (e < 1. ? e : 1.);       /* min(1., exp(ratio)) keeps NaN */
+  if (klb_accept_uniform(st) < a) {
+    memcpy(ps->value, ss->sp.value, M->dp * sizeof(double));
+    memcpy(ps->gradlogtarget, ss->sp.gradlogtarget, M->dp * sizeof(double));
+    ps->logtarget = ss->sp.logtarget;
+    ps->accept = 1;
+    if (orc_counters_on(c)) tune->accepted += 1;
+  } else {
+    ps->accept = 0;
+  }
+  orc_tuner_block(c, tune);
+}
+
+static void orc_iterate_mala(const orc_model* M, orc_pstate* ps, orc_sstate* ss, orc_tune* tune,
+                             const klb_stream* st) {
+  const orc_config* c = M->cfg;
+  const int fm = c->arith == 1;
+  double* mu = ss->momentum; double* e = ss->scratch + 2 * M->dp;
+  if (orc_counters_on(c)) tune->proposed += 1;
+  const double step = tune->step, h = 0.5 * step, sq = sqrt(step), hinv = 0.5 / step;
+  orc_randn(M, st, ss->z);
+  for (int64_t i = 0; i < M->dp; ++i)
+    mu[i] = fm ? fma(h, ps->gradlogtarget[i], ps->value[i]) : ps->value[i] + h * ps->gradlogtarget[i];
+  for (int64_t i = 0; i < M->dp; ++i)
+    ss->sp.value[i] = fm ? fma(sq, ss->z[i], mu[i]) : mu[i] + sq * ss->z[i];
+  orc_upto(M, &ss->sp, ss->scratch);
+  double ratio = ss->sp.logtarget - ps->logtarget;
+  for (int64_t i = 0; i < M->dp; ++i) {
+    double df = mu[i] - ss->sp.value[i];
+    e[i] = fm ? (df * hinv) * df : 0.5 * ((df * df) / step);
+  }
+  ratio += orc_reduce(e, c->nv);
+  for (int64_t i = 0; i < M->dp; ++i)
+    mu[i] = fm ? fma(h, ss->sp.gradlogtarget[i], ss->sp.value[i]) : ss->sp.value[i] + h * ss->sp.gradlogtarget[i];
+  for (int64_t i = 0; i < M->dp; ++i) {
+    double df = mu[i] - ps->value[i];
+    e[i] = fm ? (df * hinv) * df : 0.5 * ((df * df) / step);
+  }
+  ratio -= orc_reduce(e, c->nv);
+  /* the counter-based uniform makes Julia's short-circuit (no draw when ratio > 0) unobservable */
+  if (ratio > 0 || ratio > klb_log(klb_accept_uniform(st), KLB_TAB)) {
+    memcpy(ps->value, ss->sp.value, M->dp * sizeof(double));
+    memcpy(ps->gradlogtarget, ss->sp.gradlogtarget, M->dp * sizeof(double));
+    ps->logtarget = ss->sp.logtarget;
+    ps->accept = 1;
+    if (orc_counters_on(c)) tune->accepted += 1;
+  } else {
+    ps->accept = 0;
+  }
+  orc_tuner_block(c, tune);
+}
+
+static void orc_iterate_mh(const orc_model* M, orc_pstate* ps, orc_sstate* ss, orc_tune* tune,
+                           const klb_stream* st) {
+  const orc_config* c = M->cfg;
+  if (orc_counters_on(c)) tune->proposed += 1;
+  orc_randn(M, st, ss->z);
+  /* rand(MvNormal(x, sigma)) = unwhiten (sigma .* z) then add the mean        iterate/MH.jl:77-79 */
+  for (int64_t i = 0; i < M->dp; ++i)
+    ss->sp.value[i] = (c->arith == 1) ? fma(M->sigma[i], ss->z[i], ps->value[i])
+                                      : M->sigma[i] * ss->z[i] + ps->value[i];
+  orc_logtarget(M, &ss->sp, ss->scratch);
+  double ratio = ss->sp.logtarget - ps->logtarget;
+  if (ratio > 0 || ratio > klb_log(klb_accept_uniform(st), KLB_TAB)) {
+    memcpy(ps->value, ss->sp.value, M->dp * sizeof(double));
+    ps->logtarget = ss->sp.logtarget;
+    ps->accept = 1;
+    if (orc_counters_on(c)) tune->accepted += 1;
+  } else {
+    ps->accept = 0;
+  }
+  orc_tuner_block(c, tune);
+}
+
+/* ----------------------------------------------------------------- the job */
+typedef struct {
+  double* value;       /* d x npost x nchains */
+  double* logtarget;   /* npost x nchains */
+  double* grad;        /* d x npost x nchains */
+  uint8_t* accept;     /* npost x nchains */
+} orc_output;
+
+static void orc_save(const orc_model* M, const orc_pstate* ps, const orc_output* o,
+                     int64_t chain, int64_t npost, int64_t count /* 1-based column */) {
+  const orc_config* c = M->cfg;
+  int64_t col = chain * npost + (count - 1);
+  if ((c->monitor & 1u) && o->value) memcpy(o->value + col * M->d, ps->value, M->d * sizeof(double));
+  if ((c->monitor & 2u) && o->logtarget) o->logtarget[col] = ps->logtarget;
+  if ((c->monitor & 4u) && o->grad) memcpy(o->grad + col * M->d, ps->gradlogtarget, M->d * sizeof(double));
+  if ((c->diagnostics & 1u) && o->accept) o->accept[col] = (uint8_t)ps->accept;
+}
+
+int64_t orc_npoststeps(int64_t burnin, int64_t thinning, int64_t nsteps) {
+  /* length((burnin+1):thinning:nsteps)                       src/ranges/BasicMCRange.jl:14-25 */
+  if (nsteps <= burnin) return 0;
+  return (nsteps - burnin - 1) / thinning + 1;
+}
+
+/* Run all chains: the semantics of run(::Vector{MCJob}) = map(run, job) (src/jobs/jobs.jl:212).
+ * x (d x nchains, in/out), logtarget (nchains, in/out; must already hold logtarget(x) when
+ * `initialized`, else it is computed = initialize!), tune (nchains, in/out).
+ * tparams: mu (d) for SHIFTED, C (d*d) for DENSE, {a, b, scale} for ROSEN; sigma (d) for MH.
+ * Returns 0, or -(1+chain) if that chain's initial log-target/gradient is not finite. */
+int orc_run(const orc_config* cfg, const double* tparams, const double* sigma,
+            double* x, double* logtarget, orc_tune* tune, int initialized,
+            double* out_value, double* out_logtarget, double* out_grad, uint8_t* out_accept) {
+  const int64_t d = cfg->dim, dp = 64 * (int64_t)cfg->nv, N = cfg->nchains;
+  if (dp < d) return -1000000;
+  const int64_t npost = orc_npoststeps(cfg->burnin, cfg->thinning, cfg->nsteps);
+  orc_output out = {out_value, out_logtarget, out_grad, out_accept};
+  double* mu_p = calloc(2 * dp, sizeof(double)); double* sg_p = mu_p + dp;
+  orc_model M; memset(&M, 0, sizeof M);
+  M.cfg = cfg; M.d = d; M.dp = dp; M.mu = mu_p; M.sigma = sg_p; M.C = NULL;
+  if (cfg->target == ORC_SHIFTED && tparams) memcpy(mu_p, tparams, d * sizeof(double));
+  if (cfg->target == ORC_DENSE) M.C = tparams;
+  if (cfg->target == ORC_ROSEN) { M.ra = tparams[0]; M.rb = tparams[1]; M.rscale = tparams[2]; }
+  if (sigma) memcpy(sg_p, sigma, d * sizeof(double));
+  int bad = 0;
+  int nth = cfg->nthreads > 0 ? cfg->nthreads : 1;
+  (void)nth;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nth)
+  for (int64_t c = 0; c < N; ++c) {
+    double* buf = calloc(9 * dp, sizeof(double));
+    orc_pstate ps = {buf, 0., buf + dp, 0};
+    orc_sstate ss; ss.sp.value = buf + 2 * dp; ss.sp.gradlogtarget = buf + 3 * dp; ss.sp.logtarget = NAN; ss.sp.accept = 0;
+    ss.momentum = buf + 4 * dp; ss.z = buf + 5 * dp; ss.scratch = buf + 6 * dp;
+    memcpy(ps.value, x + c * d, d * sizeof(double));
+    /* initialize!: first target (+ gradient) evaluation, finiteness asserts   HMC.jl:106-120 */
+    if (cfg->sampler == ORC_MH) orc_logtarget(&M, &ps, ss.scratch); else orc_upto(&M, &ps, ss.scratch);
+    if (initialized) ps.logtarget = logtarget[c];
+    int ok = isfinite(ps.logtarget);
+    if (cfg->sampler != ORC_MH) for (int64_t i = 0; i < d; ++i) ok = ok && isfinite(ps.gradlogtarget[i]);
+    if (!ok) {
+#pragma omp critical
+      { if (bad == 0 || -(int)(1 + c) > bad) bad = -(int)(1 + c); }
+      free(buf);
+      continue;
+    }
+    orc_tune tn = tune[c];
+    int64_t count = 0;
+    for (int64_t i = 1; i <= cfg->nsteps; ++i) {                       /* BasicMCJob.jl:219 */
+      klb_stream st = klb_stream_make(cfg->seed, cfg->chain_offset + (uint64_t)c, cfg->t0 + (uint64_t)i);
+      switch (cfg->sampler) {                                          /* BasicMCJob.jl:224 */
+        case ORC_HMC: orc_iterate_hmc(&M, &ps, &ss, &tn, &st); break;
+        case ORC_MALA: orc_iterate_mala(&M, &ps, &ss, &tn, &st); break;
+        default: orc_iterate_mh(&M, &ps, &ss, &tn, &st); break;
+      }
+      if (i > cfg->burnin && (i - cfg->burnin - 1) % cfg->thinning == 0) {   /* in(i, postrange) :226 */
+        count += 1;
+        orc_save(&M, &ps, &out, c, npost, count);
+      }
+    }
+    memcpy(x + c * d, ps.value, d * sizeof(double));
+    logtarget[c] = ps.logtarget;
+    tune[c] = tn;
+    free(buf);
+  }
+  free(mu_p);
+  return bad;
+}
+
+/* single evaluations for the closure-wiring KATs (test/BasicContMuvParameter.jl:539-563) */
+int orc_eval_target(const orc_config* cfg, const double* tparams, const double* x,
+                    double* logtarget, double* grad) {
+  const int64_t d = cfg->dim, dp = 64 * (int64_t)cfg->nv;
+  if (dp < d) return -1;
+  double* buf = calloc(6 * dp, sizeof(double));
+  orc_model M; memset(&M, 0, sizeof M);
+  M.cfg = cfg; M.d = d; M.dp = dp; M.mu = buf + 4 * dp; M.sigma = buf + 5 * dp;
+  if (cfg->target == ORC_SHIFTED) memcpy(buf + 4 * dp, tparams, d * sizeof(double));
+  if (cfg->target == ORC_DENSE) M.C = tparams;
+  if (cfg->target == ORC_ROSEN) { M.ra = tparams[0]; M.rb = tparams[1]; M.rscale = tparams[2]; }
+  orc_pstate ps = {buf, 0., buf + dp, 0};
+  memcpy(ps.value, x, d * sizeof(double));
+  orc_upto(&M, &ps, buf + 2 * dp);
+  *logtarget = ps.logtarget;
+  memcpy(grad, ps.gradlogtarget, d * sizeof(double));
+  free(buf);
+  return 0;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,198 @@
+"""ctypes binding of the CPU oracle (oracle/klb_oracle.c).  TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+import this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libklb_oracle.so")
+
+MH, MALA, HMC = 0, 1, 2
+ISO, SHIFTED, DENSE, ROSEN = 0, 1, 2, 3
+VANILLA, ACCRATE = 0, 1
+
+
+class OrcConfig(C.Structure):
+    _fields_ = [
+        ("sampler", C.c_int32), ("target", C.c_int32), ("tuner", C.c_int32), ("arith", C.c_int32),
+        ("nchains", C.c_int64), ("dim", C.c_int64), ("nsteps", C.c_int64), ("burnin", C.c_int64),
+        ("thinning", C.c_int64),
+        ("step", C.c_double), ("nleaps", C.c_int32),
+        ("target_rate", C.c_double), ("score_k", C.c_double), ("period", C.c_int64),
+        ("verbose", C.c_int32), ("monitor", C.c_uint32), ("diagnostics", C.c_uint32),
+        ("seed", C.c_uint64), ("chain_offset", C.c_uint64), ("t0", C.c_uint64),
+        ("nv", C.c_int32), ("nthreads", C.c_int32),
+    ]
+
+
+class OrcTune(C.Structure):
+    _fields_ = [("step", C.c_double), ("accepted", C.c_int64), ("proposed", C.c_int64),
+                ("totproposed", C.c_int64), ("rate", C.c_double)]
+
+
+TUNE_DTYPE = np.dtype([("step", "<f8"), ("accepted", "<i8"), ("proposed", "<i8"),
+                       ("totproposed", "<i8"), ("rate", "<f8")])
+
+
+def build(force=False):
+    """Compile the oracle with oracle/Makefile (gcc, no GPU needed)."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+            os.path.getmtime(os.path.join(_HERE, p)) > os.path.getmtime(_LIB_PATH)
+            for p in ("klb_oracle.c", "../klara.jl_b200/csrc/klb_math.h", "../klara.jl_b200/csrc/klb_tables.h")):
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        dbl = C.c_double
+        L.orc_logistic.restype = dbl
+        L.orc_logistic.argtypes = [dbl] * 5
+        L.orc_logistic_rate_score.restype = dbl
+        L.orc_logistic_rate_score.argtypes = [dbl, dbl]
+        L.orc_erf_rate_score.restype = dbl
+        L.orc_erf_rate_score.argtypes = [dbl, dbl]
+        L.orc_exp.restype = dbl
+        L.orc_exp.argtypes = [dbl]
+        L.orc_log.restype = dbl
+        L.orc_log.argtypes = [dbl]
+        L.orc_uniform.restype = dbl
+        L.orc_uniform.argtypes = [C.c_uint64] * 3
+        L.orc_normals.restype = None
+        L.orc_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
+        L.orc_philox.restype = None
+        L.orc_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_plan_nv.restype = C.c_int
+        L.orc_plan_nv.argtypes = [C.c_int64]
+        L.orc_dot.restype = dbl
+        L.orc_dot.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int]
+        L.orc_npoststeps.restype = C.c_int64
+        L.orc_npoststeps.argtypes = [C.c_int64] * 3
+        L.orc_tuner_state.restype = None
+        L.orc_tuner_state.argtypes = [C.POINTER(OrcConfig), C.c_void_p]
+        L.orc_run.restype = C.c_int
+        L.orc_run.argtypes = [C.POINTER(OrcConfig)] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4
+        L.orc_eval_target.restype = C.c_int
+        L.orc_eval_target.argtypes = [C.POINTER(OrcConfig)] + [C.c_void_p] * 4
+        L.orc_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def philox(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32)
+    k = np.asarray(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    lib().orc_philox(_ptr(c), _ptr(k), _ptr(out))
+    return out
+
+
+def normals(seed, chain, t, n):
+    out = np.empty(n, dtype=np.float64)
+    lib().orc_normals(seed, chain, t, n, _ptr(out))
+    return out
+
+
+def uniform(seed, chain, t):
+    return lib().orc_uniform(seed, chain, t)
+
+
+def exp(x):
+    return lib().orc_exp(float(x))
+
+
+def log(x):
+    return lib().orc_log(float(x))
+
+
+def plan_nv(dim):
+    return lib().orc_plan_nv(dim)
+
+
+def dot(a, b, nv=None, arith=0):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    nv = plan_nv(a.size) if nv is None else nv
+    return lib().orc_dot(_ptr(a), _ptr(b), a.size, nv, arith)
+
+
+def npoststeps(burnin, thinning, nsteps):
+    return lib().orc_npoststeps(burnin, thinning, nsteps)
+
+
+def make_config(sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, step=0.1, nleaps=10,
+                tuner=VANILLA, target_rate=0.574, score_k=7.0, period=100, verbose=0,
+                monitor=1, diagnostics=0, seed=0, chain_offset=0, t0=0, arith=0, nv=None, nthreads=1):
+    cfg = OrcConfig()
+    cfg.sampler, cfg.target, cfg.tuner, cfg.arith = sampler, target, tuner, arith
+    cfg.nchains, cfg.dim, cfg.nsteps, cfg.burnin, cfg.thinning = nchains, dim, nsteps, burnin, thinning
+    cfg.step, cfg.nleaps = step, nleaps
+    cfg.target_rate, cfg.score_k, cfg.period, cfg.verbose = target_rate, score_k, period, verbose
+    cfg.monitor, cfg.diagnostics = monitor, diagnostics
+    cfg.seed, cfg.chain_offset, cfg.t0 = seed, chain_offset, t0
+    cfg.nv = plan_nv(dim) if nv is None else nv
+    cfg.nthreads = nthreads
+    return cfg
+
+
+def tuner_state(cfg):
+    t = np.zeros(cfg.nchains, dtype=TUNE_DTYPE)
+    one = OrcTune()
+    lib().orc_tuner_state(C.byref(cfg), C.byref(one))
+    t["step"], t["accepted"], t["proposed"] = one.step, one.accepted, one.proposed
+    t["totproposed"], t["rate"] = one.totproposed, one.rate
+    return t
+
+
+def eval_target(cfg, x, tparams=None):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    tp = None if tparams is None else np.ascontiguousarray(tparams, dtype=np.float64)
+    lt = C.c_double()
+    g = np.empty_like(x)
+    rc = lib().orc_eval_target(C.byref(cfg), _ptr(tp), _ptr(x), C.byref(lt), _ptr(g))
+    if rc:
+        raise ValueError("orc_eval_target failed: %d" % rc)
+    return lt.value, g
+
+
+def run(cfg, x0, tparams=None, sigma=None, tune=None, logtarget=None):
+    """Run all chains.  x0: (nchains, dim) array (row c = chain c, i.e. Julia's d x nchains
+    column-major matrix).  Returns dict with final state, tune records and the monitored output
+    in the NState layout: value (nchains, npost, dim), logtarget / accept (nchains, npost)."""
+    N, d = cfg.nchains, cfg.dim
+    x = np.array(x0, dtype=np.float64, order="C").reshape(N, d).copy()
+    npost = npoststeps(cfg.burnin, cfg.thinning, cfg.nsteps)
+    tp = None if tparams is None else np.ascontiguousarray(tparams, dtype=np.float64)
+    sg = None if sigma is None else np.ascontiguousarray(sigma, dtype=np.float64)
+    tune = tuner_state(cfg) if tune is None else tune.copy()
+    initialized = logtarget is not None
+    lt = np.zeros(N) if logtarget is None else np.array(logtarget, dtype=np.float64)
+    ov = np.zeros((N, npost, d)) if cfg.monitor & 1 else None
+    ol = np.zeros((N, npost)) if cfg.monitor & 2 else None
+    og = np.zeros((N, npost, d)) if cfg.monitor & 4 else None
+    oa = np.zeros((N, npost), dtype=np.uint8) if cfg.diagnostics & 1 else None
+    rc = lib().orc_run(C.byref(cfg), _ptr(tp), _ptr(sg), _ptr(x), _ptr(lt), _ptr(tune), int(initialized),
+                       _ptr(ov), _ptr(ol), _ptr(og), _ptr(oa))
+    if rc:
+        raise ValueError("oracle: initial log-target/gradient not finite in chain %d" % (-rc - 1))
+    return {"x": x, "logtarget_state": lt, "tune": tune, "value": ov, "logtarget": ol,
+            "gradlogtarget": og, "accept": oa, "npost": npost}
+
+
+def max_threads():
+    return lib().orc_max_threads()
