@@ -1,0 +1,200 @@
+/* klara_b200.h -- C ABI of libklara_b200.so: the B200-native replacement for the MCMC
+ * inner loop of JuliaStats/Klara.jl (one BasicContMuvParameter, MH / MALA / HMC, batched
+ * over independent chains).
+ *
+ * The reference has no FFI on this path; its extension points are Julia closures and
+ * multiple dispatch.  Each entry point below therefore names the reference routine(s)
+ * whose work it takes over (paths relative to the Klara.jl checkout, commit ffa4f6d0);
+ * INTEGRATION.md shows the `ccall` stubs a Klara maintainer would add, and
+ * klara.jl_b200/ the Python mirror of Klara's user surface used by the tests.
+ *
+ * Conventions
+ *   - every call returns KLB_OK (0) or a negative KLB_E* code and never throws; the
+ *     message of the last failure on the calling thread is klb_last_error()
+ *   - host buffers are caller-owned and only touched during the call
+ *   - device memory is library-owned, freed by klb_job_destroy
+ *   - a job handle is not thread-safe (like the reference's mutable BasicMCJob);
+ *     distinct handles are independent
+ *   - matrices are Julia-style column-major: the state is `dim x nchains` (one chain =
+ *     one contiguous column), monitored values are `dim x npoststeps x nchains`
+ *     (BasicContMuvParameterNState.value is `size x n`,
+ *      src/nstates/ParameterNStates/BasicContMuvParameterNState.jl:1-21, one per chain)
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     KLB_ECUDA
+ */
+#ifndef KLARA_B200_H
+#define KLARA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KLB_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define KLB_OK 0
+#define KLB_EINVAL (-1)     /* invalid configuration / argument (the reference's @assert failures) */
+#define KLB_ECUDA (-2)      /* CUDA runtime error, or no device */
+#define KLB_ENOTFINITE (-3) /* initial log-target / gradient not finite (src/samplers/HMC.jl:113-114) */
+#define KLB_ESTATE (-4)     /* call out of order (e.g. run before set_state, output overrun) */
+#define KLB_EUNSUPPORTED (-5)
+#define KLB_ENOMEM (-6)
+
+/* sampler: src/samplers/MH.jl:47-66 (symmetric normal random walk), MALA.jl:61-70, HMC.jl:89-100 */
+#define KLB_SAMPLER_MH 0
+#define KLB_SAMPLER_MALA 1
+#define KLB_SAMPLER_HMC 2
+
+/* target descriptors (device-resident replacements of the logtarget / gradlogtarget closures of
+ * BasicContMuvParameter, src/variables/parameters/BasicContMuvParameter.jl:174-201) */
+#define KLB_TARGET_ISO 0        /* -z.z, -2z                        README.md:153-155 */
+#define KLB_TARGET_SHIFTED_ISO 1 /* -(z-mu).(z-mu), -2(z-mu)        test/BasicContMuvParameter.jl:539-563 */
+#define KLB_TARGET_DENSE 2      /* -z'Cz, -2Cz   doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9 */
+#define KLB_TARGET_ROSENBROCK 3 /* -scale*sum_k [b(x_2k+1 - x_2k^2)^2 + (a - x_2k)^2]  (this repo) */
+
+/* tuner: src/tuners/VanillaMCTuner.jl:6-16, src/tuners/AcceptanceRateMCTuner.jl:25-46 */
+#define KLB_TUNER_VANILLA 0
+#define KLB_TUNER_ACCEPTANCE_RATE 1
+
+/* arithmetic: 0 = every product and sum rounded separately, in the reference's evaluation order
+ * ((0.5*step)*g first, then the addition: src/samplers/samplers.jl:130-133); 1 = a*b+c contracted
+ * to fma (faster, differs from the reference by <= 1 ulp per operation) */
+#define KLB_ARITH_REFERENCE 0
+#define KLB_ARITH_FMA 1
+
+/* monitor / diagnostics bit masks (outopts[:monitor], outopts[:diagnostics], src/jobs/jobs.jl:9-43) */
+#define KLB_MONITOR_VALUE 1u
+#define KLB_MONITOR_LOGTARGET 2u
+#define KLB_MONITOR_GRADLOGTARGET 4u
+#define KLB_DIAG_ACCEPT 1u
+
+/* outopts[:destination]: :nstate (device-resident buffer) or :none */
+#define KLB_DEST_NSTATE 0
+#define KLB_DEST_NONE 1
+
+/* which = argument of klb_job_set_target_f64 */
+#define KLB_PARAM_MU 0     /* dim doubles */
+#define KLB_PARAM_C 1      /* dim*dim doubles, symmetric precision matrix */
+#define KLB_PARAM_SIGMA 2  /* dim doubles: MH(sigma::Vector) proposal standard deviations (src/samplers/MH.jl:64) */
+#define KLB_PARAM_ROSEN 3  /* 3 doubles: a, b, scale */
+
+/* field = argument of klb_job_output / klb_job_device_ptr */
+#define KLB_OUT_VALUE 0          /* double  dim x npost x nchains */
+#define KLB_OUT_LOGTARGET 1      /* double  npost x nchains */
+#define KLB_OUT_GRADLOGTARGET 2  /* double  dim x npost x nchains */
+#define KLB_OUT_ACCEPT 3         /* uint8   npost x nchains */
+#define KLB_OUT_STATE 4          /* double  dim x nchains      current pstate.value */
+#define KLB_OUT_STATE_LOGTARGET 5 /* double nchains            current pstate.logtarget */
+#define KLB_OUT_TUNE_STEP 6      /* double  nchains            sstate.tune.step */
+#define KLB_OUT_TUNE_COUNTERS 7  /* int64   3 x nchains        accepted, proposed, totproposed */
+#define KLB_OUT_TUNE_RATE 8      /* double  nchains            sstate.tune.rate (NaN after reset_burnin!) */
+
+typedef struct klb_job klb_job; /* opaque, library-owned: one batched BasicMCJob */
+
+/* Everything BasicMCJob(model, sampler, mcrange, v0; tuner, outopts) is built from
+ * (src/jobs/BasicMCJob.jl:24-104), flattened. */
+typedef struct {
+  uint32_t struct_size;   /* = sizeof(klb_config), for ABI evolution */
+  int32_t sampler;        /* KLB_SAMPLER_* */
+  int32_t target;         /* KLB_TARGET_* */
+  int32_t tuner;          /* KLB_TUNER_* */
+  int32_t arith;          /* KLB_ARITH_* */
+  int64_t nchains;        /* chains in THIS job (= this rank's shard) */
+  int64_t dim;
+  int64_t nsteps, burnin, thinning; /* BasicMCRange, src/ranges/BasicMCRange.jl:7-33 */
+  double step;            /* HMC leapstep / MALA driftstep (> 0); unused by MH */
+  int32_t nleaps;         /* HMC (> 0) */
+  double target_rate;     /* AcceptanceRateMCTuner.targetrate in (0,1) */
+  double score_k;         /* steepness of logistic_rate_score (default 7) */
+  int64_t period;         /* tuner period (> 0, default 100) */
+  int32_t verbose;        /* tuner.verbose: switches the acceptance counters on (iterate/HMC.jl:129-133) */
+  uint32_t monitor;       /* KLB_MONITOR_* */
+  uint32_t diagnostics;   /* KLB_DIAG_* */
+  int32_t destination;    /* KLB_DEST_* */
+  uint64_t seed;          /* Philox key */
+  int64_t chain_offset;   /* global index of this job's first chain (RNG streams use global indices,
+                             so results do not depend on how chains are sharded over GPUs) */
+  int32_t device;         /* CUDA device ordinal */
+  int32_t reserved;
+} klb_config;
+
+/* geometry the library chose for a job (needed by the oracle to reproduce the reduction order) */
+typedef struct {
+  int32_t nv;               /* double2 units per lane: a chain is owned by one warp, lane l holds
+                               elements 2(l+32m), 2(l+32m)+1, m < nv */
+  int32_t warps_per_block;
+  int32_t regs_per_thread;
+  int32_t blocks_per_sm;
+  int64_t npoststeps;       /* length((burnin+1):thinning:nsteps) */
+  int64_t transitions_done; /* global transition counter t (RNG counter word) */
+  int64_t saved;            /* job.count: samples stored since the last reset */
+} klb_plan;
+
+int klb_version(void);
+const char* klb_last_error(void);
+int klb_device_count(void);
+
+/* BasicMCJob constructor minus initialize! (src/jobs/BasicMCJob.jl:24-104): validates the
+ * configuration exactly like the reference's @asserts (HMC.jl:93-96, MALA.jl:64-67,
+ * tuners.jl:12-20, VanillaMCTuner.jl:10-13, AcceptanceRateMCTuner.jl:31-35, BasicMCRange.jl:19-21),
+ * allocates device state / tuner records / output (initialize_output, src/jobs/jobs.jl:188-210). */
+int klb_job_create(const klb_config* cfg, klb_job** out);
+
+/* Target / proposal parameters: what reaches the closures through parameter.states
+ * (hyper-parameters, BasicContMuvParameter.jl:497-501) or through MH(sigma) (MH.jl:64). */
+int klb_job_set_target_f64(klb_job* job, int which, const double* host, int64_t n);
+
+/* initialize! (HMC.jl:106-120, MALA.jl:76-90, MH.jl:72-85) and reset(job, x) (BasicMCJob.jl:198-201):
+ * upload x0 (dim x nchains), evaluate log-target (+ gradient) of every chain, fail with
+ * KLB_ENOTFINITE naming the first offending chain; also resets the tuner records and the
+ * output cursor like reset(job). */
+int klb_job_set_state(klb_job* job, const double* x0);
+/* same, x0 already in device memory of the job's device (no host copy) */
+int klb_job_set_state_device(klb_job* job, const double* x0_dev);
+
+/* run(job) (BasicMCJob.jl:212-244): all nsteps transitions of all chains, burn-in tuning,
+ * thinning, saving.  Blocking. */
+int klb_job_run(klb_job* job);
+/* launch only (asynchronous on the job's stream); klb_job_sync waits */
+int klb_job_run_async(klb_job* job);
+int klb_job_sync(klb_job* job);
+
+/* Transitions per kernel launch (0 = the whole run in one launch, the default).  nt = 1 is the
+ * one-launch-per-iterate! lockstep schedule; results do not depend on the chunking. */
+int klb_job_set_chunk(klb_job* job, int64_t nt);
+
+/* reset(job) (BasicMCJob.jl:187-196): tuner records <- (sampler step, 0, 0, period, NaN), count <- 0.
+ * The chain state is kept (pstate persists), the RNG counter keeps advancing. */
+int klb_job_reset(klb_job* job);
+
+/* output(job) (BasicMCJob.jl:279) and job.pstate / job.sstate.tune: copy one field to host. */
+int klb_job_output(klb_job* job, int field, void* host_dst, int64_t nbytes);
+/* device address and byte size of a field (for zero-copy consumers: NCCL all-gather, torch views) */
+int klb_job_device_ptr(klb_job* job, int field, void** dev_ptr, int64_t* nbytes);
+
+int klb_job_plan(klb_job* job, klb_plan* out);
+/* kernels launched by this job so far */
+int64_t klb_job_launches(klb_job* job);
+/* CUDA-event time (ms) of the last klb_job_run / run_async+sync kernel sequence */
+double klb_job_last_run_ms(klb_job* job);
+void* klb_job_stream(klb_job* job);
+
+void klb_job_destroy(klb_job* job);
+
+/* pinned host memory for end-to-end pipelines */
+int klb_host_alloc(void** p, int64_t nbytes);
+int klb_host_free(void* p);
+
+/* Device self-tests used by the parity suite (run on the GPU, results copied to host):
+ * n standard normals of stream (seed, chain, t) / op(x[i]) with op 0 = exp, 1 = log / the
+ * accept uniform / the canonical dot product. */
+int klb_debug_normals(int device, uint64_t seed, uint64_t chain, uint64_t t, int64_t n, double* host_out);
+int klb_debug_math(int device, int op, int64_t n, const double* host_in, double* host_out);
+int klb_debug_uniform(int device, uint64_t seed, uint64_t chain, uint64_t t, double* host_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KLARA_B200_H */

@@ -1,0 +1,383 @@
+"""Python mirror of the Klara.jl user surface for the MCMC hot path, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the reference (paths relative to the Klara.jl
+checkout, commit ffa4f6d0):
+
+    BasicContMuvParameter   src/variables/parameters/BasicContMuvParameter.jl:383-411
+    likelihood_model        src/models/generators.jl:5-18
+    MH / MALA / HMC         src/samplers/MH.jl:47-66, MALA.jl:61-70, HMC.jl:89-100
+    BasicMCRange            src/ranges/BasicMCRange.jl:7-33
+    VanillaMCTuner          src/tuners/VanillaMCTuner.jl:6-16
+    AcceptanceRateMCTuner   src/tuners/AcceptanceRateMCTuner.jl:25-46
+    BasicMCJob / run / reset / output    src/jobs/BasicMCJob.jl:24-244, 279
+
+Batch extension: the initial value may be a `(nchains, dim)` array (Julia: `dim x nchains` matrix);
+every row is an independent chain with its own tuner record, i.e. `map(run, jobs)`
+(src/jobs/jobs.jl:212) executed in lockstep on the GPU.
+
+Julia symbols (`:p`, `:value`) are plain strings here; `Dict(:p => v)` is `{"p": v}`.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+from .targets import Target
+
+__all__ = ["BasicContMuvParameter", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
+           "VanillaMCTuner", "AcceptanceRateMCTuner", "BasicMCTune", "BasicMCJob", "run", "reset", "output",
+           "BasicContMuvParameterNState", "logistic", "logistic_rate_score"]
+
+
+# ----------------------------------------------------------------------------- scalars
+def logistic(x, l=1., k=1., x0=0., y0=0.):
+    """l/(1+exp(-k*(x-x0)))+y0        src/stats/logistic.jl:11"""
+    return l / (1 + math.exp(-k * (x - x0))) + y0
+
+
+def logistic_rate_score(x, k=7.):
+    """src/tuners/AcceptanceRateMCTuner.jl:9"""
+    return logistic(x, 2., k, 0., 0.)
+
+
+# ----------------------------------------------------------------------------- parameter / model
+class BasicContMuvParameter:
+    """BasicContMuvParameter(key; logtarget, gradlogtarget) with a target descriptor.
+
+    `gradlogtarget` may be omitted or must be the same descriptor: the device targets carry their
+    analytic gradient (the reference's autodiff path, src/autodiff/, is out of scope)."""
+
+    def __init__(self, key, logtarget=None, gradlogtarget=None, index=0):
+        if not isinstance(logtarget, Target):
+            raise TypeError("logtarget must be a klara_b200 target descriptor (IsoGaussian(), ...); arbitrary "
+                            "host closures cannot run inside the CUDA kernels")
+        if gradlogtarget is not None and gradlogtarget is not logtarget and gradlogtarget != logtarget.gradient:
+            raise TypeError("gradlogtarget must be omitted, the same descriptor, or descriptor.gradient")
+        self.key = key
+        self.index = index
+        self.logtarget = logtarget
+        self.gradlogtarget = logtarget.gradient
+        self.target = logtarget
+
+
+class GenericModel:
+    """The graph is only used to locate the parameter vertex (src/jobs/BasicMCJob.jl:50)."""
+
+    def __init__(self, vertices):
+        self.vertices = list(vertices)
+        self.ofkey = {v.key: i for i, v in enumerate(self.vertices)}
+
+
+def likelihood_model(vertices, isindexed=True):
+    """likelihood_model(p, false)        src/models/generators.jl:5-18"""
+    if not isinstance(vertices, (list, tuple)):
+        vertices = [vertices]
+    return GenericModel(vertices)
+
+
+# ----------------------------------------------------------------------------- samplers
+class MH:
+    """MH(sigma::Vector): Metropolis with the symmetric normal random walk MvNormal(x, sigma),
+    sigma = per-coordinate standard deviations (src/samplers/MH.jl:64)."""
+    code = L.SAMPLER_MH
+
+    def __init__(self, sigma):
+        self.sigma = np.ascontiguousarray(np.atleast_1d(sigma), dtype=np.float64)
+        if self.sigma.ndim != 1:
+            raise TypeError("only the diagonal MH(sigma::Vector) proposal is supported on the device")
+        assert np.all(self.sigma > 0), "Proposal standard deviations should be positive"
+        self.symmetric = True
+        self.normalised = True
+
+
+class MALA:
+    """MALA(driftstep=1.)        src/samplers/MALA.jl:61-70"""
+    code = L.SAMPLER_MALA
+
+    def __init__(self, driftstep=1.):
+        assert driftstep > 0, "Drift step is not positive"
+        self.driftstep = float(driftstep)
+
+
+class HMC:
+    """HMC(leapstep=0.1, nleaps=10)        src/samplers/HMC.jl:89-100"""
+    code = L.SAMPLER_HMC
+
+    def __init__(self, leapstep=0.1, nleaps=10):
+        assert leapstep > 0, "Leapfrog step is not positive"
+        assert nleaps > 0, "Number of leapfrog steps is not positive"
+        self.leapstep = float(leapstep)
+        self.nleaps = int(nleaps)
+
+
+# ----------------------------------------------------------------------------- range / tuners
+class BasicMCRange:
+    """BasicMCRange(; burnin=0, thinning=1, nsteps=100): postrange = (burnin+1):thinning:nsteps
+    (src/ranges/BasicMCRange.jl:7-33)."""
+
+    def __init__(self, burnin=0, thinning=1, nsteps=100):
+        assert burnin >= 0, "Number of burn-in iterations should be non-negative"
+        assert thinning >= 1, "Thinning should be >= 1"
+        assert nsteps > burnin, "Total number of MCMC iterations should be greater than number of burn-in iterations"
+        self.burnin, self.thinning, self.nsteps = int(burnin), int(thinning), int(nsteps)
+        self.postrange = range(self.burnin + 1, self.nsteps + 1, self.thinning)
+        self.npoststeps = len(self.postrange)
+
+
+class VanillaMCTuner:
+    """VanillaMCTuner(; period=100, verbose=false)        src/tuners/VanillaMCTuner.jl:6-16
+    `verbose` switches the acceptance counters on (iterate/HMC.jl:129-133); the per-period
+    println of the reference is not reproduced (the loop runs inside one kernel launch)."""
+    code = L.TUNER_VANILLA
+
+    def __init__(self, period=100, verbose=False):
+        assert period > 0, "Adaptation period should be positive"
+        self.period, self.verbose = int(period), bool(verbose)
+
+
+class AcceptanceRateMCTuner:
+    """AcceptanceRateMCTuner(targetrate; score=logistic_rate_score, period=100, verbose=false)
+    (src/tuners/AcceptanceRateMCTuner.jl:25-44).  `score` must be logistic_rate_score (optionally
+    with another steepness via `k`): the device evaluates 2/(1+exp(-k*(rate-target)))."""
+    code = L.TUNER_ACCEPTANCE_RATE
+
+    def __init__(self, targetrate, score=logistic_rate_score, period=100, verbose=False, k=7.):
+        assert 0 < targetrate < 1, "Target acceptance rate should be between 0 and 1"
+        assert period > 0, "Tuning period should be positive"
+        if score is not logistic_rate_score:
+            raise TypeError("only logistic_rate_score is available on the device")
+        self.targetrate, self.score, self.k = float(targetrate), score, float(k)
+        self.period, self.verbose = int(period), bool(verbose)
+
+
+class BasicMCTune:
+    """Per-chain tuner records (src/tuners/tuners.jl:5-25) as arrays over chains."""
+
+    def __init__(self, step, accepted, proposed, totproposed, rate):
+        self.step, self.accepted, self.proposed, self.totproposed, self.rate = step, accepted, proposed, totproposed, rate
+
+
+# ----------------------------------------------------------------------------- output container
+class BasicContMuvParameterNState:
+    """Monitored output (src/nstates/ParameterNStates/BasicContMuvParameterNState.jl:1-61).
+
+    numpy C-order arrays; memory layout identical to the Julia column-major NState fields:
+      value          (nchains, npost, dim)   <->  Julia  dim x npost x nchains   (value[:, i] = sample i)
+      logtarget      (nchains, npost)
+      gradlogtarget  (nchains, npost, dim)
+      diagnosticvalues (nchains, npost) uint8 accept flags
+    For a job built from a single vector the leading chain axis is dropped."""
+
+    def __init__(self, size, n):
+        self.size, self.n = size, n
+        self.value = None
+        self.logtarget = None
+        self.gradlogtarget = None
+        self.diagnosticvalues = None
+        self.diagnostickeys = []
+
+
+_MONITOR_BITS = {"value": L.MONITOR_VALUE, "logtarget": L.MONITOR_LOGTARGET, "gradlogtarget": L.MONITOR_GRADLOGTARGET}
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------- the job
+class BasicMCJob:
+    """BasicMCJob(model, sampler, mcrange, v0; tuner=VanillaMCTuner(), outopts=...)
+    (src/jobs/BasicMCJob.jl:107-185).
+
+    Extra keyword arguments of the batched GPU job:
+      seed          Philox key (the reference draws from Julia's unseeded global RNG)
+      arith         "reference" (un-fused, reference evaluation order) or "fma"
+      device        CUDA device ordinal
+      chain_offset  global index of the first chain when the chains of one logical job are sharded
+                    over several processes / GPUs
+    """
+
+    def __init__(self, model, sampler, mcrange, v0, tuner=None, outopts=None, pindex=None,
+                 seed=0, arith="reference", device=0, chain_offset=0, verbose=False):
+        tuner = VanillaMCTuner() if tuner is None else tuner
+        self.model, self.sampler, self.range, self.tuner = model, sampler, mcrange, tuner
+        self.pindex = next(i for i, v in enumerate(model.vertices) if isinstance(v, BasicContMuvParameter)) \
+            if pindex is None else pindex
+        self.parameter = model.vertices[self.pindex]
+        # outopts defaults: augment_parameter_outopts!  (src/jobs/jobs.jl:9-43)
+        oo = dict(outopts) if outopts else {}
+        oo.setdefault("destination", "nstate")
+        if oo["destination"] != "none":
+            oo.setdefault("monitor", ["value"])
+            oo.setdefault("diagnostics", [])
+        else:
+            oo.setdefault("monitor", [])
+            oo.setdefault("diagnostics", [])
+        if oo["destination"] not in ("nstate", "none"):
+            raise NotImplementedError(":destination => :iostream (CSV writers) is a 'next' row (SURVEY.md 8f)")
+        for m in oo["monitor"]:
+            if m not in _MONITOR_BITS:
+                raise KeyError("cannot monitor %r on the device path" % (m,))
+        for dg in oo["diagnostics"]:
+            if dg != "accept":
+                raise KeyError("unknown diagnostic %r" % (dg,))
+        self.outopts = oo
+
+        x0 = v0[self.parameter.key] if isinstance(v0, dict) else v0
+        x0 = np.asarray(x0, dtype=np.float64)
+        self.single = x0.ndim == 1
+        x0 = np.ascontiguousarray(np.atleast_2d(x0))
+        self.nchains, self.dim = x0.shape
+
+        cfg = L.KlbConfig()
+        cfg.struct_size = C.sizeof(L.KlbConfig)
+        cfg.sampler, cfg.target, cfg.tuner = sampler.code, self.parameter.target.code, tuner.code
+        cfg.arith = {"reference": L.ARITH_REFERENCE, "fma": L.ARITH_FMA}[arith]
+        cfg.nchains, cfg.dim = self.nchains, self.dim
+        cfg.nsteps, cfg.burnin, cfg.thinning = mcrange.nsteps, mcrange.burnin, mcrange.thinning
+        cfg.step = getattr(sampler, "leapstep", getattr(sampler, "driftstep", 1.0))
+        cfg.nleaps = getattr(sampler, "nleaps", 1)
+        cfg.target_rate = getattr(tuner, "targetrate", 0.5)
+        cfg.score_k = getattr(tuner, "k", 7.0)
+        cfg.period, cfg.verbose = tuner.period, int(tuner.verbose)
+        cfg.monitor = sum(_MONITOR_BITS[m] for m in set(oo["monitor"]))
+        cfg.diagnostics = L.DIAG_ACCEPT if "accept" in oo["diagnostics"] else 0
+        cfg.destination = L.DEST_NSTATE if oo["destination"] == "nstate" else L.DEST_NONE
+        cfg.seed, cfg.chain_offset, cfg.device = seed, chain_offset, device
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        L.check(L.lib().klb_job_create(C.byref(cfg), C.byref(self._h)))
+        try:
+            for which, arr in self.parameter.target.params(self.dim):
+                L.check(L.lib().klb_job_set_target_f64(self._h, which, _ptr(arr), arr.size))
+            if isinstance(sampler, MH):
+                if sampler.sigma.size != self.dim:
+                    raise AssertionError("MH sigma has %d entries, parameter has %d" % (sampler.sigma.size, self.dim))
+                L.check(L.lib().klb_job_set_target_f64(self._h, L.PARAM_SIGMA, _ptr(sampler.sigma), self.dim))
+            # initialize!: first target (+gradient) evaluation; finiteness asserts (HMC.jl:113-114)
+            L.check(L.lib().klb_job_set_state(self._h, _ptr(x0)))
+        except Exception:
+            self.close()
+            raise
+        self.count = 0
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib().klb_job_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference API
+    def run(self):
+        """run(job)        src/jobs/BasicMCJob.jl:212-244"""
+        L.check(L.lib().klb_job_run(self._h))
+        self.count = self.range.npoststeps
+        return self
+
+    def run_async(self):
+        L.check(L.lib().klb_job_run_async(self._h))
+        self.count = self.range.npoststeps
+
+    def sync(self):
+        L.check(L.lib().klb_job_sync(self._h))
+
+    def reset(self, x=None):
+        """reset(job) / reset(job, x)        src/jobs/BasicMCJob.jl:187-201"""
+        if x is None:
+            L.check(L.lib().klb_job_reset(self._h))
+        else:
+            x = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=np.float64)))
+            if x.shape != (self.nchains, self.dim):
+                raise AssertionError("reset value has shape %s, job has %s" % (x.shape, (self.nchains, self.dim)))
+            L.check(L.lib().klb_job_set_state(self._h, _ptr(x)))
+        self.count = 0
+        return self
+
+    def set_chunk(self, nt):
+        L.check(L.lib().klb_job_set_chunk(self._h, nt))
+
+    def _fetch(self, field, shape, dtype=np.float64):
+        out = np.empty(shape, dtype=dtype)
+        L.check(L.lib().klb_job_output(self._h, field, _ptr(out), out.nbytes))
+        return out
+
+    def output(self):
+        """output(job)        src/jobs/BasicMCJob.jl:279"""
+        if self.outopts["destination"] == "none":
+            return None
+        N, P, d = self.nchains, self.range.npoststeps, self.dim
+        ns = BasicContMuvParameterNState(d, P)
+        mon = self.outopts["monitor"]
+        if "value" in mon:
+            ns.value = self._fetch(L.OUT_VALUE, (N, P, d))
+        if "logtarget" in mon:
+            ns.logtarget = self._fetch(L.OUT_LOGTARGET, (N, P))
+        if "gradlogtarget" in mon:
+            ns.gradlogtarget = self._fetch(L.OUT_GRADLOGTARGET, (N, P, d))
+        if "accept" in self.outopts["diagnostics"]:
+            ns.diagnostickeys = ["accept"]
+            ns.diagnosticvalues = self._fetch(L.OUT_ACCEPT, (N, P), np.uint8)
+        if self.single:
+            for f in ("value", "logtarget", "gradlogtarget", "diagnosticvalues"):
+                a = getattr(ns, f)
+                if a is not None:
+                    setattr(ns, f, a[0])
+        return ns
+
+    # -- job.pstate / job.sstate.tune
+    @property
+    def pstate_value(self):
+        v = self._fetch(L.OUT_STATE, (self.nchains, self.dim))
+        return v[0] if self.single else v
+
+    @property
+    def pstate_logtarget(self):
+        v = self._fetch(L.OUT_STATE_LOGTARGET, (self.nchains,))
+        return v[0] if self.single else v
+
+    @property
+    def tune(self):
+        cnt = self._fetch(L.OUT_TUNE_COUNTERS, (self.nchains, 3), np.int64)
+        return BasicMCTune(self._fetch(L.OUT_TUNE_STEP, (self.nchains,)), cnt[:, 0].copy(), cnt[:, 1].copy(),
+                           cnt[:, 2].copy(), self._fetch(L.OUT_TUNE_RATE, (self.nchains,)))
+
+    # -- introspection
+    def plan(self):
+        p = L.KlbPlan()
+        L.check(L.lib().klb_job_plan(self._h, C.byref(p)))
+        return p
+
+    @property
+    def launches(self):
+        return L.lib().klb_job_launches(self._h)
+
+    @property
+    def last_run_ms(self):
+        return L.lib().klb_job_last_run_ms(self._h)
+
+    def device_ptr(self, field):
+        p, nb = C.c_void_p(), C.c_int64()
+        L.check(L.lib().klb_job_device_ptr(self._h, field, C.byref(p), C.byref(nb)))
+        return p.value, nb.value
+
+
+def run(job):
+    """run(job), or run(jobs::Vector) = map(run, jobs)        src/jobs/jobs.jl:212"""
+    if isinstance(job, (list, tuple)):
+        return [run(j) for j in job]
+    return job.run()
+
+
+def reset(job, x=None):
+    return job.reset(x)
+
+
+def output(job):
+    return job.output()

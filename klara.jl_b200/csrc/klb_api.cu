@@ -1,0 +1,504 @@
+// klb_api.cu -- the C ABI of libklara_b200.so (include/klara_b200.h): job objects, validation,
+// device memory, launches.  No CPU compute path exists here: without a CUDA device every
+// compute entry point fails with KLB_ECUDA.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "../../include/klara_b200.h"
+#include "klb_kernels.cuh"
+
+// per-(sampler, arithmetic) dispatchers, klb_kernels_inst.cu
+int klb_chain_0_0(const KArgs*, int, int, int*, int*, cudaStream_t);
+int klb_chain_0_1(const KArgs*, int, int, int*, int*, cudaStream_t);
+int klb_chain_1_0(const KArgs*, int, int, int*, int*, cudaStream_t);
+int klb_chain_1_1(const KArgs*, int, int, int*, int*, cudaStream_t);
+int klb_chain_2_0(const KArgs*, int, int, int*, int*, cudaStream_t);
+int klb_chain_2_1(const KArgs*, int, int, int*, int*, cudaStream_t);
+// klb_kernels_inst.cu (-DKLB_INST_INIT) / klb_aux.cu
+int klb_launch_init(const KArgs& A, int target, int nv, int fma, int check_grad, unsigned long long* flag,
+                    cudaStream_t s);
+void klb_launch_fill_tune(double* step, long long* cnt, double* rate, long long n, double step0, long long period,
+                          cudaStream_t s);
+void klb_launch_debug_normals(const uint64_t* tab, uint64_t seed, uint64_t chain, uint64_t t, long long n, double* out,
+                              cudaStream_t s);
+void klb_launch_debug_math(const uint64_t* tab, int op, long long n, const double* in, double* out, cudaStream_t s);
+void klb_launch_debug_uniform(uint64_t seed, uint64_t chain, uint64_t t, double* out, cudaStream_t s);
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess)                                                                     \
+      return fail(e_ == cudaErrorMemoryAllocation ? KLB_ENOMEM : KLB_ECUDA, "%s: %s", #call, \
+                  cudaGetErrorString(e_));                                                     \
+  } while (0)
+
+struct klb_job {
+  klb_config cfg;
+  int nv;
+  long long npost;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  // device buffers
+  double* state;
+  double* lt;
+  double* tune_step;
+  long long* tune_cnt;
+  double* tune_rate;
+  double* out_value;
+  double* out_lt;
+  double* out_grad;
+  unsigned char* out_accept;
+  double* mu;
+  double* sigma;
+  uint64_t* tab;
+  unsigned long long* flag;
+  double rosen[3];
+  bool have_mu, have_sigma, have_rosen, have_state;
+  unsigned long long t_global;  // transitions done since creation (RNG counter)
+  long long count;              // job.count
+  long long launches;
+  long long chunk;              // transitions per launch (0 = whole run)
+  int regs, bps;
+  bool timed;
+};
+
+static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int nv, int* regs, int* bps,
+                          cudaStream_t s) {
+  switch (sampler * 2 + (fma ? 1 : 0)) {
+    case 0: return klb_chain_0_0(A, target, nv, regs, bps, s);
+    case 1: return klb_chain_0_1(A, target, nv, regs, bps, s);
+    case 2: return klb_chain_1_0(A, target, nv, regs, bps, s);
+    case 3: return klb_chain_1_1(A, target, nv, regs, bps, s);
+    case 4: return klb_chain_2_0(A, target, nv, regs, bps, s);
+    case 5: return klb_chain_2_1(A, target, nv, regs, bps, s);
+  }
+  return -1;
+}
+
+static int plan_nv(long long dim) {
+  int nv = 1;
+  while (64ll * nv < dim && nv < 16) nv *= 2;
+  return 64ll * nv >= dim ? nv : -1;
+}
+
+static long long npoststeps(long long burnin, long long thinning, long long nsteps) {
+  return nsteps <= burnin ? 0 : (nsteps - burnin - 1) / thinning + 1;
+}
+
+extern "C" {
+
+int klb_version(void) { return KLB_VERSION; }
+const char* klb_last_error(void) { return g_err; }
+
+int klb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static void free_job(klb_job* j) {
+  if (!j) return;
+  cudaSetDevice(j->cfg.device);
+  cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate);
+  cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
+  cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->tab); cudaFree(j->flag);
+  if (j->ev0) cudaEventDestroy(j->ev0);
+  if (j->ev1) cudaEventDestroy(j->ev1);
+  if (j->stream) cudaStreamDestroy(j->stream);
+  delete j;
+}
+
+static void fill_args(const klb_job* j, KArgs& A) {
+  const klb_config& c = j->cfg;
+  memset(&A, 0, sizeof A);
+  A.state = j->state; A.lt = j->lt;
+  A.tune_step = j->tune_step; A.tune_cnt = j->tune_cnt; A.tune_rate = j->tune_rate;
+  A.out_value = j->out_value; A.out_lt = j->out_lt; A.out_grad = j->out_grad; A.out_accept = j->out_accept;
+  A.mu = j->mu; A.sigma = j->sigma; A.tab = j->tab;
+  A.ra = j->rosen[0]; A.rb = j->rosen[1]; A.rscale = j->rosen[2];
+  A.nchains = c.nchains; A.dim = c.dim;
+  A.burnin = c.burnin; A.thinning = c.thinning; A.npost = j->npost; A.period = c.period;
+  A.nleaps = c.nleaps; A.tuner = c.tuner;
+  // counters advance for AcceptanceRateMCTuner or a verbose tuner (iterate/HMC.jl:129-133);
+  // for MH only when verbose (iterate/MH.jl:73-75)
+  A.counters_on = (c.sampler == KLB_SAMPLER_MH) ? (c.verbose != 0)
+                                                : ((c.tuner == KLB_TUNER_ACCEPTANCE_RATE) || c.verbose != 0);
+  A.target_rate = c.target_rate; A.score_k = c.score_k;
+  A.seed = c.seed; A.chain_offset = (unsigned long long)c.chain_offset;
+}
+
+int klb_job_create(const klb_config* cfg, klb_job** out) {
+  if (!cfg || !out) return fail(KLB_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->struct_size != sizeof(klb_config))
+    return fail(KLB_EINVAL, "klb_config.struct_size = %u, library expects %zu", cfg->struct_size, sizeof(klb_config));
+  const klb_config& c = *cfg;
+  if (c.sampler < 0 || c.sampler > 2) return fail(KLB_EINVAL, "unknown sampler %d", c.sampler);
+  if (c.target == KLB_TARGET_DENSE)
+    return fail(KLB_EUNSUPPORTED, "dense-precision target is not built yet (SURVEY 8a row A8 / config C4)");
+  if (c.target != KLB_TARGET_ISO && c.target != KLB_TARGET_SHIFTED_ISO && c.target != KLB_TARGET_ROSENBROCK)
+    return fail(KLB_EINVAL, "unknown target %d", c.target);
+  if (c.tuner != KLB_TUNER_VANILLA && c.tuner != KLB_TUNER_ACCEPTANCE_RATE)
+    return fail(KLB_EINVAL, "unknown tuner %d", c.tuner);
+  if (c.arith != KLB_ARITH_REFERENCE && c.arith != KLB_ARITH_FMA) return fail(KLB_EINVAL, "unknown arith %d", c.arith);
+  if (c.nchains <= 0) return fail(KLB_EINVAL, "nchains must be positive");
+  if (c.dim <= 0) return fail(KLB_EINVAL, "dim must be positive");
+  if (c.target == KLB_TARGET_ROSENBROCK && (c.dim & 1)) return fail(KLB_EINVAL, "paired Rosenbrock needs an even dim");
+  const int nv = plan_nv(c.dim);
+  if (nv < 0) return fail(KLB_EUNSUPPORTED, "dim %lld > 1024 is not supported by the warp-per-chain kernels", (long long)c.dim);
+  // BasicMCRange asserts (src/ranges/BasicMCRange.jl:19-21)
+  if (c.burnin < 0) return fail(KLB_EINVAL, "Number of burn-in iterations should be non-negative");
+  if (c.thinning < 1) return fail(KLB_EINVAL, "Thinning should be >= 1");
+  if (c.nsteps <= c.burnin)
+    return fail(KLB_EINVAL, "Total number of MCMC iterations should be greater than number of burn-in iterations");
+  // sampler asserts (HMC.jl:93-96, MALA.jl:64-67)
+  if (c.sampler == KLB_SAMPLER_HMC) {
+    if (!(c.step > 0)) return fail(KLB_EINVAL, "Leapfrog step is not positive");
+    if (c.nleaps <= 0) return fail(KLB_EINVAL, "Number of leapfrog steps is not positive");
+  }
+  if (c.sampler == KLB_SAMPLER_MALA && !(c.step > 0)) return fail(KLB_EINVAL, "Drift step is not positive");
+  // tuner asserts (VanillaMCTuner.jl:10-13, AcceptanceRateMCTuner.jl:31-35)
+  if (c.period <= 0) return fail(KLB_EINVAL, "Adaptation period should be positive");
+  if (c.tuner == KLB_TUNER_ACCEPTANCE_RATE && !(c.target_rate > 0 && c.target_rate < 1))
+    return fail(KLB_EINVAL, "Target acceptance rate should be between 0 and 1");
+  if ((c.monitor & KLB_MONITOR_GRADLOGTARGET) && c.sampler == KLB_SAMPLER_MH)
+    return fail(KLB_EINVAL, "MH does not evaluate gradlogtarget; it cannot be monitored");
+  if (c.monitor & ~7u) return fail(KLB_EINVAL, "unknown monitor bits");
+  if (c.diagnostics & ~1u) return fail(KLB_EINVAL, "unknown diagnostics bits");
+  if (c.destination != KLB_DEST_NSTATE && c.destination != KLB_DEST_NONE) return fail(KLB_EINVAL, "unknown destination");
+  if (c.chain_offset < 0 || (unsigned long long)c.chain_offset + (unsigned long long)c.nchains > 0xFFFFFFFFull)
+    return fail(KLB_EINVAL, "global chain indices must fit 32 bits");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KLB_ECUDA, "no CUDA device available (this library has no CPU path)");
+  }
+  if (c.device < 0 || c.device >= ndev) return fail(KLB_EINVAL, "device %d out of range (%d devices)", c.device, ndev);
+  CK(cudaSetDevice(c.device));
+
+  klb_job* j = new (std::nothrow) klb_job();
+  if (!j) return fail(KLB_ENOMEM, "host allocation failed");
+  memset(j, 0, sizeof *j);
+  j->cfg = c;
+  j->nv = nv;
+  j->npost = npoststeps(c.burnin, c.thinning, c.nsteps);
+  j->rosen[0] = 1.0; j->rosen[1] = 100.0; j->rosen[2] = 0.05;
+  j->have_rosen = true;
+  const size_t N = (size_t)c.nchains, d = (size_t)c.dim, P = (size_t)j->npost, pad = 64 * (size_t)nv;
+#define CKJ(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      free_job(j);                                                                             \
+      return fail(e_ == cudaErrorMemoryAllocation ? KLB_ENOMEM : KLB_ECUDA, "%s: %s", #call, \
+                  cudaGetErrorString(e_));                                                     \
+    }                                                                                          \
+  } while (0)
+  CKJ(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
+  CKJ(cudaEventCreate(&j->ev0));
+  CKJ(cudaEventCreate(&j->ev1));
+  CKJ(cudaMalloc(&j->state, N * d * sizeof(double)));
+  CKJ(cudaMalloc(&j->lt, N * sizeof(double)));
+  CKJ(cudaMalloc(&j->tune_step, N * sizeof(double)));
+  CKJ(cudaMalloc(&j->tune_cnt, 3 * N * sizeof(long long)));
+  CKJ(cudaMalloc(&j->tune_rate, N * sizeof(double)));
+  CKJ(cudaMalloc(&j->mu, pad * sizeof(double)));
+  CKJ(cudaMalloc(&j->sigma, pad * sizeof(double)));
+  CKJ(cudaMemset(j->mu, 0, pad * sizeof(double)));
+  CKJ(cudaMemset(j->sigma, 0, pad * sizeof(double)));
+  CKJ(cudaMalloc(&j->tab, sizeof(KLB_TAB)));
+  CKJ(cudaMemcpy(j->tab, KLB_TAB, sizeof(KLB_TAB), cudaMemcpyHostToDevice));
+  CKJ(cudaMalloc(&j->flag, sizeof(unsigned long long)));
+  if (c.destination == KLB_DEST_NSTATE) {      // initialize_output, src/jobs/jobs.jl:188-210
+    if (c.monitor & KLB_MONITOR_VALUE) CKJ(cudaMalloc(&j->out_value, N * P * d * sizeof(double)));
+    if (c.monitor & KLB_MONITOR_LOGTARGET) CKJ(cudaMalloc(&j->out_lt, N * P * sizeof(double)));
+    if (c.monitor & KLB_MONITOR_GRADLOGTARGET) CKJ(cudaMalloc(&j->out_grad, N * P * d * sizeof(double)));
+    if (c.diagnostics & KLB_DIAG_ACCEPT) CKJ(cudaMalloc(&j->out_accept, N * P));
+  }
+  if (chain_dispatch(c.sampler, c.arith, nullptr, c.target, nv, &j->regs, &j->bps, j->stream) != 0) {
+    cudaGetLastError();
+    free_job(j);
+    return fail(KLB_ECUDA, "kernel image for sm_100a not loadable on this device");
+  }
+#undef CKJ
+  *out = j;
+  return KLB_OK;
+}
+
+void klb_job_destroy(klb_job* job) { free_job(job); }
+
+int klb_job_set_target_f64(klb_job* j, int which, const double* host, int64_t n) {
+  if (!j || !host) return fail(KLB_EINVAL, "null argument");
+  CK(cudaSetDevice(j->cfg.device));
+  switch (which) {
+    case KLB_PARAM_MU:
+      if (n != j->cfg.dim) return fail(KLB_EINVAL, "mu needs dim = %lld values", (long long)j->cfg.dim);
+      CK(cudaMemcpy(j->mu, host, n * sizeof(double), cudaMemcpyHostToDevice));
+      j->have_mu = true;
+      return KLB_OK;
+    case KLB_PARAM_SIGMA:
+      if (n != j->cfg.dim) return fail(KLB_EINVAL, "sigma needs dim = %lld values", (long long)j->cfg.dim);
+      CK(cudaMemcpy(j->sigma, host, n * sizeof(double), cudaMemcpyHostToDevice));
+      j->have_sigma = true;
+      return KLB_OK;
+    case KLB_PARAM_ROSEN:
+      if (n != 3) return fail(KLB_EINVAL, "rosenbrock needs 3 values (a, b, scale)");
+      memcpy(j->rosen, host, 3 * sizeof(double));
+      return KLB_OK;
+    case KLB_PARAM_C:
+      return fail(KLB_EUNSUPPORTED, "dense-precision target is not built yet");
+  }
+  return fail(KLB_EINVAL, "unknown parameter id %d", which);
+}
+
+static int reset_tune(klb_job* j) {
+  // tuner_state: BasicMCTune(step, 0, 0, tuner.period); MH gets step 1.   src/samplers/samplers.jl:29-45
+  const double step0 = j->cfg.sampler == KLB_SAMPLER_MH ? 1.0 : j->cfg.step;
+  klb_launch_fill_tune(j->tune_step, j->tune_cnt, j->tune_rate, j->cfg.nchains, step0, j->cfg.period, j->stream);
+  j->launches += 1;
+  CK(cudaGetLastError());
+  j->count = 0;
+  return KLB_OK;
+}
+
+static int init_state(klb_job* j) {
+  const klb_config& c = j->cfg;
+  if (c.target == KLB_TARGET_SHIFTED_ISO && !j->have_mu) return fail(KLB_ESTATE, "set KLB_PARAM_MU before the state");
+  if (c.sampler == KLB_SAMPLER_MH && !j->have_sigma) return fail(KLB_ESTATE, "set KLB_PARAM_SIGMA before the state");
+  KArgs A;
+  fill_args(j, A);
+  const unsigned long long none = std::numeric_limits<unsigned long long>::max();
+  CK(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
+  if (klb_launch_init(A, c.target, j->nv, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
+    return fail(KLB_EINVAL, "no init kernel for this configuration");
+  j->launches += 1;
+  CK(cudaGetLastError());
+  unsigned long long f = 0;
+  CK(cudaMemcpyAsync(&f, j->flag, sizeof f, cudaMemcpyDeviceToHost, j->stream));
+  CK(cudaStreamSynchronize(j->stream));
+  if (f != none) {
+    j->have_state = false;
+    return fail(KLB_ENOTFINITE, "Log-target%s not finite: initial value out of support (chain %llu)",
+                c.sampler != KLB_SAMPLER_MH ? " or its gradient" : "", f - 1);
+  }
+  j->have_state = true;
+  return reset_tune(j);
+}
+
+int klb_job_set_state(klb_job* j, const double* x0) {
+  if (!j || !x0) return fail(KLB_EINVAL, "null argument");
+  CK(cudaSetDevice(j->cfg.device));
+  CK(cudaMemcpyAsync(j->state, x0, (size_t)j->cfg.nchains * j->cfg.dim * sizeof(double), cudaMemcpyHostToDevice,
+                     j->stream));
+  return init_state(j);
+}
+
+int klb_job_set_state_device(klb_job* j, const double* x0_dev) {
+  if (!j || !x0_dev) return fail(KLB_EINVAL, "null argument");
+  CK(cudaSetDevice(j->cfg.device));
+  if (x0_dev != j->state)
+    CK(cudaMemcpyAsync(j->state, x0_dev, (size_t)j->cfg.nchains * j->cfg.dim * sizeof(double),
+                       cudaMemcpyDeviceToDevice, j->stream));
+  return init_state(j);
+}
+
+int klb_job_set_chunk(klb_job* j, int64_t nt) {
+  if (!j || nt < 0) return fail(KLB_EINVAL, "bad chunk");
+  j->chunk = nt;
+  return KLB_OK;
+}
+
+int klb_job_run_async(klb_job* j) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  if (!j->have_state) return fail(KLB_ESTATE, "klb_job_set_state must succeed before klb_job_run");
+  const klb_config& c = j->cfg;
+  // a second run without reset would write past column npoststeps of the NState (a BoundsError in the reference)
+  if (j->count != 0) return fail(KLB_ESTATE, "output already holds %lld samples: call klb_job_reset first", j->count);
+  CK(cudaSetDevice(c.device));
+  KArgs A;
+  fill_args(j, A);
+  CK(cudaEventRecord(j->ev0, j->stream));
+  long long done = 0, saved = 0;
+  const long long chunk = j->chunk > 0 ? j->chunk : c.nsteps;
+  while (done < c.nsteps) {
+    const long long nt = (c.nsteps - done) < chunk ? (c.nsteps - done) : chunk;
+    A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global;
+    if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->nv, nullptr, nullptr, j->stream) != 0)
+      return fail(KLB_EINVAL, "no kernel for this configuration");
+    CK(cudaGetLastError());
+    j->launches += 1;
+    done += nt;
+    j->t_global += (unsigned long long)nt;
+    saved = done <= c.burnin ? 0 : (done - c.burnin - 1) / c.thinning + 1;
+  }
+  CK(cudaEventRecord(j->ev1, j->stream));
+  j->count = j->npost;
+  j->timed = true;
+  return KLB_OK;
+}
+
+int klb_job_sync(klb_job* j) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  CK(cudaSetDevice(j->cfg.device));
+  CK(cudaStreamSynchronize(j->stream));
+  return KLB_OK;
+}
+
+int klb_job_run(klb_job* j) {
+  int rc = klb_job_run_async(j);
+  if (rc) return rc;
+  return klb_job_sync(j);
+}
+
+int klb_job_reset(klb_job* j) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  CK(cudaSetDevice(j->cfg.device));
+  return reset_tune(j);
+}
+
+static int field_ptr(klb_job* j, int field, void** p, size_t* nb) {
+  const size_t N = (size_t)j->cfg.nchains, d = (size_t)j->cfg.dim, P = (size_t)j->npost;
+  switch (field) {
+    case KLB_OUT_VALUE: *p = j->out_value; *nb = N * P * d * 8; break;
+    case KLB_OUT_LOGTARGET: *p = j->out_lt; *nb = N * P * 8; break;
+    case KLB_OUT_GRADLOGTARGET: *p = j->out_grad; *nb = N * P * d * 8; break;
+    case KLB_OUT_ACCEPT: *p = j->out_accept; *nb = N * P; break;
+    case KLB_OUT_STATE: *p = j->state; *nb = N * d * 8; break;
+    case KLB_OUT_STATE_LOGTARGET: *p = j->lt; *nb = N * 8; break;
+    case KLB_OUT_TUNE_STEP: *p = j->tune_step; *nb = N * 8; break;
+    case KLB_OUT_TUNE_COUNTERS: *p = j->tune_cnt; *nb = 3 * N * 8; break;
+    case KLB_OUT_TUNE_RATE: *p = j->tune_rate; *nb = N * 8; break;
+    default: return fail(KLB_EINVAL, "unknown field %d", field);
+  }
+  if (!*p) return fail(KLB_ESTATE, "field %d is not monitored by this job", field);
+  return KLB_OK;
+}
+
+int klb_job_output(klb_job* j, int field, void* host_dst, int64_t nbytes) {
+  if (!j || !host_dst) return fail(KLB_EINVAL, "null argument");
+  void* p; size_t nb;
+  int rc = field_ptr(j, field, &p, &nb);
+  if (rc) return rc;
+  if ((size_t)nbytes != nb) return fail(KLB_EINVAL, "field %d holds %zu bytes, caller passed %lld", field, nb, (long long)nbytes);
+  CK(cudaSetDevice(j->cfg.device));
+  CK(cudaMemcpyAsync(host_dst, p, nb, cudaMemcpyDeviceToHost, j->stream));
+  CK(cudaStreamSynchronize(j->stream));
+  return KLB_OK;
+}
+
+int klb_job_device_ptr(klb_job* j, int field, void** dev_ptr, int64_t* nbytes) {
+  if (!j || !dev_ptr || !nbytes) return fail(KLB_EINVAL, "null argument");
+  size_t nb;
+  int rc = field_ptr(j, field, dev_ptr, &nb);
+  if (rc) return rc;
+  *nbytes = (int64_t)nb;
+  return KLB_OK;
+}
+
+int klb_job_plan(klb_job* j, klb_plan* out) {
+  if (!j || !out) return fail(KLB_EINVAL, "null argument");
+  out->nv = j->nv;
+  out->warps_per_block = KLB_WPB;
+  out->regs_per_thread = j->regs;
+  out->blocks_per_sm = j->bps;
+  out->npoststeps = j->npost;
+  out->transitions_done = (int64_t)j->t_global;
+  out->saved = j->count;
+  return KLB_OK;
+}
+
+int64_t klb_job_launches(klb_job* j) { return j ? j->launches : 0; }
+
+double klb_job_last_run_ms(klb_job* j) {
+  if (!j || !j->timed) return -1.0;
+  cudaSetDevice(j->cfg.device);
+  float ms = 0.f;
+  if (cudaEventSynchronize(j->ev1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, j->ev0, j->ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+
+void* klb_job_stream(klb_job* j) { return j ? (void*)j->stream : nullptr; }
+
+int klb_host_alloc(void** p, int64_t nbytes) {
+  if (!p || nbytes <= 0) return fail(KLB_EINVAL, "bad argument");
+  CK(cudaHostAlloc(p, (size_t)nbytes, cudaHostAllocDefault));
+  return KLB_OK;
+}
+int klb_host_free(void* p) {
+  CK(cudaFreeHost(p));
+  return KLB_OK;
+}
+
+// ---------------------------------------------------------------- device self-tests
+static int dbg_setup(int device, uint64_t** tab) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KLB_ECUDA, "no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return fail(KLB_EINVAL, "device out of range");
+  CK(cudaSetDevice(device));
+  CK(cudaMalloc(tab, sizeof(KLB_TAB)));
+  CK(cudaMemcpy(*tab, KLB_TAB, sizeof(KLB_TAB), cudaMemcpyHostToDevice));
+  return KLB_OK;
+}
+
+int klb_debug_normals(int device, uint64_t seed, uint64_t chain, uint64_t t, int64_t n, double* host_out) {
+  uint64_t* tab = nullptr;
+  int rc = dbg_setup(device, &tab);
+  if (rc) return rc;
+  double* out = nullptr;
+  CK(cudaMalloc(&out, (size_t)n * 8));
+  klb_launch_debug_normals(tab, seed, chain, t, n, out, 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(host_out, out, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(out); cudaFree(tab);
+  return KLB_OK;
+}
+
+int klb_debug_math(int device, int op, int64_t n, const double* host_in, double* host_out) {
+  uint64_t* tab = nullptr;
+  int rc = dbg_setup(device, &tab);
+  if (rc) return rc;
+  double *in = nullptr, *out = nullptr;
+  CK(cudaMalloc(&in, (size_t)n * 8));
+  CK(cudaMalloc(&out, (size_t)n * 8));
+  CK(cudaMemcpy(in, host_in, (size_t)n * 8, cudaMemcpyHostToDevice));
+  klb_launch_debug_math(tab, op, n, in, out, 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(host_out, out, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  cudaFree(in); cudaFree(out); cudaFree(tab);
+  return KLB_OK;
+}
+
+int klb_debug_uniform(int device, uint64_t seed, uint64_t chain, uint64_t t, double* host_out) {
+  uint64_t* tab = nullptr;
+  int rc = dbg_setup(device, &tab);
+  if (rc) return rc;
+  double* out = nullptr;
+  CK(cudaMalloc(&out, 8));
+  klb_launch_debug_uniform(seed, chain, t, out, 0);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(host_out, out, 8, cudaMemcpyDeviceToHost));
+  cudaFree(out); cudaFree(tab);
+  return KLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+"""Target descriptors: device-resident replacements of the `logtarget` / `gradlogtarget` closures a
+user hands to Klara's BasicContMuvParameter (src/variables/parameters/BasicContMuvParameter.jl:383-411).
+
+An arbitrary host closure cannot run inside a CUDA kernel, so the boundary carries a descriptor.
+Each descriptor is also an ordinary callable on a vector (`t(z)`, `t.gradient(z)`), i.e. the same
+object is a valid plain `logtarget` function for a host implementation.
+"""
+import numpy as np
+
+from . import _lib as L
+
+
+class Target:
+    code = None
+
+    def params(self, dim):
+        """[(param id, float64 array)] uploaded through klb_job_set_target_f64."""
+        return []
+
+
+class IsoGaussian(Target):
+    """plogtarget(z) = -dot(z, z);  pgradlogtarget(z) = -2*z        (README.md:153-155)"""
+    code = L.TARGET_ISO
+
+    def __call__(self, z):
+        z = np.asarray(z, dtype=np.float64)
+        return -float(np.dot(z, z))
+
+    def gradient(self, z):
+        return -2 * np.asarray(z, dtype=np.float64)
+
+
+class ShiftedIsoGaussian(Target):
+    """-(z-mu).(z-mu), gradient -2(z-mu)        (test/BasicContMuvParameter.jl:539-563)"""
+    code = L.TARGET_SHIFTED_ISO
+
+    def __init__(self, mu):
+        self.mu = np.ascontiguousarray(mu, dtype=np.float64)
+
+    def __call__(self, z):
+        d = np.asarray(z, dtype=np.float64) - self.mu
+        return -float(np.dot(d, d))
+
+    def gradient(self, z):
+        return -2 * (np.asarray(z, dtype=np.float64) - self.mu)
+
+    def params(self, dim):
+        if self.mu.size != dim:
+            raise AssertionError("mu has %d entries, parameter has %d" % (self.mu.size, dim))
+        return [(L.PARAM_MU, self.mu)]
+
+
+class Rosenbrock(Target):
+    """Paired Rosenbrock ("banana"), this repo's definition:
+    logtarget = -scale * sum_k [ b (x[2k+1] - x[2k]^2)^2 + (a - x[2k])^2 ]   (0-based pairs)."""
+    code = L.TARGET_ROSENBROCK
+
+    def __init__(self, a=1.0, b=100.0, scale=0.05):
+        self.a, self.b, self.scale = float(a), float(b), float(scale)
+
+    def __call__(self, z):
+        z = np.asarray(z, dtype=np.float64)
+        x, y = z[0::2], z[1::2]
+        return -self.scale * float(np.sum(self.b * (y - x * x) ** 2 + (self.a - x) ** 2))
+
+    def gradient(self, z):
+        z = np.asarray(z, dtype=np.float64)
+        x, y = z[0::2], z[1::2]
+        u = y - x * x
+        g = np.empty_like(z)
+        g[0::2] = self.scale * (4 * self.b * x * u + 2 * (self.a - x))
+        g[1::2] = -self.scale * 2 * self.b * u
+        return g
+
+    def params(self, dim):
+        return [(L.PARAM_ROSEN, np.array([self.a, self.b, self.scale], dtype=np.float64))]
+
+
+class DenseGaussian(Target):
+    """-z'Cz, gradient -2Cz with a dense precision matrix C
+    (doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9)."""
+    code = L.TARGET_DENSE
+
+    def __init__(self, C):
+        self.C = np.ascontiguousarray(C, dtype=np.float64)
+
+    def __call__(self, z):
+        z = np.asarray(z, dtype=np.float64)
+        return -float(z @ (self.C @ z))
+
+    def gradient(self, z):
+        return -2 * (self.C @ np.asarray(z, dtype=np.float64))
+
+    def params(self, dim):
+        return [(L.PARAM_C, self.C.reshape(-1))]

@@ -1,0 +1,212 @@
+"""GPU parity suite: the CUDA path (through the C ABI) against the CPU oracle, bit for bit, on the
+same seeded inputs.  Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import assert_same, build_pair, compare_run, synthetic_x0
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------ primitives
+@pytest.mark.parametrize("seed,chain,t", [(0, 0, 0), (20240925, 17, 3), (2**63 + 5, 2**32 - 1, 2**40 + 9)])
+def test_device_normals_match_oracle(K, O, seed, chain, t):
+    n = 1 << 17
+    out = np.empty(n)
+    K._lib.check(K._lib.lib().klb_debug_normals(0, seed, chain, t, n, _ptr(out)))
+    assert_same("normals", out, O.normals(seed, chain, t, n))
+
+
+def test_device_uniform_matches_oracle(K, O):
+    for seed, chain, t in [(1, 0, 1), (99, 65535, 200), (2**64 - 1, 12345, 2**33)]:
+        out = np.empty(1)
+        K._lib.check(K._lib.lib().klb_debug_uniform(0, seed, chain, t, _ptr(out)))
+        assert out[0] == O.uniform(seed, chain, t)
+        assert 0.0 <= out[0] < 1.0
+
+
+def test_device_exp_log_match_oracle(K, O):
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(-750, 710, 200000), rng.uniform(-3, 3, 200000),
+                         np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 709.782712893384, 709.79, -745.2, -745.0,
+                                   -708.4, 1e-300, -1e-300])])
+    out = np.empty_like(xs)
+    K._lib.check(K._lib.lib().klb_debug_math(0, 0, xs.size, _ptr(xs), _ptr(out)))
+    assert_same("exp", out, np.array([O.exp(x) for x in xs]))
+    xl = np.concatenate([rng.uniform(0, 1, 200000), 10.0 ** rng.uniform(-320, 308, 100000),
+                         rng.uniform(0.98, 1.02, 100000),
+                         np.array([0.0, -0.0, 1.0, np.inf, -1.0, np.nan, 5e-324, 2.2250738585072014e-308])])
+    out = np.empty_like(xl)
+    K._lib.check(K._lib.lib().klb_debug_math(0, 1, xl.size, _ptr(xl), _ptr(out)))
+    assert_same("log", out, np.array([O.log(x) for x in xl]))
+
+
+# ------------------------------------------------------------------ samplers vs oracle
+DIMS = [2, 7, 64, 100, 128, 250, 512, 1024]
+
+
+@pytest.mark.parametrize("arith", ["reference", "fma"])
+@pytest.mark.parametrize("dim", DIMS)
+def test_hmc_iso_bit_exact(K, dim, arith):
+    eps = 0.3 / np.sqrt(dim) if dim > 4 else 0.2
+    job, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", nchains=37, dim=dim, nsteps=50, burnin=20, thinning=3,
+                                      step=eps, nleaps=10, seed=20240925, arith=arith)
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    acc = out.diagnosticvalues.mean()
+    assert 0.05 < acc <= 1.0
+
+
+@pytest.mark.parametrize("arith", ["reference", "fma"])
+@pytest.mark.parametrize("dim", [2, 33, 128, 256, 1000])
+def test_mala_iso_bit_exact(K, dim, arith):
+    job, cfg, x0, tp, sg = build_pair(K, "MALA", "iso", nchains=41, dim=dim, nsteps=80, burnin=30,
+                                      step=0.9 / dim ** (1 / 3), seed=7, arith=arith,
+                                      monitor=("value", "logtarget", "gradlogtarget"))
+    compare_run(job, cfg, x0, tp, sg)
+
+
+@pytest.mark.parametrize("arith", ["reference", "fma"])
+@pytest.mark.parametrize("dim", [1, 2, 65, 512])
+def test_mh_iso_bit_exact(K, dim, arith):
+    sigma = np.linspace(0.05, 0.4, dim) if dim > 1 else np.array([0.7])
+    job, cfg, x0, tp, sg = build_pair(K, "MH", "iso", nchains=29, dim=dim, nsteps=120, burnin=20, thinning=2,
+                                      seed=99, arith=arith, sigma=sigma, verbose=True)
+    compare_run(job, cfg, x0, tp, sg)
+
+
+@pytest.mark.parametrize("sampler", ["HMC", "MALA", "MH"])
+@pytest.mark.parametrize("target", ["shifted", "rosen"])
+def test_other_targets_bit_exact(K, sampler, target):
+    dim = 96
+    step = {"HMC": 0.02, "MALA": 0.002, "MH": 0.1}[sampler]
+    mon = ("value", "logtarget") if sampler == "MH" else ("value", "logtarget", "gradlogtarget")
+    for arith in ("reference", "fma"):
+        job, cfg, x0, tp, sg = build_pair(K, sampler, target, nchains=33, dim=dim, nsteps=60, burnin=10, step=step,
+                                          nleaps=7, seed=4242, arith=arith, monitor=mon,
+                                          sigma=np.full(dim, 0.02))
+        compare_run(job, cfg, x0, tp, sg)
+
+
+@pytest.mark.parametrize("sampler,step", [("HMC", 0.01), ("MALA", 0.5)])
+def test_acceptance_rate_tuner_bit_exact(K, sampler, step):
+    """burn-in adaptation: step *= logistic_rate_score(rate - target) every `period` proposals while
+    totproposed <= burnin; per-chain records must match (iterate/HMC.jl:203-224)"""
+    job, cfg, x0, tp, sg = build_pair(K, sampler, "iso", nchains=48, dim=64, nsteps=260, burnin=200, step=step,
+                                      nleaps=5, tuner="accrate", target_rate=0.574 if sampler == "MALA" else 0.8,
+                                      period=25, seed=31337)
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    tn = job.tune
+    assert (tn.totproposed == 225).all()       # period*(1 + floor(burnin/period)) = 25*9
+    assert (tn.proposed == 60).all()           # keeps counting after burn-in
+    assert not np.allclose(tn.step, step)      # adapted
+
+
+def test_verbose_vanilla_counters(K):
+    job, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", nchains=8, dim=16, nsteps=130, burnin=100, step=0.1,
+                                      nleaps=4, tuner="vanilla", verbose=True, period=50, seed=5)
+    compare_run(job, cfg, x0, tp, sg)
+    tn = job.tune
+    assert (tn.totproposed == 150).all() and (tn.proposed == 30).all()
+
+
+def test_chunked_launches_are_invariant(K):
+    """one launch per transition (lockstep) == one launch for the whole run"""
+    res = []
+    for chunk in (0, 1, 7):
+        job, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", nchains=21, dim=130, nsteps=40, burnin=11, thinning=2,
+                                          step=0.03, nleaps=6, seed=77)
+        job.set_chunk(chunk)
+        out, ref = compare_run(job, cfg, x0, tp, sg)
+        res.append(out.value)
+    assert_same("chunk 1 vs whole", res[1], res[0])
+    assert_same("chunk 7 vs whole", res[2], res[0])
+
+
+def test_sharding_is_invariant(K):
+    """chains [8, 24) of a 32-chain job computed as their own shard give the same bits (global chain
+    index in the RNG counter): the multi-GPU invariance"""
+    full, cfg, x0, tp, sg = build_pair(K, "MALA", "iso", nchains=32, dim=40, nsteps=30, burnin=5, step=0.2, seed=3)
+    full.run()
+    v = full.output().value
+    shard, cfg2, x02, _, _ = build_pair(K, "MALA", "iso", nchains=16, dim=40, nsteps=30, burnin=5, step=0.2, seed=3,
+                                        chain_offset=8)
+    assert_same("x0 shard", x02, x0[8:24])
+    shard.run()
+    assert_same("shard", shard.output().value, v[8:24])
+
+
+def test_reset_and_second_run(K):
+    """run twice without reset overruns the NState (BoundsError in the reference); after reset(job) the chain
+    continues from its current state with fresh randomness and zeroed tuner records"""
+    job, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", nchains=10, dim=20, nsteps=30, burnin=10, step=0.1, nleaps=3,
+                                      seed=11, tuner="accrate", period=5)
+    out1, ref1 = compare_run(job, cfg, x0, tp, sg)
+    with pytest.raises(K.KlaraError):
+        job.run()
+    job.reset()
+    tn = job.tune
+    assert (tn.accepted == 0).all() and (tn.proposed == 0).all() and (tn.totproposed == 5).all()
+    assert np.isnan(tn.rate).all() and (tn.step == 0.1).all()
+    out2, ref2 = compare_run(job, cfg, ref1["x"], tp, sg, t0=30)
+    assert not np.array_equal(out1.value, out2.value)
+    # reset(job, x): restart from a new value
+    job.reset(x0)
+    assert_same("state after reset(job, x)", job.pstate_value, x0)
+
+
+def test_nonfinite_initial_value_is_rejected(K):
+    x0 = synthetic_x0(1, 6, 10)
+    x0[4, 3] = np.inf
+    with pytest.raises(K.KlaraError) as ei:
+        build_pair(K, "HMC", "iso", nchains=6, dim=10, nsteps=5, x0=x0)
+    assert ei.value.code == K._lib.KLB_ENOTFINITE and "chain 4" in str(ei.value)
+
+
+def test_nan_proposals_reject(K):
+    """a divergent trajectory (huge step) yields NaN/-Inf ratios, which must reject silently
+    (iterate/HMC.jl:163-165: rand() < NaN is false)"""
+    job, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", nchains=5, dim=8, nsteps=12, step=1e200, nleaps=3, seed=2)
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    assert out.diagnosticvalues.sum() == 0
+    assert_same("state unchanged", job.pstate_value, x0)
+
+
+def test_readme_mh_example(K, O):
+    """README.md:23-55: MH(ones(2)), -z.z, one chain, nsteps 10000, burnin 1000, v0 = [5.1, -0.9]"""
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    model = K.likelihood_model(p, False)
+    job = K.BasicMCJob(model, K.MH(np.ones(2)), K.BasicMCRange(nsteps=10000, burnin=1000), {"p": [5.1, -0.9]},
+                       seed=2024)
+    K.run(job)
+    chain = K.output(job)
+    assert chain.value.shape == (9000, 2)
+    cfg = O.make_config(O.MH, O.ISO, 1, 2, 10000, 1000, seed=2024, nv=job.plan().nv)
+    ref = O.run(cfg, np.array([[5.1, -0.9]]), None, np.ones(2))
+    assert_same("README chain", chain.value, ref["value"][0])
+    # target is N(0, 1/2 I)
+    assert abs(chain.value.mean()) < 0.1 and abs(chain.value.var() - 0.5) < 0.1
+
+
+def test_full_size_properties_c3(K):
+    """BASELINE config C3 at full width (65 536 chains x 1024, HMC L=10) for a few transitions:
+    size-independent properties -- stored log-target equals -z.z of the stored value, rejected
+    transitions repeat the previous sample, acceptance is high at eps = 0.05/sqrt(d)-scale steps"""
+    N, d = 65536, 1024
+    x0 = np.random.default_rng(0).normal(size=(N, d)) * np.sqrt(0.5)
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    job = K.BasicMCJob(K.likelihood_model(p, False), K.HMC(0.01, 10), K.BasicMCRange(nsteps=6, burnin=3),
+                       {"p": x0}, outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}, seed=1)
+    job.run()
+    out = job.output()
+    v, lt, acc = out.value, out.logtarget, out.diagnosticvalues
+    np.testing.assert_allclose(lt, -(v * v).sum(-1), rtol=1e-12)
+    rej = acc[:, 1:] == 0
+    assert np.array_equal(v[:, 1:][rej], v[:, :-1][rej])
+    assert acc.mean() > 0.6
+    assert_same("final state == last sample", job.pstate_value, v[:, -1])
