@@ -122,11 +122,15 @@ typedef struct {
 
 /* geometry the library chose for a job (needed by the oracle to reproduce the reduction order) */
 typedef struct {
-  int32_t nv;               /* double2 units per lane: a chain is owned by one warp, lane l holds
-                               elements 2(l+32m), 2(l+32m)+1, m < nv */
+  int32_t nv;               /* double2 units per lane of the canonical reduction order: lane l owns
+                               elements 2(l+32m), 2(l+32m)+1, m < nv (DESIGN.md "reduction order") */
   int32_t warps_per_block;
+  int32_t warps_per_chain;  /* W: a chain is owned by W warps; warp w holds the units m = w (mod W) */
   int32_t regs_per_thread;
   int32_t blocks_per_sm;
+  int64_t ld;               /* leading dimension of the device-resident state / value / gradient columns
+                               (dim rounded up to even, so every column is 16-byte aligned); host copies
+                               made by klb_job_output are dense (leading dimension = dim) */
   int64_t npoststeps;       /* length((burnin+1):thinning:nsteps) */
   int64_t transitions_done; /* global transition counter t (RNG counter word) */
   int64_t saved;            /* job.count: samples stored since the last reset */

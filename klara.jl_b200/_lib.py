@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libklara_b200.so")
+# KLB_LIB_PATH selects an experimental build variant (klara.jl_b200/build.py KLB_VARIANT=...)
+LIB_PATH = os.environ.get("KLB_LIB_PATH") or os.path.join(HERE, "lib", "libklara_b200.so")
 
 # error codes / enums (mirror include/klara_b200.h)
 KLB_OK, KLB_EINVAL, KLB_ECUDA, KLB_ENOTFINITE, KLB_ESTATE, KLB_EUNSUPPORTED, KLB_ENOMEM = 0, -1, -2, -3, -4, -5, -6
@@ -38,8 +39,9 @@ class KlbConfig(C.Structure):
 
 
 class KlbPlan(C.Structure):
-    _fields_ = [("nv", C.c_int32), ("warps_per_block", C.c_int32), ("regs_per_thread", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("npoststeps", C.c_int64), ("transitions_done", C.c_int64),
+    _fields_ = [("nv", C.c_int32), ("warps_per_block", C.c_int32), ("warps_per_chain", C.c_int32),
+                ("regs_per_thread", C.c_int32),
+                ("blocks_per_sm", C.c_int32), ("ld", C.c_int64), ("npoststeps", C.c_int64), ("transitions_done", C.c_int64),
                 ("saved", C.c_int64)]
 
 

@@ -15,12 +15,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libklara_b200.so")
+# experiments: KLB_VARIANT=name KLB_EXTRA_FLAGS="-DKLB_RANDN_UNROLL=4" builds lib/libklara_b200_name.so
+VARIANT = os.environ.get("KLB_VARIANT", "")
+if VARIANT:
+    OBJ = os.path.join(HERE, "_build_" + VARIANT)
+LIB = os.path.join(LIBDIR, "libklara_b200%s.so" % ("_" + VARIANT if VARIANT else ""))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-fmad=false",                      # never contract a*b+c behind our back: fma is always explicit
-         "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"]
+         "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"] + os.environ.get("KLB_EXTRA_FLAGS", "").split()
 
 HEADERS = ["klb_kernels.cuh", "klb_math.h", "klb_tables.h", "../../include/klara_b200.h"]
 

@@ -14,14 +14,14 @@
 #include "klb_kernels.cuh"
 
 // per-(sampler, arithmetic) dispatchers, klb_kernels_inst.cu
-int klb_chain_0_0(const KArgs*, int, int, int*, int*, cudaStream_t);
-int klb_chain_0_1(const KArgs*, int, int, int*, int*, cudaStream_t);
-int klb_chain_1_0(const KArgs*, int, int, int*, int*, cudaStream_t);
-int klb_chain_1_1(const KArgs*, int, int, int*, int*, cudaStream_t);
-int klb_chain_2_0(const KArgs*, int, int, int*, int*, cudaStream_t);
-int klb_chain_2_1(const KArgs*, int, int, int*, int*, cudaStream_t);
+int klb_chain_0_0(const KArgs*, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_0_1(const KArgs*, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_1_0(const KArgs*, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_1_1(const KArgs*, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_2_0(const KArgs*, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_2_1(const KArgs*, int, int, int, int*, int*, cudaStream_t);
 // klb_kernels_inst.cu (-DKLB_INST_INIT) / klb_aux.cu
-int klb_launch_init(const KArgs& A, int target, int nv, int fma, int check_grad, unsigned long long* flag,
+int klb_launch_init(const KArgs& A, int target, int W, int NV, int fma, int check_grad, unsigned long long* flag,
                     cudaStream_t s);
 void klb_launch_fill_tune(double* step, long long* cnt, double* rate, long long n, double step0, long long period,
                           cudaStream_t s);
@@ -49,7 +49,9 @@ static int fail(int code, const char* fmt, ...) {
 
 struct klb_job {
   klb_config cfg;
-  int nv;
+  int gw, gnv;      // team geometry: warps per chain, double2 units per thread
+  int nv;           // = gw * gnv: units per lane of the canonical reduction order
+  long long ld;     // even leading dimension of the state / value / grad columns
   long long npost;
   cudaStream_t stream;
   cudaEvent_t ev0, ev1;
@@ -77,23 +79,34 @@ struct klb_job {
   bool timed;
 };
 
-static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int nv, int* regs, int* bps,
+static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int gw, int gnv, int* regs, int* bps,
                           cudaStream_t s) {
   switch (sampler * 2 + (fma ? 1 : 0)) {
-    case 0: return klb_chain_0_0(A, target, nv, regs, bps, s);
-    case 1: return klb_chain_0_1(A, target, nv, regs, bps, s);
-    case 2: return klb_chain_1_0(A, target, nv, regs, bps, s);
-    case 3: return klb_chain_1_1(A, target, nv, regs, bps, s);
-    case 4: return klb_chain_2_0(A, target, nv, regs, bps, s);
-    case 5: return klb_chain_2_1(A, target, nv, regs, bps, s);
+    case 0: return klb_chain_0_0(A, target, gw, gnv, regs, bps, s);
+    case 1: return klb_chain_0_1(A, target, gw, gnv, regs, bps, s);
+    case 2: return klb_chain_1_0(A, target, gw, gnv, regs, bps, s);
+    case 3: return klb_chain_1_1(A, target, gw, gnv, regs, bps, s);
+    case 4: return klb_chain_2_0(A, target, gw, gnv, regs, bps, s);
+    case 5: return klb_chain_2_1(A, target, gw, gnv, regs, bps, s);
   }
   return -1;
 }
 
-static int plan_nv(long long dim) {
-  int nv = 1;
-  while (64ll * nv < dim && nv < 16) nv *= 2;
-  return 64ll * nv >= dim ? nv : -1;
+// Team geometry by dim: (warps per chain, double2 units per thread), capacity 64*W*NV elements.
+// KLB_GEOM="W,NV" overrides the default (experiments; must be an instantiated pair with enough capacity).
+static int plan_geom(long long dim, int* gw, int* gnv) {
+  static const int geoms[][2] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {4, 4}};
+  const char* env = getenv("KLB_GEOM");
+  if (env) {
+    int w = 0, nv = 0;
+    if (sscanf(env, "%d,%d", &w, &nv) == 2 && w > 0 && nv > 0 && 64ll * w * nv >= dim) {
+      *gw = w; *gnv = nv;
+      return 0;
+    }
+  }
+  for (auto& g : geoms)
+    if (64ll * g[0] * g[1] >= dim) { *gw = g[0]; *gnv = g[1]; return 0; }
+  return -1;
 }
 
 static long long npoststeps(long long burnin, long long thinning, long long nsteps) {
@@ -131,7 +144,7 @@ static void fill_args(const klb_job* j, KArgs& A) {
   A.out_value = j->out_value; A.out_lt = j->out_lt; A.out_grad = j->out_grad; A.out_accept = j->out_accept;
   A.mu = j->mu; A.sigma = j->sigma; A.tab = j->tab;
   A.ra = j->rosen[0]; A.rb = j->rosen[1]; A.rscale = j->rosen[2];
-  A.nchains = c.nchains; A.dim = c.dim;
+  A.nchains = c.nchains; A.dim = c.dim; A.ld = j->ld;
   A.burnin = c.burnin; A.thinning = c.thinning; A.npost = j->npost; A.period = c.period;
   A.nleaps = c.nleaps; A.tuner = c.tuner;
   // counters advance for AcceptanceRateMCTuner or a verbose tuner (iterate/HMC.jl:129-133);
@@ -159,8 +172,10 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if (c.nchains <= 0) return fail(KLB_EINVAL, "nchains must be positive");
   if (c.dim <= 0) return fail(KLB_EINVAL, "dim must be positive");
   if (c.target == KLB_TARGET_ROSENBROCK && (c.dim & 1)) return fail(KLB_EINVAL, "paired Rosenbrock needs an even dim");
-  const int nv = plan_nv(c.dim);
-  if (nv < 0) return fail(KLB_EUNSUPPORTED, "dim %lld > 1024 is not supported by the warp-per-chain kernels", (long long)c.dim);
+  int gw = 0, gnv = 0;
+  if (plan_geom(c.dim, &gw, &gnv) != 0)
+    return fail(KLB_EUNSUPPORTED, "dim %lld > 1024 is not supported by the register-resident chain kernels", (long long)c.dim);
+  const int nv = gw * gnv;
   // BasicMCRange asserts (src/ranges/BasicMCRange.jl:19-21)
   if (c.burnin < 0) return fail(KLB_EINVAL, "Number of burn-in iterations should be non-negative");
   if (c.thinning < 1) return fail(KLB_EINVAL, "Thinning should be >= 1");
@@ -196,11 +211,12 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if (!j) return fail(KLB_ENOMEM, "host allocation failed");
   memset(j, 0, sizeof *j);
   j->cfg = c;
-  j->nv = nv;
+  j->nv = nv; j->gw = gw; j->gnv = gnv;
+  j->ld = (c.dim + 1) & ~1ll;
   j->npost = npoststeps(c.burnin, c.thinning, c.nsteps);
   j->rosen[0] = 1.0; j->rosen[1] = 100.0; j->rosen[2] = 0.05;
   j->have_rosen = true;
-  const size_t N = (size_t)c.nchains, d = (size_t)c.dim, P = (size_t)j->npost, pad = 64 * (size_t)nv;
+  const size_t N = (size_t)c.nchains, d = (size_t)j->ld, P = (size_t)j->npost, pad = 64 * (size_t)nv;
 #define CKJ(call)                                                                              \
   do {                                                                                         \
     cudaError_t e_ = (call);                                                                   \
@@ -214,6 +230,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   CKJ(cudaEventCreate(&j->ev0));
   CKJ(cudaEventCreate(&j->ev1));
   CKJ(cudaMalloc(&j->state, N * d * sizeof(double)));
+  CKJ(cudaMemset(j->state, 0, N * d * sizeof(double)));
   CKJ(cudaMalloc(&j->lt, N * sizeof(double)));
   CKJ(cudaMalloc(&j->tune_step, N * sizeof(double)));
   CKJ(cudaMalloc(&j->tune_cnt, 3 * N * sizeof(long long)));
@@ -227,14 +244,15 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   CKJ(cudaMalloc(&j->flag, sizeof(unsigned long long)));
   if (c.destination == KLB_DEST_NSTATE) {      // initialize_output, src/jobs/jobs.jl:188-210
     if (c.monitor & KLB_MONITOR_VALUE) CKJ(cudaMalloc(&j->out_value, N * P * d * sizeof(double)));
+    if (j->out_value && (c.dim & 1)) CKJ(cudaMemset(j->out_value, 0, N * P * d * sizeof(double)));
     if (c.monitor & KLB_MONITOR_LOGTARGET) CKJ(cudaMalloc(&j->out_lt, N * P * sizeof(double)));
     if (c.monitor & KLB_MONITOR_GRADLOGTARGET) CKJ(cudaMalloc(&j->out_grad, N * P * d * sizeof(double)));
     if (c.diagnostics & KLB_DIAG_ACCEPT) CKJ(cudaMalloc(&j->out_accept, N * P));
   }
-  if (chain_dispatch(c.sampler, c.arith, nullptr, c.target, nv, &j->regs, &j->bps, j->stream) != 0) {
+  if (chain_dispatch(c.sampler, c.arith, nullptr, c.target, gw, gnv, &j->regs, &j->bps, j->stream) != 0) {
     cudaGetLastError();
     free_job(j);
-    return fail(KLB_ECUDA, "kernel image for sm_100a not loadable on this device");
+    return fail(KLB_ECUDA, "no sm_100a kernel image for geometry (%d,%d) loadable on this device", gw, gnv);
   }
 #undef CKJ
   *out = j;
@@ -285,7 +303,7 @@ static int init_state(klb_job* j) {
   fill_args(j, A);
   const unsigned long long none = std::numeric_limits<unsigned long long>::max();
   CK(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
-  if (klb_launch_init(A, c.target, j->nv, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
+  if (klb_launch_init(A, c.target, j->gw, j->gnv, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
     return fail(KLB_EINVAL, "no init kernel for this configuration");
   j->launches += 1;
   CK(cudaGetLastError());
@@ -304,17 +322,17 @@ static int init_state(klb_job* j) {
 int klb_job_set_state(klb_job* j, const double* x0) {
   if (!j || !x0) return fail(KLB_EINVAL, "null argument");
   CK(cudaSetDevice(j->cfg.device));
-  CK(cudaMemcpyAsync(j->state, x0, (size_t)j->cfg.nchains * j->cfg.dim * sizeof(double), cudaMemcpyHostToDevice,
-                     j->stream));
+  CK(cudaMemcpy2DAsync(j->state, (size_t)j->ld * 8, x0, (size_t)j->cfg.dim * 8, (size_t)j->cfg.dim * 8,
+                       (size_t)j->cfg.nchains, cudaMemcpyHostToDevice, j->stream));
   return init_state(j);
 }
 
 int klb_job_set_state_device(klb_job* j, const double* x0_dev) {
   if (!j || !x0_dev) return fail(KLB_EINVAL, "null argument");
   CK(cudaSetDevice(j->cfg.device));
-  if (x0_dev != j->state)
-    CK(cudaMemcpyAsync(j->state, x0_dev, (size_t)j->cfg.nchains * j->cfg.dim * sizeof(double),
-                       cudaMemcpyDeviceToDevice, j->stream));
+  if (x0_dev != j->state)   // x0_dev is a dense dim x nchains matrix
+    CK(cudaMemcpy2DAsync(j->state, (size_t)j->ld * 8, x0_dev, (size_t)j->cfg.dim * 8, (size_t)j->cfg.dim * 8,
+                         (size_t)j->cfg.nchains, cudaMemcpyDeviceToDevice, j->stream));
   return init_state(j);
 }
 
@@ -339,7 +357,7 @@ int klb_job_run_async(klb_job* j) {
   while (done < c.nsteps) {
     const long long nt = (c.nsteps - done) < chunk ? (c.nsteps - done) : chunk;
     A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global;
-    if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->nv, nullptr, nullptr, j->stream) != 0)
+    if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, nullptr, nullptr, j->stream) != 0)
       return fail(KLB_EINVAL, "no kernel for this configuration");
     CK(cudaGetLastError());
     j->launches += 1;
@@ -372,14 +390,16 @@ int klb_job_reset(klb_job* j) {
   return reset_tune(j);
 }
 
-static int field_ptr(klb_job* j, int field, void** p, size_t* nb) {
+// *cols > 0: the field is a matrix of `cols` columns of cfg.dim doubles stored with leading dimension ld
+static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols) {
   const size_t N = (size_t)j->cfg.nchains, d = (size_t)j->cfg.dim, P = (size_t)j->npost;
+  *cols = 0;
   switch (field) {
-    case KLB_OUT_VALUE: *p = j->out_value; *nb = N * P * d * 8; break;
+    case KLB_OUT_VALUE: *p = j->out_value; *nb = N * P * d * 8; *cols = N * P; break;
     case KLB_OUT_LOGTARGET: *p = j->out_lt; *nb = N * P * 8; break;
-    case KLB_OUT_GRADLOGTARGET: *p = j->out_grad; *nb = N * P * d * 8; break;
+    case KLB_OUT_GRADLOGTARGET: *p = j->out_grad; *nb = N * P * d * 8; *cols = N * P; break;
     case KLB_OUT_ACCEPT: *p = j->out_accept; *nb = N * P; break;
-    case KLB_OUT_STATE: *p = j->state; *nb = N * d * 8; break;
+    case KLB_OUT_STATE: *p = j->state; *nb = N * d * 8; *cols = N; break;
     case KLB_OUT_STATE_LOGTARGET: *p = j->lt; *nb = N * 8; break;
     case KLB_OUT_TUNE_STEP: *p = j->tune_step; *nb = N * 8; break;
     case KLB_OUT_TUNE_COUNTERS: *p = j->tune_cnt; *nb = 3 * N * 8; break;
@@ -392,29 +412,35 @@ static int field_ptr(klb_job* j, int field, void** p, size_t* nb) {
 
 int klb_job_output(klb_job* j, int field, void* host_dst, int64_t nbytes) {
   if (!j || !host_dst) return fail(KLB_EINVAL, "null argument");
-  void* p; size_t nb;
-  int rc = field_ptr(j, field, &p, &nb);
+  void* p; size_t nb, cols;
+  int rc = field_ptr(j, field, &p, &nb, &cols);
   if (rc) return rc;
   if ((size_t)nbytes != nb) return fail(KLB_EINVAL, "field %d holds %zu bytes, caller passed %lld", field, nb, (long long)nbytes);
   CK(cudaSetDevice(j->cfg.device));
-  CK(cudaMemcpyAsync(host_dst, p, nb, cudaMemcpyDeviceToHost, j->stream));
+  if (cols && j->ld != j->cfg.dim)   // odd dim: device columns are padded to an even leading dimension
+    CK(cudaMemcpy2DAsync(host_dst, (size_t)j->cfg.dim * 8, p, (size_t)j->ld * 8, (size_t)j->cfg.dim * 8, cols,
+                         cudaMemcpyDeviceToHost, j->stream));
+  else
+    CK(cudaMemcpyAsync(host_dst, p, nb, cudaMemcpyDeviceToHost, j->stream));
   CK(cudaStreamSynchronize(j->stream));
   return KLB_OK;
 }
 
 int klb_job_device_ptr(klb_job* j, int field, void** dev_ptr, int64_t* nbytes) {
   if (!j || !dev_ptr || !nbytes) return fail(KLB_EINVAL, "null argument");
-  size_t nb;
-  int rc = field_ptr(j, field, dev_ptr, &nb);
+  size_t nb, cols;
+  int rc = field_ptr(j, field, dev_ptr, &nb, &cols);
   if (rc) return rc;
-  *nbytes = (int64_t)nb;
+  *nbytes = (int64_t)(cols ? cols * (size_t)j->ld * 8 : nb);   // matrices: `cols` columns with leading dimension plan.ld
   return KLB_OK;
 }
 
 int klb_job_plan(klb_job* j, klb_plan* out) {
   if (!j || !out) return fail(KLB_EINVAL, "null argument");
   out->nv = j->nv;
+  out->ld = j->ld;
   out->warps_per_block = KLB_WPB;
+  out->warps_per_chain = j->gw;
   out->regs_per_thread = j->regs;
   out->blocks_per_sm = j->bps;
   out->npoststeps = j->npost;

@@ -23,10 +23,14 @@
 
 #if defined(__CUDACC__)
 #define KLB_HD __host__ __device__ __forceinline__
+/* the rare, bulky routines (exp, log, ziggurat slow path) are real calls on the device: inlining them
+ * at every site blows the instruction cache of the chain kernels */
+#define KLB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #include <math.h>
 #include <string.h>
 #define KLB_HD static inline
+#define KLB_HD_NOINLINE static inline
 #endif
 
 /* ---------------------------------------------------------------- bit casts */
@@ -185,7 +189,7 @@ KLB_HD double klb_accept_uniform(const klb_stream* s) {
 #define KLB_EXP_SHIFT 0x1.8p52
 
 /* exp(x); tab = pointer to a copy of KLB_TAB.  |error| < 0.51 ulp (tests/test_math.py). */
-KLB_HD double klb_exp(double x, const uint64_t* tab) {
+KLB_HD_NOINLINE double klb_exp(double x, const uint64_t* tab) {
   if (!(x == x)) return x;
   if (x > 709.782712893384) return klb_u2d(0x7FF0000000000000ULL);
   if (x < -745.2) return 0.0;
@@ -220,7 +224,7 @@ KLB_HD double klb_exp(double x, const uint64_t* tab) {
 }
 
 /* log(x); error < 1 ulp, except < 2 ulp for x in (0.99, 1) (tests/test_math.py) */
-KLB_HD double klb_log(double x, const uint64_t* tab) {
+KLB_HD_NOINLINE double klb_log(double x, const uint64_t* tab) {
   uint64_t ix = klb_d2u(x);
   int64_t kadj = 0;
   if (ix - 0x0010000000000000ULL >= 0x7FE0000000000000ULL) {
@@ -274,7 +278,7 @@ KLB_HD int klb_zig_fast(uint64_t w, const uint64_t* tab, double* x) {
 /* Complete draw for element `elem` given its first candidate word w (from
  * klb_stream_draw(s, elem >> 1, KLB_TAG_NORMAL, 0), low word for even elem, high word for odd).
  * Extra randomness comes from (slot = elem, TAG_SLOW, attempt = 1, 2, ...). */
-KLB_HD double klb_normal_from_word(uint64_t w, uint32_t elem, const klb_stream* s, const uint64_t* tab) {
+KLB_HD_NOINLINE double klb_normal_from_word(uint64_t w, uint32_t elem, const klb_stream* s, const uint64_t* tab) {
   uint32_t attempt = 0;
   for (;;) {
     double x;

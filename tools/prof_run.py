@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures: one BasicMCJob of the C3 shape with fewer chains / transitions.
+    python tools/prof_run.py --nchains 9472 --nsteps 20 --burnin 10 --reps 3 [--sampler HMC] [--arith reference]
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import klara_b200 as K  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--nchains", type=int, default=9472)
+ap.add_argument("--dim", type=int, default=1024)
+ap.add_argument("--nsteps", type=int, default=20)
+ap.add_argument("--burnin", type=int, default=10)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--sampler", default="HMC")
+ap.add_argument("--arith", default="reference")
+ap.add_argument("--step", type=float, default=0.05)
+ap.add_argument("--nleaps", type=int, default=10)
+ap.add_argument("--none", action="store_true", help="destination none")
+a = ap.parse_args()
+x0 = np.random.default_rng(0).standard_normal((a.nchains, a.dim))
+p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+smp = {"HMC": K.HMC(a.step, a.nleaps), "MALA": K.MALA(a.step), "MH": K.MH(np.full(a.dim, 0.02))}[a.sampler]
+oo = {"destination": "none"} if a.none else {"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}
+job = K.BasicMCJob(K.likelihood_model(p, False), smp, K.BasicMCRange(nsteps=a.nsteps, burnin=a.burnin), {"p": x0},
+                   outopts=oo, seed=1, arith=a.arith)
+for r in range(a.reps):
+    job.reset()
+    job.run()
+    ms = job.last_run_ms
+    lf = a.nchains * a.nsteps * (a.nleaps if a.sampler == "HMC" else 1)
+    print("rep %d: %.3f ms  %.4g %s/s" % (r, ms, lf / ms * 1e3, "leapfrog-steps" if a.sampler == "HMC" else "transitions"))
