@@ -95,17 +95,18 @@ def cpu_leg(nthreads=None, target_seconds=12.0):
     O.build()
     nthreads = nthreads or os.cpu_count() or 1
     cfgp = dict(step=LEAPSTEP, nleaps=NLEAPS, monitor=3, diagnostics=1, seed=SEED, nthreads=nthreads)
-    # calibrate with one chain per thread over 20 transitions, then size the sample for ~target_seconds
-    n0 = nthreads
-    x0 = np.stack([O.normals(SEED, c, 0, DIM) for c in range(n0)])
-    cfg = O.make_config(O.HMC, O.ISO, n0, DIM, 20, 10, **cfgp)
-    t = time.perf_counter(); O.run(cfg, x0); dt = time.perf_counter() - t
-    per_chain_run = dt / 20.0 * NSTEPS            # seconds for one thread to run one chain's full job
-    nchains = max(nthreads, int(target_seconds / per_chain_run) * nthreads)
-    nchains = min(nchains, 4096)
-    x0 = np.stack([O.normals(SEED, c, 0, DIM) for c in range(nchains)])
-    cfg = O.make_config(O.HMC, O.ISO, nchains, DIM, NSTEPS, BURNIN, **cfgp)
-    t = time.perf_counter(); res = O.run(cfg, x0); dt = time.perf_counter() - t
+    def timed(nchains):
+        x0 = np.stack([O.normals(SEED, c, 0, DIM) for c in range(nchains)])
+        cfg = O.make_config(O.HMC, O.ISO, nchains, DIM, NSTEPS, BURNIN, **cfgp)
+        t = time.perf_counter()
+        res = O.run(cfg, x0)
+        return time.perf_counter() - t, res
+    # probe with two chains per thread, then size the sample so the timed run lasts ~target_seconds
+    nchains = 2 * nthreads
+    dt, res = timed(nchains)
+    if dt < 0.6 * target_seconds:
+        nchains = int(min(65536, max(nchains, nchains * target_seconds / max(dt, 1e-3))) // nthreads * nthreads)
+        dt, res = timed(nchains)
     lf = nchains * NLEAPS * NSTEPS
     return {"value": lf / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
             "sample": "%d of 65536 chains, full nsteps=%d (burnin %d), d=%d, L=%d, OpenMP over chains; %.1f s"

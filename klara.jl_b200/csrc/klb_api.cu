@@ -14,12 +14,12 @@
 #include "klb_kernels.cuh"
 
 // per-(sampler, arithmetic) dispatchers, klb_kernels_inst.cu
-int klb_chain_0_0(const KArgs*, int, int, int, int*, int*, cudaStream_t);
-int klb_chain_0_1(const KArgs*, int, int, int, int*, int*, cudaStream_t);
-int klb_chain_1_0(const KArgs*, int, int, int, int*, int*, cudaStream_t);
-int klb_chain_1_1(const KArgs*, int, int, int, int*, int*, cudaStream_t);
-int klb_chain_2_0(const KArgs*, int, int, int, int*, int*, cudaStream_t);
-int klb_chain_2_1(const KArgs*, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_0_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_0_1(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_1_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_1_1(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_2_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
+int klb_chain_2_1(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
 // klb_kernels_inst.cu (-DKLB_INST_INIT) / klb_aux.cu
 int klb_launch_init(const KArgs& A, int target, int W, int NV, int fma, int check_grad, unsigned long long* flag,
                     cudaStream_t s);
@@ -79,15 +79,15 @@ struct klb_job {
   bool timed;
 };
 
-static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int gw, int gnv, int* regs, int* bps,
+static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int gw, int gnv, int full, int* regs, int* bps,
                           cudaStream_t s) {
   switch (sampler * 2 + (fma ? 1 : 0)) {
-    case 0: return klb_chain_0_0(A, target, gw, gnv, regs, bps, s);
-    case 1: return klb_chain_0_1(A, target, gw, gnv, regs, bps, s);
-    case 2: return klb_chain_1_0(A, target, gw, gnv, regs, bps, s);
-    case 3: return klb_chain_1_1(A, target, gw, gnv, regs, bps, s);
-    case 4: return klb_chain_2_0(A, target, gw, gnv, regs, bps, s);
-    case 5: return klb_chain_2_1(A, target, gw, gnv, regs, bps, s);
+    case 0: return klb_chain_0_0(A, target, gw, gnv, full, regs, bps, s);
+    case 1: return klb_chain_0_1(A, target, gw, gnv, full, regs, bps, s);
+    case 2: return klb_chain_1_0(A, target, gw, gnv, full, regs, bps, s);
+    case 3: return klb_chain_1_1(A, target, gw, gnv, full, regs, bps, s);
+    case 4: return klb_chain_2_0(A, target, gw, gnv, full, regs, bps, s);
+    case 5: return klb_chain_2_1(A, target, gw, gnv, full, regs, bps, s);
   }
   return -1;
 }
@@ -95,7 +95,7 @@ static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int 
 // Team geometry by dim: (warps per chain, double2 units per thread), capacity 64*W*NV elements.
 // KLB_GEOM="W,NV" overrides the default (experiments; must be an instantiated pair with enough capacity).
 static int plan_geom(long long dim, int* gw, int* gnv) {
-  static const int geoms[][2] = {{1, 1}, {2, 1}, {4, 1}, {4, 2}, {4, 4}};
+  static const int geoms[][2] = {{1, 1}, {1, 2}, {1, 4}, {1, 8}, {1, 16}, {4, 16}};
   const char* env = getenv("KLB_GEOM");
   if (env) {
     int w = 0, nv = 0;
@@ -174,7 +174,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if (c.target == KLB_TARGET_ROSENBROCK && (c.dim & 1)) return fail(KLB_EINVAL, "paired Rosenbrock needs an even dim");
   int gw = 0, gnv = 0;
   if (plan_geom(c.dim, &gw, &gnv) != 0)
-    return fail(KLB_EUNSUPPORTED, "dim %lld > 1024 is not supported by the register-resident chain kernels", (long long)c.dim);
+    return fail(KLB_EUNSUPPORTED, "dim %lld > 4096 is not supported by the register-resident chain kernels", (long long)c.dim);
   const int nv = gw * gnv;
   // BasicMCRange asserts (src/ranges/BasicMCRange.jl:19-21)
   if (c.burnin < 0) return fail(KLB_EINVAL, "Number of burn-in iterations should be non-negative");
@@ -249,7 +249,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     if (c.monitor & KLB_MONITOR_GRADLOGTARGET) CKJ(cudaMalloc(&j->out_grad, N * P * d * sizeof(double)));
     if (c.diagnostics & KLB_DIAG_ACCEPT) CKJ(cudaMalloc(&j->out_accept, N * P));
   }
-  if (chain_dispatch(c.sampler, c.arith, nullptr, c.target, gw, gnv, &j->regs, &j->bps, j->stream) != 0) {
+  if (chain_dispatch(c.sampler, c.arith, nullptr, c.target, gw, gnv, c.dim == 64ll * gw * gnv, &j->regs, &j->bps, j->stream) != 0) {
     cudaGetLastError();
     free_job(j);
     return fail(KLB_ECUDA, "no sm_100a kernel image for geometry (%d,%d) loadable on this device", gw, gnv);
@@ -357,7 +357,7 @@ int klb_job_run_async(klb_job* j) {
   while (done < c.nsteps) {
     const long long nt = (c.nsteps - done) < chunk ? (c.nsteps - done) : chunk;
     A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global;
-    if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, nullptr, nullptr, j->stream) != 0)
+    if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, c.dim == 64ll * j->gw * j->gnv, nullptr, nullptr, j->stream) != 0)
       return fail(KLB_EINVAL, "no kernel for this configuration");
     CK(cudaGetLastError());
     j->launches += 1;

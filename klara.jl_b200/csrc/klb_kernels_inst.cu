@@ -3,14 +3,16 @@
 // and once with -DKLB_INST_INIT for the initialize! kernels.
 //
 // Geometries (W warps per chain, NV double2 units per thread; capacity 64 W NV elements):
-//   (1,1) 64   (2,1) 128   (4,1) 256   (4,2) 512   (4,4) 1024     <- defaults by dim
-//   (2,8) 1024 (1,16) 1024                                          <- alternatives for experiments
+//   (1,1) 64   (1,2) 128   (1,4) 256   (1,8) 512   (1,16) 1024    <- one warp per chain, defaults by dim
+//   (4,16) 4096                                                     <- four warps per chain for dim > 1024
+//   (2,8) 1024  (4,4) 1024                                          <- team alternatives kept for experiments
+// Chain kernels exist in a masked version (any dim <= capacity) and a FULL version (dim == capacity).
 #include "klb_kernels.cuh"
 
 #define KLB_CAT2(a, b, c, d) a##b##c##d
 #define KLB_CAT(a, b, c, d) KLB_CAT2(a, b, c, d)
 
-#define KLB_GEOMS(X) X(1, 1) X(2, 1) X(4, 1) X(4, 2) X(4, 4) X(2, 8) X(1, 16)
+#define KLB_GEOMS(X) X(1, 1) X(1, 2) X(1, 4) X(1, 8) X(1, 16) X(4, 16) X(2, 8) X(4, 4)
 
 #if defined(KLB_INST_INIT)
 
@@ -45,9 +47,9 @@ int klb_launch_init(const KArgs& A, int target, int W, int NV, int fma, int chec
 
 #define KLB_FN(name) KLB_CAT(name, KLB_INST_SAMPLER, _, KLB_INST_FMA)
 
-template <class T, int W, int NV>
-static int go(const KArgs* A, int* regs, int* bps, cudaStream_t s) {
-  auto kern = klb_chain_kernel<KLB_INST_SAMPLER, T, NV, W, (KLB_INST_FMA != 0)>;
+template <class T, int W, int NV, bool FULL>
+static int go2(const KArgs* A, int* regs, int* bps, cudaStream_t s) {
+  auto kern = klb_chain_kernel<KLB_INST_SAMPLER, T, NV, W, (KLB_INST_FMA != 0), FULL>;
   if (A) {
     const unsigned grid = (unsigned)((A->nchains + (KLB_WPB / W) - 1) / (KLB_WPB / W));
     kern<<<grid, 32 * KLB_WPB, 0, s>>>(*A);
@@ -59,20 +61,24 @@ static int go(const KArgs* A, int* regs, int* bps, cudaStream_t s) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, 32 * KLB_WPB, 0) != cudaSuccess) return -2;
   return 0;
 }
+template <class T, int W, int NV>
+static int go(const KArgs* A, int full, int* regs, int* bps, cudaStream_t s) {
+  return full ? go2<T, W, NV, true>(A, regs, bps, s) : go2<T, W, NV, false>(A, regs, bps, s);
+}
 template <class T>
-static int by_geo(const KArgs* A, int W, int NV, int* regs, int* bps, cudaStream_t s) {
+static int by_geo(const KArgs* A, int W, int NV, int full, int* regs, int* bps, cudaStream_t s) {
 #define X(w_, nv_) \
-  if (W == w_ && NV == nv_) return go<T, w_, nv_>(A, regs, bps, s);
+  if (W == w_ && NV == nv_) return go<T, w_, nv_>(A, full, regs, bps, s);
   KLB_GEOMS(X)
 #undef X
   return -1;
 }
 // A != null: launch.  A == null: query registers / occupancy.
-int KLB_FN(klb_chain_)(const KArgs* A, int target, int W, int NV, int* regs, int* bps, cudaStream_t s) {
+int KLB_FN(klb_chain_)(const KArgs* A, int target, int W, int NV, int full, int* regs, int* bps, cudaStream_t s) {
   switch (target) {
-    case 0: return by_geo<TgtIso>(A, W, NV, regs, bps, s);
-    case 1: return by_geo<TgtShifted>(A, W, NV, regs, bps, s);
-    case 3: return by_geo<TgtRosen>(A, W, NV, regs, bps, s);
+    case 0: return by_geo<TgtIso>(A, W, NV, full, regs, bps, s);
+    case 1: return by_geo<TgtShifted>(A, W, NV, full, regs, bps, s);
+    case 3: return by_geo<TgtRosen>(A, W, NV, full, regs, bps, s);
   }
   return -1;
 }

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz: small seeded input/output vectors of the hot path.
+
+Provenance: the reference (Klara.jl, Julia 0.6) cannot be executed in this image and never seeds its RNG,
+so these vectors are produced by THIS repo's CPU oracle (oracle/klb_oracle.c), after it has passed the
+reference's own known-answer tests (tests/test_oracle_kat.py).  They freeze the RNG / reduction-order /
+arithmetic contract: the CPU suite checks the oracle still reproduces them, the GPU suite checks the CUDA path
+reproduces them bit for bit.   python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import oracle as O  # noqa: E402
+
+CASES = {
+    # name: (sampler, target, nchains, dim, nsteps, kwargs, extra)
+    "hmc_iso_d1024": ("HMC", "iso", 3, 1024, 12, dict(burnin=4, thinning=2, step=0.05, nleaps=10, monitor=3, diagnostics=1, seed=20240925), {}),
+    "hmc_iso_d7_accrate": ("HMC", "iso", 5, 7, 90, dict(burnin=60, step=0.2, nleaps=4, tuner=O.ACCRATE, target_rate=0.8, period=20, monitor=3, diagnostics=1, seed=11), {}),
+    "mala_iso_d128": ("MALA", "iso", 4, 128, 40, dict(burnin=10, step=0.18, monitor=7, diagnostics=1, seed=5), {}),
+    "mala_rosen_d16_accrate": ("MALA", "rosen", 4, 16, 120, dict(burnin=100, step=0.01, tuner=O.ACCRATE, target_rate=0.574, period=25, monitor=3, diagnostics=1, seed=8), {}),
+    "mh_readme_d2": ("MH", "iso", 1, 2, 200, dict(burnin=100, monitor=3, diagnostics=1, seed=2024), {"x0": [[5.1, -0.9]], "sigma": [1.0, 1.0]}),
+    "hmc_shifted_d100_fma": ("HMC", "shifted", 3, 100, 20, dict(burnin=5, step=0.05, nleaps=6, monitor=3, diagnostics=1, seed=3, arith=1), {}),
+}
+SAMPLERS = {"MH": O.MH, "MALA": O.MALA, "HMC": O.HMC}
+TARGETS = {"iso": O.ISO, "shifted": O.SHIFTED, "rosen": O.ROSEN}
+
+
+def build(name):
+    smp, tgt, n, d, nsteps, kw, extra = CASES[name]
+    cfg = O.make_config(SAMPLERS[smp], TARGETS[tgt], n, d, nsteps, **kw)
+    x0 = np.array(extra["x0"], dtype=float) if "x0" in extra else np.stack([O.normals(cfg.seed, c, 0, d) for c in range(n)])
+    tparams = None
+    if tgt == "shifted":
+        tparams = np.linspace(-1.0, 1.0, d)
+    if tgt == "rosen":
+        tparams = np.array([1.0, 100.0, 0.05])
+    sigma = np.array(extra["sigma"], dtype=float) if "sigma" in extra else (np.full(d, 0.5) if smp == "MH" else None)
+    return cfg, x0, tparams, sigma
+
+
+if __name__ == "__main__":
+    for name in CASES:
+        cfg, x0, tparams, sigma = build(name)
+        r = O.run(cfg, x0, tparams, sigma)
+        out = {"x0": x0, "x": r["x"], "logtarget_state": r["logtarget_state"], "tune": r["tune"]}
+        for k in ("value", "logtarget", "gradlogtarget", "accept"):
+            if r[k] is not None:
+                out[k] = r[k]
+        if tparams is not None:
+            out["tparams"] = tparams
+        if sigma is not None:
+            out["sigma"] = sigma
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, {k: v.shape for k, v in out.items()})

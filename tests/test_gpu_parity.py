@@ -48,7 +48,7 @@ def test_device_exp_log_match_oracle(K, O):
 
 
 # ------------------------------------------------------------------ samplers vs oracle
-DIMS = [2, 7, 64, 100, 128, 250, 512, 1024]
+DIMS = [2, 7, 64, 100, 128, 250, 512, 1024, 1500, 2048, 4096]
 
 
 @pytest.mark.parametrize("arith", ["reference", "fma"])
@@ -63,7 +63,7 @@ def test_hmc_iso_bit_exact(K, dim, arith):
 
 
 @pytest.mark.parametrize("arith", ["reference", "fma"])
-@pytest.mark.parametrize("dim", [2, 33, 128, 256, 1000])
+@pytest.mark.parametrize("dim", [2, 33, 128, 256, 1000, 3000])
 def test_mala_iso_bit_exact(K, dim, arith):
     job, cfg, x0, tp, sg = build_pair(K, "MALA", "iso", nchains=41, dim=dim, nsteps=80, burnin=30,
                                       step=0.9 / dim ** (1 / 3), seed=7, arith=arith,

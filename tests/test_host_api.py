@@ -1,0 +1,124 @@
+"""CPU tests of the host side: the Python mirror of Klara's constructors (same asserts / messages as the
+reference), the C-ABI library (loads, exports every symbol the header declares, fails loudly without a GPU)
+and the layout constants shared with the header."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(K):
+    hdr = open(os.path.join(ROOT, "include", "klara_b200.h")).read()
+    declared = set(re.findall(r"\b(klb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"klb_job", "klb_config", "klb_plan"}
+    lib = C.CDLL(K._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libklara_b200.so does not export %s" % name
+    bound = {n for n, _, _ in K._lib.SYMBOLS}
+    assert declared == bound, "header and ctypes binding disagree: %s" % sorted(declared ^ bound)
+    assert K._lib.lib().klb_version() == int(re.search(r"#define KLB_VERSION (\d+)", hdr).group(1))
+
+
+def test_config_struct_matches_header(K):
+    """field order / sizes of klb_config and klb_plan as the header declares them"""
+    hdr = open(os.path.join(ROOT, "include", "klara_b200.h")).read()
+    for struct, cls in (("klb_config", K._lib.KlbConfig), ("klb_plan", K._lib.KlbPlan)):
+        body = re.search(r"typedef struct \{([^}]*)\} %s;" % struct, hdr).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
+        assert names == [f[0] for f in cls._fields_], struct
+    assert C.sizeof(K._lib.KlbConfig) == 144
+
+
+def test_enums_match_header(K):
+    hdr = open(os.path.join(ROOT, "include", "klara_b200.h")).read()
+    defs = dict(re.findall(r"#define (KLB_[A-Z0-9_]+) \(?(-?\d+)u?\)?", hdr))
+    L = K._lib
+    for py, c in [("SAMPLER_MH", "KLB_SAMPLER_MH"), ("SAMPLER_MALA", "KLB_SAMPLER_MALA"), ("SAMPLER_HMC", "KLB_SAMPLER_HMC"),
+                  ("TARGET_ISO", "KLB_TARGET_ISO"), ("TARGET_SHIFTED_ISO", "KLB_TARGET_SHIFTED_ISO"),
+                  ("TARGET_DENSE", "KLB_TARGET_DENSE"), ("TARGET_ROSENBROCK", "KLB_TARGET_ROSENBROCK"),
+                  ("TUNER_VANILLA", "KLB_TUNER_VANILLA"), ("TUNER_ACCEPTANCE_RATE", "KLB_TUNER_ACCEPTANCE_RATE"),
+                  ("KLB_ENOTFINITE", "KLB_ENOTFINITE"), ("KLB_ECUDA", "KLB_ECUDA"), ("OUT_VALUE", "KLB_OUT_VALUE"),
+                  ("OUT_TUNE_RATE", "KLB_OUT_TUNE_RATE"), ("PARAM_SIGMA", "KLB_PARAM_SIGMA"),
+                  ("MONITOR_GRADLOGTARGET", "KLB_MONITOR_GRADLOGTARGET"), ("DEST_NONE", "KLB_DEST_NONE")]:
+        assert getattr(L, py) == int(defs[c]), (py, c)
+
+
+def test_constructor_asserts_follow_the_reference(K):
+    with pytest.raises(AssertionError, match="Leapfrog step is not positive"):       # HMC.jl:93
+        K.HMC(0.0)
+    with pytest.raises(AssertionError, match="Number of leapfrog steps is not positive"):   # HMC.jl:94
+        K.HMC(0.1, 0)
+    with pytest.raises(AssertionError, match="Drift step is not positive"):           # MALA.jl:64
+        K.MALA(-1.0)
+    with pytest.raises(AssertionError, match="burn-in iterations should be non-negative"):   # BasicMCRange.jl:19
+        K.BasicMCRange(burnin=-1)
+    with pytest.raises(AssertionError, match="Thinning should be >= 1"):
+        K.BasicMCRange(thinning=0)
+    with pytest.raises(AssertionError, match="greater than number of burn-in"):
+        K.BasicMCRange(nsteps=10, burnin=10)
+    with pytest.raises(AssertionError, match="Adaptation period should be positive"):  # VanillaMCTuner.jl:10
+        K.VanillaMCTuner(period=0)
+    with pytest.raises(AssertionError, match="between 0 and 1"):                      # AcceptanceRateMCTuner.jl:31
+        K.AcceptanceRateMCTuner(1.0)
+    assert K.HMC().leapstep == 0.1 and K.HMC().nleaps == 10 and K.MALA().driftstep == 1.0   # defaults HMC.jl:100, MALA.jl:70
+    r = K.BasicMCRange(nsteps=10000, burnin=1000)
+    assert r.npoststeps == 9000 and r.postrange[0] == 1001
+    assert K.VanillaMCTuner().period == 100 and not K.VanillaMCTuner().verbose
+    assert K.AcceptanceRateMCTuner(0.574).period == 100
+
+
+def test_parameter_needs_a_descriptor(K):
+    with pytest.raises(TypeError, match="descriptor"):
+        K.BasicContMuvParameter("p", logtarget=lambda z: -np.dot(z, z))
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    assert p.logtarget([1.0, 2.0]) == -5.0                       # README.md:153: plogtarget(z) = -dot(z, z)
+    np.testing.assert_array_equal(p.gradlogtarget([1.0, 2.0]), [-2.0, -4.0])
+    m = K.likelihood_model(p, False)
+    assert m.vertices[0] is p and m.ofkey["p"] == 0
+
+
+def test_no_cpu_fallback(K):
+    """without a CUDA device the product path must fail loudly, never compute on the host"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    with pytest.raises(K.KlaraError) as ei:
+        K.BasicMCJob(K.likelihood_model(p, False), K.MH(np.ones(2)), K.BasicMCRange(nsteps=10), {"p": [5.1, -0.9]})
+    assert ei.value.code == K._lib.KLB_ECUDA and "no CPU path" in str(ei.value)
+    out = np.empty(4)
+    assert K._lib.lib().klb_debug_normals(0, 1, 2, 3, 4, out.ctypes.data_as(C.c_void_p)) == K._lib.KLB_ECUDA
+
+
+def test_product_does_not_import_the_oracle():
+    """only tests/, smoke() and bench.py may touch oracle/"""
+    pkg = os.path.join(ROOT, "klara.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "_build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("(oracle)", "").replace("the oracle", "").replace("CPU oracle", "") \
+                    .replace("oracle)", "").replace("oracle.", "oracle_") or f in ("klb_math.h",), \
+                    "%s mentions the oracle in code" % f
+                assert "import oracle" not in src and "from oracle" not in src and "klb_oracle" not in src, f
+
+
+def test_shard_ranges(K):
+    D = K.distributed
+    for n, w in [(65536, 8), (10, 3), (7, 8), (1, 1)]:
+        rs = [D.shard_range(n, r, w) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+    assert D.shard_range(65536, 3, 8) == (24576, 32768)

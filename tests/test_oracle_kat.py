@@ -1,0 +1,150 @@
+"""CPU tests: the oracle against every known-answer value the reference's own tests hold for this path
+ and against the published vectors of the primitives it is built on."""
+import math
+
+import numpy as np
+import pytest
+
+
+# ---- reference KATs (bit-exact) ------------------------------------------------------------
+def test_logistic_kat(O):
+    # test/common.jl:6
+    assert O.lib().orc_logistic(0.7, 3., 4., 2.1, 1.4) == 1.4110527196983078
+
+
+def test_logistic_rate_score_kat(O):
+    # test/AcceptanceRateMCTuner.jl:8-9
+    assert O.lib().orc_logistic_rate_score(0.25, 7.) == 1.7039056039366212
+    assert O.lib().orc_logistic_rate_score(0.5, 11.) == 1.991859724568208
+
+
+def test_erf_rate_score_kat(O):
+    # test/AcceptanceRateMCTuner.jl:13-14
+    assert O.lib().orc_erf_rate_score(-0.1, 3.) == 0.6713732405408726
+    assert O.lib().orc_erf_rate_score(0.93, 2.) == 1.9914724883356396
+
+
+def test_python_mirror_scores_match(K):
+    assert K.logistic(0.7, 3, 4, 2.1, 1.4) == 1.4110527196983078
+    assert K.logistic_rate_score(0.25) == 1.7039056039366212
+    assert K.logistic_rate_score(0.5, 11) == 1.991859724568208
+
+
+def test_function_defined_normal_target(O, K):
+    """test/BasicContMuvParameter.jl:539-563: logtarget = -(x-mu).(x-mu), gradlogtarget = -2(x-mu) at
+    pv = [-4.29, 2.91], mu = [2.2, 2.02]; 0.5*(lt - d*log(2pi)) == logpdf(MvNormal(mu, 1)), 0.5*glt == gradlogpdf"""
+    pv, mu = np.array([-4.29, 2.91]), np.array([2.2, 2.02])
+    cfg = O.make_config(O.HMC, O.SHIFTED, 1, 2, 1)
+    lt, g = O.eval_target(cfg, pv, mu)
+    assert lt == pytest.approx(-42.9122, rel=1e-14)
+    np.testing.assert_allclose(g, [12.98, -1.78], rtol=1e-14)
+    logpdf = -0.5 * (2 * math.log(2 * math.pi) + float((pv - mu) @ (pv - mu)))
+    assert 0.5 * (lt - 2 * math.log(2 * math.pi)) == pytest.approx(logpdf, rel=1e-14)
+    np.testing.assert_allclose(0.5 * g, -(pv - mu), rtol=1e-14)
+    # the descriptor evaluated on the host agrees
+    t = K.ShiftedIsoGaussian(mu)
+    assert t(pv) == pytest.approx(lt, rel=1e-14)
+    np.testing.assert_allclose(t.gradient(pv), g, rtol=1e-14)
+
+
+def test_pdf_defined_targets(O):
+    """test/BasicContMuvParameter.jl:39-80: MvNormal(mu, 1.) at the two test points, via the closed form
+    logpdf = -0.5 (d log 2pi + |x-mu|^2); the unnormalised device target is 2*logpdf + d*log(2pi)"""
+    for pv, mu in [([5.18, -7.76], [6.11, -8.5]), ([-11.87, -13.44], [-20.2, -18.91])]:
+        pv, mu = np.array(pv), np.array(mu)
+        lt, g = O.eval_target(O.make_config(O.HMC, O.SHIFTED, 1, 2, 1), pv, mu)
+        logpdf = -0.5 * (2 * math.log(2 * math.pi) + float((pv - mu) @ (pv - mu)))
+        assert 0.5 * (lt - 2 * math.log(2 * math.pi)) == pytest.approx(logpdf, rel=1e-13)
+        np.testing.assert_allclose(0.5 * g, -(pv - mu), rtol=1e-13)
+
+
+def test_nstate_column_layout(O):
+    """test/ParameterNStates.jl:137-146: copy!(nstate, state, i) puts the state in column i of `value`
+    (size x n) and entry i of `logtarget`: sample s of chain c sits at value[c, s, :]"""
+    cfg = O.make_config(O.MH, O.ISO, 3, 4, 7, burnin=2, thinning=2, monitor=3, diagnostics=1, seed=3)
+    x0 = np.arange(12, dtype=float).reshape(3, 4) / 10
+    r = O.run(cfg, x0, sigma=np.full(4, 0.3))
+    assert r["npost"] == 3 and r["value"].shape == (3, 3, 4) and r["logtarget"].shape == (3, 3)
+    np.testing.assert_allclose(r["logtarget"], -(r["value"] ** 2).sum(-1), rtol=1e-15)
+    np.testing.assert_array_equal(r["value"][:, -1], r["x"])       # last saved column = final pstate (nsteps in postrange)
+
+
+def test_range_npoststeps(O, K):
+    # src/ranges/BasicMCRange.jl:14-25: length((burnin+1):thinning:nsteps)
+    for b, t, n in [(0, 1, 100), (1000, 1, 10000), (10, 3, 100), (5, 7, 6), (99, 100, 100)]:
+        assert O.npoststeps(b, t, n) == len(range(b + 1, n + 1, t)) == K.BasicMCRange(burnin=b, thinning=t, nsteps=n).npoststeps
+
+
+# ---- primitives -----------------------------------------------------------------------------
+def test_philox_random123_kat(O):
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)"""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, want in kat:
+        assert [int(v) for v in O.philox(ctr, key)] == want
+
+
+def test_no_fp_contraction_in_oracle(O):
+    """the oracle must round a*b and +c separately in reference mode (built with -ffp-contract=off)"""
+    a = np.array([1.0 + 2.0 ** -30]); b = np.array([1.0 - 2.0 ** -30])
+    # a*b = 1 - 2^-60 rounds to 1.0; an fma(a, b, -1) contraction would return -2^-60
+    assert O.dot(a, b, nv=1, arith=0) == 1.0
+    assert math.fma(a[0], b[0], -1.0) != 0.0 if hasattr(math, "fma") else True
+
+
+def test_exp_log_accuracy(O):
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    rng = np.random.default_rng(11)
+
+    def ulps(y, t):
+        e = max(mp.floor(mp.log(abs(t), 2)), -1022)
+        return float(abs(mp.mpf(y) - t) / mp.mpf(2) ** (e - 52))
+    for x in np.concatenate([rng.uniform(-700, 700, 1500), rng.uniform(-2, 2, 1500)]):
+        assert ulps(O.exp(x), mp.exp(mp.mpf(float(x)))) < 0.52
+    for x in np.concatenate([rng.uniform(0, 1, 1500), 10.0 ** rng.uniform(-300, 300, 1000), rng.uniform(0.9, 1.1, 1500)]):
+        assert ulps(O.log(x), mp.log(mp.mpf(float(x)))) < 2.0
+    assert O.exp(0.0) == 1.0 and O.exp(-1000.0) == 0.0 and O.exp(1000.0) == math.inf and math.isnan(O.exp(math.nan))
+    assert O.log(1.0) == 0.0 and O.log(0.0) == -math.inf and math.isnan(O.log(-1.0)) and O.log(math.inf) == math.inf
+    assert O.log(5e-324) == pytest.approx(math.log(5e-324), rel=1e-15)
+    assert O.exp(-744.0) == pytest.approx(math.exp(-744.0), rel=1e-12)
+
+
+def test_exp_matches_libm_almost_everywhere(O):
+    rng = np.random.default_rng(2)
+    xs = rng.uniform(-50, 50, 20000)
+    bad = sum(O.exp(x) != math.exp(x) for x in xs)
+    assert bad < 50          # both are < 1 ulp; they may disagree only on hard-to-round arguments
+
+
+def test_normals_distribution(O):
+    sp = pytest.importorskip("scipy.stats")
+    z = np.concatenate([O.normals(12345, c, 1, 1 << 16) for c in range(16)])
+    assert abs(z.mean()) < 4 / math.sqrt(z.size)
+    assert abs(z.var() - 1) < 6 * math.sqrt(2 / z.size)
+    assert sp.kstest(z, "norm").pvalue > 1e-3
+    edges = sp.norm.ppf(np.linspace(0, 1, 101))
+    cnt, _ = np.histogram(z, edges)
+    assert sp.chisquare(cnt).pvalue > 1e-3
+    # tail beyond the ziggurat base strip r = 3.654...: exercised and correctly weighted
+    r = 3.6541528853610088
+    n_tail = int((np.abs(z) > r).sum())
+    exp_tail = 2 * sp.norm.sf(r) * z.size
+    assert abs(n_tail - exp_tail) < 5 * math.sqrt(exp_tail)
+
+
+def test_uniform_range_and_streams(O):
+    u = np.array([O.uniform(7, c, t) for c in range(50) for t in range(1, 41)])
+    assert (u >= 0).all() and (u < 1).all() and len(set(u)) == u.size
+    assert abs(u.mean() - 0.5) < 0.03
+    # streams: different chains / transitions / seeds give different normals; same key repeats
+    a = O.normals(1, 2, 3, 64)
+    assert np.array_equal(a, O.normals(1, 2, 3, 64))
+    assert not np.array_equal(a, O.normals(1, 2, 4, 64)) and not np.array_equal(a, O.normals(1, 3, 3, 64))
+    assert not np.array_equal(a, O.normals(2, 2, 3, 64))
+    # prefix property: element i does not depend on how many elements are drawn
+    assert np.array_equal(a[:10], O.normals(1, 2, 3, 10))

@@ -1,0 +1,143 @@
+"""CPU tests of the oracle's sampler semantics (the edge cases of SURVEY.md section 3.6) and of its
+statistical sanity against theory: the target exp(-z.z) is N(0, I/2)."""
+import numpy as np
+import pytest
+
+
+def _run(O, sampler, target=None, **kw):
+    target = O.ISO if target is None else target
+    n, d, nsteps = kw.pop("nchains", 8), kw.pop("dim", 4), kw.pop("nsteps", 100)
+    sigma = kw.pop("sigma", None)
+    x0 = kw.pop("x0", None)
+    tparams = kw.pop("tparams", None)
+    cfg = O.make_config(sampler, target, n, d, nsteps, nthreads=O.max_threads(), **kw)
+    if x0 is None:
+        x0 = np.stack([O.normals(cfg.seed, c, 0, d) for c in range(n)])
+    return cfg, O.run(cfg, x0, tparams, sigma)
+
+
+def test_tuner_window_hmc(O):
+    """tune events after transitions period, 2*period, ... while totproposed <= burnin; totproposed starts at
+    `period` and ends at period*(1 + floor(burnin/period)); counters keep accumulating after burn-in"""
+    cfg, r = _run(O, O.HMC, nsteps=1300, burnin=1000, step=0.05, nleaps=3, tuner=O.ACCRATE, period=100,
+                  target_rate=0.8, monitor=0, diagnostics=1, seed=5)
+    t = r["tune"]
+    assert (t["totproposed"] == 1100).all()
+    assert (t["proposed"] == 300).all()
+    assert (t["accepted"] <= 300).all() and (t["accepted"] == r["accept"].sum(1)).all()
+    assert np.isnan(t["rate"]).all()                      # reset_burnin! leaves NaN, never recomputed after burn-in
+    assert (t["step"] != 0.05).all()
+
+
+def test_counters_only_with_accrate_or_verbose(O):
+    for sampler in (O.HMC, O.MALA):
+        cfg, r = _run(O, sampler, nsteps=50, burnin=20, step=0.1, nleaps=2, tuner=O.VANILLA, verbose=0, seed=1)
+        assert (r["tune"]["proposed"] == 0).all() and (r["tune"]["accepted"] == 0).all()
+        cfg, r = _run(O, sampler, nsteps=50, burnin=20, step=0.1, nleaps=2, tuner=O.VANILLA, verbose=1, period=10, seed=1)
+        assert (r["tune"]["totproposed"] == 30).all() and (r["tune"]["proposed"] == 30).all()
+    # MH: counters only when verbose; AcceptanceRateMCTuner never adapts MH (iterate/MH.jl has no tune! call)
+    cfg, r = _run(O, O.MH, nsteps=60, burnin=30, tuner=O.ACCRATE, verbose=0, period=10, sigma=np.full(4, 0.5), seed=1)
+    assert (r["tune"]["proposed"] == 0).all() and (r["tune"]["step"] == 1.0).all()
+    cfg, r = _run(O, O.MH, nsteps=60, burnin=30, tuner=O.ACCRATE, verbose=1, period=10, sigma=np.full(4, 0.5), seed=1)
+    assert (r["tune"]["totproposed"] == 40).all() and (r["tune"]["step"] == 1.0).all()
+
+
+def test_nan_and_divergent_proposals_reject(O):
+    cfg, r = _run(O, O.HMC, nsteps=10, step=1e200, nleaps=3, monitor=1, diagnostics=1, seed=2)
+    assert r["accept"].sum() == 0
+    x0 = np.stack([O.normals(2, c, 0, 4) for c in range(8)])
+    np.testing.assert_array_equal(r["x"], x0)
+    cfg, r = _run(O, O.MALA, nsteps=10, step=1e300, monitor=1, diagnostics=1, seed=2)
+    assert r["accept"].sum() == 0
+
+
+def test_nonfinite_start_is_rejected(O):
+    x0 = np.zeros((3, 4)); x0[1, 2] = np.nan
+    with pytest.raises(ValueError, match="chain 1"):
+        _run(O, O.HMC, nchains=3, x0=x0, nsteps=3)
+
+
+def test_saved_logtarget_matches_value(O):
+    for sampler, kw in [(O.HMC, dict(step=0.1, nleaps=4)), (O.MALA, dict(step=0.3)), (O.MH, dict(sigma=np.full(6, 0.4)))]:
+        cfg, r = _run(O, sampler, dim=6, nsteps=80, burnin=13, thinning=3, monitor=3, diagnostics=1, seed=9, **kw)
+        np.testing.assert_allclose(r["logtarget"], -(r["value"] ** 2).sum(-1), rtol=1e-13)
+        rej = r["accept"][:, 1:] == 0
+        if cfg.thinning == 1:
+            assert np.array_equal(r["value"][:, 1:][rej], r["value"][:, :-1][rej])
+
+
+def test_chain_split_invariance(O):
+    """N chains in one call == the same chains run in two calls with chain_offset (map(run, jobs) semantics)"""
+    cfg, full = _run(O, O.MALA, nchains=10, dim=5, nsteps=40, step=0.2, monitor=1, seed=4)
+    x0 = np.stack([O.normals(4, c, 0, 5) for c in range(10)])
+    cfg2 = O.make_config(O.MALA, O.ISO, 6, 5, 40, step=0.2, monitor=1, seed=4, chain_offset=4)
+    part = O.run(cfg2, x0[4:])
+    assert np.array_equal(part["value"], full["value"][4:])
+
+
+def test_continuation_equals_one_long_run(O):
+    """two runs of 30 transitions (second starting at t0 = 30 from the first's state, tuner record carried)
+    produce the same final state as one run of 60: the chain state persists between runs"""
+    kw = dict(step=0.1, nleaps=3, monitor=0, diagnostics=0, seed=6, tuner=O.ACCRATE, period=7, burnin=0)
+    x0 = np.stack([O.normals(6, c, 0, 4) for c in range(5)])
+    cfg = O.make_config(O.HMC, O.ISO, 5, 4, 60, **kw)
+    one = O.run(cfg, x0)
+    cfg_a = O.make_config(O.HMC, O.ISO, 5, 4, 30, **kw)
+    a = O.run(cfg_a, x0)
+    cfg_b = O.make_config(O.HMC, O.ISO, 5, 4, 30, t0=30, **kw)
+    b = O.run(cfg_b, a["x"], tune=a["tune"], logtarget=a["logtarget_state"])
+    assert np.array_equal(one["x"], b["x"])
+
+
+@pytest.mark.parametrize("sampler,kw,lo,hi", [
+    ("HMC", dict(step=0.15, nleaps=8), 0.7, 1.0),
+    ("MALA", dict(step=0.25), 0.4, 0.95),
+    ("MH", dict(sigma=np.full(8, 0.35)), 0.15, 0.6),
+])
+def test_moments_of_the_isotropic_target(O, sampler, kw, lo, hi):
+    """exp(-z.z) = N(0, I/2): sample mean -> 0, variance -> 0.5; acceptance in a plausible band"""
+    code = {"HMC": O.HMC, "MALA": O.MALA, "MH": O.MH}[sampler]
+    cfg, r = _run(O, code, nchains=64, dim=8, nsteps=3000, burnin=500, monitor=1, diagnostics=1, seed=77, **kw)
+    v = r["value"]
+    assert abs(v.mean()) < 0.02
+    assert abs(v.var() - 0.5) < 0.02
+    assert lo < r["accept"].mean() < hi
+
+
+def test_rosenbrock_and_shifted_targets(O, K):
+    """oracle targets == the Python descriptors (closed forms) to rounding"""
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=10)
+    mu = rng.normal(size=10)
+    lt, g = O.eval_target(O.make_config(O.HMC, O.SHIFTED, 1, 10, 1), x, mu)
+    t = K.ShiftedIsoGaussian(mu)
+    assert lt == pytest.approx(t(x), rel=1e-13)
+    np.testing.assert_allclose(g, t.gradient(x), rtol=1e-13)
+    lt, g = O.eval_target(O.make_config(O.HMC, O.ROSEN, 1, 10, 1), x, np.array([1.0, 100.0, 0.05]))
+    t = K.Rosenbrock()
+    assert lt == pytest.approx(t(x), rel=1e-12)
+    np.testing.assert_allclose(g, t.gradient(x), rtol=1e-12)
+    # numerical gradient check of the Rosenbrock descriptor
+    eps = 1e-6
+    num = np.array([(t(x + eps * np.eye(10)[i]) - t(x - eps * np.eye(10)[i])) / (2 * eps) for i in range(10)])
+    np.testing.assert_allclose(num, g, rtol=1e-5, atol=1e-6)
+
+
+def test_reduction_order_is_the_documented_one(O):
+    """orc_dot reproduces the canonical order of DESIGN.md literally (numpy restatement)"""
+    rng = np.random.default_rng(1)
+    for d, nv in [(5, 1), (64, 1), (100, 2), (1024, 16), (777, 16)]:
+        a, b = rng.normal(size=d), rng.normal(size=d)
+        pa = np.zeros(64 * nv); pb = np.zeros(64 * nv); pa[:d] = a; pb[:d] = b
+        e = pa * pb
+        lanes = np.zeros(32)
+        for l in range(32):
+            acc = [0.0] * 4
+            for m in range(nv):
+                k = l + 32 * m
+                acc[m & 3] = acc[m & 3] + e[2 * k]
+                acc[m & 3] = acc[m & 3] + e[2 * k + 1]
+            lanes[l] = (acc[0] + acc[1]) + (acc[2] + acc[3])
+        for s in (16, 8, 4, 2, 1):
+            lanes = np.array([lanes[l] + lanes[l ^ s] for l in range(32)])
+        assert O.dot(a, b, nv=nv) == lanes[0]
