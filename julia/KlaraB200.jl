@@ -1,0 +1,129 @@
+# KlaraB200.jl -- thin Julia shim over libklara_b200.so (include/klara_b200.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain.  It is kept deliberately
+# thin (argument marshalling + ccall only) so that it can be reviewed against the header line by line.
+# Written for Julia >= 1.6.  It mirrors the exported names of Klara.jl for the MCMC hot path:
+#
+#   BasicContMuvParameter(:p, logtarget=IsoGaussian())      src/variables/parameters/BasicContMuvParameter.jl:383
+#   likelihood_model(p, false)                               src/models/generators.jl:18
+#   MH(sigma::Vector), MALA(driftstep), HMC(leapstep, nleaps)   src/samplers/{MH,MALA,HMC}.jl
+#   BasicMCRange(nsteps=, burnin=, thinning=)                src/ranges/BasicMCRange.jl:33
+#   VanillaMCTuner(), AcceptanceRateMCTuner(rate)            src/tuners/
+#   BasicMCJob(model, sampler, mcrange, v0; tuner, outopts), run, reset, output   src/jobs/BasicMCJob.jl
+#
+# Batch extension: v0 = Dict(:p => Matrix{Float64}(d, nchains)) (one column per chain).  Stock Klara has no
+# method for a Matrix initial value on a BasicContMuvParameter, so this hook does not conflict.
+module KlaraB200
+
+export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
+       BasicMCRange, VanillaMCTuner, AcceptanceRateMCTuner, BasicMCJob, run, reset, output
+
+const LIB = get(ENV, "KLARA_B200_LIB", "libklara_b200.so")
+
+# ---- target descriptors: also plain callables, so the same definition runs on stock Klara ----------------
+abstract type Target end
+struct IsoGaussian <: Target end
+(::IsoGaussian)(z::Vector{Float64}) = -sum(abs2, z)
+gradient(::IsoGaussian) = z -> -2z
+struct ShiftedIsoGaussian <: Target; mu::Vector{Float64}; end
+(t::ShiftedIsoGaussian)(z::Vector{Float64}) = -sum(abs2, z .- t.mu)
+gradient(t::ShiftedIsoGaussian) = z -> -2 .* (z .- t.mu)
+struct Rosenbrock <: Target; a::Float64; b::Float64; scale::Float64; end
+Rosenbrock() = Rosenbrock(1.0, 100.0, 0.05)
+code(::IsoGaussian) = 0; code(::ShiftedIsoGaussian) = 1; code(::Rosenbrock) = 3
+
+struct BasicContMuvParameter; key::Symbol; logtarget::Target; end
+BasicContMuvParameter(key::Symbol; logtarget::Target, gradlogtarget=nothing) = BasicContMuvParameter(key, logtarget)
+struct GenericModel; vertices::Vector{Any}; end
+likelihood_model(p::BasicContMuvParameter, isindexed::Bool=true) = GenericModel(Any[p])
+
+struct MH; sigma::Vector{Float64}; end
+struct MALA; driftstep::Float64; MALA(s=1.0) = (@assert s > 0 "Drift step is not positive"; new(s)); end
+struct HMC
+  leapstep::Float64; nleaps::Int
+  function HMC(leapstep=0.1, nleaps=10)
+    @assert leapstep > 0 "Leapfrog step is not positive"
+    @assert nleaps > 0 "Number of leapfrog steps is not positive"
+    new(leapstep, nleaps)
+  end
+end
+struct BasicMCRange; burnin::Int; thinning::Int; nsteps::Int; npoststeps::Int; end
+function BasicMCRange(; burnin::Int=0, thinning::Int=1, nsteps::Int=100)
+  @assert burnin >= 0 "Number of burn-in iterations should be non-negative"
+  @assert thinning >= 1 "Thinning should be >= 1"
+  @assert nsteps > burnin "Total number of MCMC iterations should be greater than number of burn-in iterations"
+  BasicMCRange(burnin, thinning, nsteps, length((burnin+1):thinning:nsteps))
+end
+struct VanillaMCTuner; period::Int; verbose::Bool; end
+VanillaMCTuner(; period::Int=100, verbose::Bool=false) = VanillaMCTuner(period, verbose)
+struct AcceptanceRateMCTuner; targetrate::Float64; k::Float64; period::Int; verbose::Bool; end
+AcceptanceRateMCTuner(rate; k=7.0, period::Int=100, verbose::Bool=false) = AcceptanceRateMCTuner(rate, k, period, verbose)
+
+# ---- klb_config, field for field (include/klara_b200.h) ---------------------------------------------------
+struct KlbConfig
+  struct_size::UInt32; sampler::Int32; target::Int32; tuner::Int32; arith::Int32
+  nchains::Int64; dim::Int64; nsteps::Int64; burnin::Int64; thinning::Int64
+  step::Float64; nleaps::Int32
+  target_rate::Float64; score_k::Float64; period::Int64
+  verbose::Int32; monitor::UInt32; diagnostics::UInt32; destination::Int32
+  seed::UInt64; chain_offset::Int64; device::Int32; reserved::Int32
+end
+
+lasterror() = unsafe_string(ccall((:klb_last_error, LIB), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : error("klara_b200 error $rc: $(lasterror())")
+
+mutable struct BasicMCJob
+  handle::Ptr{Cvoid}; nchains::Int; dim::Int; range::BasicMCRange; monitor::Vector{Symbol}; diagnostics::Vector{Symbol}
+end
+
+function BasicMCJob(model::GenericModel, sampler, range::BasicMCRange, v0::Dict;
+                    tuner=VanillaMCTuner(), outopts::Dict=Dict{Symbol,Any}(), seed::Integer=0,
+                    arith::Symbol=:reference, device::Integer=0, chain_offset::Integer=0)
+  p = model.vertices[1]::BasicContMuvParameter
+  x0 = v0[p.key]; x0 = x0 isa Vector ? reshape(Float64.(x0), :, 1) : Matrix{Float64}(x0)   # d x nchains
+  d, n = size(x0)
+  monitor = get(outopts, :monitor, [:value]); diags = get(outopts, :diagnostics, Symbol[])
+  dest = get(outopts, :destination, :nstate)
+  mon = UInt32(sum(Dict(:value=>1, :logtarget=>2, :gradlogtarget=>4)[m] for m in monitor; init=0))
+  smp = sampler isa MH ? 0 : sampler isa MALA ? 1 : 2
+  cfg = KlbConfig(sizeof(KlbConfig), smp, code(p.logtarget), tuner isa AcceptanceRateMCTuner ? 1 : 0,
+                  arith == :fma ? 1 : 0, n, d, range.nsteps, range.burnin, range.thinning,
+                  sampler isa HMC ? sampler.leapstep : sampler isa MALA ? sampler.driftstep : 1.0,
+                  sampler isa HMC ? sampler.nleaps : 1,
+                  tuner isa AcceptanceRateMCTuner ? tuner.targetrate : 0.5,
+                  tuner isa AcceptanceRateMCTuner ? tuner.k : 7.0, tuner.period, tuner.verbose,
+                  mon, (:accept in diags) ? 1 : 0, dest == :none ? 1 : 0, seed, chain_offset, device, 0)
+  h = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:klb_job_create, LIB), Cint, (Ref{KlbConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+  job = BasicMCJob(h[], n, d, range, monitor, diags)
+  finalizer(j -> ccall((:klb_job_destroy, LIB), Cvoid, (Ptr{Cvoid},), j.handle), job)
+  t = p.logtarget
+  t isa ShiftedIsoGaussian && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 0, t.mu, d))
+  t isa Rosenbrock && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 3, [t.a, t.b, t.scale], 3))
+  sampler isa MH && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 2, sampler.sigma, d))
+  GC.@preserve x0 check(ccall((:klb_job_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x0))   # initialize!
+  job
+end
+
+run(job::BasicMCJob) = (check(ccall((:klb_job_run, LIB), Cint, (Ptr{Cvoid},), job.handle)); job)
+run(jobs::Vector{BasicMCJob}) = map(run, jobs)
+reset(job::BasicMCJob) = check(ccall((:klb_job_reset, LIB), Cint, (Ptr{Cvoid},), job.handle))
+function reset(job::BasicMCJob, x::Matrix{Float64})
+  GC.@preserve x check(ccall((:klb_job_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x))
+end
+
+function fetch!(job::BasicMCJob, field::Integer, a::Array)
+  GC.@preserve a check(ccall((:klb_job_output, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), job.handle, field, a, sizeof(a)))
+  a
+end
+
+# output(job): value (d, npost, nchains), logtarget (npost, nchains), accept (npost, nchains) -- the NState layout
+function output(job::BasicMCJob)
+  P = job.range.npoststeps
+  (value = :value in job.monitor ? fetch!(job, 0, Array{Float64}(undef, job.dim, P, job.nchains)) : nothing,
+   logtarget = :logtarget in job.monitor ? fetch!(job, 1, Array{Float64}(undef, P, job.nchains)) : nothing,
+   gradlogtarget = :gradlogtarget in job.monitor ? fetch!(job, 2, Array{Float64}(undef, job.dim, P, job.nchains)) : nothing,
+   accept = :accept in job.diagnostics ? fetch!(job, 3, Array{UInt8}(undef, P, job.nchains)) .!= 0 : nothing)
+end
+
+end # module

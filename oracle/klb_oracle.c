@@ -111,10 +111,12 @@ double orc_uniform(uint64_t seed, uint64_t chain, uint64_t t) {
   klb_stream s = klb_stream_make(seed, chain, t);
   return klb_accept_uniform(&s);
 }
+/* units per lane the library uses for `dim` (klb_job_plan().nv): 1,2,4,8,16 for dim <= 1024, 64 up to 4096 */
 int orc_plan_nv(int64_t dim) {
   int nv = 1;
   while (64 * (int64_t)nv < dim && nv < 16) nv *= 2;
-  return (64 * (int64_t)nv >= dim) ? nv : -1;
+  if (64 * (int64_t)nv >= dim) return nv;
+  return dim <= 4096 ? 64 : -1;
 }
 
 /* ------------------------------------------------- canonical reduction order

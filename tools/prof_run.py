@@ -22,16 +22,21 @@ ap.add_argument("--arith", default="reference")
 ap.add_argument("--step", type=float, default=0.05)
 ap.add_argument("--nleaps", type=int, default=10)
 ap.add_argument("--none", action="store_true", help="destination none")
+ap.add_argument("--target", default="iso")
+ap.add_argument("--accrate", type=float, default=0.0, help="AcceptanceRateMCTuner target (0 = Vanilla)")
 a = ap.parse_args()
 x0 = np.random.default_rng(0).standard_normal((a.nchains, a.dim))
-p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+p = K.BasicContMuvParameter("p", logtarget={"iso": K.IsoGaussian(), "rosen": K.Rosenbrock()}[a.target])
+tuner = K.AcceptanceRateMCTuner(a.accrate) if a.accrate > 0 else K.VanillaMCTuner()
 smp = {"HMC": K.HMC(a.step, a.nleaps), "MALA": K.MALA(a.step), "MH": K.MH(np.full(a.dim, 0.02))}[a.sampler]
 oo = {"destination": "none"} if a.none else {"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}
 job = K.BasicMCJob(K.likelihood_model(p, False), smp, K.BasicMCRange(nsteps=a.nsteps, burnin=a.burnin), {"p": x0},
-                   outopts=oo, seed=1, arith=a.arith)
+                   tuner=tuner, outopts=oo, seed=1, arith=a.arith)
 for r in range(a.reps):
     job.reset()
     job.run()
     ms = job.last_run_ms
     lf = a.nchains * a.nsteps * (a.nleaps if a.sampler == "HMC" else 1)
     print("rep %d: %.3f ms  %.4g %s/s" % (r, ms, lf / ms * 1e3, "leapfrog-steps" if a.sampler == "HMC" else "transitions"))
+if not a.none:
+    print("accept rate %.3f" % job.output().diagnosticvalues.mean())
