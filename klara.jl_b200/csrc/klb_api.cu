@@ -12,6 +12,7 @@
 
 #include "../../include/klara_b200.h"
 #include "klb_kernels.cuh"
+#include "klb_dense.cuh"
 
 // per-(sampler, arithmetic) dispatchers, klb_kernels_inst.cu
 int klb_chain_0_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
@@ -67,6 +68,8 @@ struct klb_job {
   unsigned char* out_accept;
   double* mu;
   double* sigma;
+  double* Cm;       // dense precision matrix (d x d), KLB_TARGET_DENSE only
+  bool dense, have_C;
   uint64_t* tab;
   unsigned long long* flag;
   double rosen[3];
@@ -129,7 +132,7 @@ static void free_job(klb_job* j) {
   cudaSetDevice(j->cfg.device);
   cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate);
   cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
-  cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->tab); cudaFree(j->flag);
+  cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag);
   if (j->ev0) cudaEventDestroy(j->ev0);
   if (j->ev1) cudaEventDestroy(j->ev1);
   if (j->stream) cudaStreamDestroy(j->stream);
@@ -162,10 +165,11 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     return fail(KLB_EINVAL, "klb_config.struct_size = %u, library expects %zu", cfg->struct_size, sizeof(klb_config));
   const klb_config& c = *cfg;
   if (c.sampler < 0 || c.sampler > 2) return fail(KLB_EINVAL, "unknown sampler %d", c.sampler);
-  if (c.target == KLB_TARGET_DENSE)
-    return fail(KLB_EUNSUPPORTED, "dense-precision target is not built yet (SURVEY 8a row A8 / config C4)");
-  if (c.target != KLB_TARGET_ISO && c.target != KLB_TARGET_SHIFTED_ISO && c.target != KLB_TARGET_ROSENBROCK)
+  if (c.target != KLB_TARGET_ISO && c.target != KLB_TARGET_SHIFTED_ISO && c.target != KLB_TARGET_ROSENBROCK &&
+      c.target != KLB_TARGET_DENSE)
     return fail(KLB_EINVAL, "unknown target %d", c.target);
+  if (c.target == KLB_TARGET_DENSE && ((c.dim & 1) || c.dim > KLB_DENSE_MAXD))
+    return fail(KLB_EUNSUPPORTED, "the dense-precision kernels need an even dim <= %d", KLB_DENSE_MAXD);
   if (c.tuner != KLB_TUNER_VANILLA && c.tuner != KLB_TUNER_ACCEPTANCE_RATE)
     return fail(KLB_EINVAL, "unknown tuner %d", c.tuner);
   if (c.arith != KLB_ARITH_REFERENCE && c.arith != KLB_ARITH_FMA) return fail(KLB_EINVAL, "unknown arith %d", c.arith);
@@ -249,7 +253,10 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     if (c.monitor & KLB_MONITOR_GRADLOGTARGET) CKJ(cudaMalloc(&j->out_grad, N * P * d * sizeof(double)));
     if (c.diagnostics & KLB_DIAG_ACCEPT) CKJ(cudaMalloc(&j->out_accept, N * P));
   }
-  if (chain_dispatch(c.sampler, c.arith, nullptr, c.target, gw, gnv, c.dim == 64ll * gw * gnv, &j->regs, &j->bps, j->stream) != 0) {
+  j->dense = c.target == KLB_TARGET_DENSE;
+  if (j->dense) CKJ(cudaMalloc(&j->Cm, d * d * sizeof(double)));
+  if (j->dense ? klb_dense_attrs(c.sampler, c.arith, (int)c.dim, &j->regs, &j->bps) != 0
+               : chain_dispatch(c.sampler, c.arith, nullptr, c.target, gw, gnv, c.dim == 64ll * gw * gnv, &j->regs, &j->bps, j->stream) != 0) {
     cudaGetLastError();
     free_job(j);
     return fail(KLB_ECUDA, "no sm_100a kernel image for geometry (%d,%d) loadable on this device", gw, gnv);
@@ -279,8 +286,19 @@ int klb_job_set_target_f64(klb_job* j, int which, const double* host, int64_t n)
       if (n != 3) return fail(KLB_EINVAL, "rosenbrock needs 3 values (a, b, scale)");
       memcpy(j->rosen, host, 3 * sizeof(double));
       return KLB_OK;
-    case KLB_PARAM_C:
-      return fail(KLB_EUNSUPPORTED, "dense-precision target is not built yet");
+    case KLB_PARAM_C: {
+      const int64_t d = j->cfg.dim;
+      if (!j->dense) return fail(KLB_EINVAL, "this job's target takes no precision matrix");
+      if (n != d * d) return fail(KLB_EINVAL, "C needs dim*dim = %lld values", (long long)(d * d));
+      for (int64_t a = 0; a < d; ++a)          // the kernels read C by rows where the math says columns
+        for (int64_t b = a + 1; b < d; ++b)
+          if (memcmp(&host[a * d + b], &host[b * d + a], sizeof(double)) != 0)
+            return fail(KLB_EINVAL, "C must be exactly symmetric (C[%lld][%lld] != C[%lld][%lld])", (long long)a,
+                        (long long)b, (long long)b, (long long)a);
+      CK(cudaMemcpy(j->Cm, host, n * sizeof(double), cudaMemcpyHostToDevice));
+      j->have_C = true;
+      return KLB_OK;
+    }
   }
   return fail(KLB_EINVAL, "unknown parameter id %d", which);
 }
@@ -299,11 +317,16 @@ static int init_state(klb_job* j) {
   const klb_config& c = j->cfg;
   if (c.target == KLB_TARGET_SHIFTED_ISO && !j->have_mu) return fail(KLB_ESTATE, "set KLB_PARAM_MU before the state");
   if (c.sampler == KLB_SAMPLER_MH && !j->have_sigma) return fail(KLB_ESTATE, "set KLB_PARAM_SIGMA before the state");
+  if (j->dense && !j->have_C) return fail(KLB_ESTATE, "set KLB_PARAM_C before the state");
   KArgs A;
   fill_args(j, A);
   const unsigned long long none = std::numeric_limits<unsigned long long>::max();
   CK(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
-  if (klb_launch_init(A, c.target, j->gw, j->gnv, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
+  if (j->dense) {
+    DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
+    if (klb_dense_init(D, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
+      return fail(KLB_ECUDA, "dense init kernel launch failed");
+  } else if (klb_launch_init(A, c.target, j->gw, j->gnv, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
     return fail(KLB_EINVAL, "no init kernel for this configuration");
   j->launches += 1;
   CK(cudaGetLastError());
@@ -357,7 +380,10 @@ int klb_job_run_async(klb_job* j) {
   while (done < c.nsteps) {
     const long long nt = (c.nsteps - done) < chunk ? (c.nsteps - done) : chunk;
     A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global;
-    if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, c.dim == 64ll * j->gw * j->gnv, nullptr, nullptr, j->stream) != 0)
+    if (j->dense) {
+      DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
+      if (klb_dense_launch(D, c.sampler, c.arith, j->stream) != 0) return fail(KLB_ECUDA, "dense kernel launch failed");
+    } else if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, c.dim == 64ll * j->gw * j->gnv, nullptr, nullptr, j->stream) != 0)
       return fail(KLB_EINVAL, "no kernel for this configuration");
     CK(cudaGetLastError());
     j->launches += 1;

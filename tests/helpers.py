@@ -12,6 +12,14 @@ def synthetic_x0(seed, nchains, dim, chain_offset=0):
     return np.stack([O.normals(seed, chain_offset + c, 0, dim) for c in range(nchains)])
 
 
+def ar1_precision(dim, rho=0.8):
+    """C = inv(Sigma), Sigma_ij = rho^|i-j|: the d-dim analogue of the reference's bivariate example
+    (doc/examples/BivariateNormal/MALA/function/analytical.jl:21); made exactly symmetric"""
+    idx = np.arange(dim)
+    C = np.linalg.inv(rho ** np.abs(idx[:, None] - idx[None, :]))
+    return np.ascontiguousarray((C + C.T) / 2)
+
+
 def make_target(K, name, dim, rng):
     if name == "iso":
         return K.IsoGaussian(), O.ISO, None
@@ -20,6 +28,9 @@ def make_target(K, name, dim, rng):
         return K.ShiftedIsoGaussian(mu), O.SHIFTED, mu
     if name == "rosen":
         return K.Rosenbrock(1.0, 100.0, 0.05), O.ROSEN, np.array([1.0, 100.0, 0.05])
+    if name == "dense":
+        C = ar1_precision(dim)
+        return K.DenseGaussian(C), O.DENSE, C.reshape(-1)
     raise KeyError(name)
 
 

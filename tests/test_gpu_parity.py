@@ -93,6 +93,49 @@ def test_other_targets_bit_exact(K, sampler, target):
         compare_run(job, cfg, x0, tp, sg)
 
 
+@pytest.mark.parametrize("arith", ["reference", "fma"])
+@pytest.mark.parametrize("dim", [2, 64, 130, 512])
+@pytest.mark.parametrize("sampler", ["HMC", "MALA", "MH"])
+def test_dense_precision_target_bit_exact(K, sampler, dim, arith):
+    """-z'Cz, -2Cz with C = inv(AR(1) covariance): the matrix-vector kernels (klb_dense.cuh) against the oracle;
+    13 chains = one full CTA tile of 8 plus a ragged one"""
+    step = {"HMC": 0.05, "MALA": 0.02, "MH": 0.1}[sampler]
+    mon = ("value", "logtarget") if sampler == "MH" else ("value", "logtarget", "gradlogtarget")
+    job, cfg, x0, tp, sg = build_pair(K, sampler, "dense", nchains=13, dim=dim, nsteps=30, burnin=6, thinning=2,
+                                      step=step, nleaps=5, seed=99, arith=arith, monitor=mon,
+                                      sigma=np.full(dim, 0.05), tuner="accrate", period=5, target_rate=0.6)
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    assert out.diagnosticvalues.mean() > 0.05
+
+
+def test_dense_bivariate_normal_example(K, O):
+    """doc/examples/BivariateNormal/MALA/function/analytical.jl: MALA(0.3), C = inv([1 .8; .8 1]), p0 = [1.25, 3.11],
+    nsteps 10000, burnin 1000, monitor value/logtarget/gradlogtarget, diagnostics accept"""
+    C = np.linalg.inv(np.array([[1.0, 0.8], [0.8, 1.0]]))
+    C = (C + C.T) / 2
+    p = K.BasicContMuvParameter("p", logtarget=K.DenseGaussian(C))
+    job = K.BasicMCJob(K.likelihood_model(p, False), K.MALA(0.3), K.BasicMCRange(nsteps=10000, burnin=1000),
+                       {"p": [1.25, 3.11]},
+                       outopts={"monitor": ["value", "logtarget", "gradlogtarget"], "diagnostics": ["accept"]}, seed=7)
+    K.run(job)
+    chain = K.output(job)
+    cfg = O.make_config(O.MALA, O.DENSE, 1, 2, 10000, 1000, step=0.3, monitor=7, diagnostics=1, seed=7, nv=job.plan().nv)
+    ref = O.run(cfg, np.array([[1.25, 3.11]]), C.reshape(-1))
+    assert_same("value", chain.value, ref["value"][0])
+    assert_same("gradlogtarget", chain.gradlogtarget, ref["gradlogtarget"][0])
+    assert_same("accept", chain.diagnosticvalues, ref["accept"][0])
+    # exp(-z'Cz) is N(0, Sigma/2) with Sigma = [1 .8; .8 1]
+    cov = np.cov(chain.value.T)
+    assert abs(cov[0, 0] - 0.5) < 0.08 and abs(cov[0, 1] - 0.4) < 0.08 and abs(chain.value.mean()) < 0.1
+
+
+def test_dense_needs_symmetric_matrix(K):
+    C = np.array([[1.0, 0.5], [0.25, 1.0]])
+    p = K.BasicContMuvParameter("p", logtarget=K.DenseGaussian(C))
+    with pytest.raises(K.KlaraError, match="symmetric"):
+        K.BasicMCJob(K.likelihood_model(p, False), K.MALA(0.3), K.BasicMCRange(nsteps=10), {"p": [1.0, 2.0]})
+
+
 @pytest.mark.parametrize("sampler,step", [("HMC", 0.01), ("MALA", 0.5)])
 def test_acceptance_rate_tuner_bit_exact(K, sampler, step):
     """burn-in adaptation: step *= logistic_rate_score(rate - target) every `period` proposals while

@@ -25,8 +25,16 @@ ap.add_argument("--none", action="store_true", help="destination none")
 ap.add_argument("--target", default="iso")
 ap.add_argument("--accrate", type=float, default=0.0, help="AcceptanceRateMCTuner target (0 = Vanilla)")
 a = ap.parse_args()
-x0 = np.random.default_rng(0).standard_normal((a.nchains, a.dim))
-p = K.BasicContMuvParameter("p", logtarget={"iso": K.IsoGaussian(), "rosen": K.Rosenbrock()}[a.target])
+x0 = np.random.default_rng(0).standard_normal((a.nchains, a.dim)) * (0.3 if a.target == "dense" else 1.0)
+def _target():
+    if a.target == "dense":
+        idx = np.arange(a.dim)
+        C = np.linalg.inv(0.8 ** np.abs(idx[:, None] - idx[None, :]))
+        return K.DenseGaussian((C + C.T) / 2)
+    return {"iso": K.IsoGaussian(), "rosen": K.Rosenbrock()}[a.target]
+
+
+p = K.BasicContMuvParameter("p", logtarget=_target())
 tuner = K.AcceptanceRateMCTuner(a.accrate) if a.accrate > 0 else K.VanillaMCTuner()
 smp = {"HMC": K.HMC(a.step, a.nleaps), "MALA": K.MALA(a.step), "MH": K.MH(np.full(a.dim, 0.02))}[a.sampler]
 oo = {"destination": "none"} if a.none else {"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}
