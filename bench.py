@@ -258,6 +258,22 @@ def run_gpu(args, rank, world, local_rank):
     acc_rate = float(np.ctypeslib.as_array(C.cast(C.c_void_p(hl.value + lt_host.nbytes), C.POINTER(C.c_uint8)),
                                            shape=(nloc, NSTEPS - BURNIN)).mean())
 
+    # -------- effective sample size of the stored chains, on the device
+    tq = time.perf_counter()
+    L.check(lib.klb_job_ess(job._h, None))
+    ess_ms = (time.perf_counter() - tq) * 1e3
+    ep, enb = job.device_ptr(L.OUT_ESS)
+
+    class _IfaceE:
+        __cuda_array_interface__ = {"shape": (nloc, DIM), "typestr": "<f8", "data": (ep, False), "version": 2}
+    ess_t = torch.as_tensor(_IfaceE(), device=torch.device("cuda", local_rank))
+    ess_stats = torch.stack([ess_t.sum(), ess_t.min(), torch.isfinite(ess_t).all().double()])
+    ess_stats[1] = -ess_stats[1]
+    if world > 1:
+        s_ = ess_stats[:1].clone(); dist.all_reduce(s_); ess_stats[0] = s_[0]
+        m_ = ess_stats[1:2].clone(); dist.all_reduce(m_, op=dist.ReduceOp.MAX); ess_stats[1] = m_[0]
+    ess_sum, ess_min = float(ess_stats[0]), -float(ess_stats[1])
+
     # -------- reduce over ranks: max time
     t_dev = torch.tensor([dev_ms, wall * 1e3, e2e_wall * 1e3, last_kernel_ms], dtype=torch.float64,
                          device=state_t.device)
@@ -309,6 +325,11 @@ def run_gpu(args, rank, world, local_rank):
                     "note": "klb_job_set_state(host x0) + klb_job_run + klb_job_output(final state, logtarget chain, "
                             "accept flags) with pinned host buffers; the 50 GiB of monitored values stay in HBM "
                             "(output(job) copies them on request)"},
+            "ess": {"mean_ess_per_coordinate": ess_sum / (NCHAINS * DIM), "min_ess": ess_min, "samples_per_chain": NSTEPS - BURNIN,
+                    "independent_samples_per_sec": (ess_sum / DIM) / (dev_ms / args.steps * 1e-3),
+                    "ess_kernel_ms": ess_ms,
+                    "note": "ess(chain, :imse) per coordinate on the device (klb_job_ess); independent samples/s = "
+                            "sum over chains of the coordinate-mean ESS / device time of one run"},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
         }

@@ -90,6 +90,7 @@ extern "C" {
 #define KLB_OUT_TUNE_STEP 6      /* double  nchains            sstate.tune.step */
 #define KLB_OUT_TUNE_COUNTERS 7  /* int64   3 x nchains        accepted, proposed, totproposed */
 #define KLB_OUT_TUNE_RATE 8      /* double  nchains            sstate.tune.rate (NaN after reset_burnin!) */
+#define KLB_OUT_ESS 9            /* double  dim x nchains      filled by klb_job_ess (device_ptr only after that call) */
 
 typedef struct klb_job klb_job; /* opaque, library-owned: one batched BasicMCJob */
 
@@ -177,6 +178,11 @@ int klb_job_reset(klb_job* job);
 int klb_job_output(klb_job* job, int field, void* host_dst, int64_t nbytes);
 /* device address and byte size of a field (for zero-copy consumers: NCCL all-gather, torch views) */
 int klb_job_device_ptr(klb_job* job, int field, void** dev_ptr, int64_t* nbytes);
+
+/* ess(output(job)) = ess(chain, :imse) for every coordinate of every chain (src/stats/convergence/ess.jl:3-14,
+ * src/stats/variance/mcvar.jl:5,75-105), computed on the device over the monitored values; host_ess
+ * (dim x nchains doubles) may be NULL to leave the result on the device (KLB_OUT_ESS). */
+int klb_job_ess(klb_job* job, double* host_ess);
 
 int klb_job_plan(klb_job* job, klb_plan* out);
 /* kernels launched by this job so far */

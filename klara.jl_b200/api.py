@@ -27,7 +27,7 @@ from .targets import Target
 
 __all__ = ["BasicContMuvParameter", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
            "VanillaMCTuner", "AcceptanceRateMCTuner", "BasicMCTune", "BasicMCJob", "run", "reset", "output",
-           "BasicContMuvParameterNState", "logistic", "logistic_rate_score"]
+           "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "ess"]
 
 
 # ----------------------------------------------------------------------------- scalars
@@ -331,6 +331,16 @@ class BasicMCJob:
                     setattr(ns, f, a[0])
         return ns
 
+    def ess(self, to_host=True):
+        """ess(output(job)): effective sample size (IMSE) of every coordinate of every chain, computed on the
+        device (src/stats/convergence/ess.jl:3-14).  Returns (nchains, dim), or None when to_host=False."""
+        if to_host:
+            out = np.empty((self.nchains, self.dim))
+            L.check(L.lib().klb_job_ess(self._h, _ptr(out)))
+            return out[0] if self.single else out
+        L.check(L.lib().klb_job_ess(self._h, None))
+        return None
+
     # -- job.pstate / job.sstate.tune
     @property
     def pstate_value(self):
@@ -381,3 +391,8 @@ def reset(job, x=None):
 
 def output(job):
     return job.output()
+
+
+def ess(job):
+    """ess(chain) for the job's monitored values, on the device"""
+    return job.ess()

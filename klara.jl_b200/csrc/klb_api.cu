@@ -30,6 +30,8 @@ void klb_launch_debug_normals(const uint64_t* tab, uint64_t seed, uint64_t chain
                               cudaStream_t s);
 void klb_launch_debug_math(const uint64_t* tab, int op, long long n, const double* in, double* out, cudaStream_t s);
 void klb_launch_debug_uniform(uint64_t seed, uint64_t chain, uint64_t t, double* out, cudaStream_t s);
+void klb_launch_ess(const double* value, long long ld, long long npost, long long nchains, int dim, double* ess,
+                    cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 
@@ -72,6 +74,7 @@ struct klb_job {
   bool dense, have_C;
   uint64_t* tab;
   unsigned long long* flag;
+  double* ess;      // dim x nchains, allocated on first klb_job_ess
   double rosen[3];
   bool have_mu, have_sigma, have_rosen, have_state;
   unsigned long long t_global;  // transitions done since creation (RNG counter)
@@ -132,7 +135,7 @@ static void free_job(klb_job* j) {
   cudaSetDevice(j->cfg.device);
   cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate);
   cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
-  cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag);
+  cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess);
   if (j->ev0) cudaEventDestroy(j->ev0);
   if (j->ev1) cudaEventDestroy(j->ev1);
   if (j->stream) cudaStreamDestroy(j->stream);
@@ -430,6 +433,7 @@ static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols) 
     case KLB_OUT_TUNE_STEP: *p = j->tune_step; *nb = N * 8; break;
     case KLB_OUT_TUNE_COUNTERS: *p = j->tune_cnt; *nb = 3 * N * 8; break;
     case KLB_OUT_TUNE_RATE: *p = j->tune_rate; *nb = N * 8; break;
+    case KLB_OUT_ESS: *p = j->ess; *nb = N * d * 8; break;
     default: return fail(KLB_EINVAL, "unknown field %d", field);
   }
   if (!*p) return fail(KLB_ESTATE, "field %d is not monitored by this job", field);
@@ -458,6 +462,28 @@ int klb_job_device_ptr(klb_job* j, int field, void** dev_ptr, int64_t* nbytes) {
   int rc = field_ptr(j, field, dev_ptr, &nb, &cols);
   if (rc) return rc;
   *nbytes = (int64_t)(cols ? cols * (size_t)j->ld * 8 : nb);   // matrices: `cols` columns with leading dimension plan.ld
+  return KLB_OK;
+}
+
+int klb_job_ess(klb_job* j, double* host_ess) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  if (!j->out_value) return fail(KLB_ESTATE, "ess needs the monitored values (outopts[:monitor] must include :value)");
+  if (j->count != j->npost) return fail(KLB_ESTATE, "run the job before asking for its effective sample size");
+  if (j->cfg.nchains > 65535) {
+    // gridDim.y limit: split the chains
+  }
+  CK(cudaSetDevice(j->cfg.device));
+  const size_t N = (size_t)j->cfg.nchains, d = (size_t)j->cfg.dim;
+  if (!j->ess) CK(cudaMalloc(&j->ess, N * d * sizeof(double)));
+  for (size_t c0 = 0; c0 < N; c0 += 32768) {
+    const size_t nc = (N - c0) < 32768 ? (N - c0) : 32768;
+    klb_launch_ess(j->out_value + c0 * (size_t)j->npost * (size_t)j->ld, j->ld, j->npost, (long long)nc, (int)d,
+                   j->ess + c0 * d, j->stream);
+    j->launches += 1;
+  }
+  CK(cudaGetLastError());
+  if (host_ess) CK(cudaMemcpyAsync(host_ess, j->ess, N * d * sizeof(double), cudaMemcpyDeviceToHost, j->stream));
+  CK(cudaStreamSynchronize(j->stream));
   return KLB_OK;
 }
 

@@ -49,3 +49,54 @@ __global__ void klb_debug_uniform_kernel(uint64_t seed, uint64_t chain, uint64_t
 void klb_launch_debug_uniform(uint64_t seed, uint64_t chain, uint64_t t, double* out, cudaStream_t s) {
   klb_debug_uniform_kernel<<<1, 1, 0, s>>>(seed, chain, t, out);
 }
+
+// ------------------------------------------------------------------ post-hoc statistics on device
+// ess(chain, :imse) for every (coordinate, chain) series of the monitored values:
+//   ess = len * mcvar(:iid) / mcvar(:imse)           src/stats/convergence/ess.jl:3-14
+//   mcvar(:iid) = var(v)/len                          src/stats/variance/mcvar.jl:5
+//   mcvar(:imse): Geyer's initial monotone sequence estimator over autocov(v, 0:len-1)   mcvar.jl:75-105
+// One thread per series; consecutive threads take consecutive coordinates, so every load of sample s is a
+// coalesced row segment of the `ld x npost x nchains` value array and the CTA's working set (128 coordinates
+// x npost samples) stays in L1 across the lag passes.  Lags are evaluated pairwise until the first
+// non-positive G_j -- all the estimator reads.  Sequential, fma-accumulated sums: the oracle's order.
+__global__ void __launch_bounds__(128)
+klb_ess_kernel(const double* __restrict__ value, long long ld, long long npost, int dim, double* __restrict__ ess) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const long long c = blockIdx.y;
+  if (i >= dim) return;
+  const double* v = value + c * npost * ld + i;
+  const long long n = npost;
+  double out = klb_u2d(0x7FF8000000000000ULL);
+  if (n >= 4) {
+    double s = 0.0;
+    for (long long t = 0; t < n; ++t) s = __dadd_rn(s, v[t * ld]);
+    const double mu = __ddiv_rn(s, (double)n);
+    double s0 = 0.0;
+    for (long long t = 0; t < n; ++t) { const double z = __dsub_rn(v[t * ld], mu); s0 = __fma_rn(z, z, s0); }
+    const double iidvar = __ddiv_rn(__ddiv_rn(s0, (double)(n - 1)), (double)n);
+    const double acv0 = __ddiv_rn(s0, (double)n);
+    const long long k = (n - 2) >= 0 ? (n - 2) / 2 : -1;            // floor((maxlag-1)/2), maxlag = n-1
+    double sumg = 0.0, gprev = 0.0;
+    for (long long j = 0; j <= k; ++j) {
+      const long long l0 = 2 * j, l1 = 2 * j + 1;
+      double a = 0.0, b = 0.0;
+      for (long long t = 0; t + l0 < n; ++t)
+        a = __fma_rn(__dsub_rn(v[t * ld], mu), __dsub_rn(v[(t + l0) * ld], mu), a);
+      for (long long t = 0; t + l1 < n; ++t)
+        b = __fma_rn(__dsub_rn(v[t * ld], mu), __dsub_rn(v[(t + l1) * ld], mu), b);
+      double g = __dadd_rn(__ddiv_rn(a, (double)n), __ddiv_rn(b, (double)n));
+      if (g <= 0.0) break;
+      if (j > 0 && g > gprev) g = gprev;
+      sumg = __dadd_rn(sumg, g);
+      gprev = g;
+    }
+    const double mcvar = __ddiv_rn(__dadd_rn(-acv0, __dmul_rn(2.0, sumg)), (double)n);
+    out = __ddiv_rn(__dmul_rn((double)n, iidvar), mcvar);
+  }
+  ess[c * dim + i] = out;
+}
+void klb_launch_ess(const double* value, long long ld, long long npost, long long nchains, int dim, double* ess,
+                    cudaStream_t s) {
+  dim3 grid((unsigned)((dim + 127) / 128), (unsigned)nchains);
+  klb_ess_kernel<<<grid, 128, 0, s>>>(value, ld, npost, dim, ess);
+}

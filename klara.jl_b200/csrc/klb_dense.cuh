@@ -54,7 +54,11 @@ __device__ __forceinline__ double dense_reduce(const double* a, const double* b,
   return v;
 }
 
-// acc[r][0..1] = (C x_r)[2t, 2t+1] for the MC chains whose positions are in xs
+// acc[r][0..1] = (C x_r)[2t, 2t+1] for the MC chains whose positions are in xs.
+// C is streamed from L2 with plain read-only loads (4 rows in flight per thread).  A private cp.async ring in
+// shared memory (16 rows in flight) was measured too: it removes the long-scoreboard stalls but adds an
+// LDGSTS + LDS pair per row to an L1/shared pipe that is already the co-bottleneck (8 wavefronts per
+// 16 DFMA), and was 10 % slower (profiles/r1_summary.md, dense section).
 template <int MC>
 __device__ __forceinline__ void dense_matvec(double (&acc)[MC][2], const double* __restrict__ Cm, const double* xs,
                                              int d, int i0, bool active) {

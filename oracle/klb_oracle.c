@@ -523,6 +523,50 @@ int orc_eval_target(const orc_config* cfg, const double* tparams, const double* 
   return 0;
 }
 
+/* ------------------------------------------------------------ post-hoc statistics
+ * ess(v) = len * mcvar(v, :iid) / mcvar(v, :imse)                src/stats/convergence/ess.jl:3-14
+ * mcvar(v, :iid)  = var(v)/length(v)                             src/stats/variance/mcvar.jl:5
+ * mcvar(v, :imse, maxlag = length(v)-1): Geyer's initial monotone sequence estimator over
+ *   acv = StatsBase.autocov(v, 0:maxlag) (demeaned, each lag divided by length(v))   mcvar.jl:75-105
+ * Summation order (unspecified in Julia: pairwise sum / BLAS dot): sequential in t, fma-accumulated,
+ * the same as the device kernel.  Lags are evaluated pairwise until the first non-positive G_j, which is
+ * all the estimator ever reads. */
+double orc_ess_series(const double* v, int64_t n, int64_t stride, double* iact_out) {
+  if (n < 4) { if (iact_out) *iact_out = NAN; return NAN; }
+  double s = 0.;
+  for (int64_t t = 0; t < n; ++t) s = s + v[t * stride];
+  const double mu = s / (double)n;
+  double s0 = 0.;
+  for (int64_t t = 0; t < n; ++t) { double z = v[t * stride] - mu; s0 = fma(z, z, s0); }
+  const double iidvar = (s0 / (double)(n - 1)) / (double)n;       /* var(v)/length(v) */
+  const double acv0 = s0 / (double)n;
+  const int64_t maxlag = n - 1;
+  const int64_t k = (int64_t)floor((double)(maxlag - 1) / 2.);
+  double sumg = 0., gprev = 0.;
+  for (int64_t j = 0; j <= k; ++j) {
+    double a = 0., b = 0.;
+    const int64_t l0 = 2 * j, l1 = 2 * j + 1;
+    for (int64_t t = 0; t + l0 < n; ++t) a = fma(v[t * stride] - mu, v[(t + l0) * stride] - mu, a);
+    for (int64_t t = 0; t + l1 < n; ++t) b = fma(v[t * stride] - mu, v[(t + l1) * stride] - mu, b);
+    double g = a / (double)n + b / (double)n;                     /* acv[2j+1]+acv[2j+2] (1-based) */
+    if (g <= 0) break;                                            /* m = j */
+    if (j > 0 && g > gprev) g = gprev;                            /* monotone sequence */
+    sumg = sumg + g;
+    gprev = g;
+  }
+  const double mcvar = (-acv0 + 2 * sumg) / (double)n;
+  if (iact_out) *iact_out = mcvar / iidvar;                       /* src/stats/convergence/iact.jl:3 */
+  return (double)n * iidvar / mcvar;
+}
+
+/* value: (nchains, npost, d) as stored by orc_run; ess: (nchains, d) */
+void orc_ess(const double* value, int64_t nchains, int64_t npost, int64_t d, double* ess, int nthreads) {
+  (void)nthreads;
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t c = 0; c < nchains; ++c)
+    for (int64_t i = 0; i < d; ++i) ess[c * d + i] = orc_ess_series(value + c * npost * d + i, npost, d, NULL);
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

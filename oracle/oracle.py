@@ -86,6 +86,10 @@ def lib():
         L.orc_eval_target.restype = C.c_int
         L.orc_eval_target.argtypes = [C.POINTER(OrcConfig)] + [C.c_void_p] * 4
         L.orc_max_threads.restype = C.c_int
+        L.orc_ess.restype = None
+        L.orc_ess.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        L.orc_ess_series.restype = dbl
+        L.orc_ess_series.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         _lib = L
     return _lib
 
@@ -196,3 +200,14 @@ def run(cfg, x0, tparams=None, sigma=None, tune=None, logtarget=None):
 
 def max_threads():
     return lib().orc_max_threads()
+
+
+def ess(value, nthreads=None):
+    """ess(chain, :imse) per (chain, coordinate) of a (nchains, npost, dim) value array"""
+    v = np.ascontiguousarray(value, dtype=np.float64)
+    if v.ndim == 2:
+        v = v[None]
+    N, P, d = v.shape
+    out = np.empty((N, d))
+    lib().orc_ess(_ptr(v), N, P, d, _ptr(out), nthreads or max_threads())
+    return out

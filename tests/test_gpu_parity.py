@@ -253,3 +253,24 @@ def test_full_size_properties_c3(K):
     assert np.array_equal(v[:, 1:][rej], v[:, :-1][rej])
     assert acc.mean() > 0.6
     assert_same("final state == last sample", job.pstate_value, v[:, -1])
+
+
+def test_ess_on_device_matches_oracle(K, O):
+    """ess(chain, :imse) per coordinate (src/stats/convergence/ess.jl, variance/mcvar.jl:75-105): device == oracle
+    bit for bit on the values the job stored; MALA with a small step gives visibly correlated chains"""
+    for sampler, step, dim in (("MALA", 0.05, 24), ("HMC", 0.1, 130), ("MH", 0.0, 7)):
+        job, cfg, x0, tp, sg = build_pair(K, sampler, "iso", nchains=19, dim=dim, nsteps=400, burnin=100, step=step,
+                                          nleaps=4, seed=21, sigma=np.full(dim, 0.3))
+        job.run()
+        e_gpu = job.ess()
+        v = job.output().value
+        e_ref = O.ess(v)
+        assert_same("ess", e_gpu, e_ref)
+        assert np.isfinite(e_gpu).all() and (e_gpu > 1).all() and (e_gpu < 3 * 300).all()
+    # an iid-looking chain (well-tuned HMC) has ESS near the number of samples, a sticky one far less
+    job, *_ = build_pair(K, "HMC", "iso", nchains=64, dim=16, nsteps=1100, burnin=100, step=0.3, nleaps=6, seed=5)
+    job.run()
+    assert 600 < job.ess().mean() < 2200
+    job, *_ = build_pair(K, "MH", "iso", nchains=64, dim=16, nsteps=1100, burnin=100, sigma=np.full(16, 0.05), seed=5)
+    job.run()
+    assert job.ess().mean() < 60

@@ -141,3 +141,42 @@ def test_reduction_order_is_the_documented_one(O):
         for s in (16, 8, 4, 2, 1):
             lanes = np.array([lanes[l] + lanes[l ^ s] for l in range(32)])
         assert O.dot(a, b, nv=nv) == lanes[0]
+
+
+def _ess_numpy(v):
+    """literal numpy restatement of mcvar(v, Val{:imse}) / mcvar(v, Val{:iid}) / ess
+    (src/stats/variance/mcvar.jl:5,75-105, src/stats/convergence/ess.jl:3-5; StatsBase.autocov divides by n)"""
+    n = len(v)
+    z = v - v.mean()
+    acv = np.array([np.dot(z[:n - k], z[k:]) / n for k in range(n)])
+    maxlag = n - 1
+    k = int(np.floor((maxlag - 1) / 2))
+    m = k + 1
+    g = np.zeros(k + 1)
+    for j in range(k + 1):
+        g[j] = acv[2 * j] + acv[2 * j + 1]
+        if g[j] <= 0:
+            m = j
+            break
+    for j in range(1, m):
+        if g[j] > g[j - 1]:
+            g[j] = g[j - 1]
+    mcvar = (-acv[0] + 2 * g[:m].sum()) / n
+    return n * (v.var(ddof=1) / n) / mcvar
+
+
+def test_ess_follows_the_reference_estimator(O):
+    rng = np.random.default_rng(3)
+    n = 500
+    ar = np.zeros((3, n, 4))
+    e = rng.normal(size=(3, n, 4))
+    for t in range(1, n):
+        ar[:, t] = 0.6 * ar[:, t - 1] + e[:, t]
+    got = O.ess(ar)
+    for c in range(3):
+        for i in range(4):
+            assert got[c, i] == pytest.approx(_ess_numpy(ar[c, :, i]), rel=1e-10)
+    # theory: AR(1) with rho = 0.6 has ESS ~ n (1-rho)/(1+rho) = n/4; iid noise has ESS ~ n
+    assert 0.5 * n / 4 < got.mean() < 2 * n / 4
+    assert 0.7 * n < O.ess(rng.normal(size=(4, n, 4))).mean() < 1.4 * n
+    assert np.isnan(O.ess(rng.normal(size=(1, 3, 2)))).all()          # fewer than 4 samples: undefined
