@@ -267,10 +267,11 @@ def test_ess_on_device_matches_oracle(K, O):
         e_ref = O.ess(v)
         assert_same("ess", e_gpu, e_ref)
         assert np.isfinite(e_gpu).all() and (e_gpu > 1).all() and (e_gpu < 3 * 300).all()
-    # an iid-looking chain (well-tuned HMC) has ESS near the number of samples, a sticky one far less
-    job, *_ = build_pair(K, "HMC", "iso", nchains=64, dim=16, nsteps=1100, burnin=100, step=0.3, nleaps=6, seed=5)
+    # a well-mixing chain (HMC, trajectory ~ a quarter period) has ESS of the order of the number of samples
+    # (a longer trajectory makes the chain antithetic and the IMSE estimate exceeds n), a sticky one far less
+    job, *_ = build_pair(K, "HMC", "iso", nchains=64, dim=16, nsteps=1100, burnin=100, step=0.25, nleaps=4, seed=5)
     job.run()
-    assert 600 < job.ess().mean() < 2200
+    assert 400 < job.ess().mean() < 1000
     job, *_ = build_pair(K, "MH", "iso", nchains=64, dim=16, nsteps=1100, burnin=100, sigma=np.full(16, 0.05), seed=5)
     job.run()
     assert job.ess().mean() < 60
