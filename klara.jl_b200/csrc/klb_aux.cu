@@ -71,27 +71,43 @@ klb_ess_kernel(const double* __restrict__ value, long long ld, long long npost, 
     double s = 0.0;
     for (long long t = 0; t < n; ++t) s = __dadd_rn(s, v[t * ld]);
     const double mu = __ddiv_rn(s, (double)n);
-    double s0 = 0.0;
-    for (long long t = 0; t < n; ++t) { const double z = __dsub_rn(v[t * ld], mu); s0 = __fma_rn(z, z, s0); }
-    const double iidvar = __ddiv_rn(__ddiv_rn(s0, (double)(n - 1)), (double)n);
-    const double acv0 = __ddiv_rn(s0, (double)n);
-    const long long k = (n - 2) >= 0 ? (n - 2) / 2 : -1;            // floor((maxlag-1)/2), maxlag = n-1
-    double sumg = 0.0, gprev = 0.0;
-    for (long long j = 0; j <= k; ++j) {
-      const long long l0 = 2 * j, l1 = 2 * j + 1;
-      double a = 0.0, b = 0.0;
-      for (long long t = 0; t + l0 < n; ++t)
-        a = __fma_rn(__dsub_rn(v[t * ld], mu), __dsub_rn(v[(t + l0) * ld], mu), a);
-      for (long long t = 0; t + l1 < n; ++t)
-        b = __fma_rn(__dsub_rn(v[t * ld], mu), __dsub_rn(v[(t + l1) * ld], mu), b);
-      double g = __dadd_rn(__ddiv_rn(a, (double)n), __ddiv_rn(b, (double)n));
-      if (g <= 0.0) break;
-      if (j > 0 && g > gprev) g = gprev;
-      sumg = __dadd_rn(sumg, g);
-      gprev = g;
+    const double dn = (double)n;
+    const long long k = (n - 2) / 2;                                // floor((maxlag-1)/2), maxlag = n-1
+    double sumg = 0.0, gprev = 0.0, s0 = 0.0;
+    bool done = false;
+    // eight lags per pass over the series: a sliding register window holds z[t+L .. t+L+7], so a pass costs two
+    // loads per eight fma; every lag's sum still runs sequentially in t (the oracle's order)
+    for (long long L = 0; !done && L <= 2 * k + 1; L += 8) {
+      double acc[8], w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { acc[q] = 0.0; w[q] = (L + q < n) ? __dsub_rn(v[(L + q) * ld], mu) : 0.0; }
+      for (long long t = 0; t + L < n; ++t) {
+        const double zt = __dsub_rn(v[t * ld], mu);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = __fma_rn(zt, w[q], acc[q]);
+#pragma unroll
+        for (int q = 0; q < 7; ++q) w[q] = w[q + 1];
+        w[7] = (t + L + 8 < n) ? __dsub_rn(v[(t + L + 8) * ld], mu) : 0.0;
+      }
+      if (L == 0) s0 = acc[0];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const long long j = L / 2 + q;
+        if (!done && j <= k) {
+          double g = __dadd_rn(__ddiv_rn(acc[2 * q], dn), __ddiv_rn(acc[2 * q + 1], dn));
+          if (g <= 0.0) done = true;
+          else {
+            if (j > 0 && g > gprev) g = gprev;
+            sumg = __dadd_rn(sumg, g);
+            gprev = g;
+          }
+        }
+      }
     }
-    const double mcvar = __ddiv_rn(__dadd_rn(-acv0, __dmul_rn(2.0, sumg)), (double)n);
-    out = __ddiv_rn(__dmul_rn((double)n, iidvar), mcvar);
+    const double iidvar = __ddiv_rn(__ddiv_rn(s0, (double)(n - 1)), dn);
+    const double acv0 = __ddiv_rn(s0, dn);
+    const double mcvar = __ddiv_rn(__dadd_rn(-acv0, __dmul_rn(2.0, sumg)), dn);
+    out = __ddiv_rn(__dmul_rn(dn, iidvar), mcvar);
   }
   ess[c * dim + i] = out;
 }
