@@ -13,6 +13,7 @@
 #include "../../include/klara_b200.h"
 #include "klb_kernels.cuh"
 #include "klb_dense.cuh"
+#include "klb_dense_mma.cuh"
 
 // per-(sampler, arithmetic) dispatchers, klb_kernels_inst.cu
 int klb_chain_0_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
@@ -72,6 +73,7 @@ struct klb_job {
   double* sigma;
   double* Cm;       // dense precision matrix (d x d), KLB_TARGET_DENSE only
   bool dense, have_C;
+  bool dense_mma;   // HMC + dense + dim in {64,128,256,512}: matrix-vector products on the fp64 tensor pipe
   uint64_t* tab;
   unsigned long long* flag;
   double* ess;      // dim x nchains, allocated on first klb_job_ess
@@ -258,7 +260,13 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   }
   j->dense = c.target == KLB_TARGET_DENSE;
   if (j->dense) CKJ(cudaMalloc(&j->Cm, d * d * sizeof(double)));
-  if (j->dense ? klb_dense_attrs(c.sampler, c.arith, (int)c.dim, &j->regs, &j->bps) != 0
+  {
+    const char* env = getenv("KLB_DENSE_MMA");     // KLB_DENSE_MMA=0 forces the DFMA register-tile kernel (experiments)
+    j->dense_mma = j->dense && c.sampler == KLB_SAMPLER_HMC && !(env && env[0] == '0') &&
+                   (c.dim == 64 || c.dim == 128 || c.dim == 256 || c.dim == 512);
+  }
+  if (j->dense_mma ? klb_dense_mma_attrs(c.arith, (int)c.dim, &j->regs, &j->bps) != 0
+      : j->dense ? klb_dense_attrs(c.sampler, c.arith, (int)c.dim, &j->regs, &j->bps) != 0
                : chain_dispatch(c.sampler, c.arith, nullptr, c.target, gw, gnv, c.dim == 64ll * gw * gnv, &j->regs, &j->bps, j->stream) != 0) {
     cudaGetLastError();
     free_job(j);
@@ -385,7 +393,8 @@ int klb_job_run_async(klb_job* j) {
     A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global;
     if (j->dense) {
       DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
-      if (klb_dense_launch(D, c.sampler, c.arith, j->stream) != 0) return fail(KLB_ECUDA, "dense kernel launch failed");
+      if ((j->dense_mma ? klb_dense_mma_launch(D, c.arith, j->stream) : klb_dense_launch(D, c.sampler, c.arith, j->stream)) != 0)
+        return fail(KLB_ECUDA, "dense kernel launch failed");
     } else if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, c.dim == 64ll * j->gw * j->gnv, nullptr, nullptr, j->stream) != 0)
       return fail(KLB_EINVAL, "no kernel for this configuration");
     CK(cudaGetLastError());

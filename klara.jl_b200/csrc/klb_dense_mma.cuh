@@ -1,0 +1,330 @@
+// klb_dense_mma.cuh -- HMC on the dense-precision Gaussian target with the matrix-vector products on the
+// fp64 tensor pipe (mma.sync.aligned.m8n8k4.f64 = DMMA.8x8x4 on sm_100a).
+//
+// Why it is legal: tools/dmma_order_test.cu (run on the B200) shows that the instruction accumulates exactly
+// like the fma chain in increasing k, so chaining the k-steps through the C operand reproduces the oracle's
+// `acc = fma(C[i][j], x[j], acc)`, j = 0..d-1, bit for bit.
+// Why it pays: the DFMA register tile of klb_dense.cuh needs 8 L1/shared wavefronts per 16 DFMA (512 FMA); a warp
+// tile of 16 chains x (8 NT) columns reuses every A fragment NT times and every B fragment twice:
+// (2 + NT) fragment loads (2 wavefronts each) per 2 NT DMMA (256 FMA each), i.e. 10x fewer wavefronts per FMA
+// at NT = 8.
+//
+// CTA = 256 threads = 8 warps, 16 chains.  Warp w owns columns [w*8NT, (w+1)*8NT) (d = 64 NT) of all 16 chains:
+// thread (g = lane/4, q = lane%4) holds, for tile (mt, nt), elements (chain mt*8+g, column w*8NT + nt*8 + 2q + {0,1})
+// of p, of C x and of the cached gradient -- the D-fragment layout of the instruction, and a double2 unit of
+// the RNG / reduction contracts.  Positions live in shared memory (xs[chain][col], the A operand), C is
+// streamed from L2 in 16-row slabs through a two-stage cp.async buffer shared by the CTA (the B operand).
+#pragma once
+#include "klb_dense.cuh"
+
+#define KLB_MMA_MC 16
+#define KLB_MMA_KB 16  /* rows of C per slab */
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// acc[mt][nt][0..1] = (C x)[chain mt*8+g][col ...] for the 16 chains in xs
+template <int NT>
+__device__ __forceinline__ void mma_matvec(double (&acc)[2][NT][2], const double* __restrict__ Cm, const double* xs,
+                                           double* slab, int d, int ldx, int ldc, int w, int g, int q) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+  const int nslab = d / KLB_MMA_KB;
+  const int chunks = KLB_MMA_KB * (d / 2);                  // 16-byte chunks per slab
+  auto issue = [&](int s) {
+    double* dst = slab + (size_t)(s & 1) * KLB_MMA_KB * ldc;
+    const double* src = Cm + (size_t)s * KLB_MMA_KB * d;
+    for (int ch = threadIdx.x; ch < chunks; ch += KLB_DENSE_THREADS) {
+      const int row = ch / (d / 2), cp = ch - row * (d / 2);
+      cp_async16(dst + (size_t)row * ldc + 2 * cp, src + (size_t)row * d + 2 * cp);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int s = 0; s < nslab; ++s) {
+    if (s + 1 < nslab) { issue(s + 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();                                         // slab s is complete for every thread
+    const double* cs = slab + (size_t)(s & 1) * KLB_MMA_KB * ldc + (size_t)w * 8 * NT + g;
+    const double* xa = xs + (size_t)g * ldx + (size_t)s * KLB_MMA_KB + q;
+#pragma unroll
+    for (int kk = 0; kk < KLB_MMA_KB / 4; ++kk) {
+      const double a0 = xa[kk * 4], a1 = xa[(size_t)8 * ldx + kk * 4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const double b = cs[(size_t)(kk * 4 + q) * ldc + nt * 8];
+        dmma884(acc[0][nt][0], acc[0][nt][1], a0, b);
+        dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
+      }
+    }
+    __syncthreads();                                         // buffer s&1 may be refilled (by the issue of slab s+2)
+  }
+}
+
+template <int NT, bool FMA>
+__global__ void __launch_bounds__(KLB_DENSE_THREADS)
+klb_dense_mma_kernel(const DArgs D) {
+  constexpr int MC = KLB_MMA_MC;
+  const KArgs& A = D.k;
+  extern __shared__ __align__(16) unsigned char dsm[];
+  const int d = 64 * NT;
+  const int ldx = d + 4, ldc = d + 4;                        // = 4 (mod 16): conflict-free fragment loads
+  // dynamic shared memory: tab | xs[16*ldx] | slab[2*KB*ldc] (also the reduction scratch) | DenseShared
+  uint64_t* tab = reinterpret_cast<uint64_t*>(dsm);
+  double* xs = reinterpret_cast<double*>(dsm + ((KLB_TAB_LEN * 8 + 15) & ~15));
+  double* slab = xs + (size_t)MC * ldx;
+  DenseShared<MC>& S = *reinterpret_cast<DenseShared<MC>*>(slab + (size_t)2 * KLB_MMA_KB * ldc);
+  double* scA = slab;                                        // [16][d] scratch, valid between matvecs
+  double* scB = slab + (size_t)MC * d;
+
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, g = lane >> 2, q = lane & 3;
+  for (int i = t; i < KLB_TAB_LEN; i += blockDim.x) tab[i] = A.tab[i];
+  const long long c0 = (long long)blockIdx.x * MC;
+  const double* Cm = D.Cm;
+
+  if (t < MC) {
+    const long long c = c0 + t;
+    const bool live = c < A.nchains;
+    S.lt_cur[t] = live ? A.lt[c] : 0.0;
+    S.step[t] = live ? A.tune_step[c] : 1.0;
+    S.accepted[t] = live ? A.tune_cnt[3 * c] : 0;
+    S.proposed[t] = live ? A.tune_cnt[3 * c + 1] : 0;
+    S.totproposed[t] = live ? A.tune_cnt[3 * c + 2] : 0;
+    S.rate[t] = live ? A.tune_rate[c] : 0.0;
+  }
+  // element ownership: chain r(mt) = mt*8+g, column col(nt) = w*8NT + nt*8 + 2q (+1)
+  auto colof = [&](int nt) { return w * 8 * NT + nt * 8 + 2 * q; };
+  // positions -> shared memory
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int r = mt * 8 + g;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      double2 v = make_double2(0.0, 0.0);
+      if (c0 + r < A.nchains) v = *reinterpret_cast<const double2*>(A.state + (c0 + r) * A.ld + colof(nt));
+      *reinterpret_cast<double2*>(xs + (size_t)r * ldx + colof(nt)) = v;
+    }
+  }
+  __syncthreads();
+  double gc[2][NT][2];
+  mma_matvec<NT>(gc, Cm, xs, slab, d, ldx, ldc, w, g, q);      // cached C x of the starting point
+
+  const bool saving = (A.out_value != nullptr) || (A.out_lt != nullptr) || (A.out_grad != nullptr) ||
+                      (A.out_accept != nullptr);
+  long long count = A.count0;
+  long long thin = (A.i0 > A.burnin) ? klb_mod(A.i0 - A.burnin - 1, A.thinning) : 0;
+
+  for (long long it = 0; it < A.nt; ++it) {
+    const long long irun = A.i0 + it;
+    const unsigned long long tglob = A.t0 + 1ull + (unsigned long long)it;
+    double p[2][NT][2], acc[2][NT][2];
+
+    // ---------------- momentum: unit k = col/2 of chain r
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = mt * 8 + g;
+      const klb_stream st = klb_stream_make(A.seed, A.chain_offset + (unsigned long long)(c0 + r), tglob);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int col = colof(nt);
+        uint64_t w0, w1;
+        klb_stream_draw(&st, (unsigned)(col >> 1), KLB_TAG_NORMAL, 0u, &w0, &w1);
+        double a, b;
+        if (!klb_zig_fast(w0, tab, &a)) a = klb_normal_from_word(w0, (unsigned)col, &st, tab);
+        if (!klb_zig_fast(w1, tab, &b)) b = klb_normal_from_word(w1, (unsigned)col + 1u, &st, tab);
+        p[mt][nt][0] = a; p[mt][nt][1] = b;
+        *reinterpret_cast<double2*>(scA + (size_t)r * d + col) = make_double2(a, b);
+      }
+    }
+    __syncthreads();
+    // old kinetic energy (canonical order: one warp per chain over the scratch copy of p)
+    for (int r = w; r < MC; r += KLB_DENSE_THREADS / 32) {
+      double a4[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int m = 0; m < D.nv; ++m) {
+        const int i = 2 * (lane + 32 * m);
+        double2 v = make_double2(0.0, 0.0);
+        if (i < d) v = *reinterpret_cast<const double2*>(scA + (size_t)r * d + i);
+        a4[m & 3] = Ar<FMA>::ma(v.x, v.x, a4[m & 3]);
+        a4[m & 3] = Ar<FMA>::ma(v.y, v.y, a4[m & 3]);
+      }
+      double v = __dadd_rn(__dadd_rn(a4[0], a4[1]), __dadd_rn(a4[2], a4[3]));
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, s));
+      if (lane == 0) S.k0[r] = v;
+    }
+    // ---------------- leapfrog
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = gc[mt][nt][0]; acc[mt][nt][1] = gc[mt][nt][1]; }
+    for (int s = 1; s <= A.nleaps; ++s) {
+      __syncthreads();                       // scratch / xs readers are done
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 8 + g;
+        const double step = S.step[r];
+        const double h = __dmul_rn(0.5, step);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          double2* xp = reinterpret_cast<double2*>(xs + (size_t)r * ldx + colof(nt));
+          double2 xv = *xp;
+          p[mt][nt][0] = Ar<FMA>::ma(h, __dmul_rn(-2.0, acc[mt][nt][0]), p[mt][nt][0]);   // p += (h g)
+          p[mt][nt][1] = Ar<FMA>::ma(h, __dmul_rn(-2.0, acc[mt][nt][1]), p[mt][nt][1]);
+          xv.x = Ar<FMA>::ma(step, p[mt][nt][0], xv.x);                                  // x += step p
+          xv.y = Ar<FMA>::ma(step, p[mt][nt][1], xv.y);
+          *xp = xv;
+        }
+      }
+      __syncthreads();
+      mma_matvec<NT>(acc, Cm, xs, slab, d, ldx, ldc, w, g, q);                           // g = -2 C x
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const double h = __dmul_rn(0.5, S.step[mt * 8 + g]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          p[mt][nt][0] = Ar<FMA>::ma(h, __dmul_rn(-2.0, acc[mt][nt][0]), p[mt][nt][0]);
+          p[mt][nt][1] = Ar<FMA>::ma(h, __dmul_rn(-2.0, acc[mt][nt][1]), p[mt][nt][1]);
+        }
+      }
+    }
+    // ---------------- log-target of the proposal and new kinetic energy (the slab region is free again)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = mt * 8 + g;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int col = colof(nt);
+        *reinterpret_cast<double2*>(scA + (size_t)r * d + col) = make_double2(p[mt][nt][0], p[mt][nt][1]);
+        *reinterpret_cast<double2*>(scB + (size_t)r * d + col) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      }
+    }
+    __syncthreads();
+    for (int r = w; r < MC; r += KLB_DENSE_THREADS / 32) {
+      double k4[4] = {0.0, 0.0, 0.0, 0.0}, l4[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int m = 0; m < D.nv; ++m) {
+        const int i = 2 * (lane + 32 * m);
+        double2 pv = make_double2(0.0, 0.0), cv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
+        if (i < d) {
+          pv = *reinterpret_cast<const double2*>(scA + (size_t)r * d + i);
+          cv = *reinterpret_cast<const double2*>(scB + (size_t)r * d + i);
+          xv = *reinterpret_cast<const double2*>(xs + (size_t)r * ldx + i);
+        }
+        k4[m & 3] = Ar<FMA>::ma(pv.x, pv.x, k4[m & 3]);
+        k4[m & 3] = Ar<FMA>::ma(pv.y, pv.y, k4[m & 3]);
+        l4[m & 3] = Ar<FMA>::ma(xv.x, cv.x, l4[m & 3]);
+        l4[m & 3] = Ar<FMA>::ma(xv.y, cv.y, l4[m & 3]);
+      }
+      double k1 = __dadd_rn(__dadd_rn(k4[0], k4[1]), __dadd_rn(k4[2], k4[3]));
+      double xcx = __dadd_rn(__dadd_rn(l4[0], l4[1]), __dadd_rn(l4[2], l4[3]));
+#pragma unroll
+      for (int s = 16; s >= 1; s >>= 1) {
+        const double tk = __shfl_xor_sync(0xffffffffu, k1, s), tx = __shfl_xor_sync(0xffffffffu, xcx, s);
+        k1 = __dadd_rn(k1, tk); xcx = __dadd_rn(xcx, tx);
+      }
+      if (lane == 0) {
+        const long long c = c0 + r;
+        const double lt_new = -xcx;
+        const double oldh = __dsub_rn(S.lt_cur[r], __dmul_rn(0.5, S.k0[r]));
+        const double newh = __dsub_rn(lt_new, __dmul_rn(0.5, k1));
+        const double ratio = __dsub_rn(newh, oldh);
+        bool acc_ = false;
+        if (ratio >= 0.0) acc_ = true;
+        else {
+          const klb_stream st = klb_stream_make(A.seed, A.chain_offset + (unsigned long long)c, tglob);
+          const double ex = klb_exp(ratio, tab);
+          const double a = (ex != ex) ? ex : (ex < 1.0 ? ex : 1.0);
+          acc_ = klb_accept_uniform(&st) < a;
+        }
+        S.lt_new[r] = lt_new;
+        S.accept[r] = (acc_ && c < A.nchains) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    // ---------------- per-chain epilogue: counters, tuner
+    if (t < MC) {
+      const int r = t;
+      if (A.counters_on) { S.proposed[r] += 1; if (S.accept[r]) S.accepted[r] += 1; }
+      if (S.accept[r]) S.lt_cur[r] = S.lt_new[r];
+      Tune tn;
+      tn.step = S.step[r]; tn.accepted = S.accepted[r]; tn.proposed = S.proposed[r]; tn.totproposed = S.totproposed[r];
+      tn.rate = S.rate[r];
+      tuner_block<2>(A, tn, tab);
+      S.step[r] = tn.step; S.accepted[r] = tn.accepted; S.proposed[r] = tn.proposed; S.totproposed[r] = tn.totproposed;
+      S.rate[r] = tn.rate;
+    }
+    // ---------------- accept: publish x to the state column, keep C x; reject: restore x from the column
+    const bool do_save = (irun > A.burnin) && (thin == 0);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = mt * 8 + g;
+      const long long c = c0 + r;
+      const bool live = c < A.nchains;
+      const bool acc_ = S.accept[r] != 0;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const int col = colof(nt);
+        double2* xp = reinterpret_cast<double2*>(xs + (size_t)r * ldx + col);
+        if (acc_) {
+          gc[mt][nt][0] = acc[mt][nt][0]; gc[mt][nt][1] = acc[mt][nt][1];
+          if (live) *reinterpret_cast<double2*>(A.state + c * A.ld + col) = *xp;
+        } else if (live) {
+          *xp = *reinterpret_cast<const double2*>(A.state + c * A.ld + col);
+        } else {
+          *xp = make_double2(0.0, 0.0);
+        }
+      }
+    }
+    __syncthreads();
+    if (do_save && saving) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 8 + g;
+        const long long c = c0 + r;
+        if (c < A.nchains) {
+          const long long colidx = c * A.npost + count;
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            const int col = colof(nt);
+            if (A.out_value)
+              *reinterpret_cast<double2*>(A.out_value + colidx * A.ld + col) =
+                  *reinterpret_cast<const double2*>(xs + (size_t)r * ldx + col);
+            if (A.out_grad)
+              *reinterpret_cast<double2*>(A.out_grad + colidx * A.ld + col) =
+                  make_double2(__dmul_rn(-2.0, gc[mt][nt][0]), __dmul_rn(-2.0, gc[mt][nt][1]));
+          }
+          if (w == 0 && q == 0) {
+            if (A.out_lt) A.out_lt[colidx] = S.lt_cur[r];
+            if (A.out_accept) A.out_accept[colidx] = (unsigned char)S.accept[r];
+          }
+        }
+      }
+    }
+    if (irun > A.burnin) {
+      if (thin == 0) count += 1;
+      thin = (thin + 1 == A.thinning) ? 0 : thin + 1;
+    }
+  }
+
+  // the state columns are current (written on every accept); per-chain scalars
+  if (t < MC && c0 + t < A.nchains) {
+    const long long c = c0 + t;
+    A.lt[c] = S.lt_cur[t];
+    A.tune_step[c] = S.step[t];
+    A.tune_cnt[3 * c] = S.accepted[t]; A.tune_cnt[3 * c + 1] = S.proposed[t]; A.tune_cnt[3 * c + 2] = S.totproposed[t];
+    A.tune_rate[c] = S.rate[t];
+  }
+}
+
+int klb_dense_mma_launch(const DArgs& D, int fma, cudaStream_t s);   // returns -1 when dim is not 64, 128, 256 or 512
+int klb_dense_mma_attrs(int fma, int dim, int* regs, int* bps);

@@ -94,7 +94,7 @@ def test_other_targets_bit_exact(K, sampler, target):
 
 
 @pytest.mark.parametrize("arith", ["reference", "fma"])
-@pytest.mark.parametrize("dim", [2, 64, 130, 512])
+@pytest.mark.parametrize("dim", [2, 64, 128, 130, 256, 512])
 @pytest.mark.parametrize("sampler", ["HMC", "MALA", "MH"])
 def test_dense_precision_target_bit_exact(K, sampler, dim, arith):
     """-z'Cz, -2Cz with C = inv(AR(1) covariance): the matrix-vector kernels (klb_dense.cuh) against the oracle;
@@ -127,6 +127,20 @@ def test_dense_bivariate_normal_example(K, O):
     # exp(-z'Cz) is N(0, Sigma/2) with Sigma = [1 .8; .8 1]
     cov = np.cov(chain.value.T)
     assert abs(cov[0, 0] - 0.5) < 0.08 and abs(cov[0, 1] - 0.4) < 0.08 and abs(chain.value.mean()) < 0.1
+
+
+def test_dense_mma_and_dfma_kernels_agree(K, monkeypatch):
+    """HMC on the dense target: the tensor-pipe kernel (DMMA, default for dim 64/128/256/512) and the DFMA
+    register-tile kernel (KLB_DENSE_MMA=0) produce the same bits -- both follow the increasing-j fma chain"""
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("KLB_DENSE_MMA", flag)
+        job, cfg, x0, tp, sg = build_pair(K, "HMC", "dense", nchains=37, dim=256, nsteps=12, burnin=2, step=0.05,
+                                          nleaps=4, seed=17)
+        job.run()
+        outs.append((job.output().value, job.output().diagnosticvalues, job.plan().regs_per_thread))
+    assert_same("value", outs[0][0], outs[1][0])
+    assert_same("accept", outs[0][1], outs[1][1])
 
 
 def test_dense_needs_symmetric_matrix(K):
