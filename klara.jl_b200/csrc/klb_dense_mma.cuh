@@ -18,7 +18,9 @@
 #include "klb_dense.cuh"
 
 #define KLB_MMA_MC 16
-#define KLB_MMA_KB 16  /* rows of C per slab */
+#define KLB_MMA_KB 16     /* rows of C per slab */
+#define KLB_MMA_STAGES 2  /* ring depth.  4 stages x 8 rows (same bytes in flight) measured the same: the ring (132 KB)
+                             is what shared memory leaves after the positions; see profiles/r1_summary.md */
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -32,31 +34,42 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// acc[mt][nt][0..1] = (C x)[chain mt*8+g][col ...] for the 16 chains in xs
+// slab s of C (KB rows) -> ring buffer s % STAGES, one commit group
+__device__ __forceinline__ void mma_issue_slab(const double* __restrict__ Cm, double* slab, int d, int ldc, int s) {
+  double* dst = slab + (size_t)(s % KLB_MMA_STAGES) * KLB_MMA_KB * ldc;
+  const double* src = Cm + (size_t)s * KLB_MMA_KB * d;
+  const int chunks = KLB_MMA_KB * (d / 2);                  // 16-byte chunks per slab
+  for (int ch = threadIdx.x; ch < chunks; ch += KLB_DENSE_THREADS) {
+    const int row = ch / (d / 2), cp = ch - row * (d / 2);
+    cp_async16(dst + (size_t)row * ldc + 2 * cp, src + (size_t)row * d + 2 * cp);
+  }
+  cp_async_commit();
+}
+__device__ __forceinline__ void mma_prefetch(const double* __restrict__ Cm, double* slab, int d, int ldc) {
+#pragma unroll
+  for (int s = 0; s < KLB_MMA_STAGES - 1; ++s) mma_issue_slab(Cm, slab, d, ldc, s);
+}
+
+// acc[mt][nt][0..1] = (C x)[chain mt*8+g][col ...] for the 16 chains in xs.  `prefetched`: the first
+// STAGES-1 slabs are already in flight (issued at the end of the previous product).  `prefetch_next`: issue them
+// again on the way out, so the next product starts without an exposed L2 round trip (only legal when the caller
+// does not use the slab region as scratch before that product).
 template <int NT>
 __device__ __forceinline__ void mma_matvec(double (&acc)[2][NT][2], const double* __restrict__ Cm, const double* xs,
-                                           double* slab, int d, int ldx, int ldc, int w, int g, int q) {
+                                           double* slab, int d, int ldx, int ldc, int w, int g, int q,
+                                           bool prefetched, bool prefetch_next) {
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
   const int nslab = d / KLB_MMA_KB;
-  const int chunks = KLB_MMA_KB * (d / 2);                  // 16-byte chunks per slab
-  auto issue = [&](int s) {
-    double* dst = slab + (size_t)(s & 1) * KLB_MMA_KB * ldc;
-    const double* src = Cm + (size_t)s * KLB_MMA_KB * d;
-    for (int ch = threadIdx.x; ch < chunks; ch += KLB_DENSE_THREADS) {
-      const int row = ch / (d / 2), cp = ch - row * (d / 2);
-      cp_async16(dst + (size_t)row * ldc + 2 * cp, src + (size_t)row * d + 2 * cp);
-    }
-    cp_async_commit();
-  };
-  issue(0);
+  if (!prefetched) mma_prefetch(Cm, slab, d, ldc);
   for (int s = 0; s < nslab; ++s) {
-    if (s + 1 < nslab) { issue(s + 1); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
-    __syncthreads();                                         // slab s is complete for every thread
-    const double* cs = slab + (size_t)(s & 1) * KLB_MMA_KB * ldc + (size_t)w * 8 * NT + g;
+    cp_async_wait<KLB_MMA_STAGES - 2>();                     // this thread's chunks of slab s have landed
+    __syncthreads();                                         // ... everybody's; and slab s-1 is consumed by all
+    if (s + KLB_MMA_STAGES - 1 < nslab) mma_issue_slab(Cm, slab, d, ldc, s + KLB_MMA_STAGES - 1);
+    else cp_async_commit();                                  // empty group keeps the wait arithmetic uniform
+    const double* cs = slab + (size_t)(s % KLB_MMA_STAGES) * KLB_MMA_KB * ldc + (size_t)w * 8 * NT + g;
     const double* xa = xs + (size_t)g * ldx + (size_t)s * KLB_MMA_KB + q;
 #pragma unroll
     for (int kk = 0; kk < KLB_MMA_KB / 4; ++kk) {
@@ -68,8 +81,10 @@ __device__ __forceinline__ void mma_matvec(double (&acc)[2][NT][2], const double
         dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
       }
     }
-    __syncthreads();                                         // buffer s&1 may be refilled (by the issue of slab s+2)
   }
+  cp_async_wait<0>();
+  __syncthreads();                                           // the ring and xs are free
+  if (prefetch_next) mma_prefetch(Cm, slab, d, ldc);
 }
 
 template <int NT, bool FMA>
@@ -80,11 +95,11 @@ klb_dense_mma_kernel(const DArgs D) {
   extern __shared__ __align__(16) unsigned char dsm[];
   const int d = 64 * NT;
   const int ldx = d + 4, ldc = d + 4;                        // = 4 (mod 16): conflict-free fragment loads
-  // dynamic shared memory: tab | xs[16*ldx] | slab[2*KB*ldc] (also the reduction scratch) | DenseShared
+  // dynamic shared memory: tab | xs[16*ldx] | slab ring[STAGES*KB*ldc] (also the reduction scratch) | DenseShared
   uint64_t* tab = reinterpret_cast<uint64_t*>(dsm);
   double* xs = reinterpret_cast<double*>(dsm + ((KLB_TAB_LEN * 8 + 15) & ~15));
   double* slab = xs + (size_t)MC * ldx;
-  DenseShared<MC>& S = *reinterpret_cast<DenseShared<MC>*>(slab + (size_t)2 * KLB_MMA_KB * ldc);
+  DenseShared<MC>& S = *reinterpret_cast<DenseShared<MC>*>(slab + (size_t)KLB_MMA_STAGES * KLB_MMA_KB * ldc);
   double* scA = slab;                                        // [16][d] scratch, valid between matvecs
   double* scB = slab + (size_t)MC * d;
 
@@ -118,7 +133,7 @@ klb_dense_mma_kernel(const DArgs D) {
   }
   __syncthreads();
   double gc[2][NT][2];
-  mma_matvec<NT>(gc, Cm, xs, slab, d, ldx, ldc, w, g, q);      // cached C x of the starting point
+  mma_matvec<NT>(gc, Cm, xs, slab, d, ldx, ldc, w, g, q, false, false);      // cached C x of the starting point
 
   const bool saving = (A.out_value != nullptr) || (A.out_lt != nullptr) || (A.out_grad != nullptr) ||
                       (A.out_accept != nullptr);
@@ -187,7 +202,7 @@ klb_dense_mma_kernel(const DArgs D) {
         }
       }
       __syncthreads();
-      mma_matvec<NT>(acc, Cm, xs, slab, d, ldx, ldc, w, g, q);                           // g = -2 C x
+      mma_matvec<NT>(acc, Cm, xs, slab, d, ldx, ldc, w, g, q, s > 1, s < A.nleaps);      // g = -2 C x
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const double h = __dmul_rn(0.5, S.step[mt * 8 + g]);

@@ -2,7 +2,7 @@
 #include "klb_dense_mma.cuh"
 
 static size_t mma_smem(int d) {
-  return ((KLB_TAB_LEN * 8 + 15) & ~15) + (size_t)KLB_MMA_MC * (d + 4) * 8 + (size_t)2 * KLB_MMA_KB * (d + 4) * 8 +
+  return ((KLB_TAB_LEN * 8 + 15) & ~15) + (size_t)KLB_MMA_MC * (d + 4) * 8 + (size_t)KLB_MMA_STAGES * KLB_MMA_KB * (d + 4) * 8 +
          sizeof(DenseShared<KLB_MMA_MC>);
 }
 template <int NT, bool F>
