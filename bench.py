@@ -117,7 +117,6 @@ def cpu_leg(nthreads=None, target_seconds=12.0):
 def run_reference(args, rank):
     if rank != 0:
         return
-    lines = []
     t_all = time.perf_counter()
     for _ in range(args.warmup):
         cpu_leg(target_seconds=1.0)
@@ -202,7 +201,6 @@ def run_gpu(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches0 = job.launches
     for _ in range(args.warmup):
         one_step()
     barrier()
@@ -212,7 +210,6 @@ def run_gpu(args, rank, world, local_rank):
         sampler.start()
         time.sleep(0.3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms = []
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
@@ -220,7 +217,6 @@ def run_gpu(args, rank, world, local_rank):
         one_step()
         if args.per_step_sync:
             job.sync()
-        kern_ms.append(None)
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0

@@ -15,7 +15,9 @@
 # method for a Matrix initial value on a BasicContMuvParameter, so this hook does not conflict.
 module KlaraB200
 
-export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
+using LinearAlgebra: dot
+
+export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, DenseGaussian, ess, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
        BasicMCRange, VanillaMCTuner, AcceptanceRateMCTuner, BasicMCJob, run, reset, output
 
 const LIB = get(ENV, "KLARA_B200_LIB", "libklara_b200.so")
@@ -30,7 +32,11 @@ struct ShiftedIsoGaussian <: Target; mu::Vector{Float64}; end
 gradient(t::ShiftedIsoGaussian) = z -> -2 .* (z .- t.mu)
 struct Rosenbrock <: Target; a::Float64; b::Float64; scale::Float64; end
 Rosenbrock() = Rosenbrock(1.0, 100.0, 0.05)
-code(::IsoGaussian) = 0; code(::ShiftedIsoGaussian) = 1; code(::Rosenbrock) = 3
+# -z'Cz, -2Cz with a symmetric precision matrix (doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9)
+struct DenseGaussian <: Target; C::Matrix{Float64}; end
+(t::DenseGaussian)(z::Vector{Float64}) = -dot(z, t.C*z)
+gradient(t::DenseGaussian) = z -> -2 .* (t.C*z)
+code(::IsoGaussian) = 0; code(::ShiftedIsoGaussian) = 1; code(::DenseGaussian) = 2; code(::Rosenbrock) = 3
 
 struct BasicContMuvParameter; key::Symbol; logtarget::Target; end
 BasicContMuvParameter(key::Symbol; logtarget::Target, gradlogtarget=nothing) = BasicContMuvParameter(key, logtarget)
@@ -100,6 +106,7 @@ function BasicMCJob(model::GenericModel, sampler, range::BasicMCRange, v0::Dict;
   t = p.logtarget
   t isa ShiftedIsoGaussian && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 0, t.mu, d))
   t isa Rosenbrock && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 3, [t.a, t.b, t.scale], 3))
+  t isa DenseGaussian && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 1, t.C, d*d))
   sampler isa MH && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 2, sampler.sigma, d))
   GC.@preserve x0 check(ccall((:klb_job_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x0))   # initialize!
   job
@@ -124,6 +131,14 @@ function output(job::BasicMCJob)
    logtarget = :logtarget in job.monitor ? fetch!(job, 1, Array{Float64}(undef, P, job.nchains)) : nothing,
    gradlogtarget = :gradlogtarget in job.monitor ? fetch!(job, 2, Array{Float64}(undef, job.dim, P, job.nchains)) : nothing,
    accept = :accept in job.diagnostics ? fetch!(job, 3, Array{UInt8}(undef, P, job.nchains)) .!= 0 : nothing)
+end
+
+# ess(output(job)): effective sample size (IMSE) per coordinate and chain, computed on the device
+# (src/stats/convergence/ess.jl:3-14)
+function ess(job::BasicMCJob)
+  e = Array{Float64}(undef, job.dim, job.nchains)
+  GC.@preserve e check(ccall((:klb_job_ess, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, e))
+  e
 end
 
 end # module

@@ -478,13 +478,10 @@ int klb_job_ess(klb_job* j, double* host_ess) {
   if (!j) return fail(KLB_EINVAL, "null argument");
   if (!j->out_value) return fail(KLB_ESTATE, "ess needs the monitored values (outopts[:monitor] must include :value)");
   if (j->count != j->npost) return fail(KLB_ESTATE, "run the job before asking for its effective sample size");
-  if (j->cfg.nchains > 65535) {
-    // gridDim.y limit: split the chains
-  }
   CK(cudaSetDevice(j->cfg.device));
   const size_t N = (size_t)j->cfg.nchains, d = (size_t)j->cfg.dim;
   if (!j->ess) CK(cudaMalloc(&j->ess, N * d * sizeof(double)));
-  for (size_t c0 = 0; c0 < N; c0 += 32768) {
+  for (size_t c0 = 0; c0 < N; c0 += 32768) {   // gridDim.y <= 65535: chains go in blocks
     const size_t nc = (N - c0) < 32768 ? (N - c0) : 32768;
     klb_launch_ess(j->out_value + c0 * (size_t)j->npost * (size_t)j->ld, j->ld, j->npost, (long long)nc, (int)d,
                    j->ess + c0 * d, j->stream);
