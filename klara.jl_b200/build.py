@@ -26,7 +26,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-fmad=false",                      # never contract a*b+c behind our back: fma is always explicit
          "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"] + os.environ.get("KLB_EXTRA_FLAGS", "").split()
 
-HEADERS = ["klb_kernels.cuh", "klb_dense.cuh", "klb_dense_mma.cuh", "klb_math.h", "klb_tables.h", "../../include/klara_b200.h"]
+HEADERS = ["klb_kernels.cuh", "klb_dense.cuh", "klb_dense_mma.cuh", "klb_hmc_ws.cuh", "klb_math.h", "klb_tables.h", "../../include/klara_b200.h"]
 
 
 def units():
@@ -37,6 +37,8 @@ def units():
         for fma in (0, 1):
             u.append(("klb_chain_%d_%d" % (smp, fma), "klb_kernels_inst.cu",
                       ["-DKLB_INST_SAMPLER=%d" % smp, "-DKLB_INST_FMA=%d" % fma]))
+    for fma in (0, 1):
+        u.append(("klb_hmc_ws_%d" % fma, "klb_hmc_ws_inst.cu", ["-DKLB_INST_FMA=%d" % fma]))
     return u
 
 

@@ -22,6 +22,9 @@ int klb_chain_1_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
 int klb_chain_1_1(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
 int klb_chain_2_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
 int klb_chain_2_1(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
+// warp-specialised HMC kernels, klb_hmc_ws_inst.cu
+int klb_hmc_ws_0(const KArgs*, int target, int nv, int full, int* regs, int* bps, cudaStream_t);
+int klb_hmc_ws_1(const KArgs*, int target, int nv, int full, int* regs, int* bps, cudaStream_t);
 // klb_kernels_inst.cu (-DKLB_INST_INIT) / klb_aux.cu
 int klb_launch_init(const KArgs& A, int target, int W, int NV, int fma, int check_grad, unsigned long long* flag,
                     cudaStream_t s);
@@ -87,8 +90,17 @@ struct klb_job {
   bool timed;
 };
 
+// HMC with one warp per chain and 8 or 16 units per lane (dim 257..1024) runs the warp-specialised kernel
+// (klb_hmc_ws.cuh) unless KLB_HMC_WS=0 (experiments: the fused single-role kernel of klb_kernels.cuh).
+static bool use_hmc_ws(int sampler, int gw, int gnv) {
+  const char* env = getenv("KLB_HMC_WS");
+  return sampler == KLB_SAMPLER_HMC && gw == 1 && (gnv == 8 || gnv == 16) && !(env && env[0] == '0');
+}
+
 static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int gw, int gnv, int full, int* regs, int* bps,
                           cudaStream_t s) {
+  if (use_hmc_ws(sampler, gw, gnv))
+    return fma ? klb_hmc_ws_1(A, target, gnv, full, regs, bps, s) : klb_hmc_ws_0(A, target, gnv, full, regs, bps, s);
   switch (sampler * 2 + (fma ? 1 : 0)) {
     case 0: return klb_chain_0_0(A, target, gw, gnv, full, regs, bps, s);
     case 1: return klb_chain_0_1(A, target, gw, gnv, full, regs, bps, s);
@@ -497,7 +509,7 @@ int klb_job_plan(klb_job* j, klb_plan* out) {
   if (!j || !out) return fail(KLB_EINVAL, "null argument");
   out->nv = j->nv;
   out->ld = j->ld;
-  out->warps_per_block = KLB_WPB;
+  out->warps_per_block = use_hmc_ws(j->cfg.sampler, j->gw, j->gnv) && !j->dense ? 8 : KLB_WPB;
   out->warps_per_chain = j->gw;
   out->regs_per_thread = j->regs;
   out->blocks_per_sm = j->bps;

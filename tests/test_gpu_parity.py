@@ -143,6 +143,24 @@ def test_dense_mma_and_dfma_kernels_agree(K, monkeypatch):
     assert_same("accept", outs[0][1], outs[1][1])
 
 
+def test_hmc_warp_specialised_and_fused_kernels_agree(K, monkeypatch):
+    """dim 257..1024 HMC defaults to the producer/consumer kernel (klb_hmc_ws.cuh); KLB_HMC_WS=0 selects the fused
+    single-role kernel.  Same bits, including a ragged last CTA (nchains not a multiple of 4) and a masked dim."""
+    for dim in (1024, 700, 512):
+        outs = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("KLB_HMC_WS", flag)
+            job, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", nchains=37, dim=dim, nsteps=14, burnin=3, thinning=2,
+                                              step=0.3 / np.sqrt(dim), nleaps=5, seed=23, tuner="accrate", period=4,
+                                              target_rate=0.9)
+            job.run()
+            outs.append((job.output().value, job.output().diagnosticvalues, job.tune.step, job.plan().warps_per_block))
+        assert outs[0][3] == 8 and outs[1][3] == 4
+        assert_same("value", outs[0][0], outs[1][0])
+        assert_same("accept", outs[0][1], outs[1][1])
+        assert_same("step", outs[0][2], outs[1][2])
+
+
 def test_dense_needs_symmetric_matrix(K):
     C = np.array([[1.0, 0.5], [0.25, 1.0]])
     p = K.BasicContMuvParameter("p", logtarget=K.DenseGaussian(C))
