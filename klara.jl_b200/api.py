@@ -214,8 +214,12 @@ class BasicMCJob:
         else:
             oo.setdefault("monitor", [])
             oo.setdefault("diagnostics", [])
-        if oo["destination"] not in ("nstate", "none"):
-            raise NotImplementedError(":destination => :iostream (CSV writers) is a 'next' row (SURVEY.md 8f)")
+        if oo["destination"] not in ("nstate", "iostream", "none"):
+            raise ValueError(":destination must be set to :nstate or :iostream or :none, got %r" % (oo["destination"],))
+        if oo["destination"] == "iostream":         # augment_variable_outopts!  (src/jobs/jobs.jl:17-29)
+            oo.setdefault("filepath", "")
+            oo.setdefault("filesuffix", "csv")
+            oo.setdefault("flush", False)
         for m in oo["monitor"]:
             if m not in _MONITOR_BITS:
                 raise KeyError("cannot monitor %r on the device path" % (m,))
@@ -243,7 +247,7 @@ class BasicMCJob:
         cfg.period, cfg.verbose = tuner.period, int(tuner.verbose)
         cfg.monitor = sum(_MONITOR_BITS[m] for m in set(oo["monitor"]))
         cfg.diagnostics = L.DIAG_ACCEPT if "accept" in oo["diagnostics"] else 0
-        cfg.destination = L.DEST_NSTATE if oo["destination"] == "nstate" else L.DEST_NONE
+        cfg.destination = L.DEST_NONE if oo["destination"] == "none" else L.DEST_NSTATE
         cfg.seed, cfg.chain_offset, cfg.device = seed, chain_offset, device
         self.cfg = cfg
         self._h = C.c_void_p()
@@ -279,6 +283,11 @@ class BasicMCJob:
         """run(job)        src/jobs/BasicMCJob.jl:212-244"""
         L.check(L.lib().klb_job_run(self._h))
         self.count = self.range.npoststeps
+        if self.outopts["destination"] == "iostream":
+            # the samples are produced on the device; the CSV files of the reference's iostream destination are
+            # written from the fetched NState when the run ends (README.md:117-146)
+            from .iostream import write_job_output
+            self.iostream = write_job_output(self, self._fetch_nstate())
         return self
 
     def run_async(self):
@@ -312,6 +321,11 @@ class BasicMCJob:
         """output(job)        src/jobs/BasicMCJob.jl:279"""
         if self.outopts["destination"] == "none":
             return None
+        if self.outopts["destination"] == "iostream":
+            return self.iostream            # output(job) is the VariableIOStream in the reference
+        return self._fetch_nstate()
+
+    def _fetch_nstate(self):
         N, P, d = self.nchains, self.range.npoststeps, self.dim
         ns = BasicContMuvParameterNState(d, P)
         mon = self.outopts["monitor"]

@@ -1,6 +1,7 @@
 """GPU parity suite: the CUDA path (through the C ABI) against the CPU oracle, bit for bit, on the
 same seeded inputs.  Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -307,3 +308,29 @@ def test_ess_on_device_matches_oracle(K, O):
     job, *_ = build_pair(K, "MH", "iso", nchains=64, dim=16, nsteps=1100, burnin=100, sigma=np.full(16, 0.05), seed=5)
     job.run()
     assert job.ess().mean() < 60
+
+
+def test_iostream_destination(K, tmp_path):
+    """README.md:117-146: :destination => :iostream writes value.csv / logtarget.csv / diagnosticvalues.csv"""
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    outopts = {"monitor": ["value", "logtarget"], "diagnostics": ["accept"], "destination": "iostream",
+               "filepath": str(tmp_path)}
+    job = K.BasicMCJob(K.likelihood_model(p, False), K.MH(np.ones(2)), K.BasicMCRange(nsteps=300, burnin=100),
+                       {"p": [5.1, -0.9]}, tuner=K.VanillaMCTuner(verbose=True), outopts=outopts, seed=3)
+    K.run(job)
+    stream = K.output(job)
+    back = stream.read()
+    ref = K.BasicMCJob(K.likelihood_model(p, False), K.MH(np.ones(2)), K.BasicMCRange(nsteps=300, burnin=100),
+                       {"p": [5.1, -0.9]}, tuner=K.VanillaMCTuner(verbose=True),
+                       outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}, seed=3)
+    chain = K.output(K.run(ref))
+    assert_same("value.csv", back["value"], chain.value)
+    assert_same("logtarget.csv", back["logtarget"], chain.logtarget)
+    assert np.array_equal(back["diagnosticvalues"][:, 0], chain.diagnosticvalues.astype(bool))
+    # batched job: one directory per chain
+    job = K.BasicMCJob(K.likelihood_model(p, False), K.MALA(0.5), K.BasicMCRange(nsteps=20, burnin=5),
+                       {"p": np.ones((3, 4))}, outopts={"destination": "iostream", "filepath": str(tmp_path / "b")},
+                       seed=1)
+    K.run(job)
+    assert sorted(os.listdir(tmp_path / "b")) == ["chain1", "chain2", "chain3"]
+    assert len(open(tmp_path / "b" / "chain2" / "value.csv").read().splitlines()) == 15

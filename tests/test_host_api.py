@@ -120,3 +120,34 @@ def test_shard_ranges(K):
         assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
         assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
     assert D.shard_range(65536, 3, 8) == (24576, 32768)
+
+
+def test_julia_float_formatting(K):
+    """string(::Float64) as Julia prints it: shortest digits; exponential form iff pt <= -4 or pt > 6"""
+    f = K.iostream.julia_float
+    cases = {5.1: "5.1", -0.9: "-0.9", 1.0: "1.0", 100.0: "100.0", 123456.0: "123456.0", 1234567.0: "1.234567e6",
+             1e6: "1.0e6", 999999.0: "999999.0", 0.0001: "0.0001", 0.00012: "0.00012", 0.00001: "1.0e-5",
+             1.5e-7: "1.5e-7", 1e21: "1.0e21", 1e-300: "1.0e-300", 0.1: "0.1", 0.30000000000000004: "0.30000000000000004",
+             -42.9122: "-42.9122", 12.98: "12.98", 2.5e10: "2.5e10", 0.0: "0.0",
+             float("nan"): "NaN", float("inf"): "Inf", float("-inf"): "-Inf", 1.4110527196983078: "1.4110527196983078"}
+    for x, want in cases.items():
+        assert f(x) == want, (x, f(x), want)
+    assert f(-0.0) == "-0.0"
+    rng = np.random.default_rng(0)
+    for x in np.concatenate([rng.normal(size=200), 10.0 ** rng.uniform(-12, 12, 200) * rng.choice([-1, 1], 200)]):
+        assert float(f(x)) == x                      # round-trips exactly
+
+
+def test_iostream_round_trip(K, tmp_path):
+    """write one line per saved state, read back (test/ParameterIOStreams.jl:150-177 pattern)"""
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=(4, 2)); lt = -(v * v).sum(1); acc = np.array([1, 0, 1, 1], dtype=np.uint8)
+    st = K.BasicContParamIOStream(2, 4, ["value", "logtarget"], str(tmp_path), "csv", ["accept"])
+    st.write_nstate(value=v, logtarget=lt, diagnosticvalues=acc)
+    assert sorted(os.listdir(tmp_path)) == ["diagnosticvalues.csv", "logtarget.csv", "value.csv"]
+    back = st.read()
+    assert np.array_equal(back["value"], v) and np.array_equal(back["logtarget"], lt)
+    assert np.array_equal(back["diagnosticvalues"][:, 0], acc.astype(bool))
+    lines = open(os.path.join(tmp_path, "value.csv")).read().splitlines()
+    assert len(lines) == 4 and lines[0] == ",".join(K.iostream.julia_float(x) for x in v[0])
+    assert open(os.path.join(tmp_path, "diagnosticvalues.csv")).read().splitlines() == ["true", "false", "true", "true"]
