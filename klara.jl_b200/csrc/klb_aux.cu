@@ -111,8 +111,90 @@ klb_ess_kernel(const double* __restrict__ value, long long ld, long long npost, 
   }
   ess[c * dim + i] = out;
 }
+// Same estimator with the CTA's series staged once in shared memory: tile[t][TC] holds the centred samples of
+// TC coordinates of one chain (npost x TC x 8 bytes).  The global-memory version above re-reads the values on
+// every lag pass; with 16 CTAs per SM its working set does not fit L2 and the kernel is DRAM bound on ~5 x
+// the stored bytes (profiles/r1_summary.md).  Here the values cross DRAM once.  Same sums in the same order.
+template <int TC>
+__global__ void __launch_bounds__(TC)
+klb_ess_tile_kernel(const double* __restrict__ value, long long ld, long long npost, int dim, double* __restrict__ ess) {
+  extern __shared__ double tile[];                              // [npost][TC]
+  const int i = blockIdx.x * TC + threadIdx.x;
+  const long long c = blockIdx.y;
+  const bool act = i < dim;
+  const double* v = value + c * npost * ld + (act ? i : 0);
+  const int n = (int)npost;
+  double s = 0.0;
+  for (int t = 0; t < n; ++t) {                                  // coalesced row segments
+    const double x = act ? v[(long long)t * ld] : 0.0;
+    tile[t * TC + threadIdx.x] = x;
+    s = __dadd_rn(s, x);
+  }
+  if (!act) return;                                              // every thread only ever reads its own column
+  double out = klb_u2d(0x7FF8000000000000ULL);
+  if (n >= 4) {
+    const double dn = (double)n;
+    const double mu = __ddiv_rn(s, dn);
+    double* z = tile + threadIdx.x;
+    for (int t = 0; t < n; ++t) z[t * TC] = __dsub_rn(z[t * TC], mu);
+    const int k = (n - 2) / 2;
+    double sumg = 0.0, gprev = 0.0, s0 = 0.0;
+    bool done = false;
+    for (int L = 0; !done && L <= 2 * k + 1; L += 8) {
+      double acc[8], w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { acc[q] = 0.0; w[q] = (L + q < n) ? z[(L + q) * TC] : 0.0; }
+      for (int t = 0; t + L < n; ++t) {
+        const double zt = z[t * TC];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = __fma_rn(zt, w[q], acc[q]);
+#pragma unroll
+        for (int q = 0; q < 7; ++q) w[q] = w[q + 1];
+        w[7] = (t + L + 8 < n) ? z[(t + L + 8) * TC] : 0.0;
+      }
+      if (L == 0) s0 = acc[0];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = L / 2 + q;
+        if (!done && j <= k) {
+          double g = __dadd_rn(__ddiv_rn(acc[2 * q], dn), __ddiv_rn(acc[2 * q + 1], dn));
+          if (g <= 0.0) done = true;
+          else {
+            if (j > 0 && g > gprev) g = gprev;
+            sumg = __dadd_rn(sumg, g);
+            gprev = g;
+          }
+        }
+      }
+    }
+    const double iidvar = __ddiv_rn(__ddiv_rn(s0, (double)(n - 1)), dn);
+    const double acv0 = __ddiv_rn(s0, dn);
+    const double mcvar = __ddiv_rn(__dadd_rn(-acv0, __dmul_rn(2.0, sumg)), dn);
+    out = __ddiv_rn(__dmul_rn(dn, iidvar), mcvar);
+  }
+  ess[c * dim + i] = out;
+}
+
+template <int TC>
+static bool launch_ess_tile(const double* value, long long ld, long long npost, long long nchains, int dim, double* ess,
+                            cudaStream_t s) {
+  const size_t sm = (size_t)npost * TC * sizeof(double);
+  if (sm > 100 * 1024) return false;                              // two CTAs per SM
+  auto kern = klb_ess_tile_kernel<TC>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  dim3 grid((unsigned)((dim + TC - 1) / TC), (unsigned)nchains);
+  kern<<<grid, TC, sm, s>>>(value, ld, npost, dim, ess);
+  return true;
+}
+
 void klb_launch_ess(const double* value, long long ld, long long npost, long long nchains, int dim, double* ess,
                     cudaStream_t s) {
-  dim3 grid((unsigned)((dim + 127) / 128), (unsigned)nchains);
+  if (launch_ess_tile<128>(value, ld, npost, nchains, dim, ess, s)) return;
+  if (launch_ess_tile<64>(value, ld, npost, nchains, dim, ess, s)) return;
+  if (launch_ess_tile<32>(value, ld, npost, nchains, dim, ess, s)) return;
+  dim3 grid((unsigned)((dim + 127) / 128), (unsigned)nchains);    // very long chains: stream from global memory
   klb_ess_kernel<<<grid, 128, 0, s>>>(value, ld, npost, dim, ess);
 }
