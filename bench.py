@@ -304,17 +304,17 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this launch at N=1 (ncu --set full,
-                         # profiles/r1_summary.md capture E), scaled to this rank's chains
-                         "traffic": 54.85e9 * nloc / NCHAINS if arith == "reference" else None,
-                         "traffic_source": "profiles/r1_kernel_metrics.csv column E_bench_final",
+                         # profiles/r1_summary.md capture G), scaled to this rank's chains
+                         "traffic": 54.91e9 * nloc / NCHAINS if arith == "reference" else None,
+                         "traffic_source": "profiles/r1_kernel_metrics.csv column G_ws_bench_final",
                          "peak_source": peak_src,
-                         "kernel": "klb_chain_kernel<HMC, TgtIso, NV=16>", "kernel_ms": kernel_ms,
+                         "kernel": "klb_hmc_ws_kernel<TgtIso, NV=16> (warp-specialised: 4 consumer + 4 producer warps per CTA)", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_launch,
                          "fp64": {"achieved_tops": fp64_ops / (kernel_ms * 1e-3) / 1e12,
                                   "peak_tops": 148 * 64 * 1.965e-3,
                                   "note": "leapfrog fp64 instructions only (5 d per step, un-fused: DADD/DMUL count 1 each) "
                                           "against 148 SMs x 64 lanes x 1.965 GHz; the kernel is fp64-issue bound, not HBM bound "
-                                          "(ncu: fp64 pipe 57.6 % busy, DRAM 8.8 %): profiles/r1_summary.md"}},
+                                          "(ncu: fp64 pipe 60.4 % busy, DRAM 9.2 %): profiles/r1_summary.md"}},
             "cpu_baseline": cb,
             "e2e": {"value": lf_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
