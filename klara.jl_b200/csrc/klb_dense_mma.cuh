@@ -34,6 +34,71 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// ---- thread-block-cluster path: one L2 read of a slab feeds every CTA of the cluster -----------------------
+// cp.async.bulk ... .multicast::cluster (the 1-D form of the TMA copy) writes the same bytes at the same
+// shared-memory offset of every CTA in the mask and signals each CTA's own mbarrier.  Each CTA issues 1/CL of
+// the rows of a slab; FULL barriers count bytes (expect_tx), EMPTY barriers count one release per CTA.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* b, unsigned cta) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(b)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, unsigned bytes, uint64_t* bar,
+                                                   unsigned short mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+template <int CL>
+struct McPipe {
+  uint64_t* full;        // [2]  bytes of a whole slab have landed in this CTA
+  uint64_t* empty;       // [2]  all CL CTAs have finished reading the stage
+  unsigned full_par;     // bit s: parity to wait for on full[s]  (every thread)
+  unsigned empty_par;    // bit s: parity to wait for on empty[s] (thread 0)
+  unsigned rank;
+};
+
+// thread 0 of every CTA: rows [rank*KB/CL, (rank+1)*KB/CL) of slab s -> stage s&1 of every CTA
+template <int CL>
+__device__ __forceinline__ void mc_issue_slab(McPipe<CL>& P, const double* __restrict__ Cm, double* slab, int d, int ldc,
+                                              int s) {
+  if (threadIdx.x != 0) return;
+  const int st = s & 1;
+  mbar_wait(P.empty + st, (P.empty_par >> st) & 1u);
+  P.empty_par ^= 1u << st;
+  mbar_expect_tx(P.full + st, (unsigned)(KLB_MMA_KB * d * 8));
+  double* dst = slab + (size_t)st * KLB_MMA_KB * ldc;
+  const double* src = Cm + (size_t)s * KLB_MMA_KB * d;
+  constexpr int RPC = KLB_MMA_KB / CL;
+#pragma unroll
+  for (int r = 0; r < RPC; ++r) {
+    const int row = (int)P.rank * RPC + r;
+    bulk_g2s_multicast(dst + (size_t)row * ldc, src + (size_t)row * d, (unsigned)(d * 8), P.full + st,
+                       (unsigned short)((1u << CL) - 1u));
+  }
+}
+
 // slab s of C (KB rows) -> ring buffer s % STAGES, one commit group
 __device__ __forceinline__ void mma_issue_slab(const double* __restrict__ Cm, double* slab, int d, int ldc, int s) {
   double* dst = slab + (size_t)(s % KLB_MMA_STAGES) * KLB_MMA_KB * ldc;
@@ -54,21 +119,34 @@ __device__ __forceinline__ void mma_prefetch(const double* __restrict__ Cm, doub
 // STAGES-1 slabs are already in flight (issued at the end of the previous product).  `prefetch_next`: issue them
 // again on the way out, so the next product starts without an exposed L2 round trip (only legal when the caller
 // does not use the slab region as scratch before that product).
-template <int NT>
+template <int NT, int CL>
 __device__ __forceinline__ void mma_matvec(double (&acc)[2][NT][2], const double* __restrict__ Cm, const double* xs,
                                            double* slab, int d, int ldx, int ldc, int w, int g, int q,
-                                           bool prefetched, bool prefetch_next) {
+                                           bool prefetched, bool prefetch_next, McPipe<CL>& P) {
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
   const int nslab = d / KLB_MMA_KB;
-  if (!prefetched) mma_prefetch(Cm, slab, d, ldc);
+  if (CL == 1) {
+    if (!prefetched) mma_prefetch(Cm, slab, d, ldc);
+  } else if (!prefetched) {
+    // the slab region was used as generic-proxy scratch: order it before the async-proxy fills, cluster-wide
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    cluster_sync_all();
+    mc_issue_slab<CL>(P, Cm, slab, d, ldc, 0);
+  }
   for (int s = 0; s < nslab; ++s) {
-    cp_async_wait<KLB_MMA_STAGES - 2>();                     // this thread's chunks of slab s have landed
-    __syncthreads();                                         // ... everybody's; and slab s-1 is consumed by all
-    if (s + KLB_MMA_STAGES - 1 < nslab) mma_issue_slab(Cm, slab, d, ldc, s + KLB_MMA_STAGES - 1);
-    else cp_async_commit();                                  // empty group keeps the wait arithmetic uniform
+    if (CL == 1) {
+      cp_async_wait<KLB_MMA_STAGES - 2>();                     // this thread's chunks of slab s have landed
+      __syncthreads();                                         // ... everybody's; and slab s-1 is consumed by all
+      if (s + KLB_MMA_STAGES - 1 < nslab) mma_issue_slab(Cm, slab, d, ldc, s + KLB_MMA_STAGES - 1);
+      else cp_async_commit();                                  // empty group keeps the wait arithmetic uniform
+    } else {
+      if (s + 1 < nslab) mc_issue_slab<CL>(P, Cm, slab, d, ldc, s + 1);
+      mbar_wait(P.full + (s & 1), (P.full_par >> (s & 1)) & 1u);
+      P.full_par ^= 1u << (s & 1);
+    }
     const double* cs = slab + (size_t)(s % KLB_MMA_STAGES) * KLB_MMA_KB * ldc + (size_t)w * 8 * NT + g;
     const double* xa = xs + (size_t)g * ldx + (size_t)s * KLB_MMA_KB + q;
 #pragma unroll
@@ -81,15 +159,27 @@ __device__ __forceinline__ void mma_matvec(double (&acc)[2][NT][2], const double
         dmma884(acc[1][nt][0], acc[1][nt][1], a1, b);
       }
     }
+    if (CL > 1) {
+      __syncthreads();                                         // this CTA is done with stage s&1 ...
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int cta = 0; cta < CL; ++cta) mbar_arrive_cluster(P.empty + (s & 1), (unsigned)cta);   // ... tell every issuer
+      }
+    }
   }
-  cp_async_wait<0>();
-  __syncthreads();                                           // the ring and xs are free
-  if (prefetch_next) mma_prefetch(Cm, slab, d, ldc);
+  if (CL == 1) {
+    cp_async_wait<0>();
+    __syncthreads();                                           // the ring and xs are free
+    if (prefetch_next) mma_prefetch(Cm, slab, d, ldc);
+  } else if (prefetch_next) {
+    mc_issue_slab<CL>(P, Cm, slab, d, ldc, 0);
+  }
 }
 
-template <int NT, bool FMA>
+template <int NT, bool FMA, int CL>
 __global__ void __launch_bounds__(KLB_DENSE_THREADS)
 klb_dense_mma_kernel(const DArgs D) {
+  static_assert(CL == 1 || KLB_MMA_STAGES == 2, "the multicast pipeline is two-stage");
   constexpr int MC = KLB_MMA_MC;
   const KArgs& A = D.k;
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -100,6 +190,7 @@ klb_dense_mma_kernel(const DArgs D) {
   double* xs = reinterpret_cast<double*>(dsm + ((KLB_TAB_LEN * 8 + 15) & ~15));
   double* slab = xs + (size_t)MC * ldx;
   DenseShared<MC>& S = *reinterpret_cast<DenseShared<MC>*>(slab + (size_t)KLB_MMA_STAGES * KLB_MMA_KB * ldc);
+  uint64_t* mbars = reinterpret_cast<uint64_t*>(&S + 1);     // full[2], empty[2] (cluster path)
   double* scA = slab;                                        // [16][d] scratch, valid between matvecs
   double* scB = slab + (size_t)MC * d;
 
@@ -118,6 +209,17 @@ klb_dense_mma_kernel(const DArgs D) {
     S.totproposed[t] = live ? A.tune_cnt[3 * c + 2] : 0;
     S.rate[t] = live ? A.tune_rate[c] : 0.0;
   }
+  McPipe<CL> P;
+  P.full = mbars; P.empty = mbars + 2; P.full_par = 0u; P.empty_par = 3u; P.rank = 0u;
+  if (CL > 1) {
+    P.rank = cluster_rank();
+    if (t == 0) {
+      mbar_init(P.full, 1u); mbar_init(P.full + 1, 1u);
+      mbar_init(P.empty, (unsigned)CL); mbar_init(P.empty + 1, (unsigned)CL);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_sync_all();                                      // every CTA's barriers exist before anyone signals them
+  }
   // element ownership: chain r(mt) = mt*8+g, column col(nt) = w*8NT + nt*8 + 2q (+1)
   auto colof = [&](int nt) { return w * 8 * NT + nt * 8 + 2 * q; };
   // positions -> shared memory
@@ -133,7 +235,8 @@ klb_dense_mma_kernel(const DArgs D) {
   }
   __syncthreads();
   double gc[2][NT][2];
-  mma_matvec<NT>(gc, Cm, xs, slab, d, ldx, ldc, w, g, q, false, false);      // cached C x of the starting point
+  mma_matvec<NT, CL>(gc, Cm, xs, slab, d, ldx, ldc, w, g, q, false, false, P);   // cached C x of the starting point
+  if (CL > 1) __syncthreads();
 
   const bool saving = (A.out_value != nullptr) || (A.out_lt != nullptr) || (A.out_grad != nullptr) ||
                       (A.out_accept != nullptr);
@@ -202,7 +305,8 @@ klb_dense_mma_kernel(const DArgs D) {
         }
       }
       __syncthreads();
-      mma_matvec<NT>(acc, Cm, xs, slab, d, ldx, ldc, w, g, q, s > 1, s < A.nleaps);      // g = -2 C x
+      mma_matvec<NT, CL>(acc, Cm, xs, slab, d, ldx, ldc, w, g, q, s > 1, s < A.nleaps, P);   // g = -2 C x
+      if (CL > 1) __syncthreads();
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const double h = __dmul_rn(0.5, S.step[mt * 8 + g]);
@@ -331,6 +435,7 @@ klb_dense_mma_kernel(const DArgs D) {
     }
   }
 
+  if (CL > 1) cluster_sync_all();     // nobody leaves while a peer may still signal its barriers
   // the state columns are current (written on every accept); per-chain scalars
   if (t < MC && c0 + t < A.nchains) {
     const long long c = c0 + t;
@@ -341,5 +446,5 @@ klb_dense_mma_kernel(const DArgs D) {
   }
 }
 
-int klb_dense_mma_launch(const DArgs& D, int fma, cudaStream_t s);   // returns -1 when dim is not 64, 128, 256 or 512
+int klb_dense_mma_launch(const DArgs& D, int fma, int cluster, cudaStream_t s);   // -1 when dim is not 64, 128, 256 or 512
 int klb_dense_mma_attrs(int fma, int dim, int* regs, int* bps);
