@@ -405,8 +405,8 @@ int klb_job_run_async(klb_job* j) {
     A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global;
     if (j->dense) {
       DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
-      const char* cl = getenv("KLB_DENSE_CLUSTER");    // 2: thread-block clusters of two CTAs share every slab of C
-      const int cluster = (cl && cl[0] == '2') ? 2 : 1;
+      const char* cl = getenv("KLB_DENSE_CLUSTER");    // thread-block clusters of 2 (default) or 4 CTAs share every slab of C; 1 = no clusters
+      const int cluster = (cl && cl[0] == '4') ? 4 : (cl && cl[0] == '1') ? 1 : 2;   // default: pairs
       if ((j->dense_mma ? klb_dense_mma_launch(D, c.arith, cluster, j->stream) : klb_dense_launch(D, c.sampler, c.arith, j->stream)) != 0)
         return fail(KLB_ECUDA, "dense kernel launch failed");
     } else if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, c.dim == 64ll * j->gw * j->gnv, nullptr, nullptr, j->stream) != 0)

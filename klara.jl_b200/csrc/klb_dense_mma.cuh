@@ -37,7 +37,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ---- thread-block-cluster path: one L2 read of a slab feeds every CTA of the cluster -----------------------
 // cp.async.bulk ... .multicast::cluster (the 1-D form of the TMA copy) writes the same bytes at the same
 // shared-memory offset of every CTA in the mask and signals each CTA's own mbarrier.  Each CTA issues 1/CL of
-// the rows of a slab; FULL barriers count bytes (expect_tx), EMPTY barriers count one release per CTA.
+// the rows of a slab; FULL barriers count bytes (expect_tx), EMPTY barriers count one release per warp of every CTA.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
@@ -73,7 +73,7 @@ __device__ __forceinline__ unsigned cluster_rank() {
 template <int CL>
 struct McPipe {
   uint64_t* full;        // [2]  bytes of a whole slab have landed in this CTA
-  uint64_t* empty;       // [2]  all CL CTAs have finished reading the stage
+  uint64_t* empty;       // [2]  every warp of all CL CTAs has finished reading the stage
   unsigned full_par;     // bit s: parity to wait for on full[s]  (every thread)
   unsigned empty_par;    // bit s: parity to wait for on empty[s] (thread 0)
   unsigned rank;
@@ -160,10 +160,12 @@ __device__ __forceinline__ void mma_matvec(double (&acc)[2][NT][2], const double
       }
     }
     if (CL > 1) {
-      __syncthreads();                                         // this CTA is done with stage s&1 ...
-      if (threadIdx.x == 0) {
+      // this warp is done with stage s&1: tell every issuer of the cluster (no CTA-wide barrier in the loop:
+      // the warps of a CTA may run up to one slab apart)
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-        for (int cta = 0; cta < CL; ++cta) mbar_arrive_cluster(P.empty + (s & 1), (unsigned)cta);   // ... tell every issuer
+        for (int cta = 0; cta < CL; ++cta) mbar_arrive_cluster(P.empty + (s & 1), (unsigned)cta);
       }
     }
   }
@@ -215,7 +217,7 @@ klb_dense_mma_kernel(const DArgs D) {
     P.rank = cluster_rank();
     if (t == 0) {
       mbar_init(P.full, 1u); mbar_init(P.full + 1, 1u);
-      mbar_init(P.empty, (unsigned)CL); mbar_init(P.empty + 1, (unsigned)CL);
+      mbar_init(P.empty, (unsigned)(CL * (KLB_DENSE_THREADS / 32))); mbar_init(P.empty + 1, (unsigned)(CL * (KLB_DENSE_THREADS / 32)));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     cluster_sync_all();                                      // every CTA's barriers exist before anyone signals them

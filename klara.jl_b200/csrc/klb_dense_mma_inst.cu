@@ -39,6 +39,7 @@ static int by_dim(const DArgs* D, int dim, int* regs, int* bps, cudaStream_t st)
 }
 int klb_dense_mma_launch(const DArgs& D, int fma, int cluster, cudaStream_t s) {
   const int dim = (int)D.k.dim;
+  if (cluster == 4) return fma ? by_dim<true, 4>(&D, dim, nullptr, nullptr, s) : by_dim<false, 4>(&D, dim, nullptr, nullptr, s);
   if (cluster == 2) return fma ? by_dim<true, 2>(&D, dim, nullptr, nullptr, s) : by_dim<false, 2>(&D, dim, nullptr, nullptr, s);
   return fma ? by_dim<true, 1>(&D, dim, nullptr, nullptr, s) : by_dim<false, 1>(&D, dim, nullptr, nullptr, s);
 }
