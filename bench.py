@@ -255,6 +255,24 @@ def run_gpu(args, rank, world, local_rank):
     acc_rate = float(np.ctypeslib.as_array(C.cast(C.c_void_p(hl.value + lt_host.nbytes), C.POINTER(C.c_uint8)),
                                            shape=(nloc, NSTEPS - BURNIN)).mean())
 
+    # -------- optional: end-to-end with EVERY monitored field copied to the host (50 GiB of values at N=1)
+    e2e_full = None
+    if args.e2e_full:
+        vbytes = nloc * (NSTEPS - BURNIN) * DIM * 8
+        hv = C.c_void_p()
+        L.check(lib.klb_host_alloc(C.byref(hv), vbytes))
+
+        def full_step():
+            e2e_step()
+            L.check(lib.klb_job_output(job._h, L.OUT_VALUE, hv, vbytes))
+        full_step()
+        barrier()
+        tf = time.perf_counter()
+        full_step()
+        barrier()
+        e2e_full = {"ms_per_step": (time.perf_counter() - tf) * 1e3, "d2h_bytes_per_step": (d2h + vbytes) * world}
+        lib.klb_host_free(hv)
+
     # -------- effective sample size of the stored chains, on the device
     tq = time.perf_counter()
     L.check(lib.klb_job_ess(job._h, None))
@@ -327,6 +345,9 @@ def run_gpu(args, rank, world, local_rank):
                     "ess_kernel_ms": ess_ms,
                     "note": "ess(chain, :imse) per coordinate on the device (klb_job_ess); independent samples/s = "
                             "sum over chains of the coordinate-mean ESS / device time of one run"},
+            "e2e_full_output": None if e2e_full is None else dict(
+                e2e_full, value=lf_per_step / (e2e_full["ms_per_step"] * 1e-3), unit=UNIT,
+                note="as e2e, plus klb_job_output(KLB_OUT_VALUE): all monitored samples copied to pinned host memory"),
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
         }
@@ -348,6 +369,7 @@ def main():
     ap.add_argument("--arith", default="reference", choices=["reference", "fma"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--per-step-sync", action="store_true")
+    ap.add_argument("--e2e-full", action="store_true", help="also time an end-to-end step that copies every monitored sample to the host")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -124,12 +124,18 @@ klb_ess_tile_kernel(const double* __restrict__ value, long long ld, long long np
   const bool act = i < dim;
   const double* v = value + c * npost * ld + (act ? i : 0);
   const int n = (int)npost;
-  double s = 0.0;
-  for (int t = 0; t < n; ++t) {                                  // coalesced row segments
-    const double x = act ? v[(long long)t * ld] : 0.0;
-    tile[t * TC + threadIdx.x] = x;
-    s = __dadd_rn(s, x);
+  // stage the column with 8-byte cp.async copies: all npost row segments are in flight at once (a plain
+  // load / store loop keeps one or two loads in flight per warp and is latency bound on DRAM)
+  if (act) {
+    for (int t = 0; t < n; ++t) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(tile + t * TC + threadIdx.x);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(v + (long long)t * ld) : "memory");
+    }
   }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  double s = 0.0;
+  if (act)
+    for (int t = 0; t < n; ++t) s = __dadd_rn(s, tile[t * TC + threadIdx.x]);
   if (!act) return;                                              // every thread only ever reads its own column
   double out = klb_u2d(0x7FF8000000000000ULL);
   if (n >= 4) {
