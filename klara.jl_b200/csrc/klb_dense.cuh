@@ -30,8 +30,8 @@ struct DenseShared {
   int accept[MC];
 };
 
-// canonical reduction of one chain's addends by one warp.  MODE 0: sum of a[i]*b[i] (products rounded
-// separately in reference arithmetic, fma-accumulated in fma arithmetic); MODE 1: plain sum of a[i].
+// canonical reduction of one chain's addends by one warp.  MODE 0: dot product sum of a[i]*b[i]
+// (fma-accumulated, see dotacc); MODE 1: plain sum of a[i].
 template <int MC, bool FMA, int MODE>
 __device__ __forceinline__ double dense_reduce(const double* a, const double* b, int r, int d, int nv, int lane) {
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -41,8 +41,8 @@ __device__ __forceinline__ double dense_reduce(const double* a, const double* b,
     if (i < d) { a0 = a[(size_t)i * MC + r]; if (MODE == 0) b0 = b[(size_t)i * MC + r]; }
     if (i + 1 < d) { a1 = a[(size_t)(i + 1) * MC + r]; if (MODE == 0) b1 = b[(size_t)(i + 1) * MC + r]; }
     if (MODE == 0) {
-      acc[m & 3] = Ar<FMA>::ma(a0, b0, acc[m & 3]);
-      acc[m & 3] = Ar<FMA>::ma(a1, b1, acc[m & 3]);
+      acc[m & 3] = dotacc(a0, b0, acc[m & 3]);
+      acc[m & 3] = dotacc(a1, b1, acc[m & 3]);
     } else {
       acc[m & 3] = __dadd_rn(acc[m & 3], a0);
       acc[m & 3] = __dadd_rn(acc[m & 3], a1);

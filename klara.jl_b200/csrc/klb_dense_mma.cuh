@@ -275,8 +275,8 @@ klb_dense_mma_kernel(const DArgs D) {
         const int i = 2 * (lane + 32 * m);
         double2 v = make_double2(0.0, 0.0);
         if (i < d) v = *reinterpret_cast<const double2*>(scA + (size_t)r * d + i);
-        a4[m & 3] = Ar<FMA>::ma(v.x, v.x, a4[m & 3]);
-        a4[m & 3] = Ar<FMA>::ma(v.y, v.y, a4[m & 3]);
+        a4[m & 3] = dotacc(v.x, v.x, a4[m & 3]);
+        a4[m & 3] = dotacc(v.y, v.y, a4[m & 3]);
       }
       double v = __dadd_rn(__dadd_rn(a4[0], a4[1]), __dadd_rn(a4[2], a4[3]));
 #pragma unroll
@@ -341,10 +341,10 @@ klb_dense_mma_kernel(const DArgs D) {
           cv = *reinterpret_cast<const double2*>(scB + (size_t)r * d + i);
           xv = *reinterpret_cast<const double2*>(xs + (size_t)r * ldx + i);
         }
-        k4[m & 3] = Ar<FMA>::ma(pv.x, pv.x, k4[m & 3]);
-        k4[m & 3] = Ar<FMA>::ma(pv.y, pv.y, k4[m & 3]);
-        l4[m & 3] = Ar<FMA>::ma(xv.x, cv.x, l4[m & 3]);
-        l4[m & 3] = Ar<FMA>::ma(xv.y, cv.y, l4[m & 3]);
+        k4[m & 3] = dotacc(pv.x, pv.x, k4[m & 3]);
+        k4[m & 3] = dotacc(pv.y, pv.y, k4[m & 3]);
+        l4[m & 3] = dotacc(xv.x, cv.x, l4[m & 3]);
+        l4[m & 3] = dotacc(xv.y, cv.y, l4[m & 3]);
       }
       double k1 = __dadd_rn(__dadd_rn(k4[0], k4[1]), __dadd_rn(k4[2], k4[3]));
       double xcx = __dadd_rn(__dadd_rn(l4[0], l4[1]), __dadd_rn(l4[2], l4[3]));

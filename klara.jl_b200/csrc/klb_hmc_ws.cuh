@@ -103,8 +103,8 @@ klb_hmc_ws_kernel(const KArgs A) {
     double acc[3][4] = {};
 #pragma unroll
     for (int j = 0; j < NV; ++j) {                                           // old kinetic energy
-      acc[0][j & 3] = Ar<FMA>::ma(y[2 * j], y[2 * j], acc[0][j & 3]);
-      acc[0][j & 3] = Ar<FMA>::ma(y[2 * j + 1], y[2 * j + 1], acc[0][j & 3]);
+      acc[0][j & 3] = dotacc(y[2 * j], y[2 * j], acc[0][j & 3]);
+      acc[0][j & 3] = dotacc(y[2 * j + 1], y[2 * j + 1], acc[0][j & 3]);
     }
     // leapfrog! (src/samplers/samplers.jl:122-134): see klb_chain_kernel for the exact-rewrite notes
 #pragma unroll
@@ -128,8 +128,8 @@ klb_hmc_ws_kernel(const KArgs A) {
       x[2 * j + 1] = Ar<FMA>::ma(step, y[2 * j + 1], x[2 * j + 1]);
       T::template kick<FMA, false>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
       acc[1][j & 3] = T::template lt_acc<FMA>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], acc[1][j & 3]);
-      acc[2][j & 3] = Ar<FMA>::ma(y[2 * j], y[2 * j], acc[2][j & 3]);
-      acc[2][j & 3] = Ar<FMA>::ma(y[2 * j + 1], y[2 * j + 1], acc[2][j & 3]);
+      acc[2][j & 3] = dotacc(y[2 * j], y[2 * j], acc[2][j & 3]);
+      acc[2][j & 3] = dotacc(y[2 * j + 1], y[2 * j + 1], acc[2][j & 3]);
     }
     double sums[3];
     team_allsum<3, 1>(acc, sums, nullptr, 0, lane, 0);

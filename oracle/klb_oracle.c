@@ -160,23 +160,27 @@ static double orc_reduce_fma(const double* a, const double* b, int nv) {
   return lane[0];
 }
 
-/* dot(a, b) over padded vectors */
+/* dot(a, b) over padded vectors.  Julia's dot on Vector{Float64} is BLAS ddot: an fma kernel with an
+ * unspecified order on every FMA-capable CPU.  Here: fma-accumulated in the canonical order, in both
+ * arithmetic modes (only the elementwise broadcast expressions of the reference are un-fused). */
 static double orc_dot_m(const orc_model* M, const double* a, const double* b, double* scratch) {
-  if (M->cfg->arith == 1) return orc_reduce_fma(a, b, M->cfg->nv);
-  for (int64_t i = 0; i < M->dp; ++i) scratch[i] = a[i] * b[i];
-  return orc_reduce(scratch, M->cfg->nv);
+  (void)scratch;
+  return orc_reduce_fma(a, b, M->cfg->nv);
 }
 /* exported for tests */
 double orc_dot(const double* a, const double* b, int64_t d, int nv, int arith) {
   int64_t dp = 64 * (int64_t)nv;
   double* pa = calloc(3 * dp, sizeof(double)); double* pb = pa + dp; double* sc = pb + dp;
   memcpy(pa, a, d * sizeof(double)); memcpy(pb, b, d * sizeof(double));
-  double r;
-  if (arith == 1) r = orc_reduce_fma(pa, pb, nv);
-  else { for (int64_t i = 0; i < dp; ++i) sc[i] = pa[i] * pb[i]; r = orc_reduce(sc, nv); }
+  (void)arith; (void)sc;
+  double r = orc_reduce_fma(pa, pb, nv);
   free(pa);
   return r;
 }
+
+/* a*b + c as the elementwise expressions evaluate it: two roundings in reference arithmetic, one in fma
+ * arithmetic (exported for the test that the build really keeps them apart) */
+double orc_ma(double a, double b, double c, int arith) { return arith == 1 ? fma(a, b, c) : a * b + c; }
 
 /* ------------------------------------------------------------ target library
  * Device targets are descriptors, not closures (a Julia closure cannot run on the GPU);

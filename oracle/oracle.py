@@ -86,6 +86,8 @@ def lib():
         L.orc_eval_target.restype = C.c_int
         L.orc_eval_target.argtypes = [C.POINTER(OrcConfig)] + [C.c_void_p] * 4
         L.orc_max_threads.restype = C.c_int
+        L.orc_ma.restype = dbl
+        L.orc_ma.argtypes = [dbl, dbl, dbl, C.c_int]
         L.orc_ess.restype = None
         L.orc_ess.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
         L.orc_ess_series.restype = dbl

@@ -89,11 +89,11 @@ def test_philox_random123_kat(O):
 
 
 def test_no_fp_contraction_in_oracle(O):
-    """the oracle must round a*b and +c separately in reference mode (built with -ffp-contract=off)"""
-    a = np.array([1.0 + 2.0 ** -30]); b = np.array([1.0 - 2.0 ** -30])
-    # a*b = 1 - 2^-60 rounds to 1.0; an fma(a, b, -1) contraction would return -2^-60
-    assert O.dot(a, b, nv=1, arith=0) == 1.0
-    assert math.fma(a[0], b[0], -1.0) != 0.0 if hasattr(math, "fma") else True
+    """the oracle must round a*b and +c separately in reference arithmetic (built with -ffp-contract=off)"""
+    a, b = 1.0 + 2.0 ** -30, 1.0 - 2.0 ** -30
+    # a*b = 1 - 2^-60 rounds to 1.0, so a*b - 1 = 0 un-fused; the fused result is -2^-60
+    assert O.lib().orc_ma(a, b, -1.0, 0) == 0.0
+    assert O.lib().orc_ma(a, b, -1.0, 1) == -(2.0 ** -60)
 
 
 def test_exp_log_accuracy(O):

@@ -124,19 +124,24 @@ def test_rosenbrock_and_shifted_targets(O, K):
 
 
 def test_reduction_order_is_the_documented_one(O):
-    """orc_dot reproduces the canonical order of DESIGN.md literally (numpy restatement)"""
+    """orc_dot reproduces the canonical order of DESIGN.md literally (exact-arithmetic restatement: every term
+    is accumulated by one fma, i.e. acc <- round(acc + a*b) with a single rounding)"""
+    from fractions import Fraction
+
+    def fma(a, b, c):
+        return float(Fraction(a) * Fraction(b) + Fraction(c))
+
     rng = np.random.default_rng(1)
     for d, nv in [(5, 1), (64, 1), (100, 2), (1024, 16), (777, 16)]:
         a, b = rng.normal(size=d), rng.normal(size=d)
         pa = np.zeros(64 * nv); pb = np.zeros(64 * nv); pa[:d] = a; pb[:d] = b
-        e = pa * pb
         lanes = np.zeros(32)
         for l in range(32):
             acc = [0.0] * 4
             for m in range(nv):
                 k = l + 32 * m
-                acc[m & 3] = acc[m & 3] + e[2 * k]
-                acc[m & 3] = acc[m & 3] + e[2 * k + 1]
+                acc[m & 3] = fma(pa[2 * k], pb[2 * k], acc[m & 3])
+                acc[m & 3] = fma(pa[2 * k + 1], pb[2 * k + 1], acc[m & 3])
             lanes[l] = (acc[0] + acc[1]) + (acc[2] + acc[3])
         for s in (16, 8, 4, 2, 1):
             lanes = np.array([lanes[l] + lanes[l ^ s] for l in range(32)])
