@@ -184,6 +184,26 @@ int klb_job_device_ptr(klb_job* job, int field, void** dev_ptr, int64_t* nbytes)
  * (dim x nchains doubles) may be NULL to leave the result on the device (KLB_OUT_ESS). */
 int klb_job_ess(klb_job* job, double* host_ess);
 
+/* The other post-hoc estimators of the monitored output, computed on the device by the same pass:
+ *   KLB_STAT_MEAN        mean(s)                    src/stats/mean.jl:7-11
+ *   KLB_STAT_MCVAR_IID   mcvar(s, Val{:iid})        src/stats/variance/mcvar.jl:5,15-16
+ *   KLB_STAT_MCVAR_IMSE  mcvar(s, Val{:imse})       src/stats/variance/mcvar.jl:75-105
+ *   KLB_STAT_ESS         ess(s)                     src/stats/convergence/ess.jl:3-14
+ *   KLB_STAT_IACT        iact(s)                    src/stats/convergence/iact.jl:3-5
+ * each dim x nchains doubles (coordinate fastest), and per chain (nchains doubles)
+ *   KLB_STAT_ACCEPTANCE        acceptance(s)                     mean of the :accept diagnostic  src/stats/acceptance.jl:28-34
+ *   KLB_STAT_ACCEPTANCE_VALUE  acceptance(s, diagnostics=false)  fraction of saved states that differ from the
+ *                              previous saved state (first one counted)                          src/stats/acceptance.jl:3-14,33
+ * host_dst may be NULL (result stays on the device).  Series shorter than 4 samples give NaN for all but the mean. */
+#define KLB_STAT_MEAN 0
+#define KLB_STAT_MCVAR_IID 1
+#define KLB_STAT_MCVAR_IMSE 2
+#define KLB_STAT_ESS 3
+#define KLB_STAT_IACT 4
+#define KLB_STAT_ACCEPTANCE 5
+#define KLB_STAT_ACCEPTANCE_VALUE 6
+int klb_job_stat(klb_job* job, int stat, double* host_dst);
+
 int klb_job_plan(klb_job* job, klb_plan* out);
 /* kernels launched by this job so far */
 int64_t klb_job_launches(klb_job* job);

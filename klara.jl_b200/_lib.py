@@ -23,6 +23,7 @@ DEST_NSTATE, DEST_NONE = 0, 1
 PARAM_MU, PARAM_C, PARAM_SIGMA, PARAM_ROSEN = 0, 1, 2, 3
 (OUT_VALUE, OUT_LOGTARGET, OUT_GRADLOGTARGET, OUT_ACCEPT, OUT_STATE, OUT_STATE_LOGTARGET,
  OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS) = range(10)
+(STAT_MEAN, STAT_MCVAR_IID, STAT_MCVAR_IMSE, STAT_ESS, STAT_IACT, STAT_ACCEPTANCE, STAT_ACCEPTANCE_VALUE) = range(7)
 
 
 class KlbConfig(C.Structure):
@@ -69,6 +70,7 @@ SYMBOLS = [
     ("klb_job_output", _int, [_vp, _int, _vp, _i64]),
     ("klb_job_device_ptr", _int, [_vp, _int, C.POINTER(_vp), C.POINTER(_i64)]),
     ("klb_job_ess", _int, [_vp, _vp]),
+    ("klb_job_stat", _int, [_vp, _int, _vp]),
     ("klb_job_plan", _int, [_vp, C.POINTER(KlbPlan)]),
     ("klb_job_launches", _i64, [_vp]),
     ("klb_job_last_run_ms", _dbl, [_vp]),

@@ -27,7 +27,8 @@ from .targets import Target
 
 __all__ = ["BasicContMuvParameter", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
            "VanillaMCTuner", "AcceptanceRateMCTuner", "BasicMCTune", "BasicMCJob", "run", "reset", "output",
-           "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "ess"]
+           "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "ess", "mean", "mcvar", "mcse", "iact",
+           "acceptance"]
 
 
 # ----------------------------------------------------------------------------- scalars
@@ -355,6 +356,37 @@ class BasicMCJob:
         L.check(L.lib().klb_job_ess(self._h, None))
         return None
 
+    def _stat(self, code, per_chain=False):
+        out = np.empty(self.nchains if per_chain else (self.nchains, self.dim))
+        L.check(L.lib().klb_job_stat(self._h, code, _ptr(out)))
+        return out[0] if self.single else out
+
+    def mean(self):
+        """mean(output(job)): per coordinate of every chain (src/stats/mean.jl:7-11); (nchains, dim)"""
+        return self._stat(L.STAT_MEAN)
+
+    def mcvar(self, vtype="imse"):
+        """mcvar(output(job), Val{vtype}) for vtype "iid" (var/len, src/stats/variance/mcvar.jl:5) or "imse"
+        (Geyer's initial monotone sequence estimator, mcvar.jl:75-105); (nchains, dim)"""
+        vtype = str(vtype).lstrip(":")
+        if vtype not in ("iid", "imse"):
+            raise ValueError("mcvar on the device supports :iid and :imse, got %r" % vtype)
+        return self._stat(L.STAT_MCVAR_IID if vtype == "iid" else L.STAT_MCVAR_IMSE)
+
+    def mcse(self, vtype="imse"):
+        """mcse = sqrt(mcvar) (src/stats/variance/mcvar.jl:20,112)"""
+        return np.sqrt(self.mcvar(vtype))
+
+    def iact(self):
+        """iact(output(job)) = mcvar(:imse)/mcvar(:iid) (src/stats/convergence/iact.jl:3-5); (nchains, dim)"""
+        return self._stat(L.STAT_IACT)
+
+    def acceptance(self, diagnostics=True):
+        """acceptance(output(job); diagnostics): mean of the :accept diagnostic, or, with diagnostics=False, the
+        fraction of saved states that differ from their predecessor (src/stats/acceptance.jl:3-14,28-34); one
+        number per chain"""
+        return self._stat(L.STAT_ACCEPTANCE if diagnostics else L.STAT_ACCEPTANCE_VALUE, per_chain=True)
+
     # -- job.pstate / job.sstate.tune
     @property
     def pstate_value(self):
@@ -410,3 +442,23 @@ def output(job):
 def ess(job):
     """ess(chain) for the job's monitored values, on the device"""
     return job.ess()
+
+
+def mean(job):
+    return job.mean()
+
+
+def mcvar(job, vtype="imse"):
+    return job.mcvar(vtype)
+
+
+def mcse(job, vtype="imse"):
+    return job.mcse(vtype)
+
+
+def iact(job):
+    return job.iact()
+
+
+def acceptance(job, diagnostics=True):
+    return job.acceptance(diagnostics)

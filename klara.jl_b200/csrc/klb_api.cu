@@ -36,6 +36,10 @@ void klb_launch_debug_math(const uint64_t* tab, int op, long long n, const doubl
 void klb_launch_debug_uniform(uint64_t seed, uint64_t chain, uint64_t t, double* out, cudaStream_t s);
 void klb_launch_ess(const double* value, long long ld, long long npost, long long nchains, int dim, double* ess,
                     cudaStream_t s);
+void klb_launch_stats(const double* value, long long ld, long long npost, long long nchains, int dim,
+                      double* const stats[5], cudaStream_t s);
+void klb_launch_acceptance(const unsigned char* accept, const double* value, long long ld, long long npost,
+                           long long nchains, int dim, double* out, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 
@@ -80,6 +84,9 @@ struct klb_job {
   uint64_t* tab;
   unsigned long long* flag;
   double* ess;      // dim x nchains, allocated on first klb_job_ess
+  double* stat[5];  // mean, mcvar(:iid), mcvar(:imse), ess, iact: dim x nchains each, allocated on first klb_job_stat
+  double* accrate;  // nchains
+  unsigned long long stat_epoch;  // t_global + 1 when stat[] was filled (0 = never)
   double rosen[3];
   bool have_mu, have_sigma, have_rosen, have_state;
   unsigned long long t_global;  // transitions done since creation (RNG counter)
@@ -149,7 +156,8 @@ static void free_job(klb_job* j) {
   cudaSetDevice(j->cfg.device);
   cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate);
   cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
-  cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess);
+  cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess); cudaFree(j->accrate);
+  for (int q = 0; q < 5; ++q) if (q != KLB_STAT_ESS) cudaFree(j->stat[q]);
   if (j->ev0) cudaEventDestroy(j->ev0);
   if (j->ev1) cudaEventDestroy(j->ev1);
   if (j->stream) cudaStreamDestroy(j->stream);
@@ -503,6 +511,50 @@ int klb_job_ess(klb_job* j, double* host_ess) {
   }
   CK(cudaGetLastError());
   if (host_ess) CK(cudaMemcpyAsync(host_ess, j->ess, N * d * sizeof(double), cudaMemcpyDeviceToHost, j->stream));
+  CK(cudaStreamSynchronize(j->stream));
+  return KLB_OK;
+}
+
+// mean / mcvar / ess / iact / acceptance of the monitored output, on the device (src/stats/*.jl)
+int klb_job_stat(klb_job* j, int stat, double* host_dst) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  if (stat < 0 || stat > KLB_STAT_ACCEPTANCE_VALUE) return fail(KLB_EINVAL, "unknown statistic %d", stat);
+  if (j->count != j->npost) return fail(KLB_ESTATE, "run the job before asking for statistics of its output");
+  CK(cudaSetDevice(j->cfg.device));
+  const size_t N = (size_t)j->cfg.nchains, d = (size_t)j->cfg.dim;
+  if (stat == KLB_STAT_ACCEPTANCE || stat == KLB_STAT_ACCEPTANCE_VALUE) {
+    const bool diag = stat == KLB_STAT_ACCEPTANCE;
+    if (diag && !j->out_accept)
+      return fail(KLB_ESTATE, "acceptance needs the :accept diagnostic (outopts[:diagnostics] must include :accept)");
+    if (!diag && !j->out_value)
+      return fail(KLB_ESTATE, "acceptance(diagnostics=false) needs the monitored values (outopts[:monitor] must include :value)");
+    if (!j->accrate) CK(cudaMalloc(&j->accrate, N * sizeof(double)));
+    klb_launch_acceptance(diag ? j->out_accept : nullptr, j->out_value, j->ld, j->npost, (long long)N, (int)d, j->accrate,
+                          j->stream);
+    j->launches += 1;
+    CK(cudaGetLastError());
+    if (host_dst) CK(cudaMemcpyAsync(host_dst, j->accrate, N * sizeof(double), cudaMemcpyDeviceToHost, j->stream));
+    CK(cudaStreamSynchronize(j->stream));
+    return KLB_OK;
+  }
+  if (!j->out_value) return fail(KLB_ESTATE, "statistics need the monitored values (outopts[:monitor] must include :value)");
+  if (j->stat_epoch != j->t_global + 1) {
+    if (!j->ess) CK(cudaMalloc(&j->ess, N * d * sizeof(double)));
+    j->stat[KLB_STAT_ESS] = j->ess;
+    for (int q = 0; q < 5; ++q)
+      if (!j->stat[q]) CK(cudaMalloc(&j->stat[q], N * d * sizeof(double)));
+    for (size_t c0 = 0; c0 < N; c0 += 32768) {   // gridDim.y <= 65535: chains go in blocks
+      const size_t nc = (N - c0) < 32768 ? (N - c0) : 32768;
+      double* st[5];
+      for (int q = 0; q < 5; ++q) st[q] = j->stat[q] + c0 * d;
+      klb_launch_stats(j->out_value + c0 * (size_t)j->npost * (size_t)j->ld, j->ld, j->npost, (long long)nc, (int)d, st,
+                       j->stream);
+      j->launches += 1;
+    }
+    CK(cudaGetLastError());
+    j->stat_epoch = j->t_global + 1;
+  }
+  if (host_dst) CK(cudaMemcpyAsync(host_dst, j->stat[stat], N * d * sizeof(double), cudaMemcpyDeviceToHost, j->stream));
   CK(cudaStreamSynchronize(j->stream));
   return KLB_OK;
 }

@@ -59,18 +59,39 @@ void klb_launch_debug_uniform(uint64_t seed, uint64_t chain, uint64_t t, double*
 // coalesced row segment of the `ld x npost x nchains` value array and the CTA's working set (128 coordinates
 // x npost samples) stays in L1 across the lag passes.  Lags are evaluated pairwise until the first
 // non-positive G_j -- all the estimator reads.  Sequential, fma-accumulated sums: the oracle's order.
+// Every estimator the reference derives from one series shares the same sums, so one pass fills them all
+// (any pointer may be null):
+//   mean   = mean(s, i)                                src/stats/mean.jl:9
+//   iid    = mcvar(s, Val{:iid}, i) = var(v)/len       src/stats/variance/mcvar.jl:5
+//   imse   = mcvar(s, Val{:imse}, i)                   src/stats/variance/mcvar.jl:75-105
+//   ess    = len*iid/imse                              src/stats/convergence/ess.jl:3
+//   iact   = imse/iid                                  src/stats/convergence/iact.jl:3
+struct KlbStatPtrs { double *mean, *iid, *imse, *ess, *iact; };
+__device__ __forceinline__ void stat_store(const KlbStatPtrs& S, long long idx, double mean, double iid, double imse,
+                                           double ess, double iact) {
+  if (S.mean) S.mean[idx] = mean;
+  if (S.iid) S.iid[idx] = iid;
+  if (S.imse) S.imse[idx] = imse;
+  if (S.ess) S.ess[idx] = ess;
+  if (S.iact) S.iact[idx] = iact;
+}
+
 __global__ void __launch_bounds__(128)
-klb_ess_kernel(const double* __restrict__ value, long long ld, long long npost, int dim, double* __restrict__ ess) {
+klb_ess_kernel(const double* __restrict__ value, long long ld, long long npost, int dim, const KlbStatPtrs S) {
   const int i = blockIdx.x * 128 + threadIdx.x;
   const long long c = blockIdx.y;
   if (i >= dim) return;
   const double* v = value + c * npost * ld + i;
   const long long n = npost;
-  double out = klb_u2d(0x7FF8000000000000ULL);
-  if (n >= 4) {
+  const double qnan = klb_u2d(0x7FF8000000000000ULL);
+  double out = qnan, o_mean = qnan, o_iid = qnan, o_imse = qnan, o_iact = qnan;
+  if (n >= 1) {
     double s = 0.0;
     for (long long t = 0; t < n; ++t) s = __dadd_rn(s, v[t * ld]);
-    const double mu = __ddiv_rn(s, (double)n);
+    o_mean = __ddiv_rn(s, (double)n);
+  }
+  if (n >= 4) {
+    const double mu = o_mean;
     const double dn = (double)n;
     const long long k = (n - 2) / 2;                                // floor((maxlag-1)/2), maxlag = n-1
     double sumg = 0.0, gprev = 0.0, s0 = 0.0;
@@ -108,8 +129,9 @@ klb_ess_kernel(const double* __restrict__ value, long long ld, long long npost, 
     const double acv0 = __ddiv_rn(s0, dn);
     const double mcvar = __ddiv_rn(__dadd_rn(-acv0, __dmul_rn(2.0, sumg)), dn);
     out = __ddiv_rn(__dmul_rn(dn, iidvar), mcvar);
+    o_iid = iidvar; o_imse = mcvar; o_iact = __ddiv_rn(mcvar, iidvar);
   }
-  ess[c * dim + i] = out;
+  stat_store(S, c * dim + i, o_mean, o_iid, o_imse, out, o_iact);
 }
 // Same estimator with the CTA's series staged once in shared memory: tile[t][TC] holds the centred samples of
 // TC coordinates of one chain (npost x TC x 8 bytes).  The global-memory version above re-reads the values on
@@ -117,7 +139,7 @@ klb_ess_kernel(const double* __restrict__ value, long long ld, long long npost, 
 // the stored bytes (profiles/r1_summary.md).  Here the values cross DRAM once.  Same sums in the same order.
 template <int TC>
 __global__ void __launch_bounds__(TC)
-klb_ess_tile_kernel(const double* __restrict__ value, long long ld, long long npost, int dim, double* __restrict__ ess) {
+klb_ess_tile_kernel(const double* __restrict__ value, long long ld, long long npost, int dim, const KlbStatPtrs S) {
   extern __shared__ double tile[];                              // [npost][TC]
   const int i = blockIdx.x * TC + threadIdx.x;
   const long long c = blockIdx.y;
@@ -137,10 +159,12 @@ klb_ess_tile_kernel(const double* __restrict__ value, long long ld, long long np
   if (act)
     for (int t = 0; t < n; ++t) s = __dadd_rn(s, tile[t * TC + threadIdx.x]);
   if (!act) return;                                              // every thread only ever reads its own column
-  double out = klb_u2d(0x7FF8000000000000ULL);
+  const double qnan = klb_u2d(0x7FF8000000000000ULL);
+  double out = qnan, o_iid = qnan, o_imse = qnan, o_iact = qnan;
+  const double o_mean = n >= 1 ? __ddiv_rn(s, (double)n) : qnan;
   if (n >= 4) {
     const double dn = (double)n;
-    const double mu = __ddiv_rn(s, dn);
+    const double mu = o_mean;
     double* z = tile + threadIdx.x;
     for (int t = 0; t < n; ++t) z[t * TC] = __dsub_rn(z[t * TC], mu);
     const int k = (n - 2) / 2;
@@ -177,13 +201,14 @@ klb_ess_tile_kernel(const double* __restrict__ value, long long ld, long long np
     const double acv0 = __ddiv_rn(s0, dn);
     const double mcvar = __ddiv_rn(__dadd_rn(-acv0, __dmul_rn(2.0, sumg)), dn);
     out = __ddiv_rn(__dmul_rn(dn, iidvar), mcvar);
+    o_iid = iidvar; o_imse = mcvar; o_iact = __ddiv_rn(mcvar, iidvar);
   }
-  ess[c * dim + i] = out;
+  stat_store(S, c * dim + i, o_mean, o_iid, o_imse, out, o_iact);
 }
 
 template <int TC>
-static bool launch_ess_tile(const double* value, long long ld, long long npost, long long nchains, int dim, double* ess,
-                            cudaStream_t s) {
+static bool launch_ess_tile(const double* value, long long ld, long long npost, long long nchains, int dim,
+                            const KlbStatPtrs& S, cudaStream_t s) {
   const size_t sm = (size_t)npost * TC * sizeof(double);
   if (sm > 100 * 1024) return false;                              // two CTAs per SM
   auto kern = klb_ess_tile_kernel<TC>;
@@ -192,15 +217,53 @@ static bool launch_ess_tile(const double* value, long long ld, long long npost, 
     return false;
   }
   dim3 grid((unsigned)((dim + TC - 1) / TC), (unsigned)nchains);
-  kern<<<grid, TC, sm, s>>>(value, ld, npost, dim, ess);
+  kern<<<grid, TC, sm, s>>>(value, ld, npost, dim, S);
   return true;
 }
 
+// stats[5] = {mean, mcvar_iid, mcvar_imse, ess, iact}: device arrays of nchains*dim doubles, null to skip
+void klb_launch_stats(const double* value, long long ld, long long npost, long long nchains, int dim,
+                      double* const stats[5], cudaStream_t s) {
+  const KlbStatPtrs S = {stats[0], stats[1], stats[2], stats[3], stats[4]};
+  if (launch_ess_tile<128>(value, ld, npost, nchains, dim, S, s)) return;
+  if (launch_ess_tile<64>(value, ld, npost, nchains, dim, S, s)) return;
+  if (launch_ess_tile<32>(value, ld, npost, nchains, dim, S, s)) return;
+  dim3 grid((unsigned)((dim + 127) / 128), (unsigned)nchains);    // very long chains: stream from global memory
+  klb_ess_kernel<<<grid, 128, 0, s>>>(value, ld, npost, dim, S);
+}
 void klb_launch_ess(const double* value, long long ld, long long npost, long long nchains, int dim, double* ess,
                     cudaStream_t s) {
-  if (launch_ess_tile<128>(value, ld, npost, nchains, dim, ess, s)) return;
-  if (launch_ess_tile<64>(value, ld, npost, nchains, dim, ess, s)) return;
-  if (launch_ess_tile<32>(value, ld, npost, nchains, dim, ess, s)) return;
-  dim3 grid((unsigned)((dim + 127) / 128), (unsigned)nchains);    // very long chains: stream from global memory
-  klb_ess_kernel<<<grid, 128, 0, s>>>(value, ld, npost, dim, ess);
+  double* const stats[5] = {nullptr, nullptr, nullptr, ess, nullptr};
+  klb_launch_stats(value, ld, npost, nchains, dim, stats, s);
+}
+
+// acceptance(s; diagnostics=true): mean of the :accept diagnostic of one chain          src/stats/acceptance.jl:28-34
+// acceptance(s; diagnostics=false): 1 + #{t >= 2 : value[:, t] != value[:, t-1]}, over n  src/stats/acceptance.jl:3-14,33
+// One warp per chain; the value variant compares consecutive saved states coordinate by coordinate.
+__global__ void __launch_bounds__(256)
+klb_acceptance_kernel(const unsigned char* __restrict__ accept, const double* __restrict__ value, long long ld,
+                      long long npost, long long nchains, int dim, double* __restrict__ out) {
+  const long long c = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= nchains) return;
+  long long cnt = 0;
+  if (accept) {
+    const unsigned char* a = accept + c * npost;
+    for (long long t = lane; t < npost; t += 32) cnt += a[t] ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  } else {
+    const double* v = value + c * npost * ld;
+    cnt = npost > 0 ? 1 : 0;
+    for (long long t = 1; t < npost; ++t) {
+      bool diff = false;
+      for (int i = lane; i < dim; i += 32) diff |= (v[t * ld + i] != v[(t - 1) * ld + i]);
+      if (__any_sync(0xffffffffu, diff)) cnt += 1;
+    }
+  }
+  if (lane == 0) out[c] = __ddiv_rn((double)cnt, (double)npost);
+}
+void klb_launch_acceptance(const unsigned char* accept, const double* value, long long ld, long long npost,
+                           long long nchains, int dim, double* out, cudaStream_t s) {
+  klb_acceptance_kernel<<<(unsigned)((nchains + 7) / 8), 256, 0, s>>>(accept, value, ld, npost, nchains, dim, out);
 }

@@ -535,11 +535,15 @@ int orc_eval_target(const orc_config* cfg, const double* tparams, const double* 
  * Summation order (unspecified in Julia: pairwise sum / BLAS dot): sequential in t, fma-accumulated,
  * the same as the device kernel.  Lags are evaluated pairwise until the first non-positive G_j, which is
  * all the estimator ever reads. */
-double orc_ess_series(const double* v, int64_t n, int64_t stride, double* iact_out) {
-  if (n < 4) { if (iact_out) *iact_out = NAN; return NAN; }
+/* out[5] = {mean (mean.jl:9), mcvar iid (mcvar.jl:5), mcvar imse (mcvar.jl:75-105), ess (ess.jl:3), iact (iact.jl:3)} */
+void orc_stats_series(const double* v, int64_t n, int64_t stride, double out[5]) {
+  for (int q = 0; q < 5; ++q) out[q] = NAN;
+  if (n < 1) return;
   double s = 0.;
   for (int64_t t = 0; t < n; ++t) s = s + v[t * stride];
   const double mu = s / (double)n;
+  out[0] = mu;
+  if (n < 4) return;
   double s0 = 0.;
   for (int64_t t = 0; t < n; ++t) { double z = v[t * stride] - mu; s0 = fma(z, z, s0); }
   const double iidvar = (s0 / (double)(n - 1)) / (double)n;       /* var(v)/length(v) */
@@ -559,8 +563,50 @@ double orc_ess_series(const double* v, int64_t n, int64_t stride, double* iact_o
     gprev = g;
   }
   const double mcvar = (-acv0 + 2 * sumg) / (double)n;
-  if (iact_out) *iact_out = mcvar / iidvar;                       /* src/stats/convergence/iact.jl:3 */
-  return (double)n * iidvar / mcvar;
+  out[1] = iidvar;
+  out[2] = mcvar;
+  out[3] = (double)n * iidvar / mcvar;                            /* src/stats/convergence/ess.jl:3 */
+  out[4] = mcvar / iidvar;                                        /* src/stats/convergence/iact.jl:3 */
+}
+
+double orc_ess_series(const double* v, int64_t n, int64_t stride, double* iact_out) {
+  double o[5];
+  orc_stats_series(v, n, stride, o);
+  if (iact_out) *iact_out = o[4];
+  return o[3];
+}
+
+/* value: (nchains, npost, d); out: (5, nchains, d) in the order of orc_stats_series */
+void orc_stats(const double* value, int64_t nchains, int64_t npost, int64_t d, double* out, int nthreads) {
+  (void)nthreads;
+#pragma omp parallel for num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t c = 0; c < nchains; ++c)
+    for (int64_t i = 0; i < d; ++i) {
+      double o[5];
+      orc_stats_series(value + c * npost * d + i, npost, d, o);
+      for (int q = 0; q < 5; ++q) out[((int64_t)q * nchains + c) * d + i] = o[q];
+    }
+}
+
+/* acceptance(v::AbstractArray{Bool}) = mean(v) (diag != 0), or the change-count form of acceptance.jl:3-14 over the
+ * saved states of each chain (value (nchains, npost, d)); out: nchains */
+void orc_acceptance(const unsigned char* accept, const double* value, int64_t nchains, int64_t npost, int64_t d,
+                    double* out) {
+  for (int64_t c = 0; c < nchains; ++c) {
+    int64_t cnt = 0;
+    if (accept) {
+      for (int64_t t = 0; t < npost; ++t) cnt += accept[c * npost + t] ? 1 : 0;
+    } else {
+      cnt = npost > 0 ? 1 : 0;
+      for (int64_t t = 1; t < npost; ++t) {
+        int diff = 0;
+        for (int64_t i = 0; i < d && !diff; ++i)
+          diff = value[(c * npost + t) * d + i] != value[(c * npost + t - 1) * d + i];
+        cnt += diff;
+      }
+    }
+    out[c] = (double)cnt / (double)npost;
+  }
 }
 
 /* value: (nchains, npost, d) as stored by orc_run; ess: (nchains, d) */

@@ -90,6 +90,10 @@ def lib():
         L.orc_ma.argtypes = [dbl, dbl, dbl, C.c_int]
         L.orc_ess.restype = None
         L.orc_ess.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        L.orc_stats.restype = None
+        L.orc_stats.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]
+        L.orc_acceptance.restype = None
+        L.orc_acceptance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
         L.orc_ess_series.restype = dbl
         L.orc_ess_series.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
         _lib = L
@@ -212,4 +216,35 @@ def ess(value, nthreads=None):
     N, P, d = v.shape
     out = np.empty((N, d))
     lib().orc_ess(_ptr(v), N, P, d, _ptr(out), nthreads or max_threads())
+    return out
+
+
+STAT_NAMES = ("mean", "mcvar_iid", "mcvar_imse", "ess", "iact")
+
+
+def stats(value, nthreads=None):
+    """mean / mcvar(:iid) / mcvar(:imse) / ess / iact per (chain, coordinate) of a (nchains, npost, dim) value
+    array: dict of (nchains, dim) arrays"""
+    v = np.ascontiguousarray(value, dtype=np.float64)
+    if v.ndim == 2:
+        v = v[None]
+    N, P, d = v.shape
+    out = np.empty((5, N, d))
+    lib().orc_stats(_ptr(v), N, P, d, _ptr(out), nthreads or max_threads())
+    return dict(zip(STAT_NAMES, out))
+
+
+def acceptance(accept=None, value=None):
+    """acceptance(s) from the :accept diagnostic (nchains, npost), or acceptance(s, diagnostics=false) from the
+    values (nchains, npost, dim)"""
+    if accept is not None:
+        a = np.ascontiguousarray(accept, dtype=np.uint8)
+        N, P = a.shape
+        out = np.empty(N)
+        lib().orc_acceptance(_ptr(a), None, N, P, 0, _ptr(out))
+        return out
+    v = np.ascontiguousarray(value, dtype=np.float64)
+    N, P, d = v.shape
+    out = np.empty(N)
+    lib().orc_acceptance(None, _ptr(v), N, P, d, _ptr(out))
     return out

@@ -313,6 +313,35 @@ def test_ess_on_device_matches_oracle(K, O):
     assert job.ess().mean() < 60
 
 
+def test_stats_on_device_match_oracle(K, O):
+    """mean / mcvar(:iid) / mcvar(:imse) / ess / iact / acceptance of the stored output (src/stats/mean.jl:7-11,
+    variance/mcvar.jl:5,75-105, convergence/{ess,iact}.jl, acceptance.jl): device == oracle bit for bit"""
+    for sampler, step, dim, nsteps in (("MALA", 0.05, 24, 400), ("HMC", 0.1, 130, 200), ("MH", 0.0, 7, 400),
+                                       ("MALA", 0.1, 40, 800)):
+        job, cfg, x0, tp, sg = build_pair(K, sampler, "iso", nchains=19, dim=dim, nsteps=nsteps, burnin=100, step=step,
+                                          nleaps=4, seed=22, sigma=np.full(dim, 0.3))
+        job.run()
+        out = job.output()
+        ref = O.stats(out.value)
+        assert_same("mean", job.mean(), ref["mean"])
+        assert_same("mcvar iid", job.mcvar("iid"), ref["mcvar_iid"])
+        assert_same("mcvar imse", job.mcvar(":imse"), ref["mcvar_imse"])
+        assert_same("ess", job.ess(), ref["ess"])
+        assert_same("iact", job.iact(), ref["iact"])
+        assert_same("mcse", job.mcse("iid"), np.sqrt(ref["mcvar_iid"]))
+        acc = out.diagnosticvalues
+        assert_same("acceptance", job.acceptance(), O.acceptance(accept=acc))
+        assert_same("acceptance from values", job.acceptance(diagnostics=False), O.acceptance(value=out.value))
+        # an accepted continuous proposal always moves the chain: both forms agree up to the first sample
+        n = acc.shape[1]
+        assert np.array_equal(job.acceptance(diagnostics=False), ((acc[:, 1:] != 0).sum(axis=1) + 1) / n)
+        assert np.allclose(job.iact() * job.ess(), n, rtol=1e-12)
+    with pytest.raises(K.KlaraError):
+        build_pair(K, "HMC", "iso", nchains=4, dim=8, nsteps=20, burnin=0)[0].mean()      # not run yet
+    with pytest.raises(ValueError):
+        job.mcvar("bm")
+
+
 def test_iostream_destination(K, tmp_path):
     """README.md:117-146: :destination => :iostream writes value.csv / logtarget.csv / diagnosticvalues.csv"""
     p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())

@@ -185,3 +185,35 @@ def test_ess_follows_the_reference_estimator(O):
     assert 0.5 * n / 4 < got.mean() < 2 * n / 4
     assert 0.7 * n < O.ess(rng.normal(size=(4, n, 4))).mean() < 1.4 * n
     assert np.isnan(O.ess(rng.normal(size=(1, 3, 2)))).all()          # fewer than 4 samples: undefined
+
+
+def test_stats_follow_the_reference_estimators(O):
+    """mean (src/stats/mean.jl:9), mcvar(:iid) = var/len (mcvar.jl:5), mcvar(:imse) (mcvar.jl:75-105),
+    ess = len*iid/imse (ess.jl:3), iact = imse/iid (iact.jl:3), acceptance (acceptance.jl:1-14) against literal
+    numpy restatements"""
+    rng = np.random.default_rng(11)
+    n = 300
+    ar = np.zeros((2, n, 3))
+    e = rng.normal(size=(2, n, 3))
+    for t in range(1, n):
+        ar[:, t] = 0.5 * ar[:, t - 1] + e[:, t]
+    st = O.stats(ar)
+    for c in range(2):
+        for i in range(3):
+            v = ar[c, :, i]
+            iid = v.var(ddof=1) / n
+            ess = _ess_numpy(v)
+            assert st["mean"][c, i] == pytest.approx(v.mean(), rel=1e-12, abs=1e-15)
+            assert st["mcvar_iid"][c, i] == pytest.approx(iid, rel=1e-11)
+            assert st["ess"][c, i] == pytest.approx(ess, rel=1e-10)
+            assert st["mcvar_imse"][c, i] == pytest.approx(n * iid / ess, rel=1e-10)
+            assert st["iact"][c, i] == pytest.approx(n / ess, rel=1e-10)
+    assert np.array_equal(st["ess"], O.ess(ar))
+    short = O.stats(rng.normal(size=(1, 3, 2)))
+    assert np.isfinite(short["mean"]).all() and all(np.isnan(short[k]).all() for k in O.STAT_NAMES[1:])
+    # acceptance(v::AbstractArray{Bool}) = mean(v); acceptance(values) counts the changes, the first sample included
+    acc = rng.random((4, 50)) < 0.7
+    assert np.array_equal(O.acceptance(accept=acc), acc.mean(axis=1))
+    vals = np.cumsum(acc[:, :, None] * rng.normal(size=(4, 50, 3)), axis=1)
+    expect = [(1 + sum((vals[c, t] != vals[c, t - 1]).any() for t in range(1, 50))) / 50 for c in range(4)]
+    assert np.array_equal(O.acceptance(value=vals), np.array(expect))
