@@ -16,8 +16,9 @@
 module KlaraB200
 
 using LinearAlgebra: dot
+import Statistics: mean      # Klara adds methods to mean (src/stats/mean.jl:7-11); so does the shim
 
-export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, DenseGaussian, ess, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
+export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, DenseGaussian, ess, mcvar, mcse, iact, acceptance, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
        BasicMCRange, VanillaMCTuner, AcceptanceRateMCTuner, BasicMCJob, run, reset, output
 
 const LIB = get(ENV, "KLARA_B200_LIB", "libklara_b200.so")
@@ -140,5 +141,20 @@ function ess(job::BasicMCJob)
   GC.@preserve e check(ccall((:klb_job_ess, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, e))
   e
 end
+
+# The other post-hoc estimators of the stored output, same device pass (KLB_STAT_* of include/klara_b200.h):
+#   mean (src/stats/mean.jl:7-11), mcvar(:iid | :imse) (src/stats/variance/mcvar.jl:5,75-105),
+#   iact (src/stats/convergence/iact.jl:3-5), acceptance (src/stats/acceptance.jl:3-14,28-34)
+function stat(job::BasicMCJob, code::Integer, perchain::Bool=false)
+  r = perchain ? Array{Float64}(undef, job.nchains) : Array{Float64}(undef, job.dim, job.nchains)
+  GC.@preserve r check(ccall((:klb_job_stat, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), job.handle, code, r))
+  r
+end
+mean(job::BasicMCJob) = stat(job, 0)
+mcvar(job::BasicMCJob, vtype::Symbol=:imse) =
+  vtype == :iid ? stat(job, 1) : vtype == :imse ? stat(job, 2) : error("mcvar on the device supports :iid and :imse")
+mcse(job::BasicMCJob, vtype::Symbol=:imse) = sqrt.(mcvar(job, vtype))
+iact(job::BasicMCJob) = stat(job, 4)
+acceptance(job::BasicMCJob; diagnostics::Bool=true) = stat(job, diagnostics ? 5 : 6, true)
 
 end # module
