@@ -53,6 +53,10 @@ extern "C" {
 #define KLB_TARGET_SHIFTED_ISO 1 /* -(z-mu).(z-mu), -2(z-mu)        test/BasicContMuvParameter.jl:539-563 */
 #define KLB_TARGET_DENSE 2      /* -z'Cz, -2Cz   doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9 */
 #define KLB_TARGET_ROSENBROCK 3 /* -scale*sum_k [b(x_2k+1 - x_2k^2)^2 + (a - x_2k)^2]  (this repo) */
+#define KLB_TARGET_LOGIT 4      /* Bayesian logistic regression, N(0, lambda I) prior, hyper-parameters [lambda, X, y]:
+                                   dot(Xp,y) - sum(log.(1+exp.(Xp))) - 0.5*(dot(p,p)/lambda + d*log(2*pi*lambda)),
+                                   X'*(y - 1./(1+exp.(-X*p))) - p/lambda
+                                   doc/examples/swiss/HMC/noadaptation/analytical.jl:11-20 (dim <= 16) */
 
 /* tuner: src/tuners/VanillaMCTuner.jl:6-16, src/tuners/AcceptanceRateMCTuner.jl:25-46 */
 #define KLB_TUNER_VANILLA 0
@@ -79,6 +83,9 @@ extern "C" {
 #define KLB_PARAM_C 1      /* dim*dim doubles, symmetric precision matrix */
 #define KLB_PARAM_SIGMA 2  /* dim doubles: MH(sigma::Vector) proposal standard deviations (src/samplers/MH.jl:64) */
 #define KLB_PARAM_ROSEN 3  /* 3 doubles: a, b, scale */
+#define KLB_PARAM_LOGIT_X 4      /* ndata*dim doubles: design matrix Data(:X), row-major (row i = observation i) */
+#define KLB_PARAM_LOGIT_Y 5      /* ndata doubles: outcomes Data(:y) */
+#define KLB_PARAM_LOGIT_LAMBDA 6 /* 1 double: prior variance Hyperparameter(:lambda) (> 0) */
 
 /* field = argument of klb_job_output / klb_job_device_ptr */
 #define KLB_OUT_VALUE 0          /* double  dim x npost x nchains */
@@ -124,7 +131,8 @@ typedef struct {
 /* geometry the library chose for a job (needed by the oracle to reproduce the reduction order) */
 typedef struct {
   int32_t nv;               /* double2 units per lane of the canonical reduction order: lane l owns
-                               elements 2(l+32m), 2(l+32m)+1, m < nv (DESIGN.md "reduction order") */
+                               elements 2(l+32m), 2(l+32m)+1, m < nv (DESIGN.md "reduction order");
+                               0 = sequential order (thread-per-chain kernels of KLB_TARGET_LOGIT) */
   int32_t warps_per_block;
   int32_t warps_per_chain;  /* W: a chain is owned by W warps; warp w holds the units m = w (mod W) */
   int32_t regs_per_thread;

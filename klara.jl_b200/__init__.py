@@ -10,7 +10,7 @@ from .iostream import BasicContParamIOStream
 from ._lib import KlaraError
 from .api import *  # noqa: F401,F403
 from .api import __all__ as _api_all
-from .targets import DenseGaussian, IsoGaussian, Rosenbrock, ShiftedIsoGaussian, Target
+from .targets import BayesLogit, DenseGaussian, IsoGaussian, Rosenbrock, ShiftedIsoGaussian, Target
 
-__all__ = list(_api_all) + ["IsoGaussian", "ShiftedIsoGaussian", "Rosenbrock", "DenseGaussian", "Target",
+__all__ = list(_api_all) + ["IsoGaussian", "ShiftedIsoGaussian", "Rosenbrock", "DenseGaussian", "BayesLogit", "Target",
                             "KlaraError", "BasicContParamIOStream"]

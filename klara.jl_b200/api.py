@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib as L
 from .targets import Target
 
-__all__ = ["BasicContMuvParameter", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
+__all__ = ["BasicContMuvParameter", "Hyperparameter", "Data", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
            "VanillaMCTuner", "AcceptanceRateMCTuner", "BasicMCTune", "BasicMCJob", "run", "reset", "output",
            "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "ess", "mean", "mcvar", "mcse", "iact",
            "acceptance"]
@@ -49,17 +49,37 @@ class BasicContMuvParameter:
     `gradlogtarget` may be omitted or must be the same descriptor: the device targets carry their
     analytic gradient (the reference's autodiff path, src/autodiff/, is out of scope)."""
 
-    def __init__(self, key, logtarget=None, gradlogtarget=None, index=0):
+    def __init__(self, key, logtarget=None, gradlogtarget=None, loglikelihood=None, logprior=None, nkeys=0, index=0):
+        # loglikelihood= + logprior= (logtarget = their sum, BasicContMuvParameter.jl:185-190): the bound methods of
+        # one descriptor, as in doc/examples/swiss/*/analytical.jl
+        if logtarget is None and loglikelihood is not None:
+            owner = getattr(loglikelihood, "__self__", None)
+            if not isinstance(owner, Target) or getattr(logprior, "__self__", None) is not owner:
+                raise TypeError("loglikelihood and logprior must be the .loglikelihood / .logprior of one target descriptor")
+            logtarget = owner
+        self.nkeys = nkeys
         if not isinstance(logtarget, Target):
             raise TypeError("logtarget must be a klara_b200 target descriptor (IsoGaussian(), ...); arbitrary "
                             "host closures cannot run inside the CUDA kernels")
-        if gradlogtarget is not None and gradlogtarget is not logtarget and gradlogtarget != logtarget.gradient:
+        if gradlogtarget is not None and gradlogtarget is not logtarget and gradlogtarget != logtarget.gradient:  # noqa: E501
             raise TypeError("gradlogtarget must be omitted, the same descriptor, or descriptor.gradient")
         self.key = key
         self.index = index
         self.logtarget = logtarget
         self.gradlogtarget = logtarget.gradient
         self.target = logtarget
+
+
+class Hyperparameter:
+    """Hyperparameter(key) = Constant: a vertex whose value is fixed by v0 (src/variables/variables.jl:41-60).
+    Its value reaches the parameter's closures through the states vector (BasicContMuvParameter.jl:497-501)."""
+
+    def __init__(self, key, index=0):
+        self.key, self.index = key, index
+
+
+class Data(Hyperparameter):
+    """Data(key)        src/variables/variables.jl:64-95"""
 
 
 class GenericModel:
@@ -229,6 +249,15 @@ class BasicMCJob:
                 raise KeyError("unknown diagnostic %r" % (dg,))
         self.outopts = oo
 
+        # hyper-parameters / data: the states of the model's other vertices, in vertex order, are what the
+        # reference passes to the closures as `v` (BasicContMuvParameter.jl:497-501; `nkeys` only tested > 0)
+        others = [v for i, v in enumerate(model.vertices) if i != self.pindex]
+        if others:
+            if not isinstance(v0, dict):
+                raise TypeError("a model with Hyperparameter / Data vertices needs v0 as a Dict of initial values")
+            if not hasattr(self.parameter.target, "bind"):
+                raise TypeError("target %s takes no hyper-parameters" % type(self.parameter.target).__name__)
+            self.parameter.target.bind([v0[v.key] for v in others])
         x0 = v0[self.parameter.key] if isinstance(v0, dict) else v0
         x0 = np.asarray(x0, dtype=np.float64)
         self.single = x0.ndim == 1

@@ -26,13 +26,13 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-fmad=false",                      # never contract a*b+c behind our back: fma is always explicit
          "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"] + os.environ.get("KLB_EXTRA_FLAGS", "").split()
 
-HEADERS = ["klb_kernels.cuh", "klb_dense.cuh", "klb_dense_mma.cuh", "klb_hmc_ws.cuh", "klb_math.h", "klb_tables.h", "../../include/klara_b200.h"]
+HEADERS = ["klb_kernels.cuh", "klb_dense.cuh", "klb_dense_mma.cuh", "klb_hmc_ws.cuh", "klb_glm.cuh", "klb_math.h", "klb_tables.h", "../../include/klara_b200.h"]
 
 
 def units():
     u = [("klb_api", "klb_api.cu", []), ("klb_aux", "klb_aux.cu", []),
          ("klb_init", "klb_kernels_inst.cu", ["-DKLB_INST_INIT"]), ("klb_dense", "klb_dense_inst.cu", []),
-         ("klb_dense_mma", "klb_dense_mma_inst.cu", [])]
+         ("klb_dense_mma", "klb_dense_mma_inst.cu", []), ("klb_glm", "klb_glm_inst.cu", [])]
     for smp in (0, 1, 2):
         for fma in (0, 1):
             u.append(("klb_chain_%d_%d" % (smp, fma), "klb_kernels_inst.cu",

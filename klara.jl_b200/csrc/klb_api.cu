@@ -14,6 +14,7 @@
 #include "klb_kernels.cuh"
 #include "klb_dense.cuh"
 #include "klb_dense_mma.cuh"
+#include "klb_glm.cuh"
 
 // per-(sampler, arithmetic) dispatchers, klb_kernels_inst.cu
 int klb_chain_0_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
@@ -88,6 +89,13 @@ struct klb_job {
   double* accrate;  // nchains
   unsigned long long stat_epoch;  // t_global + 1 when stat[] was filled (0 = never)
   double rosen[3];
+  // KLB_TARGET_LOGIT (klb_glm.cuh): one thread per chain, design matrix padded to row pitch gdp
+  bool glm, have_X, have_y;
+  int gdp;            // padded dimension of the kernel instance: 2, 4, 8 or 16
+  double* gX;         // ndata x gdp
+  double* gy;         // ndata
+  long long ndata, ny;
+  double lambda;
   bool have_mu, have_sigma, have_rosen, have_state;
   unsigned long long t_global;  // transitions done since creation (RNG counter)
   long long count;              // job.count
@@ -157,6 +165,7 @@ static void free_job(klb_job* j) {
   cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate);
   cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
   cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess); cudaFree(j->accrate);
+  cudaFree(j->gX); cudaFree(j->gy);
   for (int q = 0; q < 5; ++q) if (q != KLB_STAT_ESS) cudaFree(j->stat[q]);
   if (j->ev0) cudaEventDestroy(j->ev0);
   if (j->ev1) cudaEventDestroy(j->ev1);
@@ -183,6 +192,18 @@ static void fill_args(const klb_job* j, KArgs& A) {
   A.seed = c.seed; A.chain_offset = (unsigned long long)c.chain_offset;
 }
 
+// dynamic shared memory of the thread-per-chain kernels: X and y are staged when they fit
+static size_t glm_smem(const klb_job* j) {
+  const size_t need = (size_t)j->ndata * (size_t)(j->gdp + 1) * sizeof(double);
+  return need <= 160 * 1024 ? need : 0;
+}
+static void fill_glm_args(const klb_job* j, const KArgs& A, GArgs& G) {
+  G.k = A;
+  G.X = j->gX; G.y = j->gy; G.ndata = j->ndata; G.lambda = j->lambda;
+  G.logc = klb_log((2 * 3.141592653589793) * j->lambda, KLB_TAB);     // log(2*pi*v[1]), same klb_log as the device
+  G.data_in_smem = glm_smem(j) > 0;
+}
+
 int klb_job_create(const klb_config* cfg, klb_job** out) {
   if (!cfg || !out) return fail(KLB_EINVAL, "null argument");
   *out = nullptr;
@@ -191,8 +212,10 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   const klb_config& c = *cfg;
   if (c.sampler < 0 || c.sampler > 2) return fail(KLB_EINVAL, "unknown sampler %d", c.sampler);
   if (c.target != KLB_TARGET_ISO && c.target != KLB_TARGET_SHIFTED_ISO && c.target != KLB_TARGET_ROSENBROCK &&
-      c.target != KLB_TARGET_DENSE)
+      c.target != KLB_TARGET_DENSE && c.target != KLB_TARGET_LOGIT)
     return fail(KLB_EINVAL, "unknown target %d", c.target);
+  if (c.target == KLB_TARGET_LOGIT && c.dim > KLB_GLM_MAXD)
+    return fail(KLB_EUNSUPPORTED, "the logistic-regression kernels hold one chain per thread: dim <= %d", KLB_GLM_MAXD);
   if (c.target == KLB_TARGET_DENSE && ((c.dim & 1) || c.dim > KLB_DENSE_MAXD))
     return fail(KLB_EUNSUPPORTED, "the dense-precision kernels need an even dim <= %d", KLB_DENSE_MAXD);
   if (c.tuner != KLB_TUNER_VANILLA && c.tuner != KLB_TUNER_ACCEPTANCE_RATE)
@@ -204,7 +227,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   int gw = 0, gnv = 0;
   if (plan_geom(c.dim, &gw, &gnv) != 0)
     return fail(KLB_EUNSUPPORTED, "dim %lld > 4096 is not supported by the register-resident chain kernels", (long long)c.dim);
-  const int nv = gw * gnv;
+  const int nv = c.target == KLB_TARGET_LOGIT ? 0 : gw * gnv;   // 0: sequential reduction order (klb_glm.cuh)
   // BasicMCRange asserts (src/ranges/BasicMCRange.jl:19-21)
   if (c.burnin < 0) return fail(KLB_EINVAL, "Number of burn-in iterations should be non-negative");
   if (c.thinning < 1) return fail(KLB_EINVAL, "Thinning should be >= 1");
@@ -245,7 +268,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   j->npost = npoststeps(c.burnin, c.thinning, c.nsteps);
   j->rosen[0] = 1.0; j->rosen[1] = 100.0; j->rosen[2] = 0.05;
   j->have_rosen = true;
-  const size_t N = (size_t)c.nchains, d = (size_t)j->ld, P = (size_t)j->npost, pad = 64 * (size_t)nv;
+  const size_t N = (size_t)c.nchains, d = (size_t)j->ld, P = (size_t)j->npost, pad = nv ? 64 * (size_t)nv : KLB_GLM_MAXD;
 #define CKJ(call)                                                                              \
   do {                                                                                         \
     cudaError_t e_ = (call);                                                                   \
@@ -280,12 +303,16 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   }
   j->dense = c.target == KLB_TARGET_DENSE;
   if (j->dense) CKJ(cudaMalloc(&j->Cm, d * d * sizeof(double)));
+  j->glm = c.target == KLB_TARGET_LOGIT;
+  j->lambda = 100.0;                               // v0 of the swiss examples; KLB_PARAM_LOGIT_LAMBDA overrides
+  for (j->gdp = 2; j->gdp < c.dim; j->gdp *= 2) {}
   {
     const char* env = getenv("KLB_DENSE_MMA");     // KLB_DENSE_MMA=0 forces the DFMA register-tile kernel (experiments)
     j->dense_mma = j->dense && c.sampler == KLB_SAMPLER_HMC && !(env && env[0] == '0') &&
                    (c.dim == 64 || c.dim == 128 || c.dim == 256 || c.dim == 512);
   }
-  if (j->dense_mma ? klb_dense_mma_attrs(c.arith, (int)c.dim, &j->regs, &j->bps) != 0
+  if (j->glm ? klb_glm_attrs(c.sampler, c.arith, j->gdp, 0, &j->regs, &j->bps) != 0
+      : j->dense_mma ? klb_dense_mma_attrs(c.arith, (int)c.dim, &j->regs, &j->bps) != 0
       : j->dense ? klb_dense_attrs(c.sampler, c.arith, (int)c.dim, &j->regs, &j->bps) != 0
                : chain_dispatch(c.sampler, c.arith, nullptr, c.target, gw, gnv, c.dim == 64ll * gw * gnv, &j->regs, &j->bps, j->stream) != 0) {
     cudaGetLastError();
@@ -331,6 +358,36 @@ int klb_job_set_target_f64(klb_job* j, int which, const double* host, int64_t n)
       return KLB_OK;
     }
   }
+  if (which == KLB_PARAM_LOGIT_X || which == KLB_PARAM_LOGIT_Y || which == KLB_PARAM_LOGIT_LAMBDA) {
+    if (!j->glm) return fail(KLB_EINVAL, "this job's target takes no regression data");
+    const int64_t d = j->cfg.dim;
+    if (which == KLB_PARAM_LOGIT_LAMBDA) {
+      if (n != 1 || !(host[0] > 0) || !std::isfinite(host[0])) return fail(KLB_EINVAL, "lambda needs 1 positive value");
+      j->lambda = host[0];
+      return KLB_OK;
+    }
+    if (which == KLB_PARAM_LOGIT_X) {
+      if (n <= 0 || n % d != 0) return fail(KLB_EINVAL, "X needs ndata*dim values (dim = %lld)", (long long)d);
+      const int64_t nd = n / d;
+      if (nd > 0x7fffffff) return fail(KLB_EINVAL, "too many observations");
+      double* packed = (double*)calloc((size_t)nd * j->gdp, sizeof(double));   // row pitch gdp, zero padded
+      if (!packed) return fail(KLB_ENOMEM, "host allocation failed");
+      for (int64_t i = 0; i < nd; ++i) memcpy(packed + i * j->gdp, host + i * d, d * sizeof(double));
+      cudaFree(j->gX); j->gX = nullptr; j->have_X = false;
+      cudaError_t e = cudaMalloc(&j->gX, (size_t)nd * j->gdp * sizeof(double));
+      if (e == cudaSuccess) e = cudaMemcpy(j->gX, packed, (size_t)nd * j->gdp * sizeof(double), cudaMemcpyHostToDevice);
+      free(packed);
+      CK(e);
+      j->ndata = nd; j->have_X = true;
+      return KLB_OK;
+    }
+    if (n <= 0) return fail(KLB_EINVAL, "y needs ndata values");
+    cudaFree(j->gy); j->gy = nullptr; j->have_y = false;
+    CK(cudaMalloc(&j->gy, (size_t)n * sizeof(double)));
+    CK(cudaMemcpy(j->gy, host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    j->ny = n; j->have_y = true;
+    return KLB_OK;
+  }
   return fail(KLB_EINVAL, "unknown parameter id %d", which);
 }
 
@@ -349,11 +406,23 @@ static int init_state(klb_job* j) {
   if (c.target == KLB_TARGET_SHIFTED_ISO && !j->have_mu) return fail(KLB_ESTATE, "set KLB_PARAM_MU before the state");
   if (c.sampler == KLB_SAMPLER_MH && !j->have_sigma) return fail(KLB_ESTATE, "set KLB_PARAM_SIGMA before the state");
   if (j->dense && !j->have_C) return fail(KLB_ESTATE, "set KLB_PARAM_C before the state");
+  if (j->glm) {
+    if (!j->have_X || !j->have_y) return fail(KLB_ESTATE, "set KLB_PARAM_LOGIT_X and KLB_PARAM_LOGIT_Y before the state");
+    if (j->ny != j->ndata) return fail(KLB_EINVAL, "X has %lld rows, y has %lld entries", j->ndata, j->ny);
+    if (klb_glm_attrs(c.sampler, c.arith, j->gdp, glm_smem(j), &j->regs, &j->bps) != 0) {
+      cudaGetLastError();
+      return fail(KLB_ECUDA, "no sm_100a kernel image for the logistic-regression kernel (dp %d)", j->gdp);
+    }
+  }
   KArgs A;
   fill_args(j, A);
   const unsigned long long none = std::numeric_limits<unsigned long long>::max();
   CK(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
-  if (j->dense) {
+  if (j->glm) {
+    GArgs G; fill_glm_args(j, A, G);
+    if (klb_glm_init(G, c.arith, j->gdp, glm_smem(j), c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
+      return fail(KLB_ECUDA, "logistic-regression init kernel launch failed");
+  } else if (j->dense) {
     DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
     if (klb_dense_init(D, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
       return fail(KLB_ECUDA, "dense init kernel launch failed");
@@ -411,7 +480,11 @@ int klb_job_run_async(klb_job* j) {
   while (done < c.nsteps) {
     const long long nt = (c.nsteps - done) < chunk ? (c.nsteps - done) : chunk;
     A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global;
-    if (j->dense) {
+    if (j->glm) {
+      GArgs G; fill_glm_args(j, A, G);
+      if (klb_glm_launch(G, c.sampler, c.arith, j->gdp, glm_smem(j), j->stream) != 0)
+        return fail(KLB_ECUDA, "logistic-regression kernel launch failed");
+    } else if (j->dense) {
       DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
       const char* cl = getenv("KLB_DENSE_CLUSTER");    // thread-block clusters of 2 (default) or 4 CTAs share every slab of C; 1 = no clusters
       const int cluster = (cl && cl[0] == '4') ? 4 : (cl && cl[0] == '1') ? 1 : 2;   // default: pairs
@@ -563,8 +636,8 @@ int klb_job_plan(klb_job* j, klb_plan* out) {
   if (!j || !out) return fail(KLB_EINVAL, "null argument");
   out->nv = j->nv;
   out->ld = j->ld;
-  out->warps_per_block = use_hmc_ws(j->cfg.sampler, j->gw, j->gnv) && !j->dense ? 8 : KLB_WPB;
-  out->warps_per_chain = j->gw;
+  out->warps_per_block = j->glm ? KLB_GLM_THREADS / 32 : use_hmc_ws(j->cfg.sampler, j->gw, j->gnv) && !j->dense ? 8 : KLB_WPB;
+  out->warps_per_chain = j->glm ? 0 : j->gw;       // 0: one THREAD per chain
   out->regs_per_thread = j->regs;
   out->blocks_per_sm = j->bps;
   out->npoststeps = j->npost;

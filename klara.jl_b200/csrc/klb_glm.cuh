@@ -1,0 +1,301 @@
+// klb_glm.cuh -- data-dependent, low-dimensional targets: Bayesian logistic regression.
+//
+// Reference closures (doc/examples/swiss/HMC/noadaptation/analytical.jl:11-20, the same three functions
+// in doc/examples/swiss/MALA/analytical.jl), hyper-parameters v = [lambda, X, y, p] in model-vertex order:
+//   ploglikelihood(p, v) = dot(Xp, y) - sum(log.(1+exp.(Xp))),   Xp = X*p
+//   plogprior(p, v)      = -0.5*(dot(p, p)/lambda + length(p)*log(2*pi*lambda))
+//   pgradlogtarget(p, v) = X'*(y - 1./(1+exp.(-X*p))) - p/lambda
+//   logtarget            = loglikelihood + logprior            BasicContMuvParameter.jl:185-190
+//
+// Geometry.  dim is tiny (4 for the swiss bank-note data) while one target evaluation walks the whole
+// data set (ndata x dim), so the warp-per-chain layout of klb_kernels.cuh would leave 28 of 32 lanes idle.
+// Here ONE THREAD owns one chain: position, cached gradient, momentum / proposal live in registers
+// (5 x DP doubles), the design matrix X (row-major, row pitch DP, zero padded) and y sit in shared memory
+// and every thread of the CTA reads the same row at the same time (one broadcast LDS.128 per two
+// coefficients), so the kernel is bound by the fp64 pipe: per data row 2 DP DFMA + one exp (+ one log for
+// the log-likelihood) + one division.
+//
+// Order of the floating-point operations (the contract shared with the CPU oracle, `nv = 0`):
+// X*p, X'*r, dot(.,.) are fma chains in increasing index (they are BLAS calls in the reference: fma kernels
+// of unspecified order), sum() is a chain of additions in increasing index; everything elementwise is
+// un-fused in arith = reference.  The cached gradient (pstate.gradlogtarget, iterate/HMC.jl:139) is not
+// stored in HBM: it is a pure function of the position and is re-evaluated when a launch starts.
+//
+// Transitions: HMC iterate/HMC.jl:124-224 + samplers.jl:101-134, MALA iterate/MALA.jl:78-152,
+// MH iterate/MH.jl:72-141 (symmetric branch); tuner block and save as in klb_kernels.cuh.
+#pragma once
+#include "klb_kernels.cuh"
+
+#define KLB_GLM_MAXD 16
+#define KLB_GLM_THREADS 64
+
+struct GArgs {
+  KArgs k;
+  const double* X;     // ndata x DP row-major, zero padded (device)
+  const double* y;     // ndata
+  long long ndata;
+  double lambda;       // prior variance
+  double logc;         // log(2*pi*lambda), evaluated once on the host with the same klb_log
+  int data_in_smem;    // X and y are staged in shared memory (they fit), else read through L1/L2
+};
+
+template <int DP, bool FMA>
+struct Glm {
+  // log-target and / or gradient at x; d = dim <= DP
+  template <bool WANT_LT, bool WANT_G>
+  static __device__ __forceinline__ void eval(const GArgs& G, const double* __restrict__ Xs,
+                                              const double* __restrict__ ys, const uint64_t* tab, int d,
+                                              const double (&x)[DP], double& lt, double (&g)[DP]) {
+    double a = 0.0, sl = 0.0;
+#pragma unroll
+    for (int j = 0; j < DP; ++j) g[j] = 0.0;
+    const int n = (int)G.ndata;
+    for (int i = 0; i < n; ++i) {
+      const double* row = Xs + (size_t)i * DP;
+      double xr[DP];
+#pragma unroll
+      for (int j = 0; j < DP; j += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(row + j);
+        xr[j] = v.x; xr[j + 1] = v.y;
+      }
+      double xp = 0.0;
+#pragma unroll
+      for (int j = 0; j < DP; ++j)
+        if (j < d) xp = __fma_rn(xr[j], x[j], xp);                          // Xp = v[2]*p
+      const double yi = ys[i];
+      if (WANT_LT) {
+        a = __fma_rn(xp, yi, a);                                            // dot(Xp, v[3])
+        sl = __dadd_rn(sl, klb_log(__dadd_rn(1.0, klb_exp(xp, tab)), tab)); // sum(log.(1+exp.(Xp)))
+      }
+      if (WANT_G) {
+        const double r = __dsub_rn(yi, __ddiv_rn(1.0, __dadd_rn(1.0, klb_exp(-xp, tab))));
+#pragma unroll
+        for (int j = 0; j < DP; ++j)
+          if (j < d) g[j] = __fma_rn(xr[j], r, g[j]);                       // v[2]'*r
+      }
+    }
+    if (WANT_LT) {
+      double pp = 0.0;
+#pragma unroll
+      for (int j = 0; j < DP; ++j)
+        if (j < d) pp = __fma_rn(x[j], x[j], pp);
+      pp = __ddiv_rn(pp, G.lambda);
+      const double dd = (double)d;
+      const double inner = FMA ? __fma_rn(dd, G.logc, pp) : __dadd_rn(pp, __dmul_rn(dd, G.logc));
+      lt = __dadd_rn(__dsub_rn(a, sl), __dmul_rn(-0.5, inner));
+    }
+    if (WANT_G) {
+#pragma unroll
+      for (int j = 0; j < DP; ++j) g[j] = (j < d) ? __dsub_rn(g[j], __ddiv_rn(x[j], G.lambda)) : 0.0;
+    }
+  }
+};
+
+// z <- randn(d): the same streams as every other kernel (pair k -> elements 2k, 2k+1)
+template <int DP>
+__device__ __forceinline__ void glm_randn(const klb_stream& st, int d, const uint64_t* tab, double (&z)[DP]) {
+#pragma unroll
+  for (int k = 0; k < DP / 2; ++k) {
+    z[2 * k] = 0.0; z[2 * k + 1] = 0.0;
+    if (2 * k < d) {
+      uint64_t w0, w1;
+      klb_stream_draw(&st, (uint32_t)k, KLB_TAG_NORMAL, 0u, &w0, &w1);
+      double v;
+      z[2 * k] = klb_zig_fast(w0, tab, &v) ? v : klb_normal_from_word(w0, 2u * k, &st, tab);
+      if (2 * k + 1 < d) z[2 * k + 1] = klb_zig_fast(w1, tab, &v) ? v : klb_normal_from_word(w1, 2u * k + 1u, &st, tab);
+    }
+  }
+}
+
+template <int DP>
+__device__ __forceinline__ void glm_load(double (&q)[DP], const double* __restrict__ col, int ld) {
+#pragma unroll
+  for (int j = 0; j < DP; j += 2) {
+    double2 v = make_double2(0.0, 0.0);
+    if (j < ld) v = *reinterpret_cast<const double2*>(col + j);
+    q[j] = v.x; q[j + 1] = v.y;
+  }
+}
+// the pad row (odd dim) is written as exactly 0
+template <int DP>
+__device__ __forceinline__ void glm_store(const double (&q)[DP], double* __restrict__ col, int d) {
+#pragma unroll
+  for (int j = 0; j < DP; j += 2)
+    if (j < d) *reinterpret_cast<double2*>(col + j) = make_double2(q[j], (j + 1 < d) ? q[j + 1] : 0.0);
+}
+
+// stage X, y and the math tables; returns the pointers the evaluation reads
+__device__ __forceinline__ void glm_stage(const GArgs& G, int DP, uint64_t* tab, double* dyn, const double*& Xs,
+                                          const double*& ys) {
+  for (int i = threadIdx.x; i < KLB_TAB_LEN; i += blockDim.x) tab[i] = G.k.tab[i];
+  if (G.data_in_smem) {
+    const long long nx = G.ndata * DP;
+    for (long long i = threadIdx.x; i < nx; i += blockDim.x) dyn[i] = G.X[i];
+    for (long long i = threadIdx.x; i < G.ndata; i += blockDim.x) dyn[nx + i] = G.y[i];
+    Xs = dyn; ys = dyn + nx;
+  } else {
+    Xs = G.X; ys = G.y;
+  }
+  __syncthreads();
+}
+
+template <int SAMPLER, int DP, bool FMA>
+__global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G) {
+  const KArgs& A = G.k;
+  __shared__ uint64_t tab[KLB_TAB_LEN];
+  extern __shared__ double2 glm_dyn2[];
+  const double *Xs, *ys;
+  glm_stage(G, DP, tab, reinterpret_cast<double*>(glm_dyn2), Xs, ys);
+
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= A.nchains) return;
+  const int d = (int)A.dim, ld = (int)A.ld;
+  double* const xcol = A.state + c * A.ld;
+
+  double x[DP], g[DP];
+  glm_load<DP>(x, xcol, ld);
+  double lt_cur = A.lt[c];
+  if (SAMPLER != 0) {                        // the cached gradient of the current state
+    double dummy;
+    Glm<DP, FMA>::template eval<false, true>(G, Xs, ys, tab, d, x, dummy, g);
+  }
+  Tune tn;
+  tn.step = A.tune_step[c];
+  tn.accepted = A.tune_cnt[3 * c]; tn.proposed = A.tune_cnt[3 * c + 1]; tn.totproposed = A.tune_cnt[3 * c + 2];
+  tn.rate = A.tune_rate[c];
+  long long count = A.count0;
+  long long thin = (A.i0 > A.burnin) ? klb_mod(A.i0 - A.burnin - 1, A.thinning) : 0;
+
+  for (long long it = 0; it < A.nt; ++it) {
+    const long long irun = A.i0 + it;
+    const klb_stream st = klb_stream_make(A.seed, A.chain_offset + (unsigned long long)c,
+                                          A.t0 + 1ull + (unsigned long long)it);
+    bool accept = false;
+    double lt_new = 0.0, ratio;
+    double xs[DP], gs[DP];
+    double z[DP];
+    glm_randn<DP>(st, d, tab, z);
+    const double step = tn.step;
+    const double h = __dmul_rn(0.5, step);
+    if (SAMPLER == 2) {
+      // ---------------------------------------------------------------- HMC
+      double k0 = 0.0;
+#pragma unroll
+      for (int j = 0; j < DP; ++j) { k0 = dotacc(z[j], z[j], k0); xs[j] = x[j]; gs[j] = g[j]; }
+      const double oldh = __dsub_rn(lt_cur, __dmul_rn(0.5, k0));             // hamiltonian()
+      for (int s = 1; s <= A.nleaps; ++s) {                                  // leapfrog!  samplers.jl:122-134
+#pragma unroll
+        for (int j = 0; j < DP; ++j) {
+          z[j] = Ar<FMA>::ma(h, gs[j], z[j]);
+          xs[j] = Ar<FMA>::ma(step, z[j], xs[j]);
+        }
+        // the last gradient evaluation also yields logtarget!(proposal): same Xp, same bits
+        if (s == A.nleaps) Glm<DP, FMA>::template eval<true, true>(G, Xs, ys, tab, d, xs, lt_new, gs);
+        else { double dummy; Glm<DP, FMA>::template eval<false, true>(G, Xs, ys, tab, d, xs, dummy, gs); }
+#pragma unroll
+        for (int j = 0; j < DP; ++j) z[j] = Ar<FMA>::ma(h, gs[j], z[j]);
+      }
+      double k1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < DP; ++j) k1 = dotacc(z[j], z[j], k1);
+      const double newh = __dsub_rn(lt_new, __dmul_rn(0.5, k1));
+      ratio = __dsub_rn(newh, oldh);
+      if (ratio >= 0.0) accept = true;
+      else {
+        const double ex = klb_exp(ratio, tab);
+        const double a = (ex != ex) ? ex : (ex < 1.0 ? ex : 1.0);
+        accept = klb_accept_uniform(&st) < a;
+      }
+    } else if (SAMPLER == 1) {
+      // ---------------------------------------------------------------- MALA
+      const double sq = __dsqrt_rn(step);
+      const double hinv = __ddiv_rn(0.5, step);
+      double mu[DP];
+      double e1 = 0.0, e2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < DP; ++j) {
+        mu[j] = Ar<FMA>::ma(h, g[j], x[j]);
+        xs[j] = Ar<FMA>::ma(sq, z[j], mu[j]);
+      }
+      Glm<DP, FMA>::template eval<true, true>(G, Xs, ys, tab, d, xs, lt_new, gs);
+#pragma unroll
+      for (int j = 0; j < DP; ++j) {
+        if (j < d) {
+          const double df = __dsub_rn(mu[j], xs[j]);
+          e1 = __dadd_rn(e1, FMA ? __dmul_rn(__dmul_rn(df, hinv), df) : __dmul_rn(0.5, __ddiv_rn(__dmul_rn(df, df), step)));
+          const double m2 = Ar<FMA>::ma(h, gs[j], xs[j]);
+          const double db = __dsub_rn(m2, x[j]);
+          e2 = __dadd_rn(e2, FMA ? __dmul_rn(__dmul_rn(db, hinv), db) : __dmul_rn(0.5, __ddiv_rn(__dmul_rn(db, db), step)));
+        }
+      }
+      ratio = __dsub_rn(lt_new, lt_cur);
+      ratio = __dadd_rn(ratio, e1);
+      ratio = __dsub_rn(ratio, e2);
+      accept = (ratio > 0.0) || (ratio > klb_log(klb_accept_uniform(&st), tab));
+    } else {
+      // ---------------------------------------------------------------- MH
+#pragma unroll
+      for (int j = 0; j < DP; ++j) xs[j] = Ar<FMA>::ma(__ldg(A.sigma + j), z[j], x[j]);
+      Glm<DP, FMA>::template eval<true, false>(G, Xs, ys, tab, d, xs, lt_new, gs);
+      ratio = __dsub_rn(lt_new, lt_cur);
+      accept = (ratio > 0.0) || (ratio > klb_log(klb_accept_uniform(&st), tab));
+    }
+
+    if (A.counters_on) { tn.proposed += 1; if (accept) tn.accepted += 1; }
+    tuner_block<SAMPLER>(A, tn, tab);
+    if (accept) {
+#pragma unroll
+      for (int j = 0; j < DP; ++j) { x[j] = xs[j]; if (SAMPLER != 0) g[j] = gs[j]; }
+      lt_cur = lt_new;
+    }
+
+    if (irun > A.burnin) {                                     // in(i, postrange) -> save(job, count)
+      if (thin == 0) {
+        const long long col = c * A.npost + count;
+        if (A.out_value) glm_store<DP>(x, A.out_value + col * A.ld, d);
+        if (A.out_grad) glm_store<DP>(g, A.out_grad + col * A.ld, d);
+        if (A.out_lt) A.out_lt[col] = lt_cur;
+        if (A.out_accept) A.out_accept[col] = accept ? 1 : 0;
+        count += 1;
+      }
+      thin = (thin + 1 == A.thinning) ? 0 : thin + 1;
+    }
+  }
+
+  glm_store<DP>(x, xcol, d);
+  A.lt[c] = lt_cur;
+  A.tune_step[c] = tn.step;
+  A.tune_cnt[3 * c] = tn.accepted; A.tune_cnt[3 * c + 1] = tn.proposed; A.tune_cnt[3 * c + 2] = tn.totproposed;
+  A.tune_rate[c] = tn.rate;
+}
+
+// initialize!: lt[c] = logtarget(x_c), finiteness of the log-target (and gradient)   HMC.jl:106-120
+template <int DP, bool FMA>
+__global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_init_kernel(const GArgs G, int check_grad,
+                                                                       unsigned long long* flag) {
+  const KArgs& A = G.k;
+  __shared__ uint64_t tab[KLB_TAB_LEN];
+  extern __shared__ double2 glm_dyn2[];
+  const double *Xs, *ys;
+  glm_stage(G, DP, tab, reinterpret_cast<double*>(glm_dyn2), Xs, ys);
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= A.nchains) return;
+  const int d = (int)A.dim;
+  double x[DP], g[DP], lt = 0.0;
+  glm_load<DP>(x, A.state + c * A.ld, (int)A.ld);
+  Glm<DP, FMA>::template eval<true, true>(G, Xs, ys, tab, d, x, lt, g);
+  bool ok = isfinite(lt);
+  if (check_grad) {
+#pragma unroll
+    for (int j = 0; j < DP; ++j)
+      if (j < d) ok = ok && isfinite(g[j]);
+  }
+  A.lt[c] = lt;
+  if (!ok) atomicMin(flag, (unsigned long long)(A.chain_offset + c + 1));
+}
+
+// host side (klb_glm_inst.cu)
+int klb_glm_launch(const GArgs& G, int sampler, int fma, int dp, size_t dyn_smem, cudaStream_t s);
+int klb_glm_init(const GArgs& G, int fma, int dp, size_t dyn_smem, int check_grad, unsigned long long* flag,
+                 cudaStream_t s);
+int klb_glm_attrs(int sampler, int fma, int dp, size_t dyn_smem, int* regs, int* bps);

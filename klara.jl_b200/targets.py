@@ -93,3 +93,59 @@ class DenseGaussian(Target):
 
     def params(self, dim):
         return [(L.PARAM_C, self.C.reshape(-1))]
+
+
+class BayesLogit(Target):
+    """Bayesian logistic regression with a N(0, lambda I) prior on the coefficients: the closures of
+    doc/examples/swiss/HMC/noadaptation/analytical.jl:11-20 (also swiss/MALA/analytical.jl), whose
+    hyper-parameters arrive as `v = [lambda, X, y, p]` in model-vertex order
+    (`likelihood_model([Hyperparameter(:λ), Data(:X), Data(:y), p], isindexed=false)`):
+
+        ploglikelihood(p, v) = dot(Xp, y) - sum(log.(1+exp.(Xp))),   Xp = X*p
+        plogprior(p, v)      = -0.5*(dot(p, p)/lambda + length(p)*log(2*pi*lambda))
+        pgradlogtarget(p, v) = X'*(y - 1./(1+exp.(-X*p))) - p/lambda
+
+    `BayesLogit(X, y, lam)` carries the data itself; `BayesLogit()` is bound by BasicMCJob from the
+    initial values of the model's other vertices (v0[:λ], v0[:X], v0[:y]) like the reference does
+    (BasicContMuvParameter.jl:497-501).  X is ndata x dim, dim <= 16."""
+    code = L.TARGET_LOGIT
+    nkeys = 4
+
+    def __init__(self, X=None, y=None, lam=None):
+        self.X = self.y = self.lam = None
+        if X is not None:
+            self.bind([lam, X, y])
+
+    def bind(self, values):
+        """values = [lambda, X, y]: the states of the other model vertices, in vertex order"""
+        lam, X, y = values
+        self.lam = 100.0 if lam is None else float(lam)
+        self.X = np.ascontiguousarray(X, dtype=np.float64)
+        self.y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        if self.X.ndim != 2 or self.X.shape[0] != self.y.size:
+            raise AssertionError("X must be ndata x dim and y must have ndata entries")
+        return self
+
+    def loglikelihood(self, p):
+        Xp = self.X @ np.asarray(p, dtype=np.float64)
+        return float(np.dot(Xp, self.y) - np.sum(np.log(1 + np.exp(Xp))))
+
+    def logprior(self, p):
+        p = np.asarray(p, dtype=np.float64)
+        return float(-0.5 * (np.dot(p, p) / self.lam + p.size * np.log(2 * np.pi * self.lam)))
+
+    def __call__(self, p):
+        return self.loglikelihood(p) + self.logprior(p)
+
+    def gradient(self, p):
+        p = np.asarray(p, dtype=np.float64)
+        return self.X.T @ (self.y - 1. / (1 + np.exp(-(self.X @ p)))) - p / self.lam
+
+    def params(self, dim):
+        if self.X is None:
+            raise AssertionError("BayesLogit has no data: pass X, y, lam or give v0 values for the model's "
+                                 "Hyperparameter / Data vertices")
+        if self.X.shape[1] != dim:
+            raise AssertionError("X has %d columns, parameter has %d entries" % (self.X.shape[1], dim))
+        return [(L.PARAM_LOGIT_LAMBDA, np.array([self.lam])), (L.PARAM_LOGIT_X, self.X.reshape(-1)),
+                (L.PARAM_LOGIT_Y, self.y)]

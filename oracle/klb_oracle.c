@@ -56,7 +56,7 @@
 #include "../klara.jl_b200/csrc/klb_math.h"
 
 enum { ORC_MH = 0, ORC_MALA = 1, ORC_HMC = 2 };
-enum { ORC_ISO = 0, ORC_SHIFTED = 1, ORC_DENSE = 2, ORC_ROSEN = 3 };
+enum { ORC_ISO = 0, ORC_SHIFTED = 1, ORC_DENSE = 2, ORC_ROSEN = 3, ORC_LOGIT = 4 };
 enum { ORC_VANILLA = 0, ORC_ACCRATE = 1 };
 
 typedef struct {
@@ -70,7 +70,9 @@ typedef struct {
   uint32_t monitor;                           /* bit0 value, bit1 logtarget, bit2 gradlogtarget */
   uint32_t diagnostics;                       /* bit0 accept */
   uint64_t seed, chain_offset, t0;
-  int32_t nv;                                 /* reduction geometry: double2 units per lane (1,2,4,8,16) */
+  int32_t nv;                                 /* reduction geometry: double2 units per lane (1,2,4,8,16,64);
+                                                 0 = sequential order (one thread per chain: the data-dependent
+                                                 targets, klb_glm.cuh) */
   int32_t nthreads;                           /* OpenMP threads over chains; 1 = map(run, jobs) semantics */
 } orc_config;
 
@@ -87,6 +89,11 @@ typedef struct {
   const double* sigma;        /* MH proposal std-devs (padded with 0) */
   const double* C;            /* dense precision, d x d row-major (symmetric) */
   double ra, rb, rscale;      /* rosenbrock */
+  /* Bayesian logistic regression (doc/examples/swiss): v = [lambda, X, y, p] */
+  int64_t ndata;
+  const double* X;            /* ndata x d, row-major */
+  const double* y;            /* ndata */
+  double lambda;              /* prior variance v[1] */
 } orc_model;
 
 /* ------------------------------------------------------------------ scalars */
@@ -124,8 +131,13 @@ int orc_plan_nv(int64_t dim) {
  * Each lane keeps four accumulators; unit m adds its two addends, even element first,
  * into accumulator m & 3; lane value = (acc0+acc1)+(acc2+acc3); lanes are combined by
  * the xor butterfly 16, 8, 4, 2, 1.  `e` holds the addends (padded length 64*nv). */
-static double orc_reduce(const double* e, int nv) {
+static double orc_reduce_n(const double* e, int nv, int64_t n) {
   double lane[32], nxt[32];
+  if (nv == 0) {                     /* sequential order (thread-per-chain kernels) */
+    double acc = 0.;
+    for (int64_t i = 0; i < n; ++i) acc = acc + e[i];
+    return acc;
+  }
   for (int l = 0; l < 32; ++l) {
     double acc[4] = {0., 0., 0., 0.};
     for (int m = 0; m < nv; ++m) {
@@ -141,9 +153,15 @@ static double orc_reduce(const double* e, int nv) {
   }
   return lane[0];
 }
-/* same order with the products folded in by fma (arith == 1) */
-static double orc_reduce_fma(const double* a, const double* b, int nv) {
+static double orc_reduce(const double* e, int nv) { return orc_reduce_n(e, nv, 0); }
+/* same order with the products folded in by fma */
+static double orc_reduce_fma_n(const double* a, const double* b, int nv, int64_t n) {
   double lane[32], nxt[32];
+  if (nv == 0) {
+    double acc = 0.;
+    for (int64_t i = 0; i < n; ++i) acc = fma(a[i], b[i], acc);
+    return acc;
+  }
   for (int l = 0; l < 32; ++l) {
     double acc[4] = {0., 0., 0., 0.};
     for (int m = 0; m < nv; ++m) {
@@ -163,9 +181,10 @@ static double orc_reduce_fma(const double* a, const double* b, int nv) {
 /* dot(a, b) over padded vectors.  Julia's dot on Vector{Float64} is BLAS ddot: an fma kernel with an
  * unspecified order on every FMA-capable CPU.  Here: fma-accumulated in the canonical order, in both
  * arithmetic modes (only the elementwise broadcast expressions of the reference are un-fused). */
+static double orc_reduce_fma(const double* a, const double* b, int nv) { return orc_reduce_fma_n(a, b, nv, 0); }
 static double orc_dot_m(const orc_model* M, const double* a, const double* b, double* scratch) {
   (void)scratch;
-  return orc_reduce_fma(a, b, M->cfg->nv);
+  return orc_reduce_fma_n(a, b, M->cfg->nv, M->d);
 }
 /* exported for tests */
 double orc_dot(const double* a, const double* b, int64_t d, int nv, int arith) {
@@ -189,6 +208,14 @@ double orc_ma(double a, double b, double c, int arith) { return arith == 1 ? fma
  *   shifted  -(x-mu).(x-mu), -2(x-mu)                    test/BasicContMuvParameter.jl:539-563
  *   dense    -p.(C p), -2 C p        doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9
  *   rosen    this repo's paired Rosenbrock; not in the reference
+ *   logit    Bayesian logistic regression with a N(0, lambda I) prior, v = [lambda, X, y, p]:
+ *              ploglikelihood(p, v) = dot(Xp, y) - sum(log.(1+exp.(Xp))),  Xp = X*p
+ *              plogprior(p, v)      = -0.5*(dot(p, p)/lambda + length(p)*log(2*pi*lambda))
+ *              pgradlogtarget(p, v) = X'*(y - 1./(1+exp.(-X*p))) - p/lambda
+ *            doc/examples/swiss/HMC/noadaptation/analytical.jl:11-20 (same closures in swiss/MALA/analytical.jl);
+ *            logtarget = loglikelihood + logprior      BasicContMuvParameter.jl:185-190
+ *            X*p, X'*r and dot are BLAS calls in the reference (fma kernels, unspecified order): here fma
+ *            chains in increasing index; sum() is a chain of additions in increasing index.
  */
 static void orc_gradlogtarget(const orc_model* M, orc_pstate* s, double* scratch);
 
@@ -231,6 +258,22 @@ static void orc_logtarget(const orc_model* M, orc_pstate* s, double* scratch) {
       s->logtarget = -(M->rscale * orc_reduce(scratch, M->cfg->nv));
       break;
     }
+    case ORC_LOGIT: {
+      const int64_t d = M->d;
+      double a = 0., sl = 0.;
+      for (int64_t i = 0; i < M->ndata; ++i) {
+        double xp = 0.;
+        for (int64_t j = 0; j < d; ++j) xp = fma(M->X[i * d + j], x[j], xp);      /* Xp = v[2]*p */
+        a = fma(xp, M->y[i], a);                                                  /* dot(Xp, v[3]) */
+        sl = sl + klb_log(1 + klb_exp(xp, KLB_TAB), KLB_TAB);                     /* sum(log.(1+exp.(Xp))) */
+      }
+      const double loglik = a - sl;
+      const double pp = orc_dot_m(M, x, x, scratch) / M->lambda;
+      const double lc = klb_log((2 * 3.141592653589793) * M->lambda, KLB_TAB);    /* log(2*pi*v[1]) */
+      const double logprior = -0.5 * (fm ? fma((double)d, lc, pp) : pp + (double)d * lc);
+      s->logtarget = loglik + logprior;
+      break;
+    }
   }
 }
 
@@ -264,8 +307,21 @@ static void orc_gradlogtarget(const orc_model* M, orc_pstate* s, double* scratch
         g[2 * k] = ga; g[2 * k + 1] = gb;
       }
       break;
+    case ORC_LOGIT: {
+      const int64_t d = M->d;
+      for (int64_t j = 0; j < M->dp; ++j) g[j] = 0.;
+      for (int64_t i = 0; i < M->ndata; ++i) {
+        double xp = 0.;
+        for (int64_t j = 0; j < d; ++j) xp = fma(M->X[i * d + j], x[j], xp);
+        /* -v[2]*p = (-X)*p = -(X*p) exactly (negation commutes with every rounding of the fma chain) */
+        const double r = M->y[i] - 1. / (1 + klb_exp(-xp, KLB_TAB));
+        for (int64_t j = 0; j < d; ++j) g[j] = fma(M->X[i * d + j], r, g[j]);     /* v[2]'*r */
+      }
+      for (int64_t j = 0; j < d; ++j) g[j] = g[j] - x[j] / M->lambda;
+      break;
+    }
   }
-  (void)scratch;
+  (void)scratch; (void)fm;
 }
 
 /* uptogradlogtarget! = logtarget! then gradlogtarget!   BasicContMuvParameter.jl:264-279 */
@@ -377,14 +433,14 @@ static void orc_iterate_mala(const orc_model* M, orc_pstate* ps, orc_sstate* ss,
     double df = mu[i] - ss->sp.value[i];
     e[i] = fm ? (df * hinv) * df : 0.5 * ((df * df) / step);
   }
-  ratio += orc_reduce(e, c->nv);
+  ratio += orc_reduce_n(e, c->nv, M->d);
   for (int64_t i = 0; i < M->dp; ++i)
     mu[i] = fm ? fma(h, ss->sp.gradlogtarget[i], ss->sp.value[i]) : ss->sp.value[i] + h * ss->sp.gradlogtarget[i];
   for (int64_t i = 0; i < M->dp; ++i) {
     double df = mu[i] - ps->value[i];
     e[i] = fm ? (df * hinv) * df : 0.5 * ((df * df) / step);
   }
-  ratio -= orc_reduce(e, c->nv);
+  ratio -= orc_reduce_n(e, c->nv, M->d);
   /* the counter-based uniform makes Julia's short-circuit (no draw when ratio > 0) unobservable */
   if (ratio > 0 || ratio > klb_log(klb_accept_uniform(st), KLB_TAB)) {
     memcpy(ps->value, ss->sp.value, M->dp * sizeof(double));
@@ -420,6 +476,14 @@ static void orc_iterate_mh(const orc_model* M, orc_pstate* ps, orc_sstate* ss, o
   orc_tuner_block(c, tune);
 }
 
+/* tparams of the logit target: {lambda, ndata, X (ndata x d, row-major), y (ndata)} */
+static void orc_model_logit(orc_model* M, const double* tparams) {
+  M->lambda = tparams[0];
+  M->ndata = (int64_t)tparams[1];
+  M->X = tparams + 2;
+  M->y = tparams + 2 + M->ndata * M->d;
+}
+
 /* ----------------------------------------------------------------- the job */
 typedef struct {
   double* value;       /* d x npost x nchains */
@@ -452,7 +516,7 @@ int64_t orc_npoststeps(int64_t burnin, int64_t thinning, int64_t nsteps) {
 int orc_run(const orc_config* cfg, const double* tparams, const double* sigma,
             double* x, double* logtarget, orc_tune* tune, int initialized,
             double* out_value, double* out_logtarget, double* out_grad, uint8_t* out_accept) {
-  const int64_t d = cfg->dim, dp = 64 * (int64_t)cfg->nv, N = cfg->nchains;
+  const int64_t d = cfg->dim, dp = cfg->nv ? 64 * (int64_t)cfg->nv : cfg->dim, N = cfg->nchains;
   if (dp < d) return -1000000;
   const int64_t npost = orc_npoststeps(cfg->burnin, cfg->thinning, cfg->nsteps);
   orc_output out = {out_value, out_logtarget, out_grad, out_accept};
@@ -462,6 +526,7 @@ int orc_run(const orc_config* cfg, const double* tparams, const double* sigma,
   if (cfg->target == ORC_SHIFTED && tparams) memcpy(mu_p, tparams, d * sizeof(double));
   if (cfg->target == ORC_DENSE) M.C = tparams;
   if (cfg->target == ORC_ROSEN) { M.ra = tparams[0]; M.rb = tparams[1]; M.rscale = tparams[2]; }
+  if (cfg->target == ORC_LOGIT) orc_model_logit(&M, tparams);
   if (sigma) memcpy(sg_p, sigma, d * sizeof(double));
   int bad = 0;
   int nth = cfg->nthreads > 0 ? cfg->nthreads : 1;
@@ -510,7 +575,7 @@ int orc_run(const orc_config* cfg, const double* tparams, const double* sigma,
 /* single evaluations for the closure-wiring KATs (test/BasicContMuvParameter.jl:539-563) */
 int orc_eval_target(const orc_config* cfg, const double* tparams, const double* x,
                     double* logtarget, double* grad) {
-  const int64_t d = cfg->dim, dp = 64 * (int64_t)cfg->nv;
+  const int64_t d = cfg->dim, dp = cfg->nv ? 64 * (int64_t)cfg->nv : cfg->dim;
   if (dp < d) return -1;
   double* buf = calloc(6 * dp, sizeof(double));
   orc_model M; memset(&M, 0, sizeof M);
@@ -518,6 +583,7 @@ int orc_eval_target(const orc_config* cfg, const double* tparams, const double* 
   if (cfg->target == ORC_SHIFTED) memcpy(buf + 4 * dp, tparams, d * sizeof(double));
   if (cfg->target == ORC_DENSE) M.C = tparams;
   if (cfg->target == ORC_ROSEN) { M.ra = tparams[0]; M.rb = tparams[1]; M.rscale = tparams[2]; }
+  if (cfg->target == ORC_LOGIT) orc_model_logit(&M, tparams);
   orc_pstate ps = {buf, 0., buf + dp, 0};
   memcpy(ps.value, x, d * sizeof(double));
   orc_upto(&M, &ps, buf + 2 * dp);

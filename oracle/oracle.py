@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libklb_oracle.so")
 
 MH, MALA, HMC = 0, 1, 2
-ISO, SHIFTED, DENSE, ROSEN = 0, 1, 2, 3
+ISO, SHIFTED, DENSE, ROSEN, LOGIT = 0, 1, 2, 3, 4
 VANILLA, ACCRATE = 0, 1
 
 
@@ -141,6 +141,12 @@ def dot(a, b, nv=None, arith=0):
     return lib().orc_dot(_ptr(a), _ptr(b), a.size, nv, arith)
 
 
+def logit_params(X, y, lam):
+    """tparams of the LOGIT target: [lambda, ndata, X (ndata x d, row-major), y]"""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    return np.concatenate([[float(lam), float(X.shape[0])], X.reshape(-1), np.asarray(y, dtype=np.float64).reshape(-1)])
+
+
 def npoststeps(burnin, thinning, nsteps):
     return lib().orc_npoststeps(burnin, thinning, nsteps)
 
@@ -155,7 +161,7 @@ def make_config(sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, ste
     cfg.target_rate, cfg.score_k, cfg.period, cfg.verbose = target_rate, score_k, period, verbose
     cfg.monitor, cfg.diagnostics = monitor, diagnostics
     cfg.seed, cfg.chain_offset, cfg.t0 = seed, chain_offset, t0
-    cfg.nv = plan_nv(dim) if nv is None else nv
+    cfg.nv = (0 if target == LOGIT else plan_nv(dim)) if nv is None else nv   # LOGIT: sequential order
     cfg.nthreads = nthreads
     return cfg
 

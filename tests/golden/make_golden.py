@@ -24,9 +24,24 @@ CASES = {
     "mala_rosen_d16_accrate": ("MALA", "rosen", 4, 16, 120, dict(burnin=100, step=0.01, tuner=O.ACCRATE, target_rate=0.574, period=25, monitor=3, diagnostics=1, seed=8), {}),
     "mh_readme_d2": ("MH", "iso", 1, 2, 200, dict(burnin=100, monitor=3, diagnostics=1, seed=2024), {"x0": [[5.1, -0.9]], "sigma": [1.0, 1.0]}),
     "hmc_shifted_d100_fma": ("HMC", "shifted", 3, 100, 20, dict(burnin=5, step=0.05, nleaps=6, monitor=3, diagnostics=1, seed=3, arith=1), {}),
+    # Bayesian logistic regression (doc/examples/swiss/HMC/noadaptation/analytical.jl), synthetic 200 x 4 data
+    "hmc_logit_d4": ("HMC", "logit", 6, 4, 60, dict(burnin=20, step=0.03, nleaps=10, monitor=7, diagnostics=1, seed=41), {}),
+    "mala_logit_d3_accrate": ("MALA", "logit", 5, 3, 150, dict(burnin=100, step=0.01, tuner=O.ACCRATE, target_rate=0.574, period=25, monitor=3, diagnostics=1, seed=42), {}),
+    "mh_logit_d4_fma": ("MH", "logit", 4, 4, 120, dict(burnin=40, thinning=2, monitor=3, diagnostics=1, seed=43, arith=1), {"sigma": [0.1, 0.15, 0.2, 0.1]}),
 }
 SAMPLERS = {"MH": O.MH, "MALA": O.MALA, "HMC": O.HMC}
-TARGETS = {"iso": O.ISO, "shifted": O.SHIFTED, "rosen": O.ROSEN}
+TARGETS = {"iso": O.ISO, "shifted": O.SHIFTED, "rosen": O.ROSEN, "logit": O.LOGIT}
+
+
+def logit_data(d, ndata=200, lam=100.0, seed=777):
+    """deterministic stand-in for the swiss data (200 x 4 standardised covariates, 0/1 outcome), drawn from the
+    oracle's own Philox streams so that it does not depend on numpy's generators"""
+    X = np.stack([O.normals(seed, i, 0, d) for i in range(ndata)])
+    X = (X - X.mean(0)) / X.std(0, ddof=1)
+    beta = O.normals(seed, ndata, 0, d)
+    u = np.array([O.uniform(seed, i, 1) for i in range(ndata)])
+    y = (u < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
+    return np.ascontiguousarray(X), y, lam
 
 
 def build(name):
@@ -38,6 +53,8 @@ def build(name):
         tparams = np.linspace(-1.0, 1.0, d)
     if tgt == "rosen":
         tparams = np.array([1.0, 100.0, 0.05])
+    if tgt == "logit":
+        tparams = O.logit_params(*logit_data(d))
     sigma = np.array(extra["sigma"], dtype=float) if "sigma" in extra else (np.full(d, 0.5) if smp == "MH" else None)
     return cfg, x0, tparams, sigma
 

@@ -31,7 +31,20 @@ def make_target(K, name, dim, rng):
     if name == "dense":
         C = ar1_precision(dim)
         return K.DenseGaussian(C), O.DENSE, C.reshape(-1)
+    if name == "logit":
+        X, y, lam = logit_data(dim, rng)
+        return K.BayesLogit(X, y, lam), O.LOGIT, O.logit_params(X, y, lam)
     raise KeyError(name)
+
+
+def logit_data(dim, rng, ndata=200, lam=100.0):
+    """Synthetic stand-in for the swiss bank-note data of doc/examples/swiss (200 x 4 standardised covariates,
+    0/1 outcome): standardised Gaussian covariates, outcomes drawn from a logistic model"""
+    X = rng.normal(size=(ndata, dim))
+    X = (X - X.mean(0)) / X.std(0, ddof=1)
+    beta = rng.normal(size=dim)
+    y = (rng.uniform(size=ndata) < 1 / (1 + np.exp(-X @ beta))).astype(np.float64)
+    return np.ascontiguousarray(X), y, lam
 
 
 def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, step=0.1, nleaps=10,

@@ -366,3 +366,81 @@ def test_iostream_destination(K, tmp_path):
     K.run(job)
     assert sorted(os.listdir(tmp_path / "b")) == ["chain1", "chain2", "chain3"]
     assert len(open(tmp_path / "b" / "chain2" / "value.csv").read().splitlines()) == 15
+
+
+# ------------------------------------------------------------------ Bayesian logistic regression (klb_glm.cuh)
+@pytest.mark.parametrize("arith", ["reference", "fma"])
+@pytest.mark.parametrize("dim", [1, 3, 4, 9, 16])
+@pytest.mark.parametrize("sampler", ["HMC", "MALA", "MH"])
+def test_logit_target_bit_exact(K, sampler, dim, arith):
+    """the closures of doc/examples/swiss/HMC/noadaptation/analytical.jl:11-20 on synthetic 200 x dim data:
+    thread-per-chain kernels against the oracle (sequential reduction order, nv = 0); 150 chains = two full CTAs
+    of 64 plus a ragged one"""
+    step = {"HMC": 0.03, "MALA": 0.004, "MH": 0.0}[sampler]
+    mon = ("value", "logtarget") if sampler == "MH" else ("value", "logtarget", "gradlogtarget")
+    job, cfg, x0, tp, sg = build_pair(K, sampler, "logit", nchains=150, dim=dim, nsteps=40, burnin=12, thinning=3,
+                                      step=step, nleaps=6, seed=77, arith=arith, monitor=mon,
+                                      sigma=np.full(dim, 0.08), tuner="accrate", period=6, target_rate=0.7)
+    assert job.plan().nv == 0 and job.plan().warps_per_chain == 0
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    assert 0.02 < out.diagnosticvalues.mean() <= 1.0
+
+
+def test_logit_data_streamed_from_global_memory(K):
+    """a data set too large for shared memory (6000 x 4 = 234 KB with y) is read through L1/L2: same bits"""
+    rng = np.random.default_rng(3)
+    from helpers import logit_data
+    X, y, lam = logit_data(4, rng, ndata=6000, lam=10.0)
+    x0 = synthetic_x0(5, 70, 4) * 0.1
+    p = K.BasicContMuvParameter("p", logtarget=K.BayesLogit(X, y, lam))
+    job = K.BasicMCJob(K.likelihood_model(p, False), K.HMC(0.005, 4), K.BasicMCRange(nsteps=8, burnin=2), {"p": x0},
+                       outopts={"monitor": ["value", "logtarget", "gradlogtarget"], "diagnostics": ["accept"]}, seed=5)
+    from oracle import oracle as O
+    cfg = O.make_config(O.HMC, O.LOGIT, 70, 4, 8, 2, step=0.005, nleaps=4, monitor=7, diagnostics=1, seed=5,
+                        nthreads=O.max_threads())
+    compare_run(job, cfg, x0, O.logit_params(X, y, lam), None)
+
+
+def test_swiss_example_model_form(K, O):
+    """doc/examples/swiss/HMC/noadaptation/analytical.jl as written: a model with Hyperparameter(:λ), Data(:X),
+    Data(:y) vertices before the parameter, whose v0 values reach the target in vertex order; HMC(0.35) needs the
+    real (wide-posterior) swiss data, so the synthetic stand-in uses a smaller step.  One chain and a batch of
+    chains give the same first chain."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as G
+    X, y, lam = G.logit_data(4)
+    t = K.BayesLogit()
+    p = K.BasicContMuvParameter("p", loglikelihood=t.loglikelihood, logprior=t.logprior, gradlogtarget=t.gradient,
+                                nkeys=4)
+    model = K.likelihood_model([K.Hyperparameter("λ"), K.Data("X"), K.Data("y"), p], isindexed=False)
+    v0 = {"λ": lam, "X": X, "y": y, "p": [5.1, -0.9, 8.2, -4.5]}
+    outopts = {"monitor": ["value", "logtarget", "gradlogtarget"], "diagnostics": ["accept"]}
+    job = K.BasicMCJob(model, K.HMC(0.05), K.BasicMCRange(nsteps=3000, burnin=1000), v0, outopts=outopts, seed=9)
+    K.run(job)
+    chain = K.output(job)
+    cfg = O.make_config(O.HMC, O.LOGIT, 1, 4, 3000, 1000, step=0.05, nleaps=10, monitor=7, diagnostics=1, seed=9)
+    ref = O.run(cfg, np.array([v0["p"]]), O.logit_params(X, y, lam))
+    assert_same("value", chain.value, ref["value"][0])
+    assert_same("gradlogtarget", chain.gradlogtarget, ref["gradlogtarget"][0])
+    assert_same("accept", chain.diagnosticvalues, ref["accept"][0])
+    assert 0.5 < K.acceptance(job) <= 1.0
+    # posterior mean close to the mode (Newton), in units of the Laplace standard deviation
+    b = np.zeros(4)
+    for _ in range(50):
+        mu = 1 / (1 + np.exp(-X @ b))
+        H = X.T @ (X * (mu * (1 - mu))[:, None]) + np.eye(4) / lam
+        b = b + np.linalg.solve(H, X.T @ (y - mu) - b / lam)
+    sd = np.sqrt(np.diag(np.linalg.inv(H)))
+    assert np.all(np.abs(K.mean(job) - b) < 0.5 * sd)
+
+
+def test_logit_needs_its_data(K):
+    p = K.BasicContMuvParameter("p", logtarget=K.BayesLogit())
+    with pytest.raises(AssertionError, match="no data"):
+        K.BasicMCJob(K.likelihood_model(p, False), K.MALA(0.1), K.BasicMCRange(nsteps=5), {"p": np.zeros(4)})
+    X = np.ones((10, 17))
+    p = K.BasicContMuvParameter("p", logtarget=K.BayesLogit(X, np.ones(10), 1.0))
+    with pytest.raises(K.KlaraError) as ei:
+        K.BasicMCJob(K.likelihood_model(p, False), K.MALA(0.1), K.BasicMCRange(nsteps=5), {"p": np.zeros(17)})
+    assert ei.value.code == K._lib.KLB_EUNSUPPORTED

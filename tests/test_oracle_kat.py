@@ -148,3 +148,82 @@ def test_uniform_range_and_streams(O):
     assert not np.array_equal(a, O.normals(2, 2, 3, 64))
     # prefix property: element i does not depend on how many elements are drawn
     assert np.array_equal(a[:10], O.normals(1, 2, 3, 10))
+
+
+# ------------------------------------------------------------------ Bayesian logistic regression target
+def test_logit_target_matches_closed_form(O):
+    """ploglikelihood + plogprior and pgradlogtarget of doc/examples/swiss/HMC/noadaptation/analytical.jl:11-20,
+    evaluated in 40-digit arithmetic, against the oracle's restatement"""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    sys_path_golden()
+    import make_golden as G
+    for d in (1, 3, 4, 16):
+        X, y, lam = G.logit_data(d)
+        tp = O.logit_params(X, y, lam)
+        rng = np.random.default_rng(d)
+        for p in rng.normal(scale=2.0, size=(4, d)):
+            for arith in (0, 1):
+                cfg = O.make_config(O.HMC, O.LOGIT, 1, d, 10, arith=arith)
+                assert cfg.nv == 0
+                lt, g = O.eval_target(cfg, p, tp)
+                Xp = [sum(mp.mpf(X[i, j]) * mp.mpf(p[j]) for j in range(d)) for i in range(X.shape[0])]
+                ll = sum(xp * mp.mpf(y[i]) for i, xp in enumerate(Xp)) - sum(mp.log(1 + mp.exp(xp)) for xp in Xp)
+                lp = -mp.mpf(0.5) * (sum(mp.mpf(v) ** 2 for v in p) / lam + d * mp.log(2 * mp.pi * lam))
+                assert abs(mp.mpf(lt) - (ll + lp)) < 1e-12 * abs(ll + lp)
+                r = [mp.mpf(y[i]) - 1 / (1 + mp.exp(-xp)) for i, xp in enumerate(Xp)]
+                for j in range(d):
+                    gj = sum(mp.mpf(X[i, j]) * r[i] for i in range(X.shape[0])) - mp.mpf(p[j]) / lam
+                    assert abs(mp.mpf(g[j]) - gj) < 1e-12 * max(1, abs(gj))
+
+
+def sys_path_golden():
+    import os
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+
+
+def test_logit_descriptor_is_the_reference_closure(K, O):
+    """the descriptor called as a plain function (numpy) agrees with the oracle: it is a valid host-side
+    `loglikelihood` / `logprior` / `gradlogtarget` triple for stock Klara"""
+    sys_path_golden()
+    import make_golden as G
+    X, y, lam = G.logit_data(4)
+    t = K.BayesLogit(X, y, lam)
+    cfg = O.make_config(O.MALA, O.LOGIT, 1, 4, 10)
+    p = np.array([5.1, -0.9, 8.2, -4.5])                     # v0[:p] of the swiss examples
+    lt, g = O.eval_target(cfg, p, O.logit_params(X, y, lam))
+    assert t(p) == pytest.approx(lt, rel=1e-12)
+    assert t.loglikelihood(p) + t.logprior(p) == t(p)
+    np.testing.assert_allclose(t.gradient(p), g, rtol=1e-11)
+
+
+def test_logit_posterior_sampling_sanity(O):
+    """HMC / MALA / MH on the logistic-regression posterior: all three agree with each other and with the
+    Laplace approximation around the posterior mode (Newton iterations in numpy)"""
+    sys_path_golden()
+    import make_golden as G
+    d = 4
+    X, y, lam = G.logit_data(d)
+    tp = O.logit_params(X, y, lam)
+    b = np.zeros(d)
+    for _ in range(50):                                      # Newton: posterior mode and Hessian
+        mu = 1 / (1 + np.exp(-X @ b))
+        H = X.T @ (X * (mu * (1 - mu))[:, None]) + np.eye(d) / lam
+        b = b + np.linalg.solve(H, X.T @ (y - mu) - b / lam)
+    sd = np.sqrt(np.diag(np.linalg.inv(H)))
+    means = {}
+    for name, smp, kw in (("HMC", O.HMC, dict(step=0.1, nleaps=8)), ("MALA", O.MALA, dict(step=0.03)),
+                          ("MH", O.MH, dict())):
+        cfg = O.make_config(smp, O.LOGIT, 32, d, 1500, burnin=500, monitor=1, diagnostics=1, seed=5,
+                            nthreads=O.max_threads(), **kw)
+        x0 = np.tile(b, (32, 1))
+        r = O.run(cfg, x0, tp, sigma=0.5 * sd if smp == O.MH else None)
+        acc = r["accept"].mean()
+        assert 0.15 < acc < 0.999, (name, acc)
+        means[name] = r["value"].reshape(-1, d).mean(0)
+        assert np.all(np.abs(means[name] - b) < 0.35 * sd), (name, means[name], b, sd)   # skewed posterior: mean != mode
+    assert np.all(np.abs(means["HMC"] - means["MALA"]) < 0.1 * sd)
+    assert np.all(np.abs(means["HMC"] - means["MH"]) < 0.15 * sd)

@@ -1,0 +1,16 @@
+import time, numpy as np, klara_b200 as K, sys
+sys.path.insert(0, "tests/golden")
+import make_golden as G
+X, y, lam = G.logit_data(4)
+for smp, name in ((K.HMC(0.05, 10), "HMC"), (K.MALA(0.02), "MALA"), (K.MH(np.full(4, 0.1)), "MH")):
+    N = 148 * 64 * 16
+    x0 = np.random.default_rng(0).normal(size=(N, 4)) * 0.3
+    p = K.BasicContMuvParameter("p", logtarget=K.BayesLogit(X, y, lam))
+    job = K.BasicMCJob(K.likelihood_model(p, False), smp, K.BasicMCRange(nsteps=200, burnin=100), {"p": x0},
+                       outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}, seed=1)
+    job.run(); job.reset(); job.run()
+    ms = job.last_run_ms
+    evals = N * 200 * (10 if name == "HMC" else 1)
+    pl = job.plan()
+    print(name, "N", N, "ms", ms, "target-evals/s %.3e" % (evals / ms * 1e3), "regs", pl.regs_per_thread, "bps", pl.blocks_per_sm,
+          "acc", K.acceptance(job).mean(), flush=True)
