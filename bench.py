@@ -237,12 +237,20 @@ def run_gpu(args, rank, world, local_rank):
     h2d = x0_host.nbytes
     d2h = x0_host.nbytes + lt_host.nbytes + acc_host.nbytes
 
+    e2e_fields = (L.KlbHostField * 3)()
+    for q, (fld, ptr, nb) in enumerate(((L.OUT_STATE, hs.value, x0_host.nbytes), (L.OUT_LOGTARGET, hl.value, lt_host.nbytes),
+                                        (L.OUT_ACCEPT, hl.value + lt_host.nbytes, acc_host.nbytes))):
+        e2e_fields[q].field, e2e_fields[q].host_dst, e2e_fields[q].nbytes = fld, ptr, nb
+
     def e2e_step():
-        L.check(lib.klb_job_set_state(job._h, hx))                 # H2D x0 + initialize! + tuner reset
-        L.check(lib.klb_job_run(job._h))
-        L.check(lib.klb_job_output(job._h, L.OUT_STATE, hs, x0_host.nbytes))
-        L.check(lib.klb_job_output(job._h, L.OUT_LOGTARGET, hl, lt_host.nbytes))
-        L.check(lib.klb_job_output(job._h, L.OUT_ACCEPT, C.c_void_p(hl.value + lt_host.nbytes), acc_host.nbytes))
+        if args.e2e_serial:                                        # the three blocking calls, one after the other
+            L.check(lib.klb_job_set_state(job._h, hx))             # H2D x0 + initialize! + tuner reset
+            L.check(lib.klb_job_run(job._h))
+            L.check(lib.klb_job_output(job._h, L.OUT_STATE, hs, x0_host.nbytes))
+            L.check(lib.klb_job_output(job._h, L.OUT_LOGTARGET, hl, lt_host.nbytes))
+            L.check(lib.klb_job_output(job._h, L.OUT_ACCEPT, C.c_void_p(hl.value + lt_host.nbytes), acc_host.nbytes))
+        else:                                                      # the same work as one pipelined call
+            L.check(lib.klb_job_run_host(job._h, hx, e2e_fields, 3, args.e2e_slices))
 
     e2e_step()
     barrier()
@@ -337,9 +345,10 @@ def run_gpu(args, rank, world, local_rank):
             "cpu_baseline": cb,
             "e2e": {"value": lf_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
-                    "note": "klb_job_set_state(host x0) + klb_job_run + klb_job_output(final state, logtarget chain, "
-                            "accept flags) with pinned host buffers; the 50 GiB of monitored values stay in HBM "
-                            "(output(job) copies them on request)"},
+                    "call": "klb_job_set_state + klb_job_run + klb_job_output x3 (serial)" if args.e2e_serial
+                            else "klb_job_run_host (chain slices pipelined over streams)",
+                    "note": "host x0 in (pinned), final state + logtarget chain + accept flags out (pinned), through the "
+                            "C ABI; the 50 GiB of monitored values stay in HBM (output(job) copies them on request)"},
             "ess": {"mean_ess_per_coordinate": ess_sum / (NCHAINS * DIM), "min_ess": ess_min, "samples_per_chain": NSTEPS - BURNIN,
                     "independent_samples_per_sec": (ess_sum / DIM) / (dev_ms / args.steps * 1e-3),
                     "ess_kernel_ms": ess_ms,
@@ -369,6 +378,8 @@ def main():
     ap.add_argument("--arith", default="reference", choices=["reference", "fma"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--per-step-sync", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e leg through the three blocking calls (set_state, run, output) instead of klb_job_run_host")
+    ap.add_argument("--e2e-slices", type=int, default=0, help="chain slices of the pipelined e2e call (0 = library default)")
     ap.add_argument("--e2e-full", action="store_true", help="also time an end-to-end step that copies every monitored sample to the host")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

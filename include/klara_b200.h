@@ -187,6 +187,22 @@ int klb_job_output(klb_job* job, int field, void* host_dst, int64_t nbytes);
 /* device address and byte size of a field (for zero-copy consumers: NCCL all-gather, torch views) */
 int klb_job_device_ptr(klb_job* job, int field, void** dev_ptr, int64_t* nbytes);
 
+/* run(job) from a host initial value to host results in ONE call:
+ *     klb_job_set_state(job, x0); klb_job_run(job); klb_job_output(job, field_i, dst_i, nbytes_i) for every i
+ * with identical results, but the chains are processed in `nslices` contiguous slices, each on its own CUDA
+ * stream, so that the host->device copy of slice s+1, the kernels of slice s and the device->host copies of
+ * slice s-1 overlap (the chains are independent: src/jobs/jobs.jl:212).  x0 may be NULL: reset(job) + run(job)
+ * from the current state.  nslices <= 0 lets the library choose (about 32 MiB of state per slice, at most 16).  Host buffers
+ * should be pinned (klb_host_alloc) for the copies to overlap; pageable memory works but serialises.
+ * Fails with KLB_ENOTFINITE like klb_job_set_state (the run of the offending job is then discarded). */
+typedef struct {
+  int32_t field;     /* KLB_OUT_* (not KLB_OUT_ESS) */
+  int32_t reserved;
+  void* host_dst;
+  int64_t nbytes;    /* full size of the field, as for klb_job_output */
+} klb_host_field;
+int klb_job_run_host(klb_job* job, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices);
+
 /* ess(output(job)) = ess(chain, :imse) for every coordinate of every chain (src/stats/convergence/ess.jl:3-14,
  * src/stats/variance/mcvar.jl:5,75-105), computed on the device over the monitored values; host_ess
  * (dim x nchains doubles) may be NULL to leave the result on the device (KLB_OUT_ESS). */

@@ -46,6 +46,10 @@ class KlbPlan(C.Structure):
                 ("saved", C.c_int64)]
 
 
+class KlbHostField(C.Structure):
+    _fields_ = [("field", C.c_int32), ("reserved", C.c_int32), ("host_dst", C.c_void_p), ("nbytes", C.c_int64)]
+
+
 class KlaraError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("klara_b200 error %d: %s" % (code, msg))
@@ -65,6 +69,7 @@ SYMBOLS = [
     ("klb_job_run", _int, [_vp]),
     ("klb_job_run_async", _int, [_vp]),
     ("klb_job_sync", _int, [_vp]),
+    ("klb_job_run_host", _int, [_vp, _vp, C.POINTER(KlbHostField), C.c_int32, C.c_int32]),
     ("klb_job_set_chunk", _int, [_vp, _i64]),
     ("klb_job_reset", _int, [_vp]),
     ("klb_job_output", _int, [_vp, _int, _vp, _i64]),

@@ -327,6 +327,27 @@ class BasicMCJob:
     def sync(self):
         L.check(L.lib().klb_job_sync(self._h))
 
+    def run_host(self, x0=None, outputs=None, nslices=0):
+        """reset(job, x0); run(job); output(job) in one pipelined call (klb_job_run_host): the chains go through in
+        `nslices` slices on their own streams so that host->device copies, kernels and device->host copies overlap.
+        `outputs` maps field codes (klara_b200._lib.OUT_*) to writable C-contiguous numpy arrays -- ideally views of
+        pinned memory (klb_host_alloc) -- that receive the fields.  Results are identical to the three separate calls."""
+        outputs = outputs or {}
+        arr = (L.KlbHostField * max(1, len(outputs)))()
+        for i, (field, buf) in enumerate(outputs.items()):
+            if not (isinstance(buf, np.ndarray) and buf.flags.c_contiguous and buf.flags.writeable):
+                raise TypeError("output buffers must be writable C-contiguous numpy arrays")
+            arr[i].field, arr[i].host_dst, arr[i].nbytes = field, buf.ctypes.data, buf.nbytes
+        xp = None
+        if x0 is not None:
+            x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, dtype=np.float64)))
+            if x0.shape != (self.nchains, self.dim):
+                raise AssertionError("initial value has shape %s, job has %s" % (x0.shape, (self.nchains, self.dim)))
+            xp = _ptr(x0)
+        L.check(L.lib().klb_job_run_host(self._h, xp, arr, len(outputs), nslices))
+        self.count = self.range.npoststeps
+        return self
+
     def reset(self, x=None):
         """reset(job) / reset(job, x)        src/jobs/BasicMCJob.jl:187-201"""
         if x is None:

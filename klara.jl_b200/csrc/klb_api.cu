@@ -42,6 +42,7 @@ void klb_launch_stats(const double* value, long long ld, long long npost, long l
 void klb_launch_acceptance(const unsigned char* accept, const double* value, long long ld, long long npost,
                            long long nchains, int dim, double* out, cudaStream_t s);
 
+#define KLB_MAX_SLICES 16
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* fmt, ...) {
@@ -103,6 +104,10 @@ struct klb_job {
   long long chunk;              // transitions per launch (0 = whole run)
   int regs, bps;
   bool timed;
+  // klb_job_run_host: chain slices pipelined over their own streams (H2D | kernels | D2H overlap)
+  cudaStream_t sl_stream[KLB_MAX_SLICES];
+  cudaEvent_t sl_done[KLB_MAX_SLICES];
+  int nsl_streams;
 };
 
 // HMC with one warp per chain and 8 or 16 units per lane (dim 257..1024) runs the warp-specialised kernel
@@ -167,6 +172,7 @@ static void free_job(klb_job* j) {
   cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess); cudaFree(j->accrate);
   cudaFree(j->gX); cudaFree(j->gy);
   for (int q = 0; q < 5; ++q) if (q != KLB_STAT_ESS) cudaFree(j->stat[q]);
+  for (int q = 0; q < j->nsl_streams; ++q) { cudaStreamDestroy(j->sl_stream[q]); cudaEventDestroy(j->sl_done[q]); }
   if (j->ev0) cudaEventDestroy(j->ev0);
   if (j->ev1) cudaEventDestroy(j->ev1);
   if (j->stream) cudaStreamDestroy(j->stream);
@@ -391,6 +397,66 @@ int klb_job_set_target_f64(klb_job* j, int which, const double* host, int64_t n)
   return fail(KLB_EINVAL, "unknown parameter id %d", which);
 }
 
+// KArgs of the chain slice [c0, c0 + nc): every per-chain array advanced to the slice, RNG streams keep their
+// global chain indices
+static void slice_args(const klb_job* j, KArgs& A, long long c0, long long nc) {
+  const long long ld = j->ld, P = j->npost;
+  A.state += c0 * ld; A.lt += c0;
+  A.tune_step += c0; A.tune_cnt += 3 * c0; A.tune_rate += c0;
+  if (A.out_value) A.out_value += c0 * P * ld;
+  if (A.out_lt) A.out_lt += c0 * P;
+  if (A.out_grad) A.out_grad += c0 * P * ld;
+  if (A.out_accept) A.out_accept += c0 * P;
+  A.nchains = nc;
+  A.chain_offset += (unsigned long long)c0;
+}
+
+// initialize!: log-target (+ gradient) of every chain of A, non-finite chains flagged     HMC.jl:106-120
+static int launch_init(klb_job* j, const KArgs& A, cudaStream_t s) {
+  const klb_config& c = j->cfg;
+  if (j->glm) {
+    GArgs G; fill_glm_args(j, A, G);
+    if (klb_glm_init(G, c.arith, j->gdp, glm_smem(j), c.sampler != KLB_SAMPLER_MH, j->flag, s) != 0)
+      return fail(KLB_ECUDA, "logistic-regression init kernel launch failed");
+  } else if (j->dense) {
+    DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
+    if (klb_dense_init(D, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, s) != 0)
+      return fail(KLB_ECUDA, "dense init kernel launch failed");
+  } else if (klb_launch_init(A, c.target, j->gw, j->gnv, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, s) != 0)
+    return fail(KLB_EINVAL, "no init kernel for this configuration");
+  j->launches += 1;
+  CK(cudaGetLastError());
+  return KLB_OK;
+}
+
+// all nsteps transitions of the chains of A (A.nt / i0 / count0 / t0 filled here), in launches of `chunk`
+static int launch_run(klb_job* j, KArgs A, cudaStream_t s) {
+  const klb_config& c = j->cfg;
+  long long done = 0, saved = 0;
+  const long long chunk = j->chunk > 0 ? j->chunk : c.nsteps;
+  while (done < c.nsteps) {
+    const long long nt = (c.nsteps - done) < chunk ? (c.nsteps - done) : chunk;
+    A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global + (unsigned long long)done;
+    if (j->glm) {
+      GArgs G; fill_glm_args(j, A, G);
+      if (klb_glm_launch(G, c.sampler, c.arith, j->gdp, glm_smem(j), s) != 0)
+        return fail(KLB_ECUDA, "logistic-regression kernel launch failed");
+    } else if (j->dense) {
+      DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
+      const char* cl = getenv("KLB_DENSE_CLUSTER");    // thread-block clusters of 2 (default) or 4 CTAs share every slab of C; 1 = no clusters
+      const int cluster = (cl && cl[0] == '4') ? 4 : (cl && cl[0] == '1') ? 1 : 2;   // default: pairs
+      if ((j->dense_mma ? klb_dense_mma_launch(D, c.arith, cluster, s) : klb_dense_launch(D, c.sampler, c.arith, s)) != 0)
+        return fail(KLB_ECUDA, "dense kernel launch failed");
+    } else if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, c.dim == 64ll * j->gw * j->gnv, nullptr, nullptr, s) != 0)
+      return fail(KLB_EINVAL, "no kernel for this configuration");
+    CK(cudaGetLastError());
+    j->launches += 1;
+    done += nt;
+    saved = done <= c.burnin ? 0 : (done - c.burnin - 1) / c.thinning + 1;
+  }
+  return KLB_OK;
+}
+
 static int reset_tune(klb_job* j) {
   // tuner_state: BasicMCTune(step, 0, 0, tuner.period); MH gets step 1.   src/samplers/samplers.jl:29-45
   const double step0 = j->cfg.sampler == KLB_SAMPLER_MH ? 1.0 : j->cfg.step;
@@ -401,7 +467,7 @@ static int reset_tune(klb_job* j) {
   return KLB_OK;
 }
 
-static int init_state(klb_job* j) {
+static int check_params(klb_job* j) {
   const klb_config& c = j->cfg;
   if (c.target == KLB_TARGET_SHIFTED_ISO && !j->have_mu) return fail(KLB_ESTATE, "set KLB_PARAM_MU before the state");
   if (c.sampler == KLB_SAMPLER_MH && !j->have_sigma) return fail(KLB_ESTATE, "set KLB_PARAM_SIGMA before the state");
@@ -414,22 +480,17 @@ static int init_state(klb_job* j) {
       return fail(KLB_ECUDA, "no sm_100a kernel image for the logistic-regression kernel (dp %d)", j->gdp);
     }
   }
+  return KLB_OK;
+}
+
+static int init_state(klb_job* j) {
+  const klb_config& c = j->cfg;
+  { int rc = check_params(j); if (rc) return rc; }
   KArgs A;
   fill_args(j, A);
   const unsigned long long none = std::numeric_limits<unsigned long long>::max();
   CK(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
-  if (j->glm) {
-    GArgs G; fill_glm_args(j, A, G);
-    if (klb_glm_init(G, c.arith, j->gdp, glm_smem(j), c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
-      return fail(KLB_ECUDA, "logistic-regression init kernel launch failed");
-  } else if (j->dense) {
-    DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
-    if (klb_dense_init(D, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
-      return fail(KLB_ECUDA, "dense init kernel launch failed");
-  } else if (klb_launch_init(A, c.target, j->gw, j->gnv, c.arith, c.sampler != KLB_SAMPLER_MH, j->flag, j->stream) != 0)
-    return fail(KLB_EINVAL, "no init kernel for this configuration");
-  j->launches += 1;
-  CK(cudaGetLastError());
+  { int rc = launch_init(j, A, j->stream); if (rc) return rc; }
   unsigned long long f = 0;
   CK(cudaMemcpyAsync(&f, j->flag, sizeof f, cudaMemcpyDeviceToHost, j->stream));
   CK(cudaStreamSynchronize(j->stream));
@@ -475,29 +536,8 @@ int klb_job_run_async(klb_job* j) {
   KArgs A;
   fill_args(j, A);
   CK(cudaEventRecord(j->ev0, j->stream));
-  long long done = 0, saved = 0;
-  const long long chunk = j->chunk > 0 ? j->chunk : c.nsteps;
-  while (done < c.nsteps) {
-    const long long nt = (c.nsteps - done) < chunk ? (c.nsteps - done) : chunk;
-    A.nt = nt; A.i0 = done + 1; A.count0 = saved; A.t0 = j->t_global;
-    if (j->glm) {
-      GArgs G; fill_glm_args(j, A, G);
-      if (klb_glm_launch(G, c.sampler, c.arith, j->gdp, glm_smem(j), j->stream) != 0)
-        return fail(KLB_ECUDA, "logistic-regression kernel launch failed");
-    } else if (j->dense) {
-      DArgs D; D.k = A; D.Cm = j->Cm; D.nv = j->nv;
-      const char* cl = getenv("KLB_DENSE_CLUSTER");    // thread-block clusters of 2 (default) or 4 CTAs share every slab of C; 1 = no clusters
-      const int cluster = (cl && cl[0] == '4') ? 4 : (cl && cl[0] == '1') ? 1 : 2;   // default: pairs
-      if ((j->dense_mma ? klb_dense_mma_launch(D, c.arith, cluster, j->stream) : klb_dense_launch(D, c.sampler, c.arith, j->stream)) != 0)
-        return fail(KLB_ECUDA, "dense kernel launch failed");
-    } else if (chain_dispatch(c.sampler, c.arith, &A, c.target, j->gw, j->gnv, c.dim == 64ll * j->gw * j->gnv, nullptr, nullptr, j->stream) != 0)
-      return fail(KLB_EINVAL, "no kernel for this configuration");
-    CK(cudaGetLastError());
-    j->launches += 1;
-    done += nt;
-    j->t_global += (unsigned long long)nt;
-    saved = done <= c.burnin ? 0 : (done - c.burnin - 1) / c.thinning + 1;
-  }
+  { int rc = launch_run(j, A, j->stream); if (rc) return rc; }
+  j->t_global += (unsigned long long)c.nsteps;
   CK(cudaEventRecord(j->ev1, j->stream));
   j->count = j->npost;
   j->timed = true;
@@ -515,6 +555,93 @@ int klb_job_run(klb_job* j) {
   int rc = klb_job_run_async(j);
   if (rc) return rc;
   return klb_job_sync(j);
+}
+
+static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols);
+
+// set_state + run + output in one pipelined call (header: klb_job_run_host)
+int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices) {
+  if (!j || (nfields > 0 && !fields) || nfields < 0) return fail(KLB_EINVAL, "null argument");
+  const klb_config& c = j->cfg;
+  CK(cudaSetDevice(c.device));
+  if (!x0 && !j->have_state) return fail(KLB_ESTATE, "no initial value: pass x0 or call klb_job_set_state first");
+  { int rc = check_params(j); if (rc) return rc; }
+  const size_t N = (size_t)c.nchains, d = (size_t)c.dim, ld = (size_t)j->ld;
+  // validate the requested fields before anything is enqueued
+  struct Fld { char* p; size_t per_chain, cols_per_chain; };
+  Fld fl[32];
+  if (nfields > 32) return fail(KLB_EINVAL, "at most 32 output fields");
+  for (int q = 0; q < nfields; ++q) {
+    void* p; size_t nb, cols;
+    int rc = field_ptr(j, fields[q].field, &p, &nb, &cols);
+    if (rc) return rc;
+    if (fields[q].field == KLB_OUT_ESS) return fail(KLB_EINVAL, "KLB_OUT_ESS is produced by klb_job_ess, not by a run");
+    if (!fields[q].host_dst) return fail(KLB_EINVAL, "null host buffer for field %d", fields[q].field);
+    if ((size_t)fields[q].nbytes != nb)
+      return fail(KLB_EINVAL, "field %d holds %zu bytes, caller passed %lld", fields[q].field, nb, (long long)fields[q].nbytes);
+    fl[q].p = (char*)p; fl[q].per_chain = nb / N; fl[q].cols_per_chain = cols / N;
+  }
+  int S = nslices;
+  if (S <= 0) {                                    // auto: ~32 MiB of state per slice, at least 2048 chains
+    const size_t bytes = N * d * 8;                // (C3 on one B200: 16 slices 74.1 ms, 8: 75.3, 4: 78.7, serial: 94.3)
+    S = (int)(bytes / (32u << 20));
+    while (S > 1 && N / (size_t)S < 2048) --S;
+  }
+  if (S < 1) S = 1;
+  if (S > KLB_MAX_SLICES) S = KLB_MAX_SLICES;
+  if ((size_t)S > N) S = (int)N;
+  while (j->nsl_streams < S) {
+    CK(cudaStreamCreateWithFlags(&j->sl_stream[j->nsl_streams], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&j->sl_done[j->nsl_streams], cudaEventDisableTiming));
+    j->nsl_streams += 1;
+  }
+  const unsigned long long none = std::numeric_limits<unsigned long long>::max();
+  if (x0) CK(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
+  CK(cudaEventRecord(j->ev0, j->stream));          // slices start after everything already queued on the job stream
+  const double step0 = c.sampler == KLB_SAMPLER_MH ? 1.0 : c.step;
+  for (int q = 0; q < S; ++q) {
+    const size_t c0 = N * (size_t)q / (size_t)S, c1 = N * (size_t)(q + 1) / (size_t)S, nc = c1 - c0;
+    cudaStream_t st = j->sl_stream[q];
+    CK(cudaStreamWaitEvent(st, j->ev0, 0));
+    KArgs A;
+    fill_args(j, A);
+    slice_args(j, A, (long long)c0, (long long)nc);
+    if (x0) {                                      // initialize! / reset(job, x) of the slice
+      CK(cudaMemcpy2DAsync(j->state + c0 * ld, ld * 8, x0 + c0 * d, d * 8, d * 8, nc, cudaMemcpyHostToDevice, st));
+      int rc = launch_init(j, A, st);
+      if (rc) return rc;
+    }
+    // reset(job): tuner records of the slice                                  samplers.jl:29-45
+    klb_launch_fill_tune(j->tune_step + c0, j->tune_cnt + 3 * c0, j->tune_rate + c0, (long long)nc, step0, c.period, st);
+    j->launches += 1;
+    CK(cudaGetLastError());
+    { int rc = launch_run(j, A, st); if (rc) return rc; }
+    for (int f = 0; f < nfields; ++f) {            // output(job), slice by slice
+      const size_t per = fl[f].per_chain, cpc = fl[f].cols_per_chain;
+      char* dst = (char*)fields[f].host_dst + c0 * per;
+      if (cpc && ld != d)                          // odd dim: device columns are padded
+        CK(cudaMemcpy2DAsync(dst, d * 8, fl[f].p + c0 * cpc * ld * 8, ld * 8, d * 8, nc * cpc, cudaMemcpyDeviceToHost, st));
+      else
+        CK(cudaMemcpyAsync(dst, fl[f].p + c0 * per, nc * per, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaEventRecord(j->sl_done[q], st));
+  }
+  for (int q = 0; q < S; ++q) CK(cudaStreamWaitEvent(j->stream, j->sl_done[q], 0));
+  CK(cudaEventRecord(j->ev1, j->stream));
+  j->t_global += (unsigned long long)c.nsteps;
+  j->count = j->npost;
+  j->timed = true;
+  unsigned long long f = none;
+  if (x0) CK(cudaMemcpyAsync(&f, j->flag, sizeof f, cudaMemcpyDeviceToHost, j->stream));
+  CK(cudaStreamSynchronize(j->stream));
+  if (f != none) {
+    j->have_state = false;
+    j->count = 0;
+    return fail(KLB_ENOTFINITE, "Log-target%s not finite: initial value out of support (chain %llu)",
+                c.sampler != KLB_SAMPLER_MH ? " or its gradient" : "", f - 1);
+  }
+  j->have_state = true;
+  return KLB_OK;
 }
 
 int klb_job_reset(klb_job* j) {

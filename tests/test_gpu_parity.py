@@ -444,3 +444,53 @@ def test_logit_needs_its_data(K):
     with pytest.raises(K.KlaraError) as ei:
         K.BasicMCJob(K.likelihood_model(p, False), K.MALA(0.1), K.BasicMCRange(nsteps=5), {"p": np.zeros(17)})
     assert ei.value.code == K._lib.KLB_EUNSUPPORTED
+
+
+# ------------------------------------------------------------------ pipelined host-to-host run
+@pytest.mark.parametrize("sampler,target,dim", [("HMC", "iso", 1024), ("MALA", "rosen", 96), ("MH", "iso", 7),
+                                                ("HMC", "dense", 128), ("HMC", "logit", 4)])
+def test_run_host_equals_separate_calls(K, sampler, target, dim):
+    """klb_job_run_host (chains sliced over streams, copies overlapped with the kernels) gives exactly what
+    set_state + run + output give, for any slice count, including slices that do not divide the chains"""
+    L = K._lib
+    N = 203
+    kw = dict(nchains=N, dim=dim, nsteps=24, burnin=7, thinning=2, step={"HMC": 0.02, "MALA": 0.002, "MH": 0.1}[sampler],
+              nleaps=5, seed=314, sigma=np.full(dim, 0.05), tuner="accrate", period=5, target_rate=0.7)
+    ref_job, cfg, x0, tp, sg = build_pair(K, sampler, target, **kw)
+    ref_job.run()
+    ref = ref_job.output()
+    for nslices in (1, 3, 16, 0):
+        job, *_ = build_pair(K, sampler, target, **kw)
+        # start from somewhere else: run_host must replace the state like reset(job, x0)
+        job.reset(x0[::-1].copy())
+        bufs = {L.OUT_VALUE: np.empty_like(ref.value), L.OUT_LOGTARGET: np.empty_like(ref.logtarget),
+                L.OUT_ACCEPT: np.empty_like(ref.diagnosticvalues), L.OUT_STATE: np.empty((N, dim)),
+                L.OUT_TUNE_STEP: np.empty(N), L.OUT_TUNE_COUNTERS: np.empty((N, 3), dtype=np.int64)}
+        job.run_host(x0, bufs, nslices)
+        assert_same("value", bufs[L.OUT_VALUE], ref.value)
+        assert_same("logtarget", bufs[L.OUT_LOGTARGET], ref.logtarget)
+        assert_same("accept", bufs[L.OUT_ACCEPT], ref.diagnosticvalues)
+        assert_same("state", bufs[L.OUT_STATE], ref_job.pstate_value)
+        assert_same("step", bufs[L.OUT_TUNE_STEP], ref_job.tune.step)
+        assert_same("counters", bufs[L.OUT_TUNE_COUNTERS][:, 2], ref_job.tune.totproposed)
+        assert_same("output() after run_host", job.output().value, ref.value)
+        assert job.last_run_ms > 0
+
+
+def test_run_host_continues_and_rejects_bad_starts(K):
+    L = K._lib
+    job, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", nchains=50, dim=33, nsteps=10, burnin=2, step=0.1, nleaps=3, seed=8)
+    two, *_ = build_pair(K, "HMC", "iso", nchains=50, dim=33, nsteps=10, burnin=2, step=0.1, nleaps=3, seed=8)
+    job.run_host(x0, {}, 4)
+    job.run_host(None, {}, 3)                       # x0 = NULL: reset(job) + run(job) from the current state
+    two.run(); two.reset(); two.run()
+    assert_same("second run", job.output().value, two.output().value)
+    bad = x0.copy()
+    bad[37, 5] = np.nan
+    with pytest.raises(K.KlaraError) as ei:
+        job.run_host(bad, {}, 4)
+    assert ei.value.code == L.KLB_ENOTFINITE and "chain 37" in str(ei.value)
+    with pytest.raises(K.KlaraError):
+        job.run()                                   # no valid state any more
+    with pytest.raises(K.KlaraError, match="bytes"):
+        two.run_host(x0, {L.OUT_STATE: np.empty((3, 3))}, 2)
