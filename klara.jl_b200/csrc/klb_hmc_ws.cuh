@@ -15,8 +15,12 @@
 // The counter-based RNG makes this legal: a draw depends on (seed, chain, transition) only.
 // Results are bit-identical to klb_chain_kernel (same per-element operations, same reduction order).
 #pragma once
+#include <type_traits>
 #include "klb_kernels.cuh"
 
+#ifndef KLB_WS_EXP
+#define KLB_WS_EXP 0
+#endif
 #ifndef KLB_WS_CONSUMER_REGS
 #define KLB_WS_CONSUMER_REGS 192
 #endif
@@ -32,10 +36,53 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
+// One inner leapfrog step of the isotropic target, x += step p; p += 2 (c x) with c = -2h (see TgtIso::kick),
+// software-pipelined by hand: the five operations of an element form a dependent chain (fp64 latency ~8 cycles,
+// issue every 2), and with only a handful of free registers ptxas used to emit the chain of one element back to
+// back (DMUL t; DADD p,t; DADD p,t), leaving the warp stalled ~6 cycles per link whenever the partner consumer
+// could not fill in.  Here each phase runs over a block of KLB_WS_BLK elements before the next phase starts, so
+// dependent instructions are KLB_WS_BLK issue slots apart.  Same operations per element, same bits.
+#ifndef KLB_WS_BLK
+#define KLB_WS_BLK 4
+#endif
+template <bool FMA, int NE>
+__device__ __forceinline__ void iso_leap_step(double (&x)[NE], double (&y)[NE], double step, double c) {
+  constexpr int B = KLB_WS_BLK;
+#pragma unroll
+  for (int b = 0; b < NE; b += B) {
+    if (FMA) {
+#pragma unroll
+      for (int k = 0; k < B; ++k) x[b + k] = __fma_rn(step, y[b + k], x[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) y[b + k] = __fma_rn(c, x[b + k], y[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) y[b + k] = __fma_rn(c, x[b + k], y[b + k]);
+    } else {
+      double t[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) t[k] = __dmul_rn(step, y[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) x[b + k] = __dadd_rn(t[k], x[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) t[k] = __dmul_rn(c, x[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) y[b + k] = __dadd_rn(y[b + k], t[k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) y[b + k] = __dadd_rn(y[b + k], t[k]);
+    }
+  }
+}
+
+struct WsChain {          // per consumer: the chain's scalars between trajectories
+  double lt_cur, step, rate, u_acc;
+  long long accepted, proposed, totproposed, count, thin;
+};
+
 template <class T, int NV, bool FMA, bool FULL>
 __global__ void __launch_bounds__(256, 2)
 klb_hmc_ws_kernel(const KArgs A) {
   constexpr int W = 1;
+  __shared__ WsChain wchain[4];
   __shared__ uint64_t tab[KLB_TAB_LEN];
   __shared__ double2 zstage[4][NV * 32];
   __shared__ unsigned short zqueue[4][KLB_QCAP];
@@ -64,7 +111,9 @@ klb_hmc_ws_kernel(const KArgs A) {
       const klb_stream st = klb_stream_make(A.seed, A.chain_offset + (unsigned long long)c,
                                             A.t0 + 1ull + (unsigned long long)it);
       if (it > 0) bar_sync(bar_empty, 64);         // the consumer has taken the previous transition's draws
+#if KLB_WS_EXP != 2      // timing experiment 2: producers idle (consumer-bound time; results meaningless)
       randn_stage<NV, W, FULL>(st, d, 0, lane, tab, zbuf, zqueue[slot]);
+#endif
       if (lane == 0) uacc[slot] = klb_accept_uniform(&st);
       bar_arrive(bar_full, 64);
     }
@@ -76,18 +125,25 @@ klb_hmc_ws_kernel(const KArgs A) {
   double* const xcol = A.state + c * A.ld;
   double x[2 * NV];
   load_chain<NV, W, FULL>(x, xcol, d, 0, lane);
-  double lt_cur = A.lt[c];
-  Tune tn;
-  tn.step = A.tune_step[c];
-  tn.accepted = A.tune_cnt[3 * c]; tn.proposed = A.tune_cnt[3 * c + 1]; tn.totproposed = A.tune_cnt[3 * c + 2];
-  tn.rate = A.tune_rate[c];
+  // Per-chain scalars that are only touched between trajectories (log-target, tuner record, output cursor, the
+  // accept uniform) are parked in shared memory, so that during the leapfrog loop the registers hold x, p and
+  // enough temporaries for the software-pipelined step (iso_leap_step).  Every lane of the warp computes the same
+  // values, so lane 0 alone writes them back.
+  volatile WsChain* const cs = &wchain[slot];
+  if (lane == 0) {
+    cs->lt_cur = A.lt[c];
+    cs->step = A.tune_step[c];
+    cs->accepted = A.tune_cnt[3 * c]; cs->proposed = A.tune_cnt[3 * c + 1]; cs->totproposed = A.tune_cnt[3 * c + 2];
+    cs->rate = A.tune_rate[c];
+    cs->count = A.count0;
+    cs->thin = (A.i0 > A.burnin) ? klb_mod(A.i0 - A.burnin - 1, A.thinning) : 0;
+  }
+  __syncwarp();
   const bool saving = (A.out_value != nullptr) || (A.out_lt != nullptr) || (A.out_grad != nullptr) ||
                       (A.out_accept != nullptr);
-  long long count = A.count0;
-  long long thin = (A.i0 > A.burnin) ? klb_mod(A.i0 - A.burnin - 1, A.thinning) : 0;
+  const int nt = (int)A.nt;                                                  // klb_job_create: nsteps < 2^31
 
-  for (long long it = 0; it < A.nt; ++it) {
-    const long long irun = A.i0 + it;
+  for (int it = 0; it < nt; ++it) {
     double y[2 * NV];
     bar_sync(bar_full, 64);                                                  // momentum[:] = randn(d) is ready
 #pragma unroll
@@ -95,16 +151,20 @@ klb_hmc_ws_kernel(const KArgs A) {
       const double2 v = zbuf[j * 32 + lane];
       y[2 * j] = v.x; y[2 * j + 1] = v.y;
     }
-    const double u_acc = uacc[slot];
-    if (it + 1 < A.nt) bar_arrive(bar_empty, 64);                            // buffer may be refilled
+    if (lane == 0) cs->u_acc = uacc[slot];
+    if (it + 1 < nt) bar_arrive(bar_empty, 64);                              // buffer may be refilled
 
-    const double step = tn.step;
+    const double step = cs->step;
     const double h = __dmul_rn(0.5, step);
-    double acc[3][4] = {};
+    double k0lane;
+    {
+      double a0[4] = {};
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {                                           // old kinetic energy
-      acc[0][j & 3] = dotacc(y[2 * j], y[2 * j], acc[0][j & 3]);
-      acc[0][j & 3] = dotacc(y[2 * j + 1], y[2 * j + 1], acc[0][j & 3]);
+      for (int j = 0; j < NV; ++j) {                                         // old kinetic energy
+        a0[j & 3] = dotacc(y[2 * j], y[2 * j], a0[j & 3]);
+        a0[j & 3] = dotacc(y[2 * j + 1], y[2 * j + 1], a0[j & 3]);
+      }
+      k0lane = __dadd_rn(__dadd_rn(a0[0], a0[1]), __dadd_rn(a0[2], a0[3]));  // the lane value of team_allsum
     }
     // leapfrog! (src/samplers/samplers.jl:122-134): see klb_chain_kernel for the exact-rewrite notes
 #pragma unroll
@@ -112,7 +172,15 @@ klb_hmc_ws_kernel(const KArgs A) {
       const int i = Geo<NV, W>::elem(j, 0, lane);
       T::template kick<FMA, false>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
     }
+#if KLB_WS_EXP == 1      // timing experiment 1: consumers skip the inner leapfrog steps (producer-bound time)
+    for (int s = A.nleaps; s < A.nleaps; ++s) {
+#else
     for (int s = 1; s < A.nleaps; ++s) {
+#endif
+      if (KLB_WS_BLK > 0 && std::is_same<T, TgtIso>::value) {
+        iso_leap_step<FMA, 2 * NV>(x, y, step, __dmul_rn(-2.0, h));
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const int i = Geo<NV, W>::elem(j, 0, lane);
@@ -121,19 +189,30 @@ klb_hmc_ws_kernel(const KArgs A) {
         T::template kick<FMA, true>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
       }
     }
+    double acc[2][4] = {};
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int i = Geo<NV, W>::elem(j, 0, lane);
       x[2 * j] = Ar<FMA>::ma(step, y[2 * j], x[2 * j]);
       x[2 * j + 1] = Ar<FMA>::ma(step, y[2 * j + 1], x[2 * j + 1]);
       T::template kick<FMA, false>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
-      acc[1][j & 3] = T::template lt_acc<FMA>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], acc[1][j & 3]);
-      acc[2][j & 3] = dotacc(y[2 * j], y[2 * j], acc[2][j & 3]);
-      acc[2][j & 3] = dotacc(y[2 * j + 1], y[2 * j + 1], acc[2][j & 3]);
+      acc[0][j & 3] = T::template lt_acc<FMA>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], acc[0][j & 3]);
+      acc[1][j & 3] = dotacc(y[2 * j], y[2 * j], acc[1][j & 3]);
+      acc[1][j & 3] = dotacc(y[2 * j + 1], y[2 * j + 1], acc[1][j & 3]);
     }
-    double sums[3];
-    team_allsum<3, 1>(acc, sums, nullptr, 0, lane, 0);
+    // canonical reduction (team_allsum, W = 1) of (old kinetic energy, log-target sum, new kinetic energy)
+    double sums[3] = {k0lane, __dadd_rn(__dadd_rn(acc[0][0], acc[0][1]), __dadd_rn(acc[0][2], acc[0][3])),
+                      __dadd_rn(__dadd_rn(acc[1][0], acc[1][1]), __dadd_rn(acc[1][2], acc[1][3]))};
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      double t[3];
+#pragma unroll
+      for (int v = 0; v < 3; ++v) t[v] = __shfl_xor_sync(0xffffffffu, sums[v], o);
+#pragma unroll
+      for (int v = 0; v < 3; ++v) sums[v] = __dadd_rn(sums[v], t[v]);
+    }
     const double lt_new = T::lt_fin(A, sums[1]);
+    double lt_cur = cs->lt_cur;
     const double oldh = __dsub_rn(lt_cur, __dmul_rn(0.5, sums[0]));          // hamiltonian()
     const double newh = __dsub_rn(lt_new, __dmul_rn(0.5, sums[2]));
     const double ratio = __dsub_rn(newh, oldh);
@@ -142,17 +221,31 @@ klb_hmc_ws_kernel(const KArgs A) {
     else {
       const double ex = klb_exp(ratio, tab);
       const double a = (ex != ex) ? ex : (ex < 1.0 ? ex : 1.0);
-      accept = u_acc < a;
+      accept = cs->u_acc < a;
     }
-    if (A.counters_on) { tn.proposed += 1; if (accept) tn.accepted += 1; }
-    tuner_block<2>(A, tn, tab);
+    if (A.counters_on) {                                                     // tuner record: lives in shared memory
+      Tune tn;
+      tn.step = step; tn.accepted = cs->accepted; tn.proposed = cs->proposed; tn.totproposed = cs->totproposed;
+      tn.rate = cs->rate;
+      tn.proposed += 1;
+      if (accept) tn.accepted += 1;
+      tuner_block<2>(A, tn, tab);
+      __syncwarp();
+      if (lane == 0) {
+        cs->step = tn.step; cs->accepted = tn.accepted; cs->proposed = tn.proposed; cs->totproposed = tn.totproposed;
+        cs->rate = tn.rate;
+      }
+    }
     if (accept) {
       store_chain<NV, W, FULL>(x, xcol, d, 0, lane);
       lt_cur = lt_new;
+      if (lane == 0) cs->lt_cur = lt_new;
     } else {
       load_chain<NV, W, FULL>(x, xcol, d, 0, lane);
     }
-    if (irun > A.burnin) {                                                   // in(i, postrange) -> save
+    if (A.i0 + it > A.burnin) {                                              // in(i, postrange) -> save
+      const long long thin = cs->thin, count = cs->count;
+      __syncwarp();
       if (thin == 0) {
         if (saving) {
           const long long col = c * A.npost + count;
@@ -173,15 +266,16 @@ klb_hmc_ws_kernel(const KArgs A) {
             if (A.out_accept) A.out_accept[col] = accept ? 1 : 0;
           }
         }
-        count += 1;
+        if (lane == 0) cs->count = count + 1;
       }
-      thin = (thin + 1 == A.thinning) ? 0 : thin + 1;
+      if (lane == 0) cs->thin = (thin + 1 == A.thinning) ? 0 : thin + 1;
     }
+    __syncwarp();
   }
   if (lane == 0) {
-    A.lt[c] = lt_cur;
-    A.tune_step[c] = tn.step;
-    A.tune_cnt[3 * c] = tn.accepted; A.tune_cnt[3 * c + 1] = tn.proposed; A.tune_cnt[3 * c + 2] = tn.totproposed;
-    A.tune_rate[c] = tn.rate;
+    A.lt[c] = cs->lt_cur;
+    A.tune_step[c] = cs->step;
+    A.tune_cnt[3 * c] = cs->accepted; A.tune_cnt[3 * c + 1] = cs->proposed; A.tune_cnt[3 * c + 2] = cs->totproposed;
+    A.tune_rate[c] = cs->rate;
   }
 }
