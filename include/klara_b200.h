@@ -61,6 +61,11 @@ extern "C" {
 /* tuner: src/tuners/VanillaMCTuner.jl:6-16, src/tuners/AcceptanceRateMCTuner.jl:25-46 */
 #define KLB_TUNER_VANILLA 0
 #define KLB_TUNER_ACCEPTANCE_RATE 1
+/* DualAveragingMCTuner(targetrate, nadapt; ε0bar, h0bar, γ, t0, κ, period, verbose) for HMC:
+ * src/tuners/DualAveragingMCTuner.jl:53-101, src/samplers/HMC.jl:124-133,192-223, iterate/HMC.jl:125-127,142-144,225-248.
+ * Per-chain step AND per-chain number of leapfrog steps, nleaps = max(1, round(λ/step)).  Elementwise and
+ * logistic-regression targets (the dense-precision kernels advance their chains in lockstep tiles). */
+#define KLB_TUNER_DUAL_AVERAGING 2
 
 /* arithmetic: 0 = every product and sum rounded separately, in the reference's evaluation order
  * ((0.5*step)*g first, then the addition: src/samplers/samplers.jl:130-133); 1 = a*b+c contracted
@@ -98,6 +103,8 @@ extern "C" {
 #define KLB_OUT_TUNE_COUNTERS 7  /* int64   3 x nchains        accepted, proposed, totproposed */
 #define KLB_OUT_TUNE_RATE 8      /* double  nchains            sstate.tune.rate (NaN after reset_burnin!) */
 #define KLB_OUT_ESS 9            /* double  dim x nchains      filled by klb_job_ess (device_ptr only after that call) */
+#define KLB_OUT_TUNE_DA 10       /* double  8 x nchains        DualAveragingMCTune: λ, μ, εbar, hbar, hweight, εweight,
+                                                               nleaps of the last transition, sstate.count */
 
 typedef struct klb_job klb_job; /* opaque, library-owned: one batched BasicMCJob */
 
@@ -126,6 +133,13 @@ typedef struct {
                              so results do not depend on how chains are sharded over GPUs) */
   int32_t device;         /* CUDA device ordinal */
   int32_t reserved;
+  /* DualAveragingMCTuner only (target_rate, period, verbose above are shared with the other tuners) */
+  int64_t da_nadapt;      /* nadapt > 0: transitions during which the step adapts */
+  int64_t da_t0;          /* t0 > 0 (default 10) */
+  double da_eps0bar;      /* ε0bar > 0 (default 1) */
+  double da_h0bar;        /* h0bar (default 0) */
+  double da_gamma;        /* γ (default 0.05) */
+  double da_kappa;        /* κ (default 0.75) */
 } klb_config;
 
 /* geometry the library chose for a job (needed by the oracle to reproduce the reduction order) */
@@ -179,7 +193,12 @@ int klb_job_sync(klb_job* job);
 int klb_job_set_chunk(klb_job* job, int64_t nt);
 
 /* reset(job) (BasicMCJob.jl:187-196): tuner records <- (sampler step, 0, 0, period, NaN), count <- 0.
- * The chain state is kept (pstate persists), the RNG counter keeps advancing. */
+ * The chain state is kept (pstate persists), the RNG counter keeps advancing.
+ * DualAveragingMCTuner: reset!(tune, ::HMC, tuner) sets step = 1 (HMC.jl:218) and re-runs initialize_step!, which
+ * in the reference throws (undefined `moment`, samplers.jl:195) as soon as the job has made one transition (the
+ * proposal state's log-target is then no longer NaN); so klb_job_reset / klb_job_set_state / klb_job_run_host(x0)
+ * of a dual-averaging job that has run return KLB_EUNSUPPORTED -- create a new job.  Before the first transition
+ * they do what the reference does: step = 1, μ = log(10). */
 int klb_job_reset(klb_job* job);
 
 /* output(job) (BasicMCJob.jl:279) and job.pstate / job.sstate.tune: copy one field to host. */

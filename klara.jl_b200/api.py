@@ -26,7 +26,7 @@ from . import _lib as L
 from .targets import Target
 
 __all__ = ["BasicContMuvParameter", "Hyperparameter", "Data", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
-           "VanillaMCTuner", "AcceptanceRateMCTuner", "BasicMCTune", "BasicMCJob", "run", "reset", "output",
+           "VanillaMCTuner", "AcceptanceRateMCTuner", "DualAveragingMCTuner", "BasicMCTune", "DualAveragingMCTune", "BasicMCJob", "run", "reset", "output",
            "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "ess", "mean", "mcvar", "mcse", "iact",
            "acceptance"]
 
@@ -172,6 +172,36 @@ class AcceptanceRateMCTuner:
         self.period, self.verbose = int(period), bool(verbose)
 
 
+class DualAveragingMCTuner:
+    """DualAveragingMCTuner(targetrate, nadapt; ε0bar=1., h0bar=0., γ=0.05, t0=10, κ=0.75, period=100, verbose=false)
+    (src/tuners/DualAveragingMCTuner.jl:53-93): Nesterov dual averaging of the HMC leapfrog step (Hoffman & Gelman),
+    with nleaps = max(1, round(λ/step)) per chain, λ = nleaps*leapstep of the sampler.  Greek keywords are spelled
+    out: eps0bar, h0bar, gamma, t0, kappa."""
+    code = L.TUNER_DUAL_AVERAGING
+
+    def __init__(self, targetrate, nadapt, eps0bar=1., h0bar=0., gamma=0.05, t0=10, kappa=0.75, period=100,
+                 verbose=False):
+        assert 0 < targetrate < 1, "Target acceptance rate should be between 0 and 1"
+        assert nadapt > 0, "Number of adaptation steps should be positive"
+        assert eps0bar > 0, "ε0bar should be positive"
+        assert period > 0, "Period over which acceptance rate is reported in verbose mode should be positive"
+        assert t0 > 0, "t0 should be positive"
+        self.targetrate, self.nadapt = float(targetrate), int(nadapt)
+        self.eps0bar, self.h0bar, self.gamma, self.t0, self.kappa = float(eps0bar), float(h0bar), float(gamma), int(t0), float(kappa)
+        self.period, self.verbose = int(period), bool(verbose)
+
+
+class DualAveragingMCTune:
+    """Per-chain DualAveragingMCTune records (src/tuners/DualAveragingMCTuner.jl:1-13) as arrays over chains;
+    `count` is sstate.count."""
+
+    def __init__(self, base, da):
+        self.step, self.accepted, self.proposed, self.totproposed, self.rate = \
+            base.step, base.accepted, base.proposed, base.totproposed, base.rate
+        (self.lam, self.mu, self.epsbar, self.hbar, self.hweight, self.epsweight) = (da[:, i].copy() for i in range(6))
+        self.nleaps, self.count = da[:, 6].astype(np.int64), da[:, 7].astype(np.int64)
+
+
 class BasicMCTune:
     """Per-chain tuner records (src/tuners/tuners.jl:5-25) as arrays over chains."""
 
@@ -279,6 +309,9 @@ class BasicMCJob:
         cfg.diagnostics = L.DIAG_ACCEPT if "accept" in oo["diagnostics"] else 0
         cfg.destination = L.DEST_NONE if oo["destination"] == "none" else L.DEST_NSTATE
         cfg.seed, cfg.chain_offset, cfg.device = seed, chain_offset, device
+        cfg.da_nadapt, cfg.da_t0 = getattr(tuner, "nadapt", 0), getattr(tuner, "t0", 10)
+        cfg.da_eps0bar, cfg.da_h0bar = getattr(tuner, "eps0bar", 1.0), getattr(tuner, "h0bar", 0.0)
+        cfg.da_gamma, cfg.da_kappa = getattr(tuner, "gamma", 0.05), getattr(tuner, "kappa", 0.75)
         self.cfg = cfg
         self._h = C.c_void_p()
         L.check(L.lib().klb_job_create(C.byref(cfg), C.byref(self._h)))
@@ -451,8 +484,11 @@ class BasicMCJob:
     @property
     def tune(self):
         cnt = self._fetch(L.OUT_TUNE_COUNTERS, (self.nchains, 3), np.int64)
-        return BasicMCTune(self._fetch(L.OUT_TUNE_STEP, (self.nchains,)), cnt[:, 0].copy(), cnt[:, 1].copy(),
+        base = BasicMCTune(self._fetch(L.OUT_TUNE_STEP, (self.nchains,)), cnt[:, 0].copy(), cnt[:, 1].copy(),
                            cnt[:, 2].copy(), self._fetch(L.OUT_TUNE_RATE, (self.nchains,)))
+        if isinstance(self.tuner, DualAveragingMCTuner):
+            return DualAveragingMCTune(base, self._fetch(L.OUT_TUNE_DA, (self.nchains, 8)))
+        return base
 
     # -- introspection
     def plan(self):

@@ -31,6 +31,7 @@ int klb_launch_init(const KArgs& A, int target, int W, int NV, int fma, int chec
                     cudaStream_t s);
 void klb_launch_fill_tune(double* step, long long* cnt, double* rate, long long n, double step0, long long period,
                           cudaStream_t s);
+void klb_launch_fill_da(double* da, long long n, double lambda, double mu, double epsbar, double hbar, cudaStream_t s);
 void klb_launch_debug_normals(const uint64_t* tab, uint64_t seed, uint64_t chain, uint64_t t, long long n, double* out,
                               cudaStream_t s);
 void klb_launch_debug_math(const uint64_t* tab, int op, long long n, const double* in, double* out, cudaStream_t s);
@@ -74,6 +75,8 @@ struct klb_job {
   double* tune_step;
   long long* tune_cnt;
   double* tune_rate;
+  double* tune_da;  // DualAveragingMCTuner: 8 doubles per chain
+  bool da, constructed;   // constructed: the first klb_job_set_state (= BasicMCJob constructor) has happened
   double* out_value;
   double* out_lt;
   double* out_grad;
@@ -167,7 +170,7 @@ int klb_device_count(void) {
 static void free_job(klb_job* j) {
   if (!j) return;
   cudaSetDevice(j->cfg.device);
-  cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate);
+  cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate); cudaFree(j->tune_da);
   cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
   cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess); cudaFree(j->accrate);
   cudaFree(j->gX); cudaFree(j->gy);
@@ -196,6 +199,7 @@ static void fill_args(const klb_job* j, KArgs& A) {
                                                 : ((c.tuner == KLB_TUNER_ACCEPTANCE_RATE) || c.verbose != 0);
   A.target_rate = c.target_rate; A.score_k = c.score_k;
   A.seed = c.seed; A.chain_offset = (unsigned long long)c.chain_offset;
+  A.tune_da = j->tune_da; A.da_nadapt = c.da_nadapt; A.da_t0 = c.da_t0; A.da_gamma = c.da_gamma; A.da_kappa = c.da_kappa;
 }
 
 // dynamic shared memory of the thread-per-chain kernels: X and y are staged when they fit
@@ -224,8 +228,21 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     return fail(KLB_EUNSUPPORTED, "the logistic-regression kernels hold one chain per thread: dim <= %d", KLB_GLM_MAXD);
   if (c.target == KLB_TARGET_DENSE && ((c.dim & 1) || c.dim > KLB_DENSE_MAXD))
     return fail(KLB_EUNSUPPORTED, "the dense-precision kernels need an even dim <= %d", KLB_DENSE_MAXD);
-  if (c.tuner != KLB_TUNER_VANILLA && c.tuner != KLB_TUNER_ACCEPTANCE_RATE)
+  if (c.tuner != KLB_TUNER_VANILLA && c.tuner != KLB_TUNER_ACCEPTANCE_RATE && c.tuner != KLB_TUNER_DUAL_AVERAGING)
     return fail(KLB_EINVAL, "unknown tuner %d", c.tuner);
+  if (c.tuner == KLB_TUNER_DUAL_AVERAGING) {
+    if (c.sampler != KLB_SAMPLER_HMC)
+      return fail(KLB_EINVAL, "DualAveragingMCTuner tunes HMC (and NUTS) only; MALA / MH have no tuner_state method for it");
+    if (c.target == KLB_TARGET_DENSE)
+      return fail(KLB_EUNSUPPORTED, "DualAveragingMCTuner gives every chain its own number of leapfrog steps; the "
+                                    "dense-precision kernels advance their chains in lockstep tiles");
+    // DualAveragingMCTuner asserts (src/tuners/DualAveragingMCTuner.jl:76-80)
+    if (!(c.target_rate > 0 && c.target_rate < 1)) return fail(KLB_EINVAL, "Target acceptance rate should be between 0 and 1");
+    if (c.da_nadapt <= 0) return fail(KLB_EINVAL, "Number of adaptation steps should be positive");
+    if (!(c.da_eps0bar > 0)) return fail(KLB_EINVAL, "ε0bar should be positive");
+    if (c.da_t0 <= 0) return fail(KLB_EINVAL, "t0 should be positive");
+  }
+  if (c.nsteps >= 0x7fffffffll) return fail(KLB_EINVAL, "nsteps must be below 2^31");
   if (c.arith != KLB_ARITH_REFERENCE && c.arith != KLB_ARITH_FMA) return fail(KLB_EINVAL, "unknown arith %d", c.arith);
   if (c.nchains <= 0) return fail(KLB_EINVAL, "nchains must be positive");
   if (c.dim <= 0) return fail(KLB_EINVAL, "dim must be positive");
@@ -293,6 +310,8 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   CKJ(cudaMalloc(&j->tune_step, N * sizeof(double)));
   CKJ(cudaMalloc(&j->tune_cnt, 3 * N * sizeof(long long)));
   CKJ(cudaMalloc(&j->tune_rate, N * sizeof(double)));
+  j->da = c.tuner == KLB_TUNER_DUAL_AVERAGING;
+  if (j->da) CKJ(cudaMalloc(&j->tune_da, 8 * N * sizeof(double)));
   CKJ(cudaMalloc(&j->mu, pad * sizeof(double)));
   CKJ(cudaMalloc(&j->sigma, pad * sizeof(double)));
   CKJ(cudaMemset(j->mu, 0, pad * sizeof(double)));
@@ -457,11 +476,34 @@ static int launch_run(klb_job* j, KArgs A, cudaStream_t s) {
   return KLB_OK;
 }
 
-static int reset_tune(klb_job* j) {
-  // tuner_state: BasicMCTune(step, 0, 0, tuner.period); MH gets step 1.   src/samplers/samplers.jl:29-45
-  const double step0 = j->cfg.sampler == KLB_SAMPLER_MH ? 1.0 : j->cfg.step;
-  klb_launch_fill_tune(j->tune_step, j->tune_cnt, j->tune_rate, j->cfg.nchains, step0, j->cfg.period, j->stream);
+// tuner_state: BasicMCTune(step, 0, 0, tuner.period); MH gets step 1 (src/samplers/samplers.jl:29-45).
+// DualAveragingMCTuner: the constructor keeps leapstep (initialize_step! returns it unchanged, see the oracle's note),
+// reset! sets step = 1 (src/samplers/HMC.jl:217-223); mu = log(10*step) either way.
+static double tune_step0(const klb_job* j) {
+  if (j->cfg.sampler == KLB_SAMPLER_MH) return 1.0;
+  if (j->da && j->constructed) return 1.0;
+  return j->cfg.step;
+}
+static int da_refuses_reset(const klb_job* j) {
+  if (j->da && j->t_global > 0)
+    return fail(KLB_EUNSUPPORTED, "reset of a DualAveragingMCTuner job that has run: the reference's reset! throws "
+                                  "(undefined `moment`, src/samplers/samplers.jl:195); create a new job");
+  return KLB_OK;
+}
+static void fill_tune_slice(klb_job* j, size_t c0, size_t nc, cudaStream_t s) {
+  const double step0 = tune_step0(j);
+  klb_launch_fill_tune(j->tune_step + c0, j->tune_cnt + 3 * c0, j->tune_rate + c0, (long long)nc, step0, j->cfg.period, s);
   j->launches += 1;
+  if (j->da) {
+    klb_launch_fill_da(j->tune_da + 8 * c0, (long long)nc, (double)j->cfg.nleaps * j->cfg.step,
+                       klb_log(10 * step0, KLB_TAB), j->cfg.da_eps0bar, j->cfg.da_h0bar, s);
+    j->launches += 1;
+  }
+}
+
+static int reset_tune(klb_job* j) {
+  fill_tune_slice(j, 0, (size_t)j->cfg.nchains, j->stream);
+  j->constructed = true;
   CK(cudaGetLastError());
   j->count = 0;
   return KLB_OK;
@@ -503,8 +545,10 @@ static int init_state(klb_job* j) {
   return reset_tune(j);
 }
 
+
 int klb_job_set_state(klb_job* j, const double* x0) {
   if (!j || !x0) return fail(KLB_EINVAL, "null argument");
+  { int rc = da_refuses_reset(j); if (rc) return rc; }
   CK(cudaSetDevice(j->cfg.device));
   CK(cudaMemcpy2DAsync(j->state, (size_t)j->ld * 8, x0, (size_t)j->cfg.dim * 8, (size_t)j->cfg.dim * 8,
                        (size_t)j->cfg.nchains, cudaMemcpyHostToDevice, j->stream));
@@ -513,6 +557,7 @@ int klb_job_set_state(klb_job* j, const double* x0) {
 
 int klb_job_set_state_device(klb_job* j, const double* x0_dev) {
   if (!j || !x0_dev) return fail(KLB_EINVAL, "null argument");
+  { int rc = da_refuses_reset(j); if (rc) return rc; }
   CK(cudaSetDevice(j->cfg.device));
   if (x0_dev != j->state)   // x0_dev is a dense dim x nchains matrix
     CK(cudaMemcpy2DAsync(j->state, (size_t)j->ld * 8, x0_dev, (size_t)j->cfg.dim * 8, (size_t)j->cfg.dim * 8,
@@ -565,6 +610,7 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
   const klb_config& c = j->cfg;
   CK(cudaSetDevice(c.device));
   if (!x0 && !j->have_state) return fail(KLB_ESTATE, "no initial value: pass x0 or call klb_job_set_state first");
+  { int rc = da_refuses_reset(j); if (rc) return rc; }
   { int rc = check_params(j); if (rc) return rc; }
   const size_t N = (size_t)c.nchains, d = (size_t)c.dim, ld = (size_t)j->ld;
   // validate the requested fields before anything is enqueued
@@ -598,7 +644,6 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
   const unsigned long long none = std::numeric_limits<unsigned long long>::max();
   if (x0) CK(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
   CK(cudaEventRecord(j->ev0, j->stream));          // slices start after everything already queued on the job stream
-  const double step0 = c.sampler == KLB_SAMPLER_MH ? 1.0 : c.step;
   for (int q = 0; q < S; ++q) {
     const size_t c0 = N * (size_t)q / (size_t)S, c1 = N * (size_t)(q + 1) / (size_t)S, nc = c1 - c0;
     cudaStream_t st = j->sl_stream[q];
@@ -612,8 +657,7 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
       if (rc) return rc;
     }
     // reset(job): tuner records of the slice                                  samplers.jl:29-45
-    klb_launch_fill_tune(j->tune_step + c0, j->tune_cnt + 3 * c0, j->tune_rate + c0, (long long)nc, step0, c.period, st);
-    j->launches += 1;
+    fill_tune_slice(j, c0, nc, st);
     CK(cudaGetLastError());
     { int rc = launch_run(j, A, st); if (rc) return rc; }
     for (int f = 0; f < nfields; ++f) {            // output(job), slice by slice
@@ -631,6 +675,7 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
   j->t_global += (unsigned long long)c.nsteps;
   j->count = j->npost;
   j->timed = true;
+  j->constructed = true;
   unsigned long long f = none;
   if (x0) CK(cudaMemcpyAsync(&f, j->flag, sizeof f, cudaMemcpyDeviceToHost, j->stream));
   CK(cudaStreamSynchronize(j->stream));
@@ -646,6 +691,7 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
 
 int klb_job_reset(klb_job* j) {
   if (!j) return fail(KLB_EINVAL, "null argument");
+  { int rc = da_refuses_reset(j); if (rc) return rc; }
   CK(cudaSetDevice(j->cfg.device));
   return reset_tune(j);
 }
@@ -665,6 +711,7 @@ static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols) 
     case KLB_OUT_TUNE_COUNTERS: *p = j->tune_cnt; *nb = 3 * N * 8; break;
     case KLB_OUT_TUNE_RATE: *p = j->tune_rate; *nb = N * 8; break;
     case KLB_OUT_ESS: *p = j->ess; *nb = N * d * 8; break;
+    case KLB_OUT_TUNE_DA: *p = j->tune_da; *nb = 8 * N * 8; break;
     default: return fail(KLB_EINVAL, "unknown field %d", field);
   }
   if (!*p) return fail(KLB_ESTATE, "field %d is not monitored by this job", field);

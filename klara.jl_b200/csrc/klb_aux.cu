@@ -17,6 +17,19 @@ void klb_launch_fill_tune(double* step, long long* cnt, double* rate, long long 
   klb_fill_tune_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(step, cnt, rate, n, step0, period);
 }
 
+// DualAveragingMCTune record of tuner_state / sampler_state / reset! for HMC (src/samplers/HMC.jl:124-133, 192-213,
+// 217-223): [lambda, mu, epsbar, hbar, hweight = NaN, epsweight = NaN, nleaps = 0, count = 0]
+__global__ void klb_fill_da_kernel(double* da, long long n, double lambda, double mu, double epsbar, double hbar) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double* r = da + 8 * c;
+  const double nan = klb_u2d(0x7FF8000000000000ULL);
+  r[0] = lambda; r[1] = mu; r[2] = epsbar; r[3] = hbar; r[4] = nan; r[5] = nan; r[6] = 0.0; r[7] = 0.0;
+}
+void klb_launch_fill_da(double* da, long long n, double lambda, double mu, double epsbar, double hbar, cudaStream_t s) {
+  klb_fill_da_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(da, n, lambda, mu, epsbar, hbar);
+}
+
 __global__ void klb_debug_normals_kernel(const uint64_t* gtab, uint64_t seed, uint64_t chain, uint64_t t, long long n,
                                          double* out) {
   __shared__ uint64_t tab[KLB_TAB_LEN];

@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
     const klb_stream st = klb_stream_make(A.seed, A.chain_offset + (unsigned long long)c,
                                           A.t0 + 1ull + (unsigned long long)it);
     bool accept = false;
-    double lt_new = 0.0, ratio;
+    double lt_new = 0.0, ratio, a_prob = 1.0;
+    int nl = A.nleaps;
     double xs[DP], gs[DP];
     double z[DP];
     glm_randn<DP>(st, d, tab, z);
@@ -183,14 +184,15 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
 #pragma unroll
       for (int j = 0; j < DP; ++j) { k0 = dotacc(z[j], z[j], k0); xs[j] = x[j]; gs[j] = g[j]; }
       const double oldh = __dsub_rn(lt_cur, __dmul_rn(0.5, k0));             // hamiltonian()
-      for (int s = 1; s <= A.nleaps; ++s) {                                  // leapfrog!  samplers.jl:122-134
+      if (A.tuner == 2) nl = da_nleaps(A, c, step);                          // DualAveragingMCTuner: per chain
+      for (int s = 1; s <= nl; ++s) {                                        // leapfrog!  samplers.jl:122-134
 #pragma unroll
         for (int j = 0; j < DP; ++j) {
           z[j] = Ar<FMA>::ma(h, gs[j], z[j]);
           xs[j] = Ar<FMA>::ma(step, z[j], xs[j]);
         }
         // the last gradient evaluation also yields logtarget!(proposal): same Xp, same bits
-        if (s == A.nleaps) Glm<DP, FMA>::template eval<true, true>(G, Xs, ys, tab, d, xs, lt_new, gs);
+        if (s == nl) Glm<DP, FMA>::template eval<true, true>(G, Xs, ys, tab, d, xs, lt_new, gs);
         else { double dummy; Glm<DP, FMA>::template eval<false, true>(G, Xs, ys, tab, d, xs, dummy, gs); }
 #pragma unroll
         for (int j = 0; j < DP; ++j) z[j] = Ar<FMA>::ma(h, gs[j], z[j]);
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
       else {
         const double ex = klb_exp(ratio, tab);
         const double a = (ex != ex) ? ex : (ex < 1.0 ? ex : 1.0);
+        a_prob = a;
         accept = klb_accept_uniform(&st) < a;
       }
     } else if (SAMPLER == 1) {
@@ -242,7 +245,8 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
     }
 
     if (A.counters_on) { tn.proposed += 1; if (accept) tn.accepted += 1; }
-    tuner_block<SAMPLER>(A, tn, tab);
+    if (SAMPLER == 2 && A.tuner == 2) da_block<false>(A, c, tn, nl, a_prob, tab, true);
+    else tuner_block<SAMPLER>(A, tn, tab);
     if (accept) {
 #pragma unroll
       for (int j = 0; j < DP; ++j) { x[j] = xs[j]; if (SAMPLER != 0) g[j] = gs[j]; }

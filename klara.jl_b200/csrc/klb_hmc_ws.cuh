@@ -156,6 +156,7 @@ klb_hmc_ws_kernel(const KArgs A) {
 
     const double step = cs->step;
     const double h = __dmul_rn(0.5, step);
+    const int nl = (A.tuner == 2) ? da_nleaps(A, c, step) : A.nleaps;         // DualAveragingMCTuner: per chain
     double k0lane;
     {
       double a0[4] = {};
@@ -173,9 +174,9 @@ klb_hmc_ws_kernel(const KArgs A) {
       T::template kick<FMA, false>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
     }
 #if KLB_WS_EXP == 1      // timing experiment 1: consumers skip the inner leapfrog steps (producer-bound time)
-    for (int s = A.nleaps; s < A.nleaps; ++s) {
+    for (int s = nl; s < nl; ++s) {
 #else
-    for (int s = 1; s < A.nleaps; ++s) {
+    for (int s = 1; s < nl; ++s) {
 #endif
       if (KLB_WS_BLK > 0 && std::is_same<T, TgtIso>::value) {
         iso_leap_step<FMA, 2 * NV>(x, y, step, __dmul_rn(-2.0, h));
@@ -217,19 +218,21 @@ klb_hmc_ws_kernel(const KArgs A) {
     const double newh = __dsub_rn(lt_new, __dmul_rn(0.5, sums[2]));
     const double ratio = __dsub_rn(newh, oldh);
     bool accept;
+    double a_prob = 1.0;
     if (ratio >= 0.0) accept = true;                                         // min(1., exp(ratio)) = 1 > rand()
     else {
       const double ex = klb_exp(ratio, tab);
       const double a = (ex != ex) ? ex : (ex < 1.0 ? ex : 1.0);
+      a_prob = a;
       accept = cs->u_acc < a;
     }
-    if (A.counters_on) {                                                     // tuner record: lives in shared memory
+    if (A.counters_on || A.tuner == 2) {                                     // tuner record: lives in shared memory
       Tune tn;
       tn.step = step; tn.accepted = cs->accepted; tn.proposed = cs->proposed; tn.totproposed = cs->totproposed;
       tn.rate = cs->rate;
-      tn.proposed += 1;
-      if (accept) tn.accepted += 1;
-      tuner_block<2>(A, tn, tab);
+      if (A.counters_on) { tn.proposed += 1; if (accept) tn.accepted += 1; }
+      if (A.tuner == 2) da_block<true>(A, c, tn, nl, a_prob, tab, lane == 0);
+      else tuner_block<2>(A, tn, tab);
       __syncwarp();
       if (lane == 0) {
         cs->step = tn.step; cs->accepted = tn.accepted; cs->proposed = tn.proposed; cs->totproposed = tn.totproposed;

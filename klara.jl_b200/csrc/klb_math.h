@@ -262,6 +262,13 @@ KLB_HD_NOINLINE double klb_log(double x, const uint64_t* tab) {
 /* ------------------------------------------------- ziggurat standard normal */
 /* Layout of a 64-bit word w:  layer = w & 255, sign = bit 8, mantissa m = w >> 12. */
 
+/* x^y for x > 0 as exp(y*log(x)): the dual-averaging tuner's count^(-kappa) (src/tuners/DualAveragingMCTuner.jl:99).
+ * Relative error <= (|y log x| + 2) ulp -- about 1e-15 for count <= 1e6, kappa = 0.75; exact 1 for x = 1.
+ * Host and device evaluate the same expression, so both sides agree bit for bit. */
+KLB_HD double klb_pow_pos(double x, double y, const uint64_t* tab) {
+  return klb_exp(klb_mul(y, klb_log(x, tab)), tab);
+}
+
 /* Fast path: candidate x = +-(t-1)*X[layer], t = 1.m in [1,2).  Returns 1 when the
  * candidate lies in the layer's rectangle below the density (accept, ~98.8 %). */
 KLB_HD int klb_zig_fast(uint64_t w, const uint64_t* tab, double* x) {

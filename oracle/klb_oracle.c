@@ -57,7 +57,7 @@
 
 enum { ORC_MH = 0, ORC_MALA = 1, ORC_HMC = 2 };
 enum { ORC_ISO = 0, ORC_SHIFTED = 1, ORC_DENSE = 2, ORC_ROSEN = 3, ORC_LOGIT = 4 };
-enum { ORC_VANILLA = 0, ORC_ACCRATE = 1 };
+enum { ORC_VANILLA = 0, ORC_ACCRATE = 1, ORC_DUALAVG = 2 };
 
 typedef struct {
   int32_t sampler, target, tuner, arith;      /* arith 0 = reference order (un-fused), 1 = fma-contracted */
@@ -74,7 +74,15 @@ typedef struct {
                                                  0 = sequential order (one thread per chain: the data-dependent
                                                  targets, klb_glm.cuh) */
   int32_t nthreads;                           /* OpenMP threads over chains; 1 = map(run, jobs) semantics */
+  /* DualAveragingMCTuner(targetrate, nadapt; e0bar, h0bar, gamma, t0, kappa, period, verbose)
+   * src/tuners/DualAveragingMCTuner.jl:53-95 (targetrate = target_rate above) */
+  int64_t da_nadapt, da_t0;
+  double da_eps0bar, da_h0bar, da_gamma, da_kappa;
+  double* da;                                 /* per chain, in/out: the DualAveragingMCTune fields below (8 doubles) */
 } orc_config;
+
+/* DualAveragingMCTune minus the BasicMCTune part (src/tuners/DualAveragingMCTuner.jl:1-13); sstate.count rides along */
+typedef struct { double lambda, mu, epsbar, hbar, hweight, epsweight, nleaps, count; } orc_da;
 
 /* per-chain BasicMCTune (src/tuners/tuners.jl:5-25) */
 typedef struct { double step; int64_t accepted, proposed, totproposed; double rate; } orc_tune;
@@ -346,7 +354,56 @@ void orc_tuner_state(const orc_config* c, orc_tune* t) {
 }
 static int orc_counters_on(const orc_config* c) {
   if (c->sampler == ORC_MH) return c->verbose != 0;                    /* iterate/MH.jl:73-75 */
-  return (c->tuner == ORC_VANILLA && c->verbose) || c->tuner == ORC_ACCRATE; /* iterate/HMC.jl:129-133 */
+  return (c->tuner == ORC_VANILLA && c->verbose) || c->tuner == ORC_ACCRATE ||
+         (c->tuner == ORC_DUALAVG && c->verbose);                      /* iterate/HMC.jl:129-133 */
+}
+
+/* ---- DualAveragingMCTuner for HMC
+ * tuner_state (src/samplers/HMC.jl:124-133) + sampler_state (HMC.jl:192-213):
+ *   step = leapstep, lambda = nleaps*leapstep, ebar = e0bar, hbar = h0bar, counters (0, 0, period), then
+ *   step = initialize_step!(...), mu = log(10*step), count = 0.
+ * initialize_step! (src/samplers/samplers.jl:170-202) returns step0 unchanged for every function-defined target:
+ * it compares hamiltonian(pstate.logtarget, momentum) of the FRESH proposal state with the old one, but its
+ * leapfrog! only calls gradlogtarget! (samplers.jl:131), so pstate.logtarget still holds the NaN the state was
+ * constructed with (BasicContMuvParameterState.jl:107) -> ratio = NaN -> a = 2*(exp(NaN) > 0.5)-1 = -1 ->
+ * `while exp(NaN)^-1 > 2` is false -> the doubling loop (and its reference to the undefined `moment`, :195) is
+ * never entered.  Its randn(d) draw and scratch leapfrog leave no trace in a counter-based RNG.
+ * reset!(tune, ::HMC, ::DualAveragingMCTuner) (HMC.jl:217-223) sets step = 1 (sic), not leapstep; `first` selects. */
+void orc_da_state(const orc_config* c, orc_tune* t, orc_da* d, int first) {
+  t->step = first ? c->step : 1.;
+  t->accepted = 0; t->proposed = 0; t->totproposed = c->period; t->rate = NAN;
+  d->lambda = (double)c->nleaps * c->step;
+  d->epsbar = c->da_eps0bar; d->hbar = c->da_h0bar;
+  d->hweight = NAN; d->epsweight = NAN; d->nleaps = 0.;
+  d->mu = klb_log(10 * t->step, KLB_TAB);
+  d->count = 0.;
+}
+/* tune!(tune, tuner, count, a)                              src/tuners/DualAveragingMCTuner.jl:95-101 */
+static void orc_da_tune(orc_tune* t, orc_da* d, const orc_config* c, double a) {
+  const double count = d->count;
+  d->hweight = 1 / (count + (double)c->da_t0);
+  d->hbar = (1 - d->hweight) * d->hbar + d->hweight * (c->target_rate - a);
+  t->step = klb_exp(d->mu - sqrt(count) * d->hbar / c->da_gamma, KLB_TAB);
+  d->epsweight = klb_pow_pos(count, -c->da_kappa, KLB_TAB);
+  d->epsbar = klb_exp((1 - d->epsweight) * klb_log(d->epsbar, KLB_TAB) + d->epsweight * klb_log(t->step, KLB_TAB), KLB_TAB);
+}
+/* nleaps = max(1, Int(round(lambda/step)))                  src/samplers/iterate/HMC.jl:142-144
+ * round = ties to even.  Int() of a NaN / infinite / huge quotient throws InexactError in the reference (a chain
+ * whose adaptation has diverged kills the job); here such a chain takes one leapfrog step per transition. */
+static int64_t orc_da_nleaps(double lambda, double step) {
+  const double q = rint(lambda / step);
+  if (!(q >= 1.)) return 1;
+  if (q > 2147483647.) return 1;
+  return (int64_t)q;
+}
+/* the DualAveragingMCTuner branch of the burn-in block         src/samplers/iterate/HMC.jl:225-248 */
+static void orc_da_block(const orc_config* c, orc_tune* t, orc_da* d, double a) {
+  if (d->count <= (double)c->da_nadapt) {
+    orc_da_tune(t, d, c, a);
+    if (c->verbose && t->proposed % c->period == 0) { orc_rate(t); orc_reset_burnin(t); }
+  } else {
+    t->step = d->epsbar;
+  }
 }
 /* the burn-in tuner block shared by HMC (:203-224) and MALA (:130-152); MH (:126-140) never tunes */
 static void orc_tuner_block(const orc_config* c, orc_tune* t) {
@@ -389,15 +446,18 @@ static void orc_randn(const orc_model* M, const klb_stream* st, double* z) {
   for (int64_t i = 0; i < M->dp; ++i) z[i] = (i < M->d) ? klb_normal(st, (uint32_t)i, KLB_TAB) : 0.;
 }
 
-static void orc_iterate_hmc(const orc_model* M, orc_pstate* ps, orc_sstate* ss, orc_tune* tune,
+static void orc_iterate_hmc(const orc_model* M, orc_pstate* ps, orc_sstate* ss, orc_tune* tune, orc_da* da,
                             const klb_stream* st) {
   const orc_config* c = M->cfg;
+  if (c->tuner == ORC_DUALAVG) da->count += 1;                         /* job.sstate.count += 1   iterate/HMC.jl:125-127 */
   if (orc_counters_on(c)) tune->proposed += 1;
   orc_randn(M, st, ss->momentum);
   double oldh = orc_hamiltonian(M, ps->logtarget, ss->momentum, ss->scratch);
   memcpy(ss->sp.value, ps->value, M->dp * sizeof(double));
   memcpy(ss->sp.gradlogtarget, ps->gradlogtarget, M->dp * sizeof(double));
-  for (int i = 0; i < c->nleaps; ++i) orc_leapfrog(M, &ss->sp, ss->momentum, tune->step, ss->scratch);
+  int64_t nleaps = c->nleaps;
+  if (c->tuner == ORC_DUALAVG) { nleaps = orc_da_nleaps(da->lambda, tune->step); da->nleaps = (double)nleaps; }
+  for (int64_t i = 0; i < nleaps; ++i) orc_leapfrog(M, &ss->sp, ss->momentum, tune->step, ss->scratch);
   orc_logtarget(M, &ss->sp, ss->scratch);
   double newh = orc_hamiltonian(M, ss->sp.logtarget, ss->momentum, ss->scratch);
   double ratio = newh - oldh;
@@ -412,7 +472,7 @@ static void orc_iterate_hmc(const orc_model* M, orc_pstate* ps, orc_sstate* ss, 
   } else {
     ps->accept = 0;
   }
-  orc_tuner_block(c, tune);
+  if (c->tuner == ORC_DUALAVG) orc_da_block(c, tune, da, a); else orc_tuner_block(c, tune);
 }
 
 static void orc_iterate_mala(const orc_model* M, orc_pstate* ps, orc_sstate* ss, orc_tune* tune,
@@ -550,11 +610,13 @@ int orc_run(const orc_config* cfg, const double* tparams, const double* sigma,
       continue;
     }
     orc_tune tn = tune[c];
+    orc_da da; memset(&da, 0, sizeof da);
+    if (cfg->tuner == ORC_DUALAVG && cfg->da) da = ((const orc_da*)cfg->da)[c];
     int64_t count = 0;
     for (int64_t i = 1; i <= cfg->nsteps; ++i) {                       /* BasicMCJob.jl:219 */
       klb_stream st = klb_stream_make(cfg->seed, cfg->chain_offset + (uint64_t)c, cfg->t0 + (uint64_t)i);
       switch (cfg->sampler) {                                          /* BasicMCJob.jl:224 */
-        case ORC_HMC: orc_iterate_hmc(&M, &ps, &ss, &tn, &st); break;
+        case ORC_HMC: orc_iterate_hmc(&M, &ps, &ss, &tn, &da, &st); break;
         case ORC_MALA: orc_iterate_mala(&M, &ps, &ss, &tn, &st); break;
         default: orc_iterate_mh(&M, &ps, &ss, &tn, &st); break;
       }
@@ -566,6 +628,7 @@ int orc_run(const orc_config* cfg, const double* tparams, const double* sigma,
     memcpy(x + c * d, ps.value, d * sizeof(double));
     logtarget[c] = ps.logtarget;
     tune[c] = tn;
+    if (cfg->tuner == ORC_DUALAVG && cfg->da) ((orc_da*)cfg->da)[c] = da;
     free(buf);
   }
   free(mu_p);

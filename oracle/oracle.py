@@ -14,7 +14,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libklb_oracle.so")
 
 MH, MALA, HMC = 0, 1, 2
 ISO, SHIFTED, DENSE, ROSEN, LOGIT = 0, 1, 2, 3, 4
-VANILLA, ACCRATE = 0, 1
+VANILLA, ACCRATE, DUALAVG = 0, 1, 2
 
 
 class OrcConfig(C.Structure):
@@ -27,6 +27,9 @@ class OrcConfig(C.Structure):
         ("verbose", C.c_int32), ("monitor", C.c_uint32), ("diagnostics", C.c_uint32),
         ("seed", C.c_uint64), ("chain_offset", C.c_uint64), ("t0", C.c_uint64),
         ("nv", C.c_int32), ("nthreads", C.c_int32),
+        ("da_nadapt", C.c_int64), ("da_t0", C.c_int64),
+        ("da_eps0bar", C.c_double), ("da_h0bar", C.c_double), ("da_gamma", C.c_double), ("da_kappa", C.c_double),
+        ("da", C.c_void_p),
     ]
 
 
@@ -35,6 +38,7 @@ class OrcTune(C.Structure):
                 ("totproposed", C.c_int64), ("rate", C.c_double)]
 
 
+DA_DTYPE = np.dtype([(n, "<f8") for n in ("lambda", "mu", "epsbar", "hbar", "hweight", "epsweight", "nleaps", "count")])
 TUNE_DTYPE = np.dtype([("step", "<f8"), ("accepted", "<i8"), ("proposed", "<i8"),
                        ("totproposed", "<i8"), ("rate", "<f8")])
 
@@ -81,6 +85,8 @@ def lib():
         L.orc_npoststeps.argtypes = [C.c_int64] * 3
         L.orc_tuner_state.restype = None
         L.orc_tuner_state.argtypes = [C.POINTER(OrcConfig), C.c_void_p]
+        L.orc_da_state.restype = None
+        L.orc_da_state.argtypes = [C.POINTER(OrcConfig), C.c_void_p, C.c_void_p, C.c_int]
         L.orc_run.restype = C.c_int
         L.orc_run.argtypes = [C.POINTER(OrcConfig)] + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 4
         L.orc_eval_target.restype = C.c_int
@@ -153,7 +159,8 @@ def npoststeps(burnin, thinning, nsteps):
 
 def make_config(sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, step=0.1, nleaps=10,
                 tuner=VANILLA, target_rate=0.574, score_k=7.0, period=100, verbose=0,
-                monitor=1, diagnostics=0, seed=0, chain_offset=0, t0=0, arith=0, nv=None, nthreads=1):
+                monitor=1, diagnostics=0, seed=0, chain_offset=0, t0=0, arith=0, nv=None, nthreads=1,
+                nadapt=1000, eps0bar=1.0, h0bar=0.0, gamma=0.05, da_t0=10, kappa=0.75):
     cfg = OrcConfig()
     cfg.sampler, cfg.target, cfg.tuner, cfg.arith = sampler, target, tuner, arith
     cfg.nchains, cfg.dim, cfg.nsteps, cfg.burnin, cfg.thinning = nchains, dim, nsteps, burnin, thinning
@@ -163,6 +170,9 @@ def make_config(sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, ste
     cfg.seed, cfg.chain_offset, cfg.t0 = seed, chain_offset, t0
     cfg.nv = (0 if target == LOGIT else plan_nv(dim)) if nv is None else nv   # LOGIT: sequential order
     cfg.nthreads = nthreads
+    cfg.da_nadapt, cfg.da_t0 = nadapt, da_t0
+    cfg.da_eps0bar, cfg.da_h0bar, cfg.da_gamma, cfg.da_kappa = eps0bar, h0bar, gamma, kappa
+    cfg.da = None
     return cfg
 
 
@@ -173,6 +183,20 @@ def tuner_state(cfg):
     t["step"], t["accepted"], t["proposed"] = one.step, one.accepted, one.proposed
     t["totproposed"], t["rate"] = one.totproposed, one.rate
     return t
+
+
+def da_state(cfg, first=True):
+    """(tune, da) records of tuner_state + sampler_state for HMC with a DualAveragingMCTuner; first=False gives
+    what reset!(tune, sampler, tuner) leaves (step = 1)"""
+    t = np.zeros(cfg.nchains, dtype=TUNE_DTYPE)
+    d = np.zeros(cfg.nchains, dtype=DA_DTYPE)
+    one, oned = OrcTune(), (C.c_double * 8)()
+    lib().orc_da_state(C.byref(cfg), C.byref(one), oned, int(first))
+    t["step"], t["accepted"], t["proposed"] = one.step, one.accepted, one.proposed
+    t["totproposed"], t["rate"] = one.totproposed, one.rate
+    for i, n in enumerate(DA_DTYPE.names):
+        d[n] = oned[i]
+    return t, d
 
 
 def eval_target(cfg, x, tparams=None):
@@ -186,7 +210,7 @@ def eval_target(cfg, x, tparams=None):
     return lt.value, g
 
 
-def run(cfg, x0, tparams=None, sigma=None, tune=None, logtarget=None):
+def run(cfg, x0, tparams=None, sigma=None, tune=None, logtarget=None, da=None):
     """Run all chains.  x0: (nchains, dim) array (row c = chain c, i.e. Julia's d x nchains
     column-major matrix).  Returns dict with final state, tune records and the monitored output
     in the NState layout: value (nchains, npost, dim), logtarget / accept (nchains, npost)."""
@@ -195,7 +219,13 @@ def run(cfg, x0, tparams=None, sigma=None, tune=None, logtarget=None):
     npost = npoststeps(cfg.burnin, cfg.thinning, cfg.nsteps)
     tp = None if tparams is None else np.ascontiguousarray(tparams, dtype=np.float64)
     sg = None if sigma is None else np.ascontiguousarray(sigma, dtype=np.float64)
-    tune = tuner_state(cfg) if tune is None else tune.copy()
+    if cfg.tuner == DUALAVG:
+        t0_, d0_ = da_state(cfg)
+        tune = t0_ if tune is None else tune.copy()
+        da = d0_ if da is None else da.copy()
+        cfg.da = da.ctypes.data
+    else:
+        tune = tuner_state(cfg) if tune is None else tune.copy()
     initialized = logtarget is not None
     lt = np.zeros(N) if logtarget is None else np.array(logtarget, dtype=np.float64)
     ov = np.zeros((N, npost, d)) if cfg.monitor & 1 else None
@@ -206,7 +236,8 @@ def run(cfg, x0, tparams=None, sigma=None, tune=None, logtarget=None):
                        _ptr(ov), _ptr(ol), _ptr(og), _ptr(oa))
     if rc:
         raise ValueError("oracle: initial log-target/gradient not finite in chain %d" % (-rc - 1))
-    return {"x": x, "logtarget_state": lt, "tune": tune, "value": ov, "logtarget": ol,
+    cfg.da = None
+    return {"x": x, "logtarget_state": lt, "tune": tune, "da": da, "value": ov, "logtarget": ol,
             "gradlogtarget": og, "accept": oa, "npost": npost}
 
 

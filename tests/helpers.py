@@ -50,7 +50,7 @@ def logit_data(dim, rng, ndata=200, lam=100.0):
 def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, step=0.1, nleaps=10,
                tuner="vanilla", target_rate=0.574, period=100, verbose=False, monitor=("value", "logtarget"),
                diagnostics=("accept",), seed=1234, arith="reference", chain_offset=0, x0=None, sigma=None,
-               device=0, rng_seed=0):
+               device=0, rng_seed=0, nadapt=1000):
     rng = np.random.default_rng(rng_seed)
     tgt, tcode, tparams = make_target(K, target, dim, rng)
     if x0 is None:
@@ -62,7 +62,9 @@ def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, s
         smp = K.MALA(step)
     else:
         smp = K.HMC(step, nleaps)
+    da_kw = dict(nadapt=nadapt, eps0bar=1.0, h0bar=0.0, gamma=0.05, t0=10, kappa=0.75)
     tun = K.VanillaMCTuner(period=period, verbose=verbose) if tuner == "vanilla" else \
+        K.DualAveragingMCTuner(target_rate, period=period, verbose=verbose, **da_kw) if tuner == "dualavg" else \
         K.AcceptanceRateMCTuner(target_rate, period=period, verbose=verbose)
     p = K.BasicContMuvParameter("p", logtarget=tgt)
     model = K.likelihood_model(p, False)
@@ -72,9 +74,10 @@ def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, s
                        chain_offset=chain_offset, device=device)
     mon = sum({"value": 1, "logtarget": 2, "gradlogtarget": 4}[m] for m in monitor)
     cfg = O.make_config(SAMPLERS[sampler], tcode, nchains, dim, nsteps, burnin, thinning, step, nleaps,
-                        O.VANILLA if tuner == "vanilla" else O.ACCRATE, target_rate, 7.0, period, int(verbose),
-                        mon, 1 if "accept" in diagnostics else 0, seed, chain_offset, 0,
-                        1 if arith == "fma" else 0, job.plan().nv, O.max_threads())
+                        {"vanilla": O.VANILLA, "accrate": O.ACCRATE, "dualavg": O.DUALAVG}[tuner], target_rate, 7.0,
+                        period, int(verbose), mon, 1 if "accept" in diagnostics else 0, seed, chain_offset, 0,
+                        1 if arith == "fma" else 0, job.plan().nv, O.max_threads(), nadapt=nadapt, eps0bar=1.0, h0bar=0.0,
+                        gamma=0.05, da_t0=10, kappa=0.75)
     return job, cfg, x0, tparams, sigma
 
 
@@ -114,4 +117,10 @@ def compare_run(job, cfg, x0, tparams, sigma, t0=0):
     assert_same("tune.proposed", tn.proposed, ref["tune"]["proposed"])
     assert_same("tune.totproposed", tn.totproposed, ref["tune"]["totproposed"])
     assert_same("tune.rate", tn.rate, ref["tune"]["rate"])
+    if ref.get("da") is not None:
+        for mine, theirs in (("lam", "lambda"), ("mu", "mu"), ("epsbar", "epsbar"), ("hbar", "hbar"), ("hweight", "hweight"),
+                             ("epsweight", "epsweight")):
+            assert_same("tune." + mine, getattr(tn, mine), ref["da"][theirs])
+        assert_same("tune.nleaps", tn.nleaps, ref["da"]["nleaps"].astype(np.int64))
+        assert_same("sstate.count", tn.count, ref["da"]["count"].astype(np.int64))
     return out, ref

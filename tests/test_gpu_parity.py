@@ -494,3 +494,58 @@ def test_run_host_continues_and_rejects_bad_starts(K):
         job.run()                                   # no valid state any more
     with pytest.raises(K.KlaraError, match="bytes"):
         two.run_host(x0, {L.OUT_STATE: np.empty((3, 3))}, 2)
+
+
+# ------------------------------------------------------------------ DualAveragingMCTuner (HMC)
+@pytest.mark.parametrize("arith", ["reference", "fma"])
+@pytest.mark.parametrize("target,dim", [("iso", 1024), ("iso", 700), ("iso", 64), ("iso", 7), ("iso", 2048),
+                                        ("shifted", 100), ("rosen", 96), ("logit", 4)])
+def test_dual_averaging_hmc_bit_exact(K, target, dim, arith):
+    """DualAveragingMCTuner (src/tuners/DualAveragingMCTuner.jl:95-101, iterate/HMC.jl:125-127,142-144,225-248):
+    per-chain step and per-chain nleaps = max(1, round(λ/step)); adaptation for nadapt transitions, then step = εbar.
+    Warp-specialised kernel (dim 1024, 700), fused kernel, 4-warp teams (2048), thread-per-chain (logit)."""
+    step = {"iso": 0.8 / np.sqrt(dim), "shifted": 0.08, "rosen": 0.01, "logit": 0.02}[target]
+    job, cfg, x0, tp, sg = build_pair(K, "HMC", target, nchains=37, dim=dim, nsteps=70, burnin=20, thinning=2, step=step,
+                                      nleaps=40 if target == "iso" else 6, seed=2718, arith=arith, tuner="dualavg", target_rate=0.651, nadapt=45,
+                                      verbose=(dim % 2 == 0), period=10)
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    tn = job.tune
+    assert (tn.count == 70).all() and len(np.unique(tn.step)) > 1 and (tn.step == tn.epsbar).all()
+    assert 0.2 < out.diagnosticvalues.mean() <= 1.0
+    if target == "iso":
+        assert len(np.unique(tn.nleaps)) > 1            # chains really run different numbers of leapfrog steps
+
+
+def test_dual_averaging_chunks_shards_and_reset_rule(K, O):
+    L = K._lib
+    kw = dict(nchains=24, dim=130, nsteps=40, burnin=10, step=0.05, nleaps=8, seed=99, tuner="dualavg", target_rate=0.8,
+              nadapt=25)
+    whole, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", **kw)
+    whole.run()
+    chunked, *_ = build_pair(K, "HMC", "iso", **kw)
+    chunked.set_chunk(7)
+    chunked.run()
+    assert_same("chunked", chunked.output().value, whole.output().value)
+    assert_same("chunked step", chunked.tune.step, whole.tune.step)
+    shard, *_ = build_pair(K, "HMC", "iso", **dict(kw, nchains=10), chain_offset=5)
+    shard.run()
+    assert_same("shard", shard.output().value, whole.output().value[5:15])
+    # reset!(tune, ::HMC, ::DualAveragingMCTuner) throws in the reference once the job has run
+    for call in (lambda: whole.reset(), lambda: whole.reset(x0), lambda: whole.run_host(x0, {}, 2)):
+        with pytest.raises(K.KlaraError) as ei:
+            call()
+        assert ei.value.code == L.KLB_EUNSUPPORTED
+    # before the first transition reset gives step = 1, mu = log(10)                    (src/samplers/HMC.jl:217-223)
+    fresh, *_ = build_pair(K, "HMC", "iso", **kw)
+    assert (fresh.tune.step == 0.05).all() and np.allclose(fresh.tune.mu, np.log(0.5), rtol=1e-15)
+    fresh.reset()
+    tn = fresh.tune
+    assert (tn.step == 1.0).all() and np.allclose(tn.mu, np.log(10.0), rtol=1e-15) and (tn.lam == 8 * 0.05).all()
+    t_ref, d_ref = O.da_state(cfg, first=False)
+    assert_same("reset mu", tn.mu, d_ref["mu"][:24])
+    # dual averaging is an HMC tuner; dense targets are refused
+    with pytest.raises(K.KlaraError):
+        build_pair(K, "MALA", "iso", nchains=4, dim=8, nsteps=5, tuner="dualavg")
+    with pytest.raises(K.KlaraError) as ei:
+        build_pair(K, "HMC", "dense", nchains=4, dim=8, nsteps=5, tuner="dualavg")
+    assert ei.value.code == L.KLB_EUNSUPPORTED

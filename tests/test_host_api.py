@@ -35,7 +35,7 @@ def test_config_struct_matches_header(K):
             if decl:
                 names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
         assert names == [f[0] for f in cls._fields_], struct
-    assert C.sizeof(K._lib.KlbConfig) == 144
+    assert C.sizeof(K._lib.KlbConfig) == 192
 
 
 def test_enums_match_header(K):
@@ -46,6 +46,8 @@ def test_enums_match_header(K):
                   ("TARGET_ISO", "KLB_TARGET_ISO"), ("TARGET_SHIFTED_ISO", "KLB_TARGET_SHIFTED_ISO"),
                   ("TARGET_DENSE", "KLB_TARGET_DENSE"), ("TARGET_ROSENBROCK", "KLB_TARGET_ROSENBROCK"),
                   ("TUNER_VANILLA", "KLB_TUNER_VANILLA"), ("TUNER_ACCEPTANCE_RATE", "KLB_TUNER_ACCEPTANCE_RATE"),
+                  ("TUNER_DUAL_AVERAGING", "KLB_TUNER_DUAL_AVERAGING"), ("TARGET_LOGIT", "KLB_TARGET_LOGIT"),
+                  ("PARAM_LOGIT_LAMBDA", "KLB_PARAM_LOGIT_LAMBDA"), ("OUT_TUNE_DA", "KLB_OUT_TUNE_DA"),
                   ("KLB_ENOTFINITE", "KLB_ENOTFINITE"), ("KLB_ECUDA", "KLB_ECUDA"), ("OUT_VALUE", "KLB_OUT_VALUE"),
                   ("OUT_TUNE_RATE", "KLB_OUT_TUNE_RATE"), ("PARAM_SIGMA", "KLB_PARAM_SIGMA"),
                   ("MONITOR_GRADLOGTARGET", "KLB_MONITOR_GRADLOGTARGET"), ("DEST_NONE", "KLB_DEST_NONE")]:

@@ -227,3 +227,70 @@ def test_logit_posterior_sampling_sanity(O):
         assert np.all(np.abs(means[name] - b) < 0.35 * sd), (name, means[name], b, sd)   # skewed posterior: mean != mode
     assert np.all(np.abs(means["HMC"] - means["MALA"]) < 0.1 * sd)
     assert np.all(np.abs(means["HMC"] - means["MH"]) < 0.15 * sd)
+
+
+# ------------------------------------------------------------------ DualAveragingMCTuner
+def test_dual_averaging_tune_formula(O):
+    """tune!(tune, tuner, count, a) (src/tuners/DualAveragingMCTuner.jl:95-101) re-evaluated with libm along the
+    accept probabilities the oracle saw: hweight, hbar, step, εweight, εbar after every transition"""
+    cfg = O.make_config(O.HMC, O.ISO, 1, 8, 60, step=0.4, nleaps=3, tuner=O.DUALAVG, target_rate=0.651, nadapt=40,
+                        monitor=3, diagnostics=1, seed=12, gamma=0.05, da_t0=10, kappa=0.75)
+    x0 = O.normals(12, 0, 0, 8)[None]
+    t0, d0 = O.da_state(cfg)
+    assert t0["step"][0] == 0.4 and d0["lambda"][0] == 3 * 0.4 and d0["mu"][0] == pytest.approx(math.log(4.0), rel=1e-15)
+    assert d0["epsbar"][0] == 1.0 and d0["hbar"][0] == 0.0 and t0["totproposed"][0] == 100 and d0["count"][0] == 0
+    tr, dr = O.da_state(cfg, first=False)                                   # reset!: step = 1 (HMC.jl:218)
+    assert tr["step"][0] == 1.0 and dr["mu"][0] == pytest.approx(math.log(10.0), rel=1e-15)
+    # replay one transition at a time (nsteps = 1 jobs chained through state, tune and da records)
+    tune, da, x, lt = t0, d0, x0, None
+    step, hbar, epsbar, mu = 0.4, 0.0, 1.0, math.log(4.0)
+    for i in range(1, 61):
+        c1 = O.make_config(O.HMC, O.ISO, 1, 8, 1, step=0.4, nleaps=3, tuner=O.DUALAVG, target_rate=0.651, nadapt=40,
+                           monitor=3, diagnostics=1, seed=12, t0=i - 1)
+        nl_expect = max(1, int(round(1.2 / step)))                           # Python round = ties to even, like Julia's
+        lt_before = -float(np.dot(x[0], x[0]))
+        r = O.run(c1, x, tune=tune, da=da, logtarget=None if lt is None else lt)
+        tune, da, x, lt = r["tune"], r["da"], r["x"], r["logtarget_state"]
+        assert da["nleaps"][0] == nl_expect and da["count"][0] == i
+        # the accept probability is not exported; recompute a = min(1, exp(H' - H)) from scratch in numpy
+        z = O.normals(12, 0, i, 8)
+        q, p = r_prev.copy() if i > 1 else x0[0].copy(), z.copy()
+        h = 0.5 * step
+        for _ in range(nl_expect):
+            p = p + h * (-2 * q); q = q + step * p; p = p + h * (-2 * q)
+        a = min(1.0, math.exp((-np.dot(q, q) - 0.5 * np.dot(p, p)) - (lt_before - 0.5 * np.dot(z, z))))
+        if i <= 40:
+            hw = 1 / (i + 10)
+            hbar = (1 - hw) * hbar + hw * (0.651 - a)
+            step = math.exp(mu - math.sqrt(i) * hbar / 0.05)
+            ew = i ** (-0.75)
+            epsbar = math.exp((1 - ew) * math.log(epsbar) + ew * math.log(step))
+            assert da["hweight"][0] == pytest.approx(hw, rel=1e-15) and da["epsweight"][0] == pytest.approx(ew, rel=1e-13)
+        else:
+            step = epsbar                                                    # iterate/HMC.jl:246
+        assert da["hbar"][0] == pytest.approx(hbar, rel=1e-9, abs=1e-12)
+        assert tune["step"][0] == pytest.approx(step, rel=1e-9)
+        assert da["epsbar"][0] == pytest.approx(epsbar, rel=1e-9)
+        step, hbar, epsbar = float(tune["step"][0]), float(da["hbar"][0]), float(da["epsbar"][0])   # no drift
+        r_prev = x[0].copy()
+    assert 0.2 < step < 1.5
+
+
+def test_dual_averaging_reaches_target_rate(O):
+    """after adaptation the acceptance rate sits near the target (Hoffman & Gelman's criterion); verbose counters
+    follow iterate/HMC.jl:129-133,229-243"""
+    # (with few leapfrog steps nleaps = round(λ/step) makes the acceptance rate a step function of the step size and
+    # the averaged εbar can land on either side of a jump; λ = 3 with ~6-9 steps is smooth enough)
+    for target in (0.651, 0.8):
+        cfg = O.make_config(O.HMC, O.ISO, 64, 64, 1200, burnin=600, step=0.1, nleaps=30, tuner=O.DUALAVG,
+                            target_rate=target, nadapt=600, monitor=1, diagnostics=1, seed=5, verbose=1, period=100,
+                            nthreads=O.max_threads())
+        x0 = np.stack([O.normals(5, c, 0, 64) for c in range(64)])
+        r = O.run(cfg, x0)
+        assert abs(r["accept"].mean() - target) < 0.06
+        assert np.all(r["da"]["count"] == 1200) and np.all(r["tune"]["step"] == r["da"]["epsbar"])
+        # 6 periods of 100 inside nadapt were reset into totproposed (initially = period); the rest keeps counting
+        assert np.all(r["tune"]["totproposed"] == 700) and np.all(r["tune"]["proposed"] == 600)
+    cfg = O.make_config(O.HMC, O.ISO, 2, 4, 50, step=0.3, nleaps=2, tuner=O.DUALAVG, nadapt=10, monitor=1, seed=5)
+    r = O.run(cfg, np.zeros((2, 4)) + 0.1)
+    assert np.all(r["tune"]["proposed"] == 0) and np.all(r["tune"]["totproposed"] == 100)    # not verbose: no counters
