@@ -8,7 +8,8 @@
 #   likelihood_model(p, false)                               src/models/generators.jl:18
 #   MH(sigma::Vector), MALA(driftstep), HMC(leapstep, nleaps)   src/samplers/{MH,MALA,HMC}.jl
 #   BasicMCRange(nsteps=, burnin=, thinning=)                src/ranges/BasicMCRange.jl:33
-#   VanillaMCTuner(), AcceptanceRateMCTuner(rate)            src/tuners/
+#   VanillaMCTuner(), AcceptanceRateMCTuner(rate), DualAveragingMCTuner(rate, nadapt)   src/tuners/
+#   Hyperparameter(:λ), Data(:X) vertices whose v0 values reach the target (BayesLogit)   src/variables/variables.jl
 #   BasicMCJob(model, sampler, mcrange, v0; tuner, outopts), run, reset, output   src/jobs/BasicMCJob.jl
 #
 # Batch extension: v0 = Dict(:p => Matrix{Float64}(d, nchains)) (one column per chain).  Stock Klara has no
@@ -18,7 +19,7 @@ module KlaraB200
 using LinearAlgebra: dot
 import Statistics: mean      # Klara adds methods to mean (src/stats/mean.jl:7-11); so does the shim
 
-export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, DenseGaussian, ess, mcvar, mcse, iact, acceptance, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
+export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, DenseGaussian, BayesLogit, Hyperparameter, Data, DualAveragingMCTuner, run_host, ess, mcvar, mcse, iact, acceptance, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
        BasicMCRange, VanillaMCTuner, AcceptanceRateMCTuner, BasicMCJob, run, reset, output
 
 const LIB = get(ENV, "KLARA_B200_LIB", "libklara_b200.so")
@@ -37,12 +38,23 @@ Rosenbrock() = Rosenbrock(1.0, 100.0, 0.05)
 struct DenseGaussian <: Target; C::Matrix{Float64}; end
 (t::DenseGaussian)(z::Vector{Float64}) = -dot(z, t.C*z)
 gradient(t::DenseGaussian) = z -> -2 .* (t.C*z)
-code(::IsoGaussian) = 0; code(::ShiftedIsoGaussian) = 1; code(::DenseGaussian) = 2; code(::Rosenbrock) = 3
+# Bayesian logistic regression, N(0, λI) prior: the closures of doc/examples/swiss/HMC/noadaptation/analytical.jl:11-20.
+# BayesLogit() is bound by BasicMCJob from v0[:λ], v0[:X], v0[:y] (the model's other vertices, in vertex order).
+mutable struct BayesLogit <: Target; lambda::Float64; X::Matrix{Float64}; y::Vector{Float64}; end
+BayesLogit() = BayesLogit(100.0, zeros(0, 0), zeros(0))
+loglikelihood(t::BayesLogit) = p -> (Xp = t.X*p; dot(Xp, t.y) - sum(log.(1 .+ exp.(Xp))))
+logprior(t::BayesLogit) = p -> -0.5*(dot(p, p)/t.lambda + length(p)*log(2*pi*t.lambda))
+(t::BayesLogit)(p::Vector{Float64}) = loglikelihood(t)(p) + logprior(t)(p)
+gradient(t::BayesLogit) = p -> t.X'*(t.y .- 1 ./ (1 .+ exp.(-t.X*p))) .- p ./ t.lambda
+code(::IsoGaussian) = 0; code(::ShiftedIsoGaussian) = 1; code(::DenseGaussian) = 2; code(::Rosenbrock) = 3; code(::BayesLogit) = 4
+struct Hyperparameter; key::Symbol; end
+const Data = Hyperparameter
 
 struct BasicContMuvParameter; key::Symbol; logtarget::Target; end
-BasicContMuvParameter(key::Symbol; logtarget::Target, gradlogtarget=nothing) = BasicContMuvParameter(key, logtarget)
+BasicContMuvParameter(key::Symbol; logtarget::Target, gradlogtarget=nothing, nkeys::Int=0) = BasicContMuvParameter(key, logtarget)
 struct GenericModel; vertices::Vector{Any}; end
 likelihood_model(p::BasicContMuvParameter, isindexed::Bool=true) = GenericModel(Any[p])
+likelihood_model(v::Vector; isindexed::Bool=true) = GenericModel(Any[v...])
 
 struct MH; sigma::Vector{Float64}; end
 struct MALA; driftstep::Float64; MALA(s=1.0) = (@assert s > 0 "Drift step is not positive"; new(s)); end
@@ -65,6 +77,13 @@ struct VanillaMCTuner; period::Int; verbose::Bool; end
 VanillaMCTuner(; period::Int=100, verbose::Bool=false) = VanillaMCTuner(period, verbose)
 struct AcceptanceRateMCTuner; targetrate::Float64; k::Float64; period::Int; verbose::Bool; end
 AcceptanceRateMCTuner(rate; k=7.0, period::Int=100, verbose::Bool=false) = AcceptanceRateMCTuner(rate, k, period, verbose)
+# src/tuners/DualAveragingMCTuner.jl:53-93 (HMC only; per-chain step and nleaps = max(1, round(λ/step)))
+struct DualAveragingMCTuner
+  targetrate::Float64; nadapt::Int; ε0bar::Float64; h0bar::Float64; γ::Float64; t0::Int; κ::Float64; period::Int; verbose::Bool
+end
+DualAveragingMCTuner(rate, nadapt; ε0bar=1.0, h0bar=0.0, γ=0.05, t0::Int=10, κ=0.75, period::Int=100, verbose::Bool=false) =
+  DualAveragingMCTuner(rate, nadapt, ε0bar, h0bar, γ, t0, κ, period, verbose)
+tunercode(::VanillaMCTuner) = 0; tunercode(::AcceptanceRateMCTuner) = 1; tunercode(::DualAveragingMCTuner) = 2
 
 # ---- klb_config, field for field (include/klara_b200.h) ---------------------------------------------------
 struct KlbConfig
@@ -74,7 +93,9 @@ struct KlbConfig
   target_rate::Float64; score_k::Float64; period::Int64
   verbose::Int32; monitor::UInt32; diagnostics::UInt32; destination::Int32
   seed::UInt64; chain_offset::Int64; device::Int32; reserved::Int32
+  da_nadapt::Int64; da_t0::Int64; da_eps0bar::Float64; da_h0bar::Float64; da_gamma::Float64; da_kappa::Float64
 end
+struct KlbHostField; field::Int32; reserved::Int32; host_dst::Ptr{Cvoid}; nbytes::Int64; end
 
 lasterror() = unsafe_string(ccall((:klb_last_error, LIB), Cstring, ()))
 check(rc::Cint) = rc == 0 ? nothing : error("klara_b200 error $rc: $(lasterror())")
@@ -86,20 +107,29 @@ end
 function BasicMCJob(model::GenericModel, sampler, range::BasicMCRange, v0::Dict;
                     tuner=VanillaMCTuner(), outopts::Dict=Dict{Symbol,Any}(), seed::Integer=0,
                     arith::Symbol=:reference, device::Integer=0, chain_offset::Integer=0)
-  p = model.vertices[1]::BasicContMuvParameter
+  pidx = findfirst(v -> v isa BasicContMuvParameter, model.vertices)
+  p = model.vertices[pidx]::BasicContMuvParameter
+  if length(model.vertices) > 1       # hyper-parameters / data reach the target in vertex order (BasicContMuvParameter.jl:497-501)
+    vals = [v0[v.key] for (i, v) in enumerate(model.vertices) if i != pidx]
+    t = p.logtarget::BayesLogit
+    t.lambda, t.X, t.y = Float64(vals[1]), Matrix{Float64}(vals[2]), Vector{Float64}(vals[3])
+  end
   x0 = v0[p.key]; x0 = x0 isa Vector ? reshape(Float64.(x0), :, 1) : Matrix{Float64}(x0)   # d x nchains
   d, n = size(x0)
   monitor = get(outopts, :monitor, [:value]); diags = get(outopts, :diagnostics, Symbol[])
   dest = get(outopts, :destination, :nstate)
   mon = UInt32(sum(Dict(:value=>1, :logtarget=>2, :gradlogtarget=>4)[m] for m in monitor; init=0))
   smp = sampler isa MH ? 0 : sampler isa MALA ? 1 : 2
-  cfg = KlbConfig(sizeof(KlbConfig), smp, code(p.logtarget), tuner isa AcceptanceRateMCTuner ? 1 : 0,
+  da = tuner isa DualAveragingMCTuner
+  cfg = KlbConfig(sizeof(KlbConfig), smp, code(p.logtarget), tunercode(tuner),
                   arith == :fma ? 1 : 0, n, d, range.nsteps, range.burnin, range.thinning,
                   sampler isa HMC ? sampler.leapstep : sampler isa MALA ? sampler.driftstep : 1.0,
                   sampler isa HMC ? sampler.nleaps : 1,
-                  tuner isa AcceptanceRateMCTuner ? tuner.targetrate : 0.5,
+                  (tuner isa AcceptanceRateMCTuner || da) ? tuner.targetrate : 0.5,
                   tuner isa AcceptanceRateMCTuner ? tuner.k : 7.0, tuner.period, tuner.verbose,
-                  mon, (:accept in diags) ? 1 : 0, dest == :none ? 1 : 0, seed, chain_offset, device, 0)
+                  mon, (:accept in diags) ? 1 : 0, dest == :none ? 1 : 0, seed, chain_offset, device, 0,
+                  da ? tuner.nadapt : 0, da ? tuner.t0 : 10, da ? tuner.ε0bar : 1.0, da ? tuner.h0bar : 0.0,
+                  da ? tuner.γ : 0.05, da ? tuner.κ : 0.75)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   check(ccall((:klb_job_create, LIB), Cint, (Ref{KlbConfig}, Ref{Ptr{Cvoid}}), cfg, h))
   job = BasicMCJob(h[], n, d, range, monitor, diags)
@@ -108,6 +138,12 @@ function BasicMCJob(model::GenericModel, sampler, range::BasicMCRange, v0::Dict;
   t isa ShiftedIsoGaussian && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 0, t.mu, d))
   t isa Rosenbrock && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 3, [t.a, t.b, t.scale], 3))
   t isa DenseGaussian && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 1, t.C, d*d))
+  if t isa BayesLogit      # X travels row-major (row i = observation i): Julia's column-major X' is exactly that
+    Xt = Matrix{Float64}(t.X')
+    check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 6, [t.lambda], 1))
+    check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 4, Xt, length(Xt)))
+    check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 5, t.y, length(t.y)))
+  end
   sampler isa MH && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 2, sampler.sigma, d))
   GC.@preserve x0 check(ccall((:klb_job_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x0))   # initialize!
   job
@@ -115,6 +151,14 @@ end
 
 run(job::BasicMCJob) = (check(ccall((:klb_job_run, LIB), Cint, (Ptr{Cvoid},), job.handle)); job)
 run(jobs::Vector{BasicMCJob}) = map(run, jobs)
+# reset(job, x0); run(job); output fields, in ONE pipelined call (klb_job_run_host): chain slices on their own streams,
+# host->device copies, kernels and device->host copies overlap.  `outputs` maps KLB_OUT_* codes to preallocated Arrays.
+function run_host(job::BasicMCJob, x0::Union{Matrix{Float64},Nothing}, outputs::Dict{Int,<:Array}; nslices::Integer=0)
+  f = [KlbHostField(Int32(k), 0, pointer(a), sizeof(a)) for (k, a) in outputs]
+  GC.@preserve x0 outputs f check(ccall((:klb_job_run_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{KlbHostField}, Int32, Int32),
+                                        job.handle, x0 === nothing ? C_NULL : x0, f, length(f), nslices))
+  job
+end
 reset(job::BasicMCJob) = check(ccall((:klb_job_reset, LIB), Cint, (Ptr{Cvoid},), job.handle))
 function reset(job::BasicMCJob, x::Matrix{Float64})
   GC.@preserve x check(ccall((:klb_job_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x))

@@ -17,6 +17,9 @@
  *   orc_logistic       <- logistic(x,l,k,x0,y0)                src/stats/logistic.jl:11
  *   orc_logistic_rate_score / orc_erf_rate_score               src/tuners/AcceptanceRateMCTuner.jl:9,17
  *   orc_tuner_state    <- tuner_state(...)                     src/samplers/samplers.jl:29-45
+ *   orc_da_state / orc_da_tune / orc_da_nleaps / orc_da_block  <- DualAveragingMCTuner for HMC:
+ *                         src/tuners/DualAveragingMCTuner.jl:95-101, src/samplers/HMC.jl:124-133,192-223,
+ *                         src/samplers/iterate/HMC.jl:125-127,142-144,225-248, src/samplers/samplers.jl:170-202
  *   orc_upto / orc_logtarget / orc_gradlogtarget               src/variables/parameters/BasicContMuvParameter.jl:174-201,264-279
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
