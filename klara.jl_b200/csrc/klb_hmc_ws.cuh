@@ -21,11 +21,15 @@
 #ifndef KLB_WS_EXP
 #define KLB_WS_EXP 0
 #endif
+// Register split of the two warpgroups (4 x consumer + 4 x producer = 1024 per lane slot, 2 CTAs per SM).  With the
+// per-chain scalars parked in shared memory the consumers need < 184; the producers spill at 64 (a local-memory reload
+// at the head of every Philox iteration) and do not at 72.  Measured on C3 (reference / fma arithmetic):
+// 192/64 13.89 / 12.27 ms, 184/72 13.61 / 11.42 ms, 176/80 13.85 / 11.31 ms per 40 transitions.
 #ifndef KLB_WS_CONSUMER_REGS
-#define KLB_WS_CONSUMER_REGS 192
+#define KLB_WS_CONSUMER_REGS 184
 #endif
 #ifndef KLB_WS_PRODUCER_REGS
-#define KLB_WS_PRODUCER_REGS 64
+#define KLB_WS_PRODUCER_REGS 72
 #endif
 
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) {
@@ -83,11 +87,13 @@ __global__ void __launch_bounds__(256, 2)
 klb_hmc_ws_kernel(const KArgs A) {
   constexpr int W = 1;
   __shared__ WsChain wchain[4];
-  __shared__ uint64_t tab[KLB_TAB_LEN];
+  __shared__ __align__(16) uint64_t tab[KLB_TAB_LEN + 512];   // + the sign-flipped ziggurat pairs (zig_build9)
   __shared__ double2 zstage[4][NV * 32];
   __shared__ unsigned short zqueue[4][KLB_QCAP];
   __shared__ double uacc[4];
   for (int i = threadIdx.x; i < KLB_TAB_LEN; i += blockDim.x) tab[i] = A.tab[i];
+  __syncthreads();
+  zig_build9(tab);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -112,7 +118,7 @@ klb_hmc_ws_kernel(const KArgs A) {
                                             A.t0 + 1ull + (unsigned long long)it);
       if (it > 0) bar_sync(bar_empty, 64);         // the consumer has taken the previous transition's draws
 #if KLB_WS_EXP != 2      // timing experiment 2: producers idle (consumer-bound time; results meaningless)
-      randn_stage<NV, W, FULL>(st, d, 0, lane, tab, zbuf, zqueue[slot]);
+      randn_stage<NV, W, FULL, true>(st, d, 0, lane, tab, zbuf, zqueue[slot]);
 #endif
       if (lane == 0) uacc[slot] = klb_accept_uniform(&st);
       bar_arrive(bar_full, 64);

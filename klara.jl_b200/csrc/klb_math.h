@@ -269,7 +269,7 @@ KLB_HD double klb_pow_pos(double x, double y, const uint64_t* tab) {
   return klb_exp(klb_mul(y, klb_log(x, tab)), tab);
 }
 
-/* Fast path: candidate x = +-(t-1)*X[layer], t = 1.m in [1,2).  Returns 1 when the
+/* Fast path: candidate x = (t-1)*(+-X[layer]), t = 1.m in [1,2).  Returns 1 when the
  * candidate lies in the layer's rectangle below the density (accept, ~98.8 %). */
 KLB_HD int klb_zig_fast(uint64_t w, const uint64_t* tab, double* x) {
   uint32_t idx = (uint32_t)w & 255u;
@@ -277,8 +277,8 @@ KLB_HD int klb_zig_fast(uint64_t w, const uint64_t* tab, double* x) {
   double X = klb_u2d(tab[KLB_TAB_ZXK + 2 * idx]);
   uint64_t kk = tab[KLB_TAB_ZXK + 2 * idx + 1];
   double t = klb_u2d(0x3FF0000000000000ULL | m);
-  double xx = klb_fma(t, X, -X);
-  *x = klb_u2d(klb_d2u(xx) ^ ((w & 256ULL) << 55));
+  double Xs = klb_u2d(klb_d2u(X) ^ ((w & 256ULL) << 55));   /* bit 8 of the word: sign of the draw */
+  *x = klb_fma(t, Xs, -Xs);                                 /* -(t X - X) = t(-X) + X exactly; signed zero for m = 0 */
   return m < kk;
 }
 
