@@ -122,8 +122,17 @@ KLB_HD void klb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
 #pragma unroll
 #endif
   for (int r = 0; r < 10; ++r) {
+#if defined(__CUDA_ARCH__)
+    /* one IMAD.WIDE per product, opaque to the optimiser: left to itself nvcc strength-reduces the first round over
+     * consecutive slots into IMAD.HI + IADD, and IMAD.HI is the most expensive integer instruction to issue next to
+     * an fp64 stream (profiles/r1_summary.md, fp64_xwarp_test) */
+    uint32_t hi0, lo0, hi1, lo1;
+    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(KLB_PHILOX_M0));
+    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0, %1}, p;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(KLB_PHILOX_M1));
+#else
     uint32_t hi0 = klb_mulhi32(KLB_PHILOX_M0, c0), lo0 = KLB_PHILOX_M0 * c0;
     uint32_t hi1 = klb_mulhi32(KLB_PHILOX_M1, c2), lo1 = KLB_PHILOX_M1 * c2;
+#endif
     uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
     k0 += KLB_PHILOX_W0; k1 += KLB_PHILOX_W1;
@@ -276,10 +285,11 @@ KLB_HD int klb_zig_fast(uint64_t w, const uint64_t* tab, double* x) {
   uint64_t m = w >> 12;
   double X = klb_u2d(tab[KLB_TAB_ZXK + 2 * idx]);
   uint64_t kk = tab[KLB_TAB_ZXK + 2 * idx + 1];
-  double t = klb_u2d(0x3FF0000000000000ULL | m);
+  uint64_t tb = 0x3FF0000000000000ULL | m;
+  double t = klb_u2d(tb);
   double Xs = klb_u2d(klb_d2u(X) ^ ((w & 256ULL) << 55));   /* bit 8 of the word: sign of the draw */
   *x = klb_fma(t, Xs, -Xs);                                 /* -(t X - X) = t(-X) + X exactly; signed zero for m = 0 */
-  return m < kk;
+  return tb < kk;                                           /* m < k[layer]: the table holds k | 0x3ff<<52 */
 }
 
 /* Complete draw for element `elem` given its first candidate word w (from

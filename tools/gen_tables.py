@@ -97,7 +97,10 @@ blob += LOGT
 off_zxk = len(blob)
 assert off_zxk % 2 == 0
 for i in range(NZ):
-    blob += [ZX[i], ZK[i]]
+    # k[i] is stored with the exponent bits of 1.0 on top, so that the acceptance test compares the bits of
+    # t = 1.m directly (the kernels test the high words only and need no extra shift)
+    assert 0 <= ZK[i] < (1 << 52)
+    blob += [ZX[i], ZK[i] | (0x3FF << 52)]
 
 consts = {
     "KLB_ZIG_R": d2u(r),
@@ -126,7 +129,7 @@ with open(dst, "w") as fh:
              " *   [%d,%d)        ziggurat f[i] = exp(-x[i]^2/2), i = 0..256 (+1 pad)\n"
              " *   [%d,%d)      exp table {tail bits, scale bits} x 128\n"
              " *   [%d,%d)      log table {invc bits, logc bits} x 128\n"
-             " *   [%d,%d)     ziggurat {x[i] bits, k[i]} pairs, i = 0..255 (last: see tools/gen_tables.py)\n"
+             " *   [%d,%d)     ziggurat {x[i] bits, k[i] | 0x3ff<<52} pairs, i = 0..255 (last: see tools/gen_tables.py)\n"
              " */\n" % (off_zf, off_exp, off_exp, off_log, off_log, off_zxk, off_zxk, len(blob)))
     fh.write("#ifndef KLB_TABLES_H\n#define KLB_TABLES_H\n#include <stdint.h>\n")
     fh.write("#define KLB_TAB_ZXK %d\n#define KLB_TAB_ZF %d\n#define KLB_TAB_EXP %d\n#define KLB_TAB_LOG %d\n"
