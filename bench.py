@@ -347,8 +347,8 @@ def run_gpu(args, rank, world, local_rank):
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this launch at N=1 (ncu --set full,
                          # profiles/r1_summary.md capture G), scaled to this rank's chains
-                         "traffic": 54.91e9 * nloc / NCHAINS if arith == "reference" else None,
-                         "traffic_source": "profiles/r1_kernel_metrics.csv column K_ws_final_bench_launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic": 54.89e9 * nloc / NCHAINS if arith == "reference" else None,
+                         "traffic_source": "profiles/r1_kernel_metrics.csv column M_ws_shipping_bench_launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                          "peak_source": peak_src,
                          "kernel": "klb_hmc_ws_kernel<TgtIso, NV=16> (warp-specialised: 4 consumer + 4 producer warps per CTA)", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_launch,
@@ -356,7 +356,7 @@ def run_gpu(args, rank, world, local_rank):
                                   "peak_tops": 148 * 64 * 1.965e-3,
                                   "note": "leapfrog fp64 instructions only (5 d per step, un-fused: DADD/DMUL count 1 each) "
                                           "against 148 SMs x 64 lanes x 1.965 GHz; the kernel is fp64-issue bound, not HBM bound "
-                                          "(ncu, column K: fp64 pipe 58.5 % busy, issue slots 58.6 %, DRAM 9.4 %): profiles/r1_summary.md"}},
+                                          "(ncu, column M: fp64 pipe 61.9 % busy, issue slots 57.7 %, DRAM 10.0 %): profiles/r1_summary.md"}},
             "cpu_baseline": cb,
             "e2e": {"value": lf_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
