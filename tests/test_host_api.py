@@ -153,3 +153,48 @@ def test_iostream_round_trip(K, tmp_path):
     lines = open(os.path.join(tmp_path, "value.csv")).read().splitlines()
     assert len(lines) == 4 and lines[0] == ",".join(K.iostream.julia_float(x) for x in v[0])
     assert open(os.path.join(tmp_path, "diagnosticvalues.csv")).read().splitlines() == ["true", "false", "true", "true"]
+
+
+def test_new_surface_validation_without_a_device(K):
+    """configuration errors are reported before the library looks for a device: the dual-averaging tuner, the
+    logistic-regression target and the hyper-parameter vertices validate on a CPU-only box"""
+    L = K._lib
+    with pytest.raises(AssertionError, match="Number of adaptation steps should be positive"):   # DualAveragingMCTuner.jl:77
+        K.DualAveragingMCTuner(0.65, 0)
+    with pytest.raises(AssertionError, match="t0 should be positive"):
+        K.DualAveragingMCTuner(0.65, 10, t0=0)
+    t = K.DualAveragingMCTuner(0.651, 1000)
+    assert (t.eps0bar, t.h0bar, t.gamma, t.t0, t.kappa, t.period, t.verbose) == (1.0, 0.0, 0.05, 10, 0.75, 100, False)
+    iso = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    x0 = np.zeros((3, 8))
+    with pytest.raises(K.KlaraError) as ei:                     # no tuner_state method for MALA + dual averaging
+        K.BasicMCJob(K.likelihood_model(iso, False), K.MALA(0.1), K.BasicMCRange(nsteps=5), {"p": x0}, tuner=t)
+    assert ei.value.code == L.KLB_EINVAL and "HMC" in str(ei.value)
+    dense = K.BasicContMuvParameter("p", logtarget=K.DenseGaussian(np.eye(8)))
+    with pytest.raises(K.KlaraError) as ei:
+        K.BasicMCJob(K.likelihood_model(dense, False), K.HMC(0.1, 3), K.BasicMCRange(nsteps=5), {"p": x0}, tuner=t)
+    assert ei.value.code == L.KLB_EUNSUPPORTED
+    logit = K.BasicContMuvParameter("p", logtarget=K.BayesLogit(np.ones((5, 17)), np.ones(5), 1.0))
+    with pytest.raises(K.KlaraError) as ei:
+        K.BasicMCJob(K.likelihood_model(logit, False), K.HMC(0.1, 3), K.BasicMCRange(nsteps=5), {"p": np.zeros(17)})
+    assert ei.value.code == L.KLB_EUNSUPPORTED and "dim <= 16" in str(ei.value)
+    # hyper-parameter / data vertices: values reach the descriptor in vertex order (BasicContMuvParameter.jl:497-501)
+    d = K.BayesLogit()
+    p = K.BasicContMuvParameter("p", loglikelihood=d.loglikelihood, logprior=d.logprior, gradlogtarget=d.gradient, nkeys=4)
+    assert p.target is d and p.nkeys == 4
+    model = K.likelihood_model([K.Hyperparameter("λ"), K.Data("X"), K.Data("y"), p], isindexed=False)
+    X, y = np.arange(12.0).reshape(4, 3) / 10, np.array([0.0, 1.0, 1.0, 0.0])
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(K.KlaraError) as ei:                 # binds, validates, then fails for want of a device
+            K.BasicMCJob(model, K.HMC(0.1, 3), K.BasicMCRange(nsteps=5), {"λ": 50.0, "X": X, "y": y, "p": np.zeros(3)})
+        assert ei.value.code == L.KLB_ECUDA
+        assert d.lam == 50.0 and d.X.shape == (4, 3) and d.y.shape == (4,)
+        # the descriptor is the reference's closure triple on the host
+        b = np.array([0.3, -0.2, 0.1])
+        xp = X @ b
+        assert d.loglikelihood(b) == pytest.approx(float(xp @ y - np.log1p(np.exp(xp)).sum()), rel=1e-14)
+        assert d.logprior(b) == pytest.approx(-0.5 * (b @ b / 50.0 + 3 * np.log(2 * np.pi * 50.0)), rel=1e-14)
+    with pytest.raises(TypeError, match="takes no hyper-parameters"):
+        K.BasicMCJob(K.likelihood_model([K.Hyperparameter("λ"), iso], isindexed=False), K.HMC(0.1, 3),
+                     K.BasicMCRange(nsteps=5), {"λ": 1.0, "p": x0})
