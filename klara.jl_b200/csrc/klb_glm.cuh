@@ -139,6 +139,8 @@ __device__ __forceinline__ void glm_stage(const GArgs& G, int DP, uint64_t* tab,
   __syncthreads();
 }
 
+// (Capping the registers at 128 for 8 CTAs = 16 warps per SM instead of 6 was measured: 339 ms against 328 ms on the
+// HMC case of tools/glm_perf.py -- more warps do not help, the per-row exp / division chains are issue-bound.)
 template <int SAMPLER, int DP, bool FMA>
 __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G) {
   const KArgs& A = G.k;

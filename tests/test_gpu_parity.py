@@ -549,3 +549,47 @@ def test_dual_averaging_chunks_shards_and_reset_rule(K, O):
     with pytest.raises(K.KlaraError) as ei:
         build_pair(K, "HMC", "dense", nchains=4, dim=8, nsteps=5, tuner="dualavg")
     assert ei.value.code == L.KLB_EUNSUPPORTED
+
+
+# ------------------------------------------------------------------ randomized sweep
+def _random_configs(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        sampler = rng.choice(["HMC", "MALA", "MH"])
+        target = rng.choice(["iso", "shifted", "rosen", "dense", "logit"])
+        if target == "logit":
+            dim = int(rng.integers(1, 17))
+        elif target == "dense":
+            dim = int(2 * rng.integers(1, 70))
+        else:
+            dim = int(rng.choice([rng.integers(1, 64), rng.integers(64, 600), rng.integers(600, 1400), rng.integers(1400, 4097)]))
+            if target == "rosen":
+                dim += dim & 1
+        tuner = rng.choice(["vanilla", "accrate", "dualavg"])
+        if tuner == "dualavg" and (sampler != "HMC" or target == "dense"):
+            continue
+        if tuner == "accrate" and sampler == "MH":
+            tuner = "vanilla"
+        nsteps = int(rng.integers(3, 40))
+        burnin = int(rng.integers(0, nsteps))
+        mon = ["value"] + (["logtarget"] if rng.random() < 0.7 else []) + \
+              (["gradlogtarget"] if sampler != "MH" and rng.random() < 0.4 else [])
+        scale = {"iso": 1.0, "shifted": 1.0, "rosen": 0.15, "dense": 0.5, "logit": 0.15}[target]
+        step = {"HMC": 0.6, "MALA": 0.5, "MH": 1.0}[sampler] * scale / max(1.0, dim) ** (0.25 if sampler == "HMC" else 1 / 3)
+        out.append(dict(sampler=str(sampler), target=str(target), dim=dim, nchains=int(rng.integers(1, 70)), nsteps=nsteps,
+                        burnin=burnin, thinning=int(rng.integers(1, 4)), step=float(step), nleaps=int(rng.integers(1, 9)),
+                        tuner=str(tuner), target_rate=float(rng.uniform(0.3, 0.9)), period=int(rng.integers(2, 12)),
+                        verbose=bool(rng.random() < 0.4), monitor=tuple(mon),
+                        diagnostics=("accept",) if rng.random() < 0.8 else (), seed=int(rng.integers(0, 2**62)),
+                        arith=str(rng.choice(["reference", "fma"])), chain_offset=int(rng.integers(0, 1000)),
+                        nadapt=int(rng.integers(1, 50)), sigma=np.full(dim, 0.3 * scale / max(1.0, dim) ** 0.5)))
+    return out
+
+
+@pytest.mark.parametrize("k,cfgd", list(enumerate(_random_configs(40, 20261017))))
+def test_random_configurations_bit_exact(K, k, cfgd):
+    """40 seeded random draws over sampler x target x dim x tuner x range x arithmetic x monitor x shard offset:
+    every field, the final state and the tuner records against the oracle, bit for bit"""
+    job, cfg, x0, tp, sg = build_pair(K, rng_seed=k, **cfgd)
+    compare_run(job, cfg, x0, tp, sg)
