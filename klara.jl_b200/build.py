@@ -49,12 +49,61 @@ def stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+# Units whose cubin gets a scheduling-control post-pass between ptxas and fatbinary (tools/sass_patch.py):
+# {unit-name prefix: sass_patch.py arguments}.  KLB_SASS_PATCH="" disables it, KLB_SASS_PATCH="--yield --stall 2" overrides.
+SASS_PATCH = {"klb_hmc_ws_": os.environ.get("KLB_SASS_PATCH", "").split()}
+PATCHER = os.path.join(os.path.dirname(HERE), "tools", "sass_patch.py")
+
+
+def compile_patched(name, cmd, patch_args):
+    """nvcc -dryrun lists the sub-commands (cicc, ptxas, fatbinary, host gcc); they are replayed one by one and the
+    cubin ptxas wrote is rewritten in place before fatbinary embeds it."""
+    import re
+    import shlex
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="klb_" + name + "_")
+    r = subprocess.run(cmd + ["-dryrun", "--keep", "--keep-dir", tmp], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc -dryrun failed for %s:\n%s" % (name, r.stderr))
+    env = dict(os.environ)
+    log = ""
+    for line in r.stderr.splitlines():
+        if not line.startswith("#$ "):
+            continue
+        line = line[3:]
+        m = re.match(r"^([A-Za-z_][A-Za-z0-9_]*)=(.*)$", line)
+        if m and not line.startswith(("gcc", "cicc", "ptxas", "fatbinary", "cudafe++", "rm", '"')):
+            val = m.group(2).strip()
+            for k, v in env.items():
+                val = val.replace("$" + k, v)
+            env[m.group(1)] = val.strip('"') if m.group(1) in ("PATH", "LD_LIBRARY_PATH", "CICC_PATH", "TOP", "NVVMIR_LIBRARY_DIR") else val
+            continue
+        if line.startswith("rm "):
+            continue
+        rr = subprocess.run(line, shell=True, env=env, capture_output=True, text=True, cwd=CSRC)
+        log += rr.stderr
+        if rr.returncode != 0:
+            raise RuntimeError("sub-command failed for %s:\n%s\n%s" % (name, line, rr.stderr))
+        if line.startswith("ptxas "):
+            cubin = shlex.split(line)[shlex.split(line).index("-o") + 1]
+            pr = subprocess.run([sys.executable, PATCHER, cubin, cubin] + patch_args, capture_output=True, text=True)
+            log += pr.stderr
+            if pr.returncode != 0:
+                raise RuntimeError("sass_patch failed for %s:\n%s" % (name, pr.stderr))
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return log
+
+
 def compile_one(name, src, defs, force):
     obj = os.path.join(OBJ, name + ".o")
-    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__), PATCHER]
     if not force and not stale(obj, deps):
         return obj, ""
     cmd = [NVCC] + FLAGS + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
+    patch = next((a for pre, a in SASS_PATCH.items() if name.startswith(pre) and a), None)
+    if patch:
+        return obj, compile_patched(name, cmd, patch)
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (name, " ".join(cmd), r.stderr))

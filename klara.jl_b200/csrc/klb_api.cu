@@ -2,6 +2,7 @@
 // device memory, launches.  No CPU compute path exists here: without a CUDA device every
 // compute entry point fails with KLB_ECUDA.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -182,6 +183,18 @@ static void free_job(klb_job* j) {
   delete j;
 }
 
+// wait for everything the job has in flight: its own stream and the slice streams of klb_job_run_host
+static int sync_all(klb_job* j) {
+  CK(cudaSetDevice(j->cfg.device));
+  cudaError_t first = cudaStreamSynchronize(j->stream);
+  for (int q = 0; q < j->nsl_streams; ++q) {
+    const cudaError_t e = cudaStreamSynchronize(j->sl_stream[q]);
+    if (first == cudaSuccess) first = e;
+  }
+  CK(first);
+  return KLB_OK;
+}
+
 static void fill_args(const klb_job* j, KArgs& A) {
   const klb_config& c = j->cfg;
   memset(&A, 0, sizeof A);
@@ -354,6 +367,12 @@ void klb_job_destroy(klb_job* job) { free_job(job); }
 int klb_job_set_target_f64(klb_job* j, int which, const double* host, int64_t n) {
   if (!j || !host) return fail(KLB_EINVAL, "null argument");
   CK(cudaSetDevice(j->cfg.device));
+  // A kernel of klb_job_run_async may still be reading the old parameters; and the cached pstate.logtarget (for HMC
+  // the accepted state's energy) belongs to the old target: the state has to be initialised again afterwards
+  // (the reference rebuilds the job when a hyper-parameter changes: parameter.states is fixed at construction,
+  // src/jobs/BasicMCJob.jl:51).
+  { int rc = sync_all(j); if (rc) return rc; }
+  j->have_state = false;
   switch (which) {
     case KLB_PARAM_MU:
       if (n != j->cfg.dim) return fail(KLB_EINVAL, "mu needs dim = %lld values", (long long)j->cfg.dim);
@@ -422,6 +441,7 @@ static void slice_args(const klb_job* j, KArgs& A, long long c0, long long nc) {
   const long long ld = j->ld, P = j->npost;
   A.state += c0 * ld; A.lt += c0;
   A.tune_step += c0; A.tune_cnt += 3 * c0; A.tune_rate += c0;
+  if (A.tune_da) A.tune_da += 8 * c0;              // DualAveragingMCTune record: indexed by the slice-local chain id
   if (A.out_value) A.out_value += c0 * P * ld;
   if (A.out_lt) A.out_lt += c0 * P;
   if (A.out_grad) A.out_grad += c0 * P * ld;
@@ -628,10 +648,13 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
     fl[q].p = (char*)p; fl[q].per_chain = nb / N; fl[q].cols_per_chain = cols / N;
   }
   int S = nslices;
-  if (S <= 0) {                                    // auto: ~32 MiB of state per slice, at least 2048 chains
-    const size_t bytes = N * d * 8;                // (C3 on one B200: 16 slices 74.1 ms, 8: 75.3, 4: 78.7, serial: 94.3)
-    S = (int)(bytes / (32u << 20));
-    while (S > 1 && N / (size_t)S < 2048) --S;
+  if (S <= 0) {                                    // auto: ~4 MiB of state per slice, at least 512 chains, at most 16 slices
+    const size_t bytes = N * d * 8;                // (C3 on one B200: 16 slices 74.1 ms, 8: 75.3, 4: 78.7, serial: 94.3;
+    size_t mib = 4;                                //  small shards -- 8192 chains per GPU at N = 8 -- need as many slices
+    if (const char* env = getenv("KLB_SLICE_MIB")) //  for their copies to hide behind the kernels of the other slices)
+      if (atoi(env) > 0) mib = (size_t)atoi(env);
+    S = (int)std::min<size_t>(KLB_MAX_SLICES, bytes / (mib << 20));
+    while (S > 1 && N / (size_t)S < 512) --S;
   }
   if (S < 1) S = 1;
   if (S > KLB_MAX_SLICES) S = KLB_MAX_SLICES;
@@ -642,49 +665,73 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
     j->nsl_streams += 1;
   }
   const unsigned long long none = std::numeric_limits<unsigned long long>::max();
-  if (x0) CK(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
-  CK(cudaEventRecord(j->ev0, j->stream));          // slices start after everything already queued on the job stream
-  for (int q = 0; q < S; ++q) {
+  // Everything below is asynchronous on the slice streams and touches caller-owned host buffers, so no error path may
+  // return before those streams are idle; and nothing of the job's bookkeeping (RNG counter, output cursor,
+  // `constructed`) moves until the whole pipeline has succeeded -- a bad x0 or a failed launch leaves a job that
+  // klb_job_set_state / klb_job_run_host can restart (a DualAveragingMCTuner job included: t_global stays 0).
+  int rc = KLB_OK;
+#define CKR(call)                                                                                              \
+  do {                                                                                                         \
+    cudaError_t e_ = (call);                                                                                   \
+    if (e_ != cudaSuccess && rc == KLB_OK)                                                                     \
+      rc = fail(e_ == cudaErrorMemoryAllocation ? KLB_ENOMEM : KLB_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+  const bool was_constructed = j->constructed;
+  if (x0) CKR(cudaMemcpyAsync(j->flag, &none, sizeof none, cudaMemcpyHostToDevice, j->stream));
+  CKR(cudaEventRecord(j->ev0, j->stream));         // slices start after everything already queued on the job stream
+  for (int q = 0; q < S && rc == KLB_OK; ++q) {
     const size_t c0 = N * (size_t)q / (size_t)S, c1 = N * (size_t)(q + 1) / (size_t)S, nc = c1 - c0;
     cudaStream_t st = j->sl_stream[q];
-    CK(cudaStreamWaitEvent(st, j->ev0, 0));
+    CKR(cudaStreamWaitEvent(st, j->ev0, 0));
     KArgs A;
     fill_args(j, A);
     slice_args(j, A, (long long)c0, (long long)nc);
-    if (x0) {                                      // initialize! / reset(job, x) of the slice
-      CK(cudaMemcpy2DAsync(j->state + c0 * ld, ld * 8, x0 + c0 * d, d * 8, d * 8, nc, cudaMemcpyHostToDevice, st));
-      int rc = launch_init(j, A, st);
-      if (rc) return rc;
+    if (x0 && rc == KLB_OK) {                      // initialize! / reset(job, x) of the slice
+      CKR(cudaMemcpy2DAsync(j->state + c0 * ld, ld * 8, x0 + c0 * d, d * 8, d * 8, nc, cudaMemcpyHostToDevice, st));
+      if (rc == KLB_OK) rc = launch_init(j, A, st);
     }
+    if (rc != KLB_OK) break;
     // reset(job): tuner records of the slice                                  samplers.jl:29-45
     fill_tune_slice(j, c0, nc, st);
-    CK(cudaGetLastError());
-    { int rc = launch_run(j, A, st); if (rc) return rc; }
-    for (int f = 0; f < nfields; ++f) {            // output(job), slice by slice
+    CKR(cudaGetLastError());
+    if (rc == KLB_OK) rc = launch_run(j, A, st);
+    for (int f = 0; f < nfields && rc == KLB_OK; ++f) {   // output(job), slice by slice
       const size_t per = fl[f].per_chain, cpc = fl[f].cols_per_chain;
       char* dst = (char*)fields[f].host_dst + c0 * per;
       if (cpc && ld != d)                          // odd dim: device columns are padded
-        CK(cudaMemcpy2DAsync(dst, d * 8, fl[f].p + c0 * cpc * ld * 8, ld * 8, d * 8, nc * cpc, cudaMemcpyDeviceToHost, st));
+        CKR(cudaMemcpy2DAsync(dst, d * 8, fl[f].p + c0 * cpc * ld * 8, ld * 8, d * 8, nc * cpc, cudaMemcpyDeviceToHost, st));
       else
-        CK(cudaMemcpyAsync(dst, fl[f].p + c0 * per, nc * per, cudaMemcpyDeviceToHost, st));
+        CKR(cudaMemcpyAsync(dst, fl[f].p + c0 * per, nc * per, cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaEventRecord(j->sl_done[q], st));
+    CKR(cudaEventRecord(j->sl_done[q], st));
+    if (rc == KLB_OK) CKR(cudaStreamWaitEvent(j->stream, j->sl_done[q], 0));
   }
-  for (int q = 0; q < S; ++q) CK(cudaStreamWaitEvent(j->stream, j->sl_done[q], 0));
-  CK(cudaEventRecord(j->ev1, j->stream));
+  unsigned long long f = none;
+  if (rc == KLB_OK) {
+    CKR(cudaEventRecord(j->ev1, j->stream));
+    if (x0) CKR(cudaMemcpyAsync(&f, j->flag, sizeof f, cudaMemcpyDeviceToHost, j->stream));
+  }
+#undef CKR
+  {                                                // idle streams before ANY return: host buffers are the caller's
+    char keep[sizeof g_err];
+    memcpy(keep, g_err, sizeof keep);
+    const int rs = sync_all(j);
+    if (rc != KLB_OK) memcpy(g_err, keep, sizeof keep); else rc = rs;
+  }
+  if (rc == KLB_OK && f != none)
+    rc = fail(KLB_ENOTFINITE, "Log-target%s not finite: initial value out of support (chain %llu)",
+              c.sampler != KLB_SAMPLER_MH ? " or its gradient" : "", f - 1);
+  if (rc != KLB_OK) {                              // roll back: the state buffers hold a discarded run
+    j->have_state = false;
+    j->count = 0;
+    j->constructed = was_constructed;
+    j->timed = false;
+    return rc;
+  }
   j->t_global += (unsigned long long)c.nsteps;
   j->count = j->npost;
   j->timed = true;
   j->constructed = true;
-  unsigned long long f = none;
-  if (x0) CK(cudaMemcpyAsync(&f, j->flag, sizeof f, cudaMemcpyDeviceToHost, j->stream));
-  CK(cudaStreamSynchronize(j->stream));
-  if (f != none) {
-    j->have_state = false;
-    j->count = 0;
-    return fail(KLB_ENOTFINITE, "Log-target%s not finite: initial value out of support (chain %llu)",
-                c.sampler != KLB_SAMPLER_MH ? " or its gradient" : "", f - 1);
-  }
   j->have_state = true;
   return KLB_OK;
 }
@@ -844,7 +891,12 @@ int klb_host_free(void* p) {
 }
 
 // ---------------------------------------------------------------- device self-tests
-static int dbg_setup(int device, uint64_t** tab) {
+// device scratch of one self-test call, released on every return path
+struct DbgBufs {
+  void* p[3] = {nullptr, nullptr, nullptr};
+  ~DbgBufs() { for (void* q : p) if (q) cudaFree(q); }
+};
+static int dbg_setup(int device, DbgBufs& b) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -852,49 +904,46 @@ static int dbg_setup(int device, uint64_t** tab) {
   }
   if (device < 0 || device >= ndev) return fail(KLB_EINVAL, "device out of range");
   CK(cudaSetDevice(device));
-  CK(cudaMalloc(tab, sizeof(KLB_TAB)));
-  CK(cudaMemcpy(*tab, KLB_TAB, sizeof(KLB_TAB), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&b.p[0], sizeof(KLB_TAB)));
+  CK(cudaMemcpy(b.p[0], KLB_TAB, sizeof(KLB_TAB), cudaMemcpyHostToDevice));
   return KLB_OK;
 }
 
 int klb_debug_normals(int device, uint64_t seed, uint64_t chain, uint64_t t, int64_t n, double* host_out) {
-  uint64_t* tab = nullptr;
-  int rc = dbg_setup(device, &tab);
+  if (!host_out || n <= 0) return fail(KLB_EINVAL, "bad argument");
+  DbgBufs b;
+  int rc = dbg_setup(device, b);
   if (rc) return rc;
-  double* out = nullptr;
-  CK(cudaMalloc(&out, (size_t)n * 8));
-  klb_launch_debug_normals(tab, seed, chain, t, n, out, 0);
+  CK(cudaMalloc(&b.p[1], (size_t)n * 8));
+  klb_launch_debug_normals((const uint64_t*)b.p[0], seed, chain, t, n, (double*)b.p[1], 0);
   CK(cudaGetLastError());
-  CK(cudaMemcpy(host_out, out, (size_t)n * 8, cudaMemcpyDeviceToHost));
-  cudaFree(out); cudaFree(tab);
+  CK(cudaMemcpy(host_out, b.p[1], (size_t)n * 8, cudaMemcpyDeviceToHost));
   return KLB_OK;
 }
 
 int klb_debug_math(int device, int op, int64_t n, const double* host_in, double* host_out) {
-  uint64_t* tab = nullptr;
-  int rc = dbg_setup(device, &tab);
+  if (!host_in || !host_out || n <= 0) return fail(KLB_EINVAL, "bad argument");
+  DbgBufs b;
+  int rc = dbg_setup(device, b);
   if (rc) return rc;
-  double *in = nullptr, *out = nullptr;
-  CK(cudaMalloc(&in, (size_t)n * 8));
-  CK(cudaMalloc(&out, (size_t)n * 8));
-  CK(cudaMemcpy(in, host_in, (size_t)n * 8, cudaMemcpyHostToDevice));
-  klb_launch_debug_math(tab, op, n, in, out, 0);
+  CK(cudaMalloc(&b.p[1], (size_t)n * 8));
+  CK(cudaMalloc(&b.p[2], (size_t)n * 8));
+  CK(cudaMemcpy(b.p[1], host_in, (size_t)n * 8, cudaMemcpyHostToDevice));
+  klb_launch_debug_math((const uint64_t*)b.p[0], op, n, (const double*)b.p[1], (double*)b.p[2], 0);
   CK(cudaGetLastError());
-  CK(cudaMemcpy(host_out, out, (size_t)n * 8, cudaMemcpyDeviceToHost));
-  cudaFree(in); cudaFree(out); cudaFree(tab);
+  CK(cudaMemcpy(host_out, b.p[2], (size_t)n * 8, cudaMemcpyDeviceToHost));
   return KLB_OK;
 }
 
 int klb_debug_uniform(int device, uint64_t seed, uint64_t chain, uint64_t t, double* host_out) {
-  uint64_t* tab = nullptr;
-  int rc = dbg_setup(device, &tab);
+  if (!host_out) return fail(KLB_EINVAL, "bad argument");
+  DbgBufs b;
+  int rc = dbg_setup(device, b);
   if (rc) return rc;
-  double* out = nullptr;
-  CK(cudaMalloc(&out, 8));
-  klb_launch_debug_uniform(seed, chain, t, out, 0);
+  CK(cudaMalloc(&b.p[1], 8));
+  klb_launch_debug_uniform(seed, chain, t, (double*)b.p[1], 0);
   CK(cudaGetLastError());
-  CK(cudaMemcpy(host_out, out, 8, cudaMemcpyDeviceToHost));
-  cudaFree(out); cudaFree(tab);
+  CK(cudaMemcpy(host_out, b.p[1], 8, cudaMemcpyDeviceToHost));
   return KLB_OK;
 }
 

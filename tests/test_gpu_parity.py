@@ -496,6 +496,49 @@ def test_run_host_continues_and_rejects_bad_starts(K):
         two.run_host(x0, {L.OUT_STATE: np.empty((3, 3))}, 2)
 
 
+@pytest.mark.parametrize("target,dim", [("iso", 1024), ("iso", 130), ("logit", 4)])
+def test_run_host_dual_averaging_slices(K, O, target, dim):
+    """klb_job_run_host on a DualAveragingMCTuner job cut into several slices: every slice must index ITS chains'
+    DualAveragingMCTune records (round-1 bug: slices shared the records of chains 0..nc-1).  Compared bit for bit
+    with reset(job, x0) + run(job) and with the oracle started from reset!'s record (step = 1, HMC.jl:217-223)."""
+    L = K._lib
+    N = 101
+    kw = dict(nchains=N, dim=dim, nsteps=36, burnin=10, thinning=2, step=0.6 / np.sqrt(dim) if target == "iso" else 0.02,
+              nleaps=12 if target == "iso" else 5, seed=1618, tuner="dualavg", target_rate=0.7, nadapt=25, period=6, verbose=True)
+    ref_job, cfg, x0, tp, sg = build_pair(K, "HMC", target, **kw)
+    ref_job.reset(x0)                                  # what run_host(x0) does first: reset!(tune) -> step = 1
+    ref_job.run()
+    ref, ref_tn = ref_job.output(), ref_job.tune
+    t_or, d_or = O.da_state(cfg, first=False)
+    orc = O.run(cfg, x0, tp, sg, tune=t_or, da=d_or)
+    assert_same("oracle value", ref.value, orc["value"])
+    for nslices in (3, 16):
+        job, *_ = build_pair(K, "HMC", target, **kw)
+        bufs = {L.OUT_VALUE: np.empty_like(ref.value), L.OUT_ACCEPT: np.empty_like(ref.diagnosticvalues),
+                L.OUT_TUNE_STEP: np.empty(N), L.OUT_TUNE_DA: np.empty((N, 8)), L.OUT_TUNE_COUNTERS: np.empty((N, 3), dtype=np.int64)}
+        job.run_host(x0, bufs, nslices)
+        assert_same("value", bufs[L.OUT_VALUE], orc["value"])
+        assert_same("accept", bufs[L.OUT_ACCEPT], orc["accept"])
+        assert_same("step", bufs[L.OUT_TUNE_STEP], orc["tune"]["step"])
+        da = bufs[L.OUT_TUNE_DA]
+        for i, name in enumerate(("lambda", "mu", "epsbar", "hbar", "hweight", "epsweight", "nleaps", "count")):
+            assert_same("da." + name, da[:, i], orc["da"][name])
+        assert_same("counters", bufs[L.OUT_TUNE_COUNTERS][:, 2], ref_tn.totproposed)
+        assert (da[:, 7] == 36).all() and len(np.unique(da[:, 2])) > N // 2
+        tn = job.tune                                  # the records left on the device are the same
+        assert_same("tune.epsbar", tn.epsbar, orc["da"]["epsbar"])
+    # a bad start must not brick the job (t_global stays 0, so reset / set_state are still the reference's)
+    job, *_ = build_pair(K, "HMC", target, **kw)
+    bad = x0.copy()
+    bad[77, 0] = np.inf
+    with pytest.raises(K.KlaraError) as ei:
+        job.run_host(bad, {}, 4)
+    assert ei.value.code == L.KLB_ENOTFINITE and "chain 77" in str(ei.value)
+    assert job.plan().transitions_done == 0
+    job.run_host(x0, {}, 5)
+    assert_same("after a rejected start", job.output().value, orc["value"])
+
+
 # ------------------------------------------------------------------ DualAveragingMCTuner (HMC)
 @pytest.mark.parametrize("arith", ["reference", "fma"])
 @pytest.mark.parametrize("target,dim", [("iso", 1024), ("iso", 700), ("iso", 64), ("iso", 7), ("iso", 2048),
