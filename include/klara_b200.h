@@ -181,6 +181,17 @@ int klb_job_set_state(klb_job* job, const double* x0);
 /* same, x0 already in device memory of the job's device (no host copy) */
 int klb_job_set_state_device(klb_job* job, const double* x0_dev);
 
+/* The synthetic initial value of the benchmark configurations, generated on the device and then initialised like
+ * klb_job_set_state:  x0[i, c] = N(0,1) of the Philox stream (cfg.seed, global chain chain_offset + c, transition 0,
+ * element i)  (SURVEY.md section 8d).  A function of the global chain index only, so a job's input does not depend
+ * on how its chains are sharded over GPUs.  (The reference's examples start from user vectors, README.md:47.) */
+int klb_job_set_state_synthetic(klb_job* job);
+
+/* Position the job's RNG streams: the next transition will be number t + 1.  The reference's unseeded global RNG
+ * (iterate/HMC.jl:135,165) cannot seek; counter-based streams can, which is what makes a run reproducible from any
+ * point and lets shards of one logical job be recomputed independently. */
+int klb_job_seek(klb_job* job, uint64_t t);
+
 /* run(job) (BasicMCJob.jl:212-244): all nsteps transitions of all chains, burn-in tuning,
  * thinning, saving.  Blocking. */
 int klb_job_run(klb_job* job);
@@ -255,6 +266,13 @@ double klb_job_last_run_ms(klb_job* job);
 void* klb_job_stream(klb_job* job);
 
 void klb_job_destroy(klb_job* job);
+
+/* Measured throughput of one device for the roofline denominators that MEASURED_PEAKS.json does not hold:
+ * KLB_PEAK_FP64 = fp64 results per second of a stream of independent DFMA (DADD / DMUL issue at the same rate),
+ * KLB_PEAK_DMMA = flop per second of a stream of independent mma.sync.m8n8k4.f64 (the fp64 tensor pipe). */
+#define KLB_PEAK_FP64 0
+#define KLB_PEAK_DMMA 1
+int klb_device_peak(int device, int kind, double* per_second);
 
 /* pinned host memory for end-to-end pipelines */
 int klb_host_alloc(void** p, int64_t nbytes);

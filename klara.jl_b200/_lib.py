@@ -23,6 +23,7 @@ DEST_NSTATE, DEST_NONE = 0, 1
 PARAM_MU, PARAM_C, PARAM_SIGMA, PARAM_ROSEN, PARAM_LOGIT_X, PARAM_LOGIT_Y, PARAM_LOGIT_LAMBDA = 0, 1, 2, 3, 4, 5, 6
 (OUT_VALUE, OUT_LOGTARGET, OUT_GRADLOGTARGET, OUT_ACCEPT, OUT_STATE, OUT_STATE_LOGTARGET,
  OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS, OUT_TUNE_DA) = range(11)
+PEAK_FP64, PEAK_DMMA = 0, 1
 (STAT_MEAN, STAT_MCVAR_IID, STAT_MCVAR_IMSE, STAT_ESS, STAT_IACT, STAT_ACCEPTANCE, STAT_ACCEPTANCE_VALUE) = range(7)
 
 
@@ -68,6 +69,8 @@ SYMBOLS = [
     ("klb_job_set_target_f64", _int, [_vp, _int, _vp, _i64]),
     ("klb_job_set_state", _int, [_vp, _vp]),
     ("klb_job_set_state_device", _int, [_vp, _vp]),
+    ("klb_job_set_state_synthetic", _int, [_vp]),
+    ("klb_job_seek", _int, [_vp, _u64]),
     ("klb_job_run", _int, [_vp]),
     ("klb_job_run_async", _int, [_vp]),
     ("klb_job_sync", _int, [_vp]),
@@ -83,6 +86,7 @@ SYMBOLS = [
     ("klb_job_last_run_ms", _dbl, [_vp]),
     ("klb_job_stream", _vp, [_vp]),
     ("klb_job_destroy", None, [_vp]),
+    ("klb_device_peak", _int, [_int, _int, C.POINTER(_dbl)]),
     ("klb_host_alloc", _int, [C.POINTER(_vp), _i64]),
     ("klb_host_free", _int, [_vp]),
     ("klb_debug_normals", _int, [_int, _u64, _u64, _u64, _i64, _vp]),

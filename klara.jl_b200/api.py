@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib as L
 from .targets import Target
 
-__all__ = ["BasicContMuvParameter", "Hyperparameter", "Data", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
+__all__ = ["SyntheticNormal", "device_peak", "BasicContMuvParameter", "Hyperparameter", "Data", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
            "VanillaMCTuner", "AcceptanceRateMCTuner", "DualAveragingMCTuner", "BasicMCTune", "DualAveragingMCTune", "BasicMCJob", "run", "reset", "output",
            "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "ess", "mean", "mcvar", "mcse", "iact",
            "acceptance"]
@@ -95,6 +95,22 @@ def likelihood_model(vertices, isindexed=True):
     if not isinstance(vertices, (list, tuple)):
         vertices = [vertices]
     return GenericModel(vertices)
+
+
+class SyntheticNormal:
+    """Initial value generated on the device: x0[c, i] = N(0,1) of the job's Philox stream (seed, global chain
+    chain_offset + c, transition 0, element i) -- the input of the benchmark configurations.
+    `{"p": SyntheticNormal(nchains, dim)}` in place of a `(nchains, dim)` array."""
+
+    def __init__(self, nchains, dim):
+        self.shape = (int(nchains), int(dim))
+
+
+def device_peak(kind="fp64", device=0):
+    """measured fp64 results/s ("fp64") or fp64 tensor-pipe flop/s ("dmma") of one device (klb_device_peak)"""
+    v = C.c_double()
+    L.check(L.lib().klb_device_peak(device, {"fp64": L.PEAK_FP64, "dmma": L.PEAK_DMMA}[kind], C.byref(v)))
+    return v.value
 
 
 # ----------------------------------------------------------------------------- samplers
@@ -289,10 +305,15 @@ class BasicMCJob:
                 raise TypeError("target %s takes no hyper-parameters" % type(self.parameter.target).__name__)
             self.parameter.target.bind([v0[v.key] for v in others])
         x0 = v0[self.parameter.key] if isinstance(v0, dict) else v0
-        x0 = np.asarray(x0, dtype=np.float64)
-        self.single = x0.ndim == 1
-        x0 = np.ascontiguousarray(np.atleast_2d(x0))
-        self.nchains, self.dim = x0.shape
+        synthetic = isinstance(x0, SyntheticNormal)
+        if synthetic:
+            self.single = False
+            self.nchains, self.dim = x0.shape
+        else:
+            x0 = np.asarray(x0, dtype=np.float64)
+            self.single = x0.ndim == 1
+            x0 = np.ascontiguousarray(np.atleast_2d(x0))
+            self.nchains, self.dim = x0.shape
 
         cfg = L.KlbConfig()
         cfg.struct_size = C.sizeof(L.KlbConfig)
@@ -323,7 +344,10 @@ class BasicMCJob:
                     raise AssertionError("MH sigma has %d entries, parameter has %d" % (sampler.sigma.size, self.dim))
                 L.check(L.lib().klb_job_set_target_f64(self._h, L.PARAM_SIGMA, _ptr(sampler.sigma), self.dim))
             # initialize!: first target (+gradient) evaluation; finiteness asserts (HMC.jl:113-114)
-            L.check(L.lib().klb_job_set_state(self._h, _ptr(x0)))
+            if synthetic:
+                L.check(L.lib().klb_job_set_state_synthetic(self._h))
+            else:
+                L.check(L.lib().klb_job_set_state(self._h, _ptr(x0)))
         except Exception:
             self.close()
             raise
@@ -391,6 +415,17 @@ class BasicMCJob:
                 raise AssertionError("reset value has shape %s, job has %s" % (x.shape, (self.nchains, self.dim)))
             L.check(L.lib().klb_job_set_state(self._h, _ptr(x)))
         self.count = 0
+        return self
+
+    def reset_synthetic(self):
+        """reset(job, x0) with the device-generated synthetic initial value (SyntheticNormal)"""
+        L.check(L.lib().klb_job_set_state_synthetic(self._h))
+        self.count = 0
+        return self
+
+    def seek(self, t):
+        """position the RNG streams: the next transition is number t + 1 (klb_job_seek)"""
+        L.check(L.lib().klb_job_seek(self._h, int(t)))
         return self
 
     def set_chunk(self, nt):

@@ -44,6 +44,10 @@ void klb_launch_stats(const double* value, long long ld, long long npost, long l
 void klb_launch_acceptance(const unsigned char* accept, const double* value, long long ld, long long npost,
                            long long nchains, int dim, double* out, cudaStream_t s);
 
+void klb_launch_synth_state(const uint64_t* tab, uint64_t seed, uint64_t chain_offset, long long nchains, int dim,
+                            long long ld, double* state, cudaStream_t s);
+int klb_measure_peak(int kind, double* per_second);
+
 #define KLB_MAX_SLICES 16
 static thread_local char g_err[512] = "";
 
@@ -585,6 +589,30 @@ int klb_job_set_state_device(klb_job* j, const double* x0_dev) {
   return init_state(j);
 }
 
+// x0 = the synthetic initial value of the benchmark configurations, generated on the device (header)
+int klb_job_set_state_synthetic(klb_job* j) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  { int rc = da_refuses_reset(j); if (rc) return rc; }
+  CK(cudaSetDevice(j->cfg.device));
+  klb_launch_synth_state(j->tab, j->cfg.seed, (uint64_t)j->cfg.chain_offset, j->cfg.nchains, (int)j->cfg.dim, j->ld,
+                         j->state, j->stream);
+  j->launches += 1;
+  CK(cudaGetLastError());
+  return init_state(j);
+}
+
+// Position the RNG: the next transition will be number t + 1 of the job's streams.  Counter-based generators
+// can seek; the reference's global MersenneTwister cannot.
+int klb_job_seek(klb_job* j, uint64_t t) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  if (t >> 48) return fail(KLB_EINVAL, "the transition counter has 48 bits");
+  if (j->da && j->t_global > 0) return fail(KLB_EUNSUPPORTED, "a DualAveragingMCTuner job that has run cannot be repositioned");
+  if (j->da && t > 0) return fail(KLB_EUNSUPPORTED, "a DualAveragingMCTuner job starts at transition 0 (reset! rule)");
+  { int rc = sync_all(j); if (rc) return rc; }
+  j->t_global = t;
+  return KLB_OK;
+}
+
 int klb_job_set_chunk(klb_job* j, int64_t nt) {
   if (!j || nt < 0) return fail(KLB_EINVAL, "bad chunk");
   j->chunk = nt;
@@ -887,6 +915,20 @@ int klb_host_alloc(void** p, int64_t nbytes) {
 }
 int klb_host_free(void* p) {
   CK(cudaFreeHost(p));
+  return KLB_OK;
+}
+
+// fp64 / DMMA throughput of one device, measured with a stream of independent instructions (roofline denominators)
+int klb_device_peak(int device, int kind, double* per_second) {
+  if (!per_second || (kind != KLB_PEAK_FP64 && kind != KLB_PEAK_DMMA)) return fail(KLB_EINVAL, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(KLB_ECUDA, "no CUDA device available (this library has no CPU path)");
+  }
+  if (device < 0 || device >= ndev) return fail(KLB_EINVAL, "device out of range");
+  CK(cudaSetDevice(device));
+  if (klb_measure_peak(kind, per_second) != 0) { cudaGetLastError(); return fail(KLB_ECUDA, "peak measurement failed"); }
   return KLB_OK;
 }
 

@@ -280,3 +280,95 @@ void klb_launch_acceptance(const unsigned char* accept, const double* value, lon
                            long long nchains, int dim, double* out, cudaStream_t s) {
   klb_acceptance_kernel<<<(unsigned)((nchains + 7) / 8), 256, 0, s>>>(accept, value, ld, npost, nchains, dim, out);
 }
+
+// ------------------------------------------------------------------ synthetic initial state
+// x0[i, c] = N(0,1) of stream (seed, global chain c, transition 0, element i): the initial value of every benchmark
+// configuration, a function of the GLOBAL chain index only, so that a job's input does not depend on how its chains
+// are sharded over GPUs.  One thread per double2 unit (klb_normal: the scalar procedure the oracle calls).
+__global__ void klb_synth_state_kernel(const uint64_t* gtab, uint64_t seed, uint64_t chain_offset, long long nchains,
+                                       int dim, long long ld, double* state) {
+  __shared__ uint64_t tab[KLB_TAB_LEN];
+  for (int i = threadIdx.x; i < KLB_TAB_LEN; i += blockDim.x) tab[i] = gtab[i];
+  __syncthreads();
+  const long long upc = ld / 2;                                // units per chain (ld is even)
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < nchains * upc; u += (long long)gridDim.x * blockDim.x) {
+    const long long c = u / upc;
+    const int i = 2 * (int)(u - c * upc);
+    const klb_stream st = klb_stream_make(seed, chain_offset + (uint64_t)c, 0ull);
+    uint64_t w0, w1;
+    klb_stream_draw(&st, (uint32_t)(i >> 1), KLB_TAG_NORMAL, 0u, &w0, &w1);
+    double2 v;
+    v.x = klb_normal_from_word(w0, (uint32_t)i, &st, tab);
+    v.y = (i + 1 < dim) ? klb_normal_from_word(w1, (uint32_t)i + 1u, &st, tab) : 0.0;   // pad row of an odd dim stays 0
+    *reinterpret_cast<double2*>(state + c * ld + i) = v;
+  }
+}
+void klb_launch_synth_state(const uint64_t* tab, uint64_t seed, uint64_t chain_offset, long long nchains, int dim,
+                            long long ld, double* state, cudaStream_t s) {
+  klb_synth_state_kernel<<<148 * 8, 256, 0, s>>>(tab, seed, chain_offset, nchains, dim, ld, state);
+}
+
+// ------------------------------------------------------------------ measured peaks (roofline denominators)
+// MEASURED_PEAKS.json holds HBM and bf16 figures only; the kernels of this library are bound by the fp64 pipe
+// (DADD / DMUL / DFMA: one warp instruction per two cycles per scheduler) or by the fp64 tensor pipe (DMMA), so
+// bench.py measures both denominators live with these two streams of independent instructions.
+__global__ void __launch_bounds__(256) klb_peak_fp64_kernel(double* out, int iters, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = 1e-3 * (threadIdx.x + q);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = __fma_rn(v[q], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += v[q];
+  if (s == 12345.678) out[0] = s;
+}
+__global__ void __launch_bounds__(256) klb_peak_dmma_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { c[q][0] = 1e-3 * (threadIdx.x + q); c[q][1] = 2e-3 * q; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                     : "+d"(c[q][0]), "+d"(c[q][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += c[q][0] + c[q][1];
+  if (s == 12345.678) out[0] = s;
+}
+// kind 0: fp64 results per second (one per lane and DFMA / DADD / DMUL instruction); kind 1: DMMA flop per second
+int klb_measure_peak(int kind, double* per_second) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return -1;
+  double* out = nullptr;
+  if (cudaMalloc(&out, 8) != cudaSuccess) return -1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int grid = sms * 8, iters = kind == 0 ? 4000 : 2000;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, 0);
+    if (kind == 0) klb_peak_fp64_kernel<<<grid, 256>>>(out, iters, 0.999999, 1e-9);
+    else klb_peak_dmma_kernel<<<grid, 256>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = 0.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double work = kind == 0 ? (double)grid * 256 * iters * 64.0                      // 64 DFMA per thread and iteration
+                                  : (double)grid * 8 * iters * 32.0 * 512.0;               // 32 DMMA (8x8x4: 512 flop) per warp
+    if (rep > 0 && ms > 0.f && work / (ms * 1e-3) > best) best = work / (ms * 1e-3);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  if (cudaGetLastError() != cudaSuccess || best == 0.0) return -1;
+  *per_second = best;
+  return 0;
+}

@@ -7,7 +7,7 @@
 //   * one warpgroup of consumers (setmaxnreg.inc): one chain each -- positions and momenta in registers,
 //     leapfrog, reductions, Metropolis test, tuner, stores: almost pure fp64 issue;
 //   * one warpgroup of producers (setmaxnreg.dec): producer s generates the next transition's momentum
-//     (Philox4x32-10 + ziggurat, slow path included) and accept uniform of consumer s into shared memory.
+//     (Philox4x32-7 + ziggurat, slow path included) and accept uniform of consumer s into shared memory.
 // Producer s and consumer s meet at two named barriers (FULL / EMPTY, 64 threads each).  Because warp w and
 // warp 4+w share a scheduler (the producers are warps 0-3, the consumers warps 4-7), every scheduler holds
 // 2 consumers + 2 producers (2 CTAs per SM): one consumer's tail overlaps the other's leapfrog, and the producers'

@@ -4,7 +4,7 @@
  *
  * Contents
  *   - bit casts, contraction-proof fp64 add/mul/fma/div/sqrt wrappers
- *   - Philox4x32-10 counter-based generator (Salmon et al., SC'11) and the
+ *   - Philox4x32 counter-based generator (Salmon et al., SC'11; 7 rounds, see klb_philox4x32_r) and the
  *     counter layout that replaces the reference's unseeded global RNG
  *     (reference draws: src/samplers/iterate/HMC.jl:135,165,
  *      src/samplers/iterate/MALA.jl:84,94, src/samplers/iterate/MH.jl:79,97)
@@ -115,13 +115,27 @@ KLB_HD uint32_t klb_mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-/* out[0..3] = Philox4x32-10(counter c0..c3, key k0,k1) */
-KLB_HD void klb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+/* out[0..3] = Philox4x32-R(counter c0..c3, key k0,k1): R rounds of the Philox4x32 bijection (Salmon, Moraes, Dror,
+ * Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11).
+ *
+ * THE CONTRACT USES R = KLB_PHILOX_ROUNDS = 7.  Philox4x32-7 is the smallest round count the authors report as
+ * Crush-resistant (it passes the complete TestU01 BigCrush battery; their Table 2); Random123 and cuRAND default to
+ * 10 rounds as a safety margin.  Round 1 of this project used 10; ncu showed the HMC kernel bound by the issue slots
+ * its 1024 normals per chain-transition take away from the fp64 pipe (every Philox instruction costs 1.3-1.8 cycles
+ * of fp64 issue, profiles/r2_summary.md), and the RNG contract is this project's own (the reference draws from
+ * Julia's unseeded global MersenneTwister), so round 2 moved to the 7-round generator: -30 % Philox instructions,
+ * +7.4 % leapfrog steps/s.  The round function and key schedule are pinned by the Random123 known-answer vectors of
+ * the 10-round generator, evaluated through the SAME code (klb_philox4x32_10 below; tests/test_oracle_kat.py,
+ * tests/test_twin.py), and the statistical tests of the normals and uniforms run on the 7-round streams. */
+#ifndef KLB_PHILOX_ROUNDS
+#define KLB_PHILOX_ROUNDS 7
+#endif
+KLB_HD void klb_philox4x32_r(int rounds, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                             uint32_t k0, uint32_t k1, uint32_t out[4]) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < rounds; ++r) {
 #if defined(__CUDA_ARCH__)
     /* one IMAD.WIDE per product, opaque to the optimiser: left to itself nvcc strength-reduces the first round over
      * consecutive slots into IMAD.HI + IADD, and IMAD.HI is the most expensive integer instruction to issue next to
@@ -138,6 +152,14 @@ KLB_HD void klb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3
     k0 += KLB_PHILOX_W0; k1 += KLB_PHILOX_W1;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+/* the contract's generator */
+KLB_HD void klb_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  klb_philox4x32_r(KLB_PHILOX_ROUNDS, c0, c1, c2, c3, k0, k1, out);
+}
+/* the published 10-round generator: known-answer tests only */
+KLB_HD void klb_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  klb_philox4x32_r(10, c0, c1, c2, c3, k0, k1, out);
 }
 
 /* Counter layout (the RNG contract, DESIGN.md section "RNG"):
@@ -171,7 +193,7 @@ KLB_HD klb_stream klb_stream_make(uint64_t seed, uint64_t chain, uint64_t t) {
 KLB_HD void klb_stream_draw(const klb_stream* s, uint32_t slot, uint32_t tag, uint32_t attempt,
                             uint64_t* w0, uint64_t* w1) {
   uint32_t o[4];
-  klb_philox4x32_10(slot, s->t_lo, s->chain, tag | (attempt << 4) | s->t_hi16, s->k0, s->k1, o);
+  klb_philox4x32(slot, s->t_lo, s->chain, tag | (attempt << 4) | s->t_hi16, s->k0, s->k1, o);
   *w0 = (uint64_t)o[0] | ((uint64_t)o[1] << 32);
   *w1 = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
 }

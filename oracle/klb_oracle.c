@@ -34,8 +34,8 @@
  *   erf_rate_score(-0.1), (0.93,2)        test/AcceptanceRateMCTuner.jl:13-14
  *   function-defined normal target values test/BasicContMuvParameter.jl:539-563
  *   NState column layout                  test/ParameterNStates.jl:137-146
- * and the random-number primitives against their published vectors (Philox4x32-10
- * Random123 KAT) and against libm / theory.
+ * and the random-number primitives against their published vectors (the Philox4x32 round
+ * function and key schedule through the 10-round Random123 KAT; the contract runs 7 rounds) and against libm / theory.
  *
  * Deliberate replacement (documented in DESIGN.md): Julia's global MersenneTwister
  * randn()/rand() are replaced by counter-based Philox streams keyed by
@@ -118,9 +118,11 @@ double orc_erf_rate_score(double x, double k) { return erf(k * x) + 1; }
 
 double orc_exp(double x) { return klb_exp(x, KLB_TAB); }
 double orc_log(double x) { return klb_log(x, KLB_TAB); }
-void orc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
-  klb_philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1], out);
+/* rounds = 10: the published generator (Random123 known-answer vectors); rounds = 7: the contract's (klb_math.h) */
+void orc_philox(const uint32_t c[4], const uint32_t k[2], int rounds, uint32_t out[4]) {
+  klb_philox4x32_r(rounds, c[0], c[1], c[2], c[3], k[0], k[1], out);
 }
+int orc_philox_rounds(void) { return KLB_PHILOX_ROUNDS; }
 void orc_normals(uint64_t seed, uint64_t chain, uint64_t t, int64_t n, double* out) {
   klb_stream s = klb_stream_make(seed, chain, t);
   for (int64_t i = 0; i < n; ++i) out[i] = klb_normal(&s, (uint32_t)i, KLB_TAB);

@@ -76,7 +76,8 @@ def lib():
         L.orc_normals.restype = None
         L.orc_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
         L.orc_philox.restype = None
-        L.orc_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_philox_rounds.restype = C.c_int
         L.orc_plan_nv.restype = C.c_int
         L.orc_plan_nv.argtypes = [C.c_int64]
         L.orc_dot.restype = dbl
@@ -110,12 +111,17 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def philox(ctr, key):
+def philox(ctr, key, rounds=10):
+    """Philox4x32-`rounds`: 10 = the published generator (known-answer vectors), 7 = the contract's"""
     c = np.asarray(ctr, dtype=np.uint32)
     k = np.asarray(key, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
-    lib().orc_philox(_ptr(c), _ptr(k), _ptr(out))
+    lib().orc_philox(_ptr(c), _ptr(k), rounds, _ptr(out))
     return out
+
+
+def philox_rounds():
+    return lib().orc_philox_rounds()
 
 
 def normals(seed, chain, t, n):

@@ -3,9 +3,12 @@
 
 Provenance: the reference (Klara.jl, Julia 0.6) cannot be executed in this image and never seeds its RNG,
 so these vectors are produced by THIS repo's CPU oracle (oracle/klb_oracle.c), after it has passed the
-reference's own known-answer tests (tests/test_oracle_kat.py).  They freeze the RNG / reduction-order /
-arithmetic contract: the CPU suite checks the oracle still reproduces them, the GPU suite checks the CUDA path
-reproduces them bit for bit.   python tests/golden/make_golden.py
+reference's own known-answer tests (tests/test_oracle_kat.py), and every vector is cross-checked here, before it
+is written, against the independent numpy / libm twin (oracle/twin.py: no shared source, libm exp/log, BLAS-order
+dot products): accept/reject sequences identical, values and log-targets within 1e-6 relative.  They freeze the
+RNG (Philox4x32-7) / reduction-order / arithmetic contract: the CPU suite checks the oracle
+still reproduces them, the GPU suite checks the CUDA path reproduces them bit for bit.  They are regression
+vectors of THIS repo's contract, not outputs of the reference.   python tests/golden/make_golden.py
 """
 import os
 import sys
@@ -59,10 +62,25 @@ def build(name):
     return cfg, x0, tparams, sigma
 
 
+def twin_crosscheck(name, cfg, x0, tparams, sigma, r):
+    sys.path.insert(0, os.path.dirname(HERE))
+    from twin_helpers import check_against_twin, twin_cfg, twin_target
+    smp, tgt, n, d, nsteps, kw, extra = CASES[name]
+    tuner = {O.VANILLA: "vanilla", O.ACCRATE: "accrate"}[kw.get("tuner", O.VANILLA)]
+    tc = twin_cfg(smp, nsteps, burnin=kw.get("burnin", 0), thinning=kw.get("thinning", 1), step=kw.get("step", 0.1),
+                  nleaps=kw.get("nleaps", 10), tuner=tuner, target_rate=kw.get("target_rate", 0.574),
+                  period=kw.get("period", 100), seed=kw["seed"], sigma=sigma)
+    w = check_against_twin(name, tc, twin_target(tgt, d, tparams), x0, range(n), r["value"], r["logtarget"], r["accept"],
+                           final_step=r["tune"]["step"] if smp != "MH" else None)
+    assert w["flips"] == 0
+    return w
+
+
 if __name__ == "__main__":
     for name in CASES:
         cfg, x0, tparams, sigma = build(name)
         r = O.run(cfg, x0, tparams, sigma)
+        print(name, "twin:", twin_crosscheck(name, cfg, x0, tparams, sigma, r))
         out = {"x0": x0, "x": r["x"], "logtarget_state": r["logtarget_state"], "tune": r["tune"]}
         for k in ("value", "logtarget", "gradlogtarget", "accept"):
             if r[k] is not None:

@@ -77,7 +77,7 @@ def test_range_npoststeps(O, K):
 
 # ---- primitives -----------------------------------------------------------------------------
 def test_philox_random123_kat(O):
-    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)"""
+    """Philox4x32 round function + key schedule: the 10-round known-answer vectors of Random123 (kat_vectors)"""
     kat = [
         ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
         ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
@@ -85,7 +85,10 @@ def test_philox_random123_kat(O):
          [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
     ]
     for ctr, key, want in kat:
-        assert [int(v) for v in O.philox(ctr, key)] == want
+        assert [int(v) for v in O.philox(ctr, key, 10)] == want
+    # the contract runs the first 7 of those rounds (klb_math.h: KLB_PHILOX_ROUNDS); same code, same key schedule
+    assert O.philox_rounds() == 7
+    assert [int(v) for v in O.philox([0, 0, 0, 0], [0, 0], 7)] != [int(v) for v in O.philox([0, 0, 0, 0], [0, 0], 10)]
 
 
 def test_no_fp_contraction_in_oracle(O):

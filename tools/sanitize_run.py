@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Small configurations of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool racecheck python tools/sanitize_run.py
+Each run is also compared with the oracle, so a sanitizer-clean run that computes garbage cannot pass."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import klara_b200 as K  # noqa: E402
+from helpers import build_pair, compare_run  # noqa: E402
+
+L = K._lib
+CASES = [
+    ("ws-hmc iso 1024 (warp-specialised producer/consumer, named barriers)", "HMC", "iso", dict(nchains=10, dim=1024, nsteps=5, burnin=2, step=0.05, nleaps=4)),
+    ("ws-hmc iso 700 (masked)", "HMC", "iso", dict(nchains=6, dim=700, nsteps=4, burnin=1, step=0.05, nleaps=3)),
+    ("ws-hmc dual averaging", "HMC", "iso", dict(nchains=6, dim=1024, nsteps=5, burnin=1, step=0.03, nleaps=3, tuner="dualavg", nadapt=3)),
+    ("fused hmc 4-warp teams 2048", "HMC", "iso", dict(nchains=3, dim=2048, nsteps=3, burnin=1, step=0.03, nleaps=3)),
+    ("fused hmc 64", "HMC", "shifted", dict(nchains=9, dim=64, nsteps=6, burnin=2, step=0.1, nleaps=3)),
+    ("mala rosen 256 + tuner", "MALA", "rosen", dict(nchains=9, dim=256, nsteps=12, burnin=8, step=0.01, tuner="accrate", period=4)),
+    ("mh iso 1024", "MH", "iso", dict(nchains=5, dim=1024, nsteps=6, burnin=2, sigma=np.full(1024, 0.02))),
+    ("dense DMMA clusters (TMA multicast, mbarriers) 128", "HMC", "dense", dict(nchains=40, dim=128, nsteps=3, burnin=1, step=0.05, nleaps=3)),
+    ("dense DMMA 512", "HMC", "dense", dict(nchains=20, dim=512, nsteps=2, burnin=0, step=0.02, nleaps=2)),
+    ("dense DFMA tile mala 30", "MALA", "dense", dict(nchains=11, dim=30, nsteps=4, burnin=1, step=0.02)),
+    ("glm hmc", "HMC", "logit", dict(nchains=70, dim=4, nsteps=4, burnin=1, step=0.02, nleaps=3)),
+]
+for name, smp, tgt, kw in CASES:
+    job, cfg, x0, tp, sg = build_pair(K, smp, tgt, seed=31, **kw)
+    compare_run(job, cfg, x0, tp, sg)
+    print("ok:", name, flush=True)
+# pipelined host-to-host call: slice streams, async copies
+job, cfg, x0, tp, sg = build_pair(K, "HMC", "iso", nchains=50, dim=1024, nsteps=4, burnin=1, step=0.05, nleaps=3, seed=5)
+val = np.empty((50, 3, 1024))
+job.run_host(x0, {L.OUT_VALUE: val}, 4)
+ref, *_ = build_pair(K, "HMC", "iso", nchains=50, dim=1024, nsteps=4, burnin=1, step=0.05, nleaps=3, seed=5)
+ref.run()
+assert np.array_equal(val, ref.output().value)
+print("ok: klb_job_run_host, 4 slices", flush=True)
+# post-hoc statistics kernels
+ref.ess(); ref.mean(); ref.acceptance()
+print("ok: ess / stats / acceptance kernels", flush=True)
