@@ -11,8 +11,15 @@ monitor [:value, :logtarget], diagnostics [:accept]  (SURVEY.md section 8d).  On
 benchmark = one complete run(job) of that BasicMCJob over all chains (reset + 200 transitions =
 2000 leapfrog steps per chain, 100 stored samples per chain).  Metric: leapfrog steps per second,
 whole job, all GPUs.  Chains are sharded over ranks (strong scaling: the 65 536 chains are fixed);
-the RNG is keyed by the global chain index so results do not depend on the number of GPUs; one
-NCCL all-gather of the final states closes every step.
+the initial value and the RNG are keyed by the GLOBAL chain index (Philox streams (seed, chain, t)),
+so inputs and results do not depend on the number of GPUs; one all-gather of the final states and
+tuner records closes every step (copy engines over NVLink by default, --gather nccl for NCCL).
+
+Besides the timed legs the run VERIFIES itself (`parity`): a fresh run from the synthetic initial value
+is compared, on a chain subset, with the CPU oracle (accept/reject sequence, log-targets, values, final
+state: bit for bit), at N > 1 chains of the OTHER ranks' shards are recomputed on rank 0 and compared with
+the all-gathered result (G-invariance), and a checksum of all final states is printed that must be the same
+for every N.  `configs` carries the other BASELINE.json configurations (C2, C4, C5, MH) at their stated sizes.
 
 Prints ONE JSON line (rank 0).
 """
@@ -32,10 +39,12 @@ sys.path.insert(0, ROOT)
 
 SEED = 20240925
 NCHAINS, DIM, NLEAPS, LEAPSTEP, NSTEPS, BURNIN = 65536, 1024, 10, 0.05, 200, 100
+NPOST = NSTEPS - BURNIN
 METRIC, UNIT = "leapfrog_steps_per_sec", "leapfrog-steps/s"
 WORKLOAD = ("C3: HMC(leapstep=0.05, nleaps=10), isotropic Gaussian logtarget -z.z, 65536 chains x 1024 dim, "
             "BasicMCRange(nsteps=200, burnin=100), monitor value+logtarget, diagnostics accept, fp64, "
             "arith=reference (un-fused)")
+VERIFY_T = 0            # the verification run replays transitions 1 .. NSTEPS of the streams (what a fresh job does)
 
 
 def measured_peaks():
@@ -44,6 +53,16 @@ def measured_peaks():
         with open(p) as fh:
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic():
+    """dram bytes per C3 launch from the committed ncu capture of this round (profiles/r2_traffic.json)"""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None, "no capture committed"
+    with open(p) as fh:
+        t = json.load(fh)
+    return t, "profiles/r2_traffic.json (%s)" % t.get("source", "ncu --set full")
 
 
 class ClockSampler(threading.Thread):
@@ -90,11 +109,13 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------
 def cpu_leg(nthreads=None, target_seconds=12.0):
     """Times the reference algorithm (oracle/klb_oracle.c; Klara.jl itself needs Julia 0.6, absent) on a
-    bounded sample of the same workload: same d, L, nsteps/burnin/monitor, fewer chains."""
+    bounded sample of the same workload: same d, L, nsteps/burnin/monitor, the FIRST chains of the job from
+    their synthetic initial value.  Its outputs are what `parity` compares the CUDA path with."""
     from oracle import oracle as O
     O.build()
     nthreads = nthreads or os.cpu_count() or 1
     cfgp = dict(step=LEAPSTEP, nleaps=NLEAPS, monitor=3, diagnostics=1, seed=SEED, nthreads=nthreads)
+
     def timed(nchains):
         x0 = np.stack([O.normals(SEED, c, 0, DIM) for c in range(nchains)])
         cfg = O.make_config(O.HMC, O.ISO, nchains, DIM, NSTEPS, BURNIN, **cfgp)
@@ -105,7 +126,7 @@ def cpu_leg(nthreads=None, target_seconds=12.0):
     nchains = 2 * nthreads
     dt, res = timed(nchains)
     if dt < 0.6 * target_seconds:
-        nchains = int(min(65536, max(nchains, nchains * target_seconds / max(dt, 1e-3))) // nthreads * nthreads)
+        nchains = int(min(16384, max(nchains, nchains * target_seconds / max(dt, 1e-3))) // nthreads * nthreads)
         dt, res = timed(nchains)
     lf = nchains * NLEAPS * NSTEPS
     return {"value": lf / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
@@ -145,76 +166,119 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # GPU leg
 # ------------------------------------------------------------------------------------------------
+def _view(torch, ptr, shape, dtype, device):
+    class _Iface:
+        __cuda_array_interface__ = {"shape": tuple(shape), "typestr": {"f8": "<f8", "u1": "|u1", "i8": "<i8"}[dtype],
+                                    "data": (ptr, False), "version": 2}
+    return torch.as_tensor(_Iface(), device=device)
+
+
+class Pinned:
+    """pinned host array (klb_host_alloc)"""
+
+    def __init__(self, L, shape, dtype=np.float64):
+        self.L, self.h = L, C.c_void_p()
+        nb = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        L.check(L.lib().klb_host_alloc(C.byref(self.h), nb))
+        ct = {np.dtype(np.float64): C.c_double, np.dtype(np.uint8): C.c_uint8}[np.dtype(dtype)]
+        self.a = np.ctypeslib.as_array(C.cast(self.h, C.POINTER(ct)), shape=shape)
+        self.nbytes = nb
+
+    def free(self):
+        if self.h:
+            self.L.lib().klb_host_free(self.h)
+            self.h, self.a = None, None
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import klara_b200 as K
     L = K._lib
+    lib = L.lib()
     dist = None
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
-    else:
-        torch.cuda.set_device(local_rank)
-    assert NCHAINS % world == 0
-    nloc = NCHAINS // world
-    off = rank * nloc
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    lo, hi = K.distributed.shard_range(NCHAINS, rank, world)
+    nloc = hi - lo
     arith = args.arith
-
-    # synthetic initial state, generated on the device from the Philox streams (seed, chain, t=0) --
-    # x0[c] = N(0, I); the resident-HBM leg starts from device memory, the e2e leg from pinned host memory
-    x0_host = np.empty((nloc, DIM))
-    lib = L.lib()
-    hx = C.c_void_p()
-    L.check(lib.klb_host_alloc(C.byref(hx), x0_host.nbytes))
-    x0_pin = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_double)), shape=(nloc, DIM))
-    rng = np.random.default_rng(SEED + rank)
-    x0_pin[:] = rng.standard_normal((nloc, DIM))
-
-    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
-    model = K.likelihood_model(p, False)
-    job = K.BasicMCJob(model, K.HMC(LEAPSTEP, NLEAPS), K.BasicMCRange(nsteps=NSTEPS, burnin=BURNIN), {"p": x0_pin},
-                       outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]},
-                       seed=SEED, arith=arith, device=local_rank, chain_offset=off)
-    plan = job.plan()
-    stream = torch.cuda.ExternalStream(lib.klb_job_stream(job._h), device=torch.device("cuda", local_rank))
-
-    # zero-copy torch view of the library-owned final state for the closing NCCL all-gather
-    sp, snb = job.device_ptr(L.OUT_STATE)
-
-    class _Iface:
-        __cuda_array_interface__ = {"shape": (nloc, DIM), "typestr": "<f8", "data": (sp, False), "version": 2}
-    state_t = torch.as_tensor(_Iface(), device=torch.device("cuda", local_rank))
-    gathered = torch.empty((world, nloc, DIM), dtype=torch.float64, device=state_t.device) if world > 1 else None
-    # The closing all-gather of run k reads a snapshot of the final states (a 64 MiB device copy at N=8) on its own
-    # stream, so that it overlaps the kernel of run k+1 instead of delaying it; everything is joined before the
-    # closing event of the timed region.
-    snapshot = torch.empty_like(state_t) if world > 1 else None
-    comm_stream = torch.cuda.Stream(device=state_t.device) if world > 1 else None
-    gather_done = torch.cuda.Event() if world > 1 else None
-
-    def one_step():
-        job.reset()
-        job.run_async()
-        if world > 1:
-            with torch.cuda.stream(stream):
-                stream.wait_event(gather_done)          # the previous gather has read the snapshot
-                snapshot.copy_(state_t, non_blocking=True)
-            comm_stream.wait_stream(stream)
-            with torch.cuda.stream(comm_stream):
-                dist.all_gather_into_tensor(gathered.view(-1), snapshot.view(-1))
-                gather_done.record(comm_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    if world > 1:
-        gather_done.record(comm_stream)
+    def allmax(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
+    # -------- the job: synthetic initial value generated on the device from the Philox streams (seed, chain, 0)
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    model = K.likelihood_model(p, False)
+    job = K.BasicMCJob(model, K.HMC(LEAPSTEP, NLEAPS), K.BasicMCRange(nsteps=NSTEPS, burnin=BURNIN),
+                       {"p": K.SyntheticNormal(nloc, DIM)},
+                       outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]},
+                       seed=SEED, arith=arith, device=local_rank, chain_offset=lo)
+    plan = job.plan()
+    stream = torch.cuda.ExternalStream(lib.klb_job_stream(job._h), device=dev)
+    x0_pin = Pinned(L, (nloc, DIM))                     # the same initial value in pinned host memory (e2e leg)
+    L.check(lib.klb_job_output(job._h, L.OUT_STATE, x0_pin.h, x0_pin.nbytes))
+    sp, _ = job.device_ptr(L.OUT_STATE)
+    state_t = _view(torch, sp, (nloc, DIM), "f8", dev)
+
+    # -------- the closing all-gather
+    gather, gathered_t, nccl = None, None, None
+    if world > 1 and args.gather == "p2p":
+        g = C.c_void_p()
+        L.check(lib.klb_gather_create(job._h, world, rank, NCHAINS, 0, C.byref(g)))
+        h = C.create_string_buffer(L.GATHER_HANDLE_BYTES)
+        L.check(lib.klb_gather_handle(g, h))
+        mine = torch.frombuffer(bytearray(h.raw), dtype=torch.uint8).to(dev)
+        allh = torch.empty(world * L.GATHER_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine)         # plumbing: the IPC handles travel over NCCL
+        raw = bytes(allh.cpu().numpy())
+        L.check(lib.klb_gather_connect(g, C.create_string_buffer(raw, len(raw))))
+        gp, gnb = C.c_void_p(), C.c_int64()
+        L.check(lib.klb_gather_device_ptr(g, L.OUT_STATE, C.byref(gp), C.byref(gnb)))
+        gathered_t = _view(torch, gp.value, (NCHAINS, DIM), "f8", dev)
+        gather = g
+    elif world > 1:
+        # NCCL all-gather of a snapshot of the final states on its own stream (round 1's path: SM-based kernel)
+        nccl = {"out": torch.empty((NCHAINS, DIM), dtype=torch.float64, device=dev), "snap": torch.empty_like(state_t),
+                "stream": torch.cuda.Stream(device=dev), "done": torch.cuda.Event()}
+        nccl["done"].record(nccl["stream"])
+        gathered_t = nccl["out"]
+
+    def push():
+        if gather is not None:
+            L.check(lib.klb_gather_push_async(gather))
+        elif nccl is not None:
+            with torch.cuda.stream(stream):
+                stream.wait_event(nccl["done"])         # the previous gather has read the snapshot
+                nccl["snap"].copy_(state_t, non_blocking=True)
+            nccl["stream"].wait_stream(stream)
+            with torch.cuda.stream(nccl["stream"]):
+                dist.all_gather_into_tensor(nccl["out"].view(-1), nccl["snap"].view(-1))
+                nccl["done"].record(nccl["stream"])
+
+    def join():                                         # the job stream waits for the last all-gather
+        if gather is not None:
+            L.check(lib.klb_gather_join(gather))
+        elif nccl is not None:
+            stream.wait_stream(nccl["stream"])
+
+    def one_step():
+        job.reset()
+        job.run_async()
+        push()
+
     for _ in range(args.warmup):
         one_step()
     barrier()
@@ -231,8 +295,7 @@ def run_gpu(args, rank, world, local_rank):
         one_step()
         if args.per_step_sync:
             job.sync()
-    if world > 1:
-        stream.wait_stream(comm_stream)                 # the last all-gather belongs to the timed region
+    join()                                              # the last all-gather belongs to the timed region
     e1.record(stream)
     barrier()
     wall = time.perf_counter() - t0
@@ -242,30 +305,27 @@ def run_gpu(args, rank, world, local_rank):
     launches_timed = job.launches - launches_w
 
     # -------- end-to-end leg: host buffers in, host buffers out, through the public API
-    lt_host = np.empty((nloc, NSTEPS - BURNIN))
-    acc_host = np.empty((nloc, NSTEPS - BURNIN), dtype=np.uint8)
-    hs = C.c_void_p()
-    L.check(lib.klb_host_alloc(C.byref(hs), x0_host.nbytes))
-    st_pin = np.ctypeslib.as_array(C.cast(hs, C.POINTER(C.c_double)), shape=(nloc, DIM))
-    hl = C.c_void_p()
-    L.check(lib.klb_host_alloc(C.byref(hl), lt_host.nbytes + acc_host.nbytes))
-    h2d = x0_host.nbytes
-    d2h = x0_host.nbytes + lt_host.nbytes + acc_host.nbytes
+    st_pin, lt_pin, ac_pin = Pinned(L, (nloc, DIM)), Pinned(L, (nloc, NPOST)), Pinned(L, (nloc, NPOST), np.uint8)
+    h2d = x0_pin.nbytes
+    d2h = st_pin.nbytes + lt_pin.nbytes + ac_pin.nbytes
 
-    e2e_fields = (L.KlbHostField * 3)()
-    for q, (fld, ptr, nb) in enumerate(((L.OUT_STATE, hs.value, x0_host.nbytes), (L.OUT_LOGTARGET, hl.value, lt_host.nbytes),
-                                        (L.OUT_ACCEPT, hl.value + lt_host.nbytes, acc_host.nbytes))):
-        e2e_fields[q].field, e2e_fields[q].host_dst, e2e_fields[q].nbytes = fld, ptr, nb
+    def fields(*extra):
+        spec = [(L.OUT_STATE, st_pin), (L.OUT_LOGTARGET, lt_pin), (L.OUT_ACCEPT, ac_pin)] + list(extra)
+        arr = (L.KlbHostField * len(spec))()
+        for q, (fld, buf) in enumerate(spec):
+            arr[q].field, arr[q].host_dst, arr[q].nbytes = fld, buf.h.value, buf.nbytes
+        return arr, len(spec)
+    e2e_fields, ne2e = fields()
 
     def e2e_step():
         if args.e2e_serial:                                        # the three blocking calls, one after the other
-            L.check(lib.klb_job_set_state(job._h, hx))             # H2D x0 + initialize! + tuner reset
+            L.check(lib.klb_job_set_state(job._h, x0_pin.h))      # H2D x0 + initialize! + tuner reset
             L.check(lib.klb_job_run(job._h))
-            L.check(lib.klb_job_output(job._h, L.OUT_STATE, hs, x0_host.nbytes))
-            L.check(lib.klb_job_output(job._h, L.OUT_LOGTARGET, hl, lt_host.nbytes))
-            L.check(lib.klb_job_output(job._h, L.OUT_ACCEPT, C.c_void_p(hl.value + lt_host.nbytes), acc_host.nbytes))
+            L.check(lib.klb_job_output(job._h, L.OUT_STATE, st_pin.h, st_pin.nbytes))
+            L.check(lib.klb_job_output(job._h, L.OUT_LOGTARGET, lt_pin.h, lt_pin.nbytes))
+            L.check(lib.klb_job_output(job._h, L.OUT_ACCEPT, ac_pin.h, ac_pin.nbytes))
         else:                                                      # the same work as one pipelined call
-            L.check(lib.klb_job_run_host(job._h, hx, e2e_fields, 3, args.e2e_slices))
+            L.check(lib.klb_job_run_host(job._h, x0_pin.h, e2e_fields, ne2e, args.e2e_slices))
 
     e2e_step()
     barrier()
@@ -275,113 +335,258 @@ def run_gpu(args, rank, world, local_rank):
         e2e_step()
     barrier()
     e2e_wall = (time.perf_counter() - te) / nrep
-    acc_rate = float(np.ctypeslib.as_array(C.cast(C.c_void_p(hl.value + lt_host.nbytes), C.POINTER(C.c_uint8)),
-                                           shape=(nloc, NSTEPS - BURNIN)).mean())
+    acc_rate = float(ac_pin.a.mean())
 
-    # -------- optional: end-to-end with EVERY monitored field copied to the host (50 GiB of values at N=1)
+    # -------- end-to-end with EVERY monitored field copied to the host: what output(job) returns in the reference
+    # (50 GiB of values at N = 1).  The values ride in the same pipelined call, slice by slice.
     e2e_full = None
-    if args.e2e_full:
-        vbytes = nloc * (NSTEPS - BURNIN) * DIM * 8
-        hv = C.c_void_p()
-        L.check(lib.klb_host_alloc(C.byref(hv), vbytes))
-
-        def full_step():
-            e2e_step()
-            L.check(lib.klb_job_output(job._h, L.OUT_VALUE, hv, vbytes))
-        full_step()
-        barrier()
-        tf = time.perf_counter()
-        full_step()
-        barrier()
-        e2e_full = {"ms_per_step": (time.perf_counter() - tf) * 1e3, "d2h_bytes_per_step": (d2h + vbytes) * world}
-        lib.klb_host_free(hv)
+    if not args.no_e2e_full:
+        try:
+            v_pin = Pinned(L, (nloc, NPOST, DIM))
+            full_fields, nfull = fields((L.OUT_VALUE, v_pin))
+            L.check(lib.klb_job_run_host(job._h, x0_pin.h, full_fields, nfull, args.e2e_slices))
+            barrier()
+            tf = time.perf_counter()
+            L.check(lib.klb_job_run_host(job._h, x0_pin.h, full_fields, nfull, args.e2e_slices))
+            barrier()
+            e2e_full = {"ms_per_step": (time.perf_counter() - tf) * 1e3, "d2h_bytes_per_step": (d2h + v_pin.nbytes) * world,
+                        "h2d_bytes_per_step": h2d * world}
+            v_pin.free()
+        except L.KlaraError as e:                       # not enough pinned host memory on this box
+            e2e_full = {"unavailable": str(e)}
 
     # -------- effective sample size of the stored chains, on the device
+    job.reset(); job.run()
+    torch.cuda.synchronize()
     tq = time.perf_counter()
     L.check(lib.klb_job_ess(job._h, None))
     ess_ms = (time.perf_counter() - tq) * 1e3
-    ep, enb = job.device_ptr(L.OUT_ESS)
-
-    class _IfaceE:
-        __cuda_array_interface__ = {"shape": (nloc, DIM), "typestr": "<f8", "data": (ep, False), "version": 2}
-    ess_t = torch.as_tensor(_IfaceE(), device=torch.device("cuda", local_rank))
-    ess_stats = torch.stack([ess_t.sum(), ess_t.min(), torch.isfinite(ess_t).all().double()])
-    ess_stats[1] = -ess_stats[1]
+    ep, _ = job.device_ptr(L.OUT_ESS)
+    ess_t = _view(torch, ep, (nloc, DIM), "f8", dev)
+    ess_stats = torch.stack([ess_t.sum(), -ess_t.min()])
     if world > 1:
         s_ = ess_stats[:1].clone(); dist.all_reduce(s_); ess_stats[0] = s_[0]
         m_ = ess_stats[1:2].clone(); dist.all_reduce(m_, op=dist.ReduceOp.MAX); ess_stats[1] = m_[0]
     ess_sum, ess_min = float(ess_stats[0]), -float(ess_stats[1])
 
+    # -------- verification run: a fresh job's first run (synthetic x0, transitions 1..nsteps), all ranks, gathered
+    job.reset_synthetic()
+    job.seek(VERIFY_T)
+    job.run_async()
+    push()
+    join()
+    job.sync()
+    if gather is not None:
+        L.check(lib.klb_gather_sync(gather))
+    barrier()
+    full_state = gathered_t if world > 1 else state_t          # (NCHAINS, DIM) on every rank
+    words = full_state.view(torch.int64).reshape(-1)
+    w = (torch.arange(words.numel(), device=dev, dtype=torch.int64) % 65521) + 1
+    checksum = "%016x-%016x" % (int(words.sum().item()) & (2 ** 64 - 1), int((words * w).sum().item()) & (2 ** 64 - 1))
+    parity = None
+    if rank == 0:
+        parity = verify(args, torch, K, L, job, nloc, lo, world, full_state, dev)
+        parity["final_state_checksum"] = checksum
+        parity["note"] = ("fresh run from the synthetic initial value: chains 0..n-1 against the CPU oracle (bit for bit; "
+                          "max_rel_* are 0 when the bits agree); at N > 1 chains of the other ranks' shards recomputed on "
+                          "rank 0 against the all-gathered states; final_state_checksum covers all 65 536 final states and "
+                          "is the same for every N")
+    cb = parity.pop("_cpu_baseline", None) if parity else None
+
     # -------- reduce over ranks: max time
-    t_dev = torch.tensor([dev_ms, wall * 1e3, e2e_wall * 1e3, last_kernel_ms], dtype=torch.float64,
-                         device=state_t.device)
-    if world > 1:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, e2e_ms, kernel_ms = [float(v) for v in t_dev.cpu()]
+    dev_ms, wall_ms, e2e_ms, kernel_ms = allmax([dev_ms, wall * 1e3, e2e_wall * 1e3, last_kernel_ms])
+    if e2e_full and "ms_per_step" in e2e_full:
+        e2e_full["ms_per_step"] = allmax([e2e_full["ms_per_step"]])[0]
+
+    # -------- free the C3 job, then the other BASELINE configurations at their stated sizes
+    if gather is not None:
+        barrier()
+        lib.klb_gather_destroy(gather)
+    job.close()
+    for b in (x0_pin, st_pin, lt_pin, ac_pin):
+        b.free()
+    del state_t, ess_t, full_state, words, w, gathered_t
+    fp64_peak = K.device_peak("fp64", local_rank)
+    dmma_peak = K.device_peak("dmma", local_rank)
+    hbm_peak, peak_src = measured_peaks()
+    configs = None
+    if not args.no_configs:
+        configs = other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak, dmma_peak, hbm_peak)
 
     lf_per_step = NCHAINS * NLEAPS * NSTEPS            # leapfrog steps in one bench step, all ranks
     value = lf_per_step * args.steps / (dev_ms * 1e-3)
     out = None
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        # algorithmic bytes per launch: per transition read x + write x (16 d) for every chain,
-        # plus (8 d + 9) per stored sample (value + logtarget + accept flag); this rank's launch covers nloc chains
-        bytes_launch = nloc * (NSTEPS * 16 * DIM + (NSTEPS - BURNIN) * (8 * DIM + 9))
-        achieved = bytes_launch / (kernel_ms * 1e-3) / 1e9
-        # fp64 issue roofline: 5 d un-fused ops per leapfrog step (+ per-transition overhead ignored)
-        fp64_ops = nloc * NSTEPS * (NLEAPS * (5 if arith == "reference" else 3) * DIM)
-        cb = None
-        if world == 1 and not args.no_cpu:
-            cb, _ = cpu_leg(target_seconds=12.0)
-            cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # fp64-issue roofline (what binds this kernel, ncu: profiles/): executed leapfrog fp64 instructions, 5 d per
+        # step in reference arithmetic (DADD / DMUL, un-fused) or 3 d (DFMA), one result per lane and instruction,
+        # against the measured issue rate of a stream of independent DFMA on this device
+        ops_launch = nloc * NSTEPS * NLEAPS * (5 if arith == "reference" else 3) * DIM
+        fp64_achieved = ops_launch / (kernel_ms * 1e-3)
+        # HBM contract figure of SURVEY.md 8d (read x + write x per transition, + the stored sample): kept beside it
+        bytes_launch = nloc * (NSTEPS * 16 * DIM + NPOST * (8 * DIM + 9))
+        hbm_achieved = bytes_launch / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = profiled_traffic()
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "chains_per_gpu": nloc, "arith": arith,
                        "l2": "inputs larger than L2 (state 512 MiB + 50 GiB of samples per step at N=1)",
+                       "x0": "Philox stream (seed, global chain, transition 0), generated on the device",
+                       "rng": "Philox4x32-7 counter streams + 256-layer ziggurat (DESIGN.md section 3)",
+                       "closing_all_gather": ("none (N=1)" if world == 1 else
+                                              "copy engines, CUDA IPC peer-to-peer over NVLink (klb_gather_*)" if gather is not None
+                                              else "NCCL all_gather_into_tensor on a side stream"),
                        "nv": plan.nv, "regs_per_thread": plan.regs_per_thread, "blocks_per_sm": plan.blocks_per_sm,
                        "accept_rate": acc_rate, "timing": "CUDA events on the job stream, max over ranks",
                        "wall_ms_per_step": wall_ms / args.steps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this launch at N=1 (ncu --set full,
-                         # profiles/r1_summary.md capture G), scaled to this rank's chains
-                         "traffic": 54.89e9 * nloc / NCHAINS if arith == "reference" else None,
-                         "traffic_source": "profiles/r1_kernel_metrics.csv column M_ws_shipping_bench_launch (dram__bytes_read.sum + dram__bytes_write.sum)",
-                         "peak_source": peak_src,
-                         "kernel": "klb_hmc_ws_kernel<TgtIso, NV=16> (warp-specialised: 4 consumer + 4 producer warps per CTA)", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": bytes_launch,
-                         "fp64": {"achieved_tops": fp64_ops / (kernel_ms * 1e-3) / 1e12,
-                                  "peak_tops": 148 * 64 * 1.965e-3,
-                                  "note": "leapfrog fp64 instructions only (5 d per step, un-fused: DADD/DMUL count 1 each) "
-                                          "against 148 SMs x 64 lanes x 1.965 GHz; the kernel is fp64-issue bound, not HBM bound "
-                                          "(ncu, column M: fp64 pipe 61.9 % busy, issue slots 57.7 %, DRAM 10.0 %): profiles/r1_summary.md"}},
+            "roofline": {"bound": "fp64_issue", "achieved": fp64_achieved / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                         "frac": fp64_achieved / fp64_peak,
+                         "flop_definition": "one fp64 result per lane and DADD / DMUL / DFMA instruction (an FMA counts 1): the pipe issues one "
+                                            "warp instruction per 2 cycles per scheduler whatever the kind, so this is the issue-rate roofline",
+                         "peak_source": "measured live: klb_device_peak(KLB_PEAK_FP64), a stream of independent DFMA on this device",
+                         "traffic": None if not traffic else traffic["dram_bytes_per_launch"] * nloc / traffic["nchains"],
+                         "traffic_source": traffic_src,
+                         "kernel": "klb_hmc_ws_kernel<TgtIso, NV=16> (warp-specialised: 4 consumer + 4 producer warps per CTA)",
+                         "kernel_ms": kernel_ms, "algorithmic_fp64_results_per_launch": ops_launch,
+                         "hbm_contract": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                                          "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src,
+                                          "note": "SURVEY.md 8d contract bytes (x read + written every transition, + stored samples). The kernel keeps "
+                                                  "the state on chip, so measured DRAM traffic is ~5x lower and HBM is NOT the binding roofline"}},
             "cpu_baseline": cb,
             "e2e": {"value": lf_per_step / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": e2e_ms,
                     "call": "klb_job_set_state + klb_job_run + klb_job_output x3 (serial)" if args.e2e_serial
                             else "klb_job_run_host (chain slices pipelined over streams)",
                     "note": "host x0 in (pinned), final state + logtarget chain + accept flags out (pinned), through the "
-                            "C ABI; the 50 GiB of monitored values stay in HBM (output(job) copies them on request)"},
-            "ess": {"mean_ess_per_coordinate": ess_sum / (NCHAINS * DIM), "min_ess": ess_min, "samples_per_chain": NSTEPS - BURNIN,
+                            "C ABI; the monitored values stay in HBM here -- e2e_full_output copies them too"},
+            "e2e_full_output": None if e2e_full is None else (e2e_full if "unavailable" in e2e_full else dict(
+                e2e_full, value=lf_per_step / (e2e_full["ms_per_step"] * 1e-3), unit=UNIT,
+                note="as e2e, plus every monitored sample (KLB_OUT_VALUE, what output(job) holds in the reference) copied to "
+                     "pinned host memory inside the same pipelined call: PCIe-bound")),
+            "ess": {"mean_ess_per_coordinate": ess_sum / (NCHAINS * DIM), "min_ess": ess_min, "samples_per_chain": NPOST,
                     "independent_samples_per_sec": (ess_sum / DIM) / (dev_ms / args.steps * 1e-3),
                     "ess_kernel_ms": ess_ms,
                     "note": "ess(chain, :imse) per coordinate on the device (klb_job_ess); independent samples/s = "
                             "sum over chains of the coordinate-mean ESS / device time of one run"},
-            "e2e_full_output": None if e2e_full is None else dict(
-                e2e_full, value=lf_per_step / (e2e_full["ms_per_step"] * 1e-3), unit=UNIT,
-                note="as e2e, plus klb_job_output(KLB_OUT_VALUE): all monitored samples copied to pinned host memory"),
+            "parity": parity,
+            "configs": configs,
+            "peaks": {"fp64_results_per_s": fp64_peak, "dmma_flop_per_s": dmma_peak, "hbm_gbs": hbm_peak},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
         }
-    job.close()
-    lib.klb_host_free(hx); lib.klb_host_free(hs); lib.klb_host_free(hl)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out), flush=True)
+
+
+def verify(args, torch, K, L, job, nloc, lo, world, full_state, dev):
+    """rank 0: the verification run against the CPU oracle (chains 0..n-1), and G-invariance probes at N > 1"""
+    lib = L.lib()
+    seconds = 12.0 if (world == 1 and not args.no_cpu) else 1.0
+    cb, ref = cpu_leg(target_seconds=seconds)
+    n = ref["accept"].shape[0]
+    n = min(n, nloc)
+    lp, _ = job.device_ptr(L.OUT_LOGTARGET)
+    ap, _ = job.device_ptr(L.OUT_ACCEPT)
+    vp, _ = job.device_ptr(L.OUT_VALUE)
+    lt = _view(torch, lp, (nloc, NPOST), "f8", dev)[:n].cpu().numpy()
+    ac = _view(torch, ap, (nloc, NPOST), "u1", dev)[:n].cpu().numpy()
+    nv = min(n, 64)
+    val = _view(torch, vp, (nloc, NPOST, DIM), "f8", dev)[:nv].cpu().numpy()
+    xf = full_state[:n].cpu().numpy()
+
+    def rel(a, b):
+        return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+    def same(a, b):
+        return bool(np.array_equal(a.view(np.uint64), b.view(np.uint64)))
+    par = {"oracle_chains": int(n), "accept_equal": bool(np.array_equal(ac, ref["accept"][:n])),
+           "max_rel_logtarget": rel(lt, ref["logtarget"][:n]), "max_rel_value": rel(val, ref["value"][:nv]),
+           "max_rel_final_state": rel(xf, ref["x"][:n]),
+           "bit_exact": same(lt, ref["logtarget"][:n]) and same(val, ref["value"][:nv]) and same(xf, ref["x"][:n]),
+           "value_chains": int(nv)}
+    if world == 1 and not args.no_cpu:
+        par["_cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if world > 1:
+        # G-invariance: the first chains of every OTHER rank's shard, recomputed here as their own small job
+        probe, ok, checked = 32, True, 0
+        p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+        for r in range(1, world):
+            rlo, rhi = K.distributed.shard_range(NCHAINS, r, world)
+            m = min(probe, rhi - rlo)
+            pj = K.BasicMCJob(K.likelihood_model(p, False), K.HMC(LEAPSTEP, NLEAPS), K.BasicMCRange(nsteps=NSTEPS, burnin=BURNIN),
+                              {"p": K.SyntheticNormal(m, DIM)}, outopts={"destination": "none"}, seed=SEED, arith=args.arith,
+                              device=dev.index, chain_offset=rlo)
+            pj.seek(VERIFY_T)
+            pj.run()
+            ok = ok and same(pj.pstate_value, full_state[rlo:rlo + m].cpu().numpy())
+            checked += m
+            pj.close()
+        par["g_invariance"] = {"equal": bool(ok), "chains_recomputed_on_rank0": checked,
+                               "what": "final states of chains owned by ranks 1..N-1 (as all-gathered) == the same chains "
+                                       "run as a separate job on rank 0"}
+    return par
+
+
+def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak, dmma_peak, hbm_peak):
+    """BASELINE.json configs C2, C4, C5 and the MH sampler at the C3 size: device-resident runs, chains sharded over
+    the ranks like C3, CUDA-event time of the run kernels (max over ranks), each with its own roofline figures."""
+    idx = np.arange(512)
+    Cm = np.linalg.inv(0.8 ** np.abs(idx[:, None] - idx[None, :]))
+    Cm = np.ascontiguousarray((Cm + Cm.T) / 2)
+    specs = [
+        # name, workload, sampler, target, N, d, nsteps, burnin, tuner, unit, work units per transition
+        ("C2", "MALA(0.9), -z.z, 4096 x 128, nsteps 2000 / burnin 1000", K.MALA(0.9), K.IsoGaussian(), 4096, 128, 2000, 1000, None, "transitions/s", 1),
+        ("C4", "HMC(0.02, 20), -z'Cz (C = inv AR(1) 0.8, dense 512 x 512, DMMA), 16384 x 512, nsteps 200 / burnin 100",
+         K.HMC(0.02, 20), K.DenseGaussian(Cm), 16384, 512, 200, 100, None, "leapfrog-steps/s", 20),
+        ("C5", "MALA(0.01) + AcceptanceRateMCTuner(0.574), paired Rosenbrock, 32768 x 256, nsteps 2000 / burnin 1000",
+         K.MALA(0.01), K.Rosenbrock(1.0, 100.0, 0.05), 32768, 256, 2000, 1000, K.AcceptanceRateMCTuner(0.574), "transitions/s", 1),
+        ("MH", "MH(sigma = 0.02), -z.z, 65536 x 1024, nsteps 200 / burnin 100", K.MH(np.full(1024, 0.02)), K.IsoGaussian(),
+         65536, 1024, 200, 100, None, "transitions/s", 1),
+    ]
+    out = {}
+    for name, workload, smp, tgt, N, d, nsteps, burnin, tuner, unit, per in specs:
+        lo, hi = K.distributed.shard_range(N, rank, world)
+        p = K.BasicContMuvParameter("p", logtarget=tgt)
+        job = K.BasicMCJob(K.likelihood_model(p, False), smp, K.BasicMCRange(nsteps=nsteps, burnin=burnin),
+                           {"p": K.SyntheticNormal(hi - lo, d)}, tuner=tuner,
+                           outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}, seed=SEED, arith=args.arith,
+                           device=local_rank, chain_offset=lo)
+        job.run()
+        ms = []
+        for _ in range(2):
+            job.reset()
+            job.run()
+            ms.append(job.last_run_ms)
+        acc = float(job.acceptance().mean())
+        job.close()
+        ms = allmax([float(np.mean(ms))])[0]
+        nloc, npost = hi - lo, nsteps - burnin
+        rate = N * nsteps * per / (ms * 1e-3)
+        bytes_launch = nloc * (nsteps * 16 * d + npost * (8 * d + 9))          # SURVEY.md 8d contract bytes, this rank
+        ent = {"workload": workload, "value": rate, "unit": unit, "ms_per_run": ms, "accept_rate": acc,
+               "hbm_contract": {"achieved": bytes_launch / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": bytes_launch / (ms * 1e-3) / 1e9 / hbm_peak}}
+        if name == "C4":
+            flop = nloc * nsteps * per * (2 * d * d)                           # the matrix-vector products on the fp64 tensor pipe
+            ent["roofline"] = {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": dmma_peak / 1e12, "unit": "TFLOP/s",
+                               "frac": flop / (ms * 1e-3) / dmma_peak, "kernel": "klb_dense_mma_kernel (DMMA m8n8k4 + cluster TMA multicast)",
+                               "peak_source": "measured live: klb_device_peak(KLB_PEAK_DMMA), independent mma.sync.m8n8k4.f64"}
+        else:
+            # algorithmic un-fused fp64 operations per transition (SURVEY.md 8d): MALA iso 19 d, MALA Rosenbrock 25 d, MH 4 d
+            ops = {"C2": 19, "C5": 25, "MH": 4}[name] * d
+            res = nloc * nsteps * ops
+            ent["roofline"] = {"bound": "issue (RNG + fp64)", "achieved": res / (ms * 1e-3) / 1e12, "peak": fp64_peak / 1e12,
+                               "unit": "TFLOP/s", "frac": res / (ms * 1e-3) / fp64_peak,
+                               "kernel": "klb_chain_kernel<%s, ...>" % type(smp).__name__,
+                               "note": "algorithmic fp64 operations of SURVEY.md 8d against the measured fp64 issue rate; these kernels spend "
+                                       "most of their issue slots on the d normals per transition (Philox + ziggurat) and, for MALA, on two fp64 "
+                                       "divisions per element: ncu figures in profiles/"}
+        out[name] = ent
+    return out
 
 
 def main():
@@ -391,11 +596,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arith", default="reference", choices=["reference", "fma"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="closing all-gather at N > 1: copy engines over CUDA IPC peer-to-peer (default) or NCCL")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline timing (the parity check still runs a 1 s oracle sample)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configurations (C2, C4, C5, MH)")
+    ap.add_argument("--no-e2e-full", action="store_true", help="skip the end-to-end step that also copies every monitored sample to the host")
     ap.add_argument("--per-step-sync", action="store_true")
     ap.add_argument("--e2e-serial", action="store_true", help="e2e leg through the three blocking calls (set_state, run, output) instead of klb_job_run_host")
     ap.add_argument("--e2e-slices", type=int, default=0, help="chain slices of the pipelined e2e call (0 = library default)")
-    ap.add_argument("--e2e-full", action="store_true", help="also time an end-to-end step that copies every monitored sample to the host")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -259,6 +259,8 @@ int klb_job_ess(klb_job* job, double* host_ess);
 int klb_job_stat(klb_job* job, int stat, double* host_dst);
 
 int klb_job_plan(klb_job* job, klb_plan* out);
+/* the configuration the job was created with */
+int klb_job_config(klb_job* job, klb_config* out);
 /* kernels launched by this job so far */
 int64_t klb_job_launches(klb_job* job);
 /* CUDA-event time (ms) of the last klb_job_run / run_async+sync kernel sequence */
@@ -266,6 +268,55 @@ double klb_job_last_run_ms(klb_job* job);
 void* klb_job_stream(klb_job* job);
 
 void klb_job_destroy(klb_job* job);
+
+/* ---- multi-GPU ------------------------------------------------------------------------------------------------
+ * run(job::Vector{MCJob}) = map(run, job) (src/jobs/jobs.jl:212) is the reference's whole multi-job facility: the
+ * chains of one logical job are independent, so they shard over GPUs -- device g of G owns the contiguous chain block
+ * [g N/G, (g+1) N/G), RNG streams use global chain indices (klb_config.chain_offset), results do not depend on G, and
+ * nothing is exchanged while sampling.  One closing all-gather leaves, on EVERY device, the final state
+ * (KLB_OUT_STATE, ld x N), log-target (KLB_OUT_STATE_LOGTARGET), tuner step (KLB_OUT_TUNE_STEP) and
+ * {accepted, proposed, totproposed} (KLB_OUT_TUNE_COUNTERS) of ALL chains.  It is done by the copy engines over
+ * NVLink / NVSwitch peer-to-peer (no kernel, no SM time), asynchronously to the job's stream.
+ *
+ * klb_multi_*: one process drives `ngpus` devices (the `ngpus` field of SURVEY.md section 8b).  cfg->nchains is the
+ * TOTAL chain count; cfg->device is ignored; devices = NULL uses devices 0 .. ngpus-1 (ngpus <= 0: all of them); the
+ * same ordinal may be listed twice.  Host arrays are those of the logical job (klb_job_* layouts with nchains = N). */
+typedef struct klb_multi klb_multi;
+int klb_multi_create(const klb_config* cfg, int32_t ngpus, const int32_t* devices, klb_multi** out);
+int klb_multi_ngpus(klb_multi* m);
+int klb_multi_job(klb_multi* m, int32_t g, klb_job** job);              /* the shard's job (klb_job_ess, klb_job_stat, ...) */
+int klb_multi_set_target_f64(klb_multi* m, int which, const double* host, int64_t n);
+int klb_multi_set_state(klb_multi* m, const double* x0);               /* dim x N */
+int klb_multi_set_state_synthetic(klb_multi* m);
+int klb_multi_reset(klb_multi* m);
+int klb_multi_seek(klb_multi* m, uint64_t t);
+int klb_multi_run(klb_multi* m);                                        /* run on every device + closing all-gather; blocking */
+int klb_multi_run_async(klb_multi* m);
+int klb_multi_sync(klb_multi* m);
+int klb_multi_output(klb_multi* m, int field, void* host_dst, int64_t nbytes);   /* output(job): shards concatenated */
+int klb_multi_gathered(klb_multi* m, int32_t g, int field, void** dev_ptr, int64_t* nbytes);  /* device g's copy of the all-gather */
+int klb_multi_gathered_output(klb_multi* m, int32_t g, int field, void* host_dst, int64_t nbytes);
+double klb_multi_last_run_ms(klb_multi* m);                             /* max over devices */
+void klb_multi_destroy(klb_multi* m);
+
+/* klb_gather_*: one end of the same all-gather per PROCESS (one process per GPU, e.g. torchrun).  Every rank creates
+ * its end on its shard's job, exports a KLB_GATHER_HANDLE_BYTES handle (a CUDA IPC memory handle plus the shard's
+ * position), the caller all-gathers the handles with whatever it has (torch.distributed, MPI, a file) and connects.
+ * klb_gather_push_async copies this rank's shard into every rank's buffers after the work queued on the job's stream;
+ * klb_gather_sync waits for this rank's copies.  Once every rank's klb_gather_sync has returned (the inter-process
+ * barrier is the caller's), every rank holds the complete all-gather.  first_chain = global index of chain 0 of the
+ * logical job. */
+#define KLB_GATHER_HANDLE_BYTES 128
+typedef struct klb_gather klb_gather;
+int klb_gather_create(klb_job* job, int32_t world, int32_t rank, int64_t nchains_total, int64_t first_chain, klb_gather** out);
+int klb_gather_handle(klb_gather* g, void* handle_out);
+int klb_gather_connect(klb_gather* g, const void* handles /* world x KLB_GATHER_HANDLE_BYTES, rank order */);
+int klb_gather_push_async(klb_gather* g);
+int klb_gather_sync(klb_gather* g);
+int klb_gather_join(klb_gather* g);   /* the job's stream waits for the last push (for device-side timing) */
+int klb_gather_device_ptr(klb_gather* g, int field, void** dev_ptr, int64_t* nbytes);
+int klb_gather_output(klb_gather* g, int field, void* host_dst, int64_t nbytes);
+void klb_gather_destroy(klb_gather* g);
 
 /* Measured throughput of one device for the roofline denominators that MEASURED_PEAKS.json does not hold:
  * KLB_PEAK_FP64 = fp64 results per second of a stream of independent DFMA (DADD / DMUL issue at the same rate),

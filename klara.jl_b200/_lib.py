@@ -24,6 +24,7 @@ PARAM_MU, PARAM_C, PARAM_SIGMA, PARAM_ROSEN, PARAM_LOGIT_X, PARAM_LOGIT_Y, PARAM
 (OUT_VALUE, OUT_LOGTARGET, OUT_GRADLOGTARGET, OUT_ACCEPT, OUT_STATE, OUT_STATE_LOGTARGET,
  OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS, OUT_TUNE_DA) = range(11)
 PEAK_FP64, PEAK_DMMA = 0, 1
+GATHER_HANDLE_BYTES = 128
 (STAT_MEAN, STAT_MCVAR_IID, STAT_MCVAR_IMSE, STAT_ESS, STAT_IACT, STAT_ACCEPTANCE, STAT_ACCEPTANCE_VALUE) = range(7)
 
 
@@ -82,10 +83,36 @@ SYMBOLS = [
     ("klb_job_ess", _int, [_vp, _vp]),
     ("klb_job_stat", _int, [_vp, _int, _vp]),
     ("klb_job_plan", _int, [_vp, C.POINTER(KlbPlan)]),
+    ("klb_job_config", _int, [_vp, C.POINTER(KlbConfig)]),
     ("klb_job_launches", _i64, [_vp]),
     ("klb_job_last_run_ms", _dbl, [_vp]),
     ("klb_job_stream", _vp, [_vp]),
     ("klb_job_destroy", None, [_vp]),
+    ("klb_multi_create", _int, [C.POINTER(KlbConfig), C.c_int32, _vp, C.POINTER(_vp)]),
+    ("klb_multi_ngpus", _int, [_vp]),
+    ("klb_multi_job", _int, [_vp, C.c_int32, C.POINTER(_vp)]),
+    ("klb_multi_set_target_f64", _int, [_vp, _int, _vp, _i64]),
+    ("klb_multi_set_state", _int, [_vp, _vp]),
+    ("klb_multi_set_state_synthetic", _int, [_vp]),
+    ("klb_multi_reset", _int, [_vp]),
+    ("klb_multi_seek", _int, [_vp, _u64]),
+    ("klb_multi_run", _int, [_vp]),
+    ("klb_multi_run_async", _int, [_vp]),
+    ("klb_multi_sync", _int, [_vp]),
+    ("klb_multi_output", _int, [_vp, _int, _vp, _i64]),
+    ("klb_multi_gathered", _int, [_vp, C.c_int32, _int, C.POINTER(_vp), C.POINTER(_i64)]),
+    ("klb_multi_gathered_output", _int, [_vp, C.c_int32, _int, _vp, _i64]),
+    ("klb_multi_last_run_ms", _dbl, [_vp]),
+    ("klb_multi_destroy", None, [_vp]),
+    ("klb_gather_create", _int, [_vp, C.c_int32, C.c_int32, _i64, _i64, C.POINTER(_vp)]),
+    ("klb_gather_handle", _int, [_vp, _vp]),
+    ("klb_gather_connect", _int, [_vp, _vp]),
+    ("klb_gather_push_async", _int, [_vp]),
+    ("klb_gather_sync", _int, [_vp]),
+    ("klb_gather_join", _int, [_vp]),
+    ("klb_gather_device_ptr", _int, [_vp, _int, C.POINTER(_vp), C.POINTER(_i64)]),
+    ("klb_gather_output", _int, [_vp, _int, _vp, _i64]),
+    ("klb_gather_destroy", None, [_vp]),
     ("klb_device_peak", _int, [_int, _int, C.POINTER(_dbl)]),
     ("klb_host_alloc", _int, [C.POINTER(_vp), _i64]),
     ("klb_host_free", _int, [_vp]),

@@ -263,10 +263,14 @@ class BasicMCJob:
       device        CUDA device ordinal
       chain_offset  global index of the first chain when the chains of one logical job are sharded
                     over several processes / GPUs
+      ngpus         shard the chains over this many devices of THIS process (klb_multi_*: contiguous chain blocks,
+                    global-chain RNG, one closing all-gather of the final states and tuner records by the copy
+                    engines); 0 = every visible device.  `devices` lists the ordinals (default 0 .. ngpus-1).
+                    Results do not depend on ngpus.
     """
 
     def __init__(self, model, sampler, mcrange, v0, tuner=None, outopts=None, pindex=None,
-                 seed=0, arith="reference", device=0, chain_offset=0, verbose=False):
+                 seed=0, arith="reference", device=0, chain_offset=0, verbose=False, ngpus=1, devices=None):
         tuner = VanillaMCTuner() if tuner is None else tuner
         self.model, self.sampler, self.range, self.tuner = model, sampler, mcrange, tuner
         self.pindex = next(i for i, v in enumerate(model.vertices) if isinstance(v, BasicContMuvParameter)) \
@@ -335,19 +339,41 @@ class BasicMCJob:
         cfg.da_gamma, cfg.da_kappa = getattr(tuner, "gamma", 0.05), getattr(tuner, "kappa", 0.75)
         self.cfg = cfg
         self._h = C.c_void_p()
-        L.check(L.lib().klb_job_create(C.byref(cfg), C.byref(self._h)))
+        self._m = None                          # klb_multi handle when the chains are sharded over devices
+        lib = L.lib()
+        if ngpus != 1 or devices is not None:
+            devs = None
+            if devices is not None:
+                ngpus = len(devices)
+                devs = (C.c_int32 * ngpus)(*devices)
+            self._m = C.c_void_p()
+            L.check(lib.klb_multi_create(C.byref(cfg), ngpus, devs, C.byref(self._m)))
+            self.ngpus = lib.klb_multi_ngpus(self._m)
+            self._shards = []                   # (job handle, first chain within the logical job, chains)
+            for g in range(self.ngpus):
+                h, c = C.c_void_p(), L.KlbConfig()
+                L.check(lib.klb_multi_job(self._m, g, C.byref(h)))
+                L.check(lib.klb_job_config(h, C.byref(c)))
+                self._shards.append((h, c.chain_offset - chain_offset, c.nchains))
+            self._h = self._shards[0][0]
+        else:
+            self.ngpus = 1
+            L.check(lib.klb_job_create(C.byref(cfg), C.byref(self._h)))
+            self._shards = [(self._h, 0, self.nchains)]
+        set_target = lib.klb_multi_set_target_f64 if self._m else lib.klb_job_set_target_f64
+        top = self._m if self._m else self._h
         try:
             for which, arr in self.parameter.target.params(self.dim):
-                L.check(L.lib().klb_job_set_target_f64(self._h, which, _ptr(arr), arr.size))
+                L.check(set_target(top, which, _ptr(arr), arr.size))
             if isinstance(sampler, MH):
                 if sampler.sigma.size != self.dim:
                     raise AssertionError("MH sigma has %d entries, parameter has %d" % (sampler.sigma.size, self.dim))
-                L.check(L.lib().klb_job_set_target_f64(self._h, L.PARAM_SIGMA, _ptr(sampler.sigma), self.dim))
+                L.check(set_target(top, L.PARAM_SIGMA, _ptr(sampler.sigma), self.dim))
             # initialize!: first target (+gradient) evaluation; finiteness asserts (HMC.jl:113-114)
             if synthetic:
-                L.check(L.lib().klb_job_set_state_synthetic(self._h))
+                L.check((lib.klb_multi_set_state_synthetic if self._m else lib.klb_job_set_state_synthetic)(top))
             else:
-                L.check(L.lib().klb_job_set_state(self._h, _ptr(x0)))
+                L.check((lib.klb_multi_set_state if self._m else lib.klb_job_set_state)(top, _ptr(x0)))
         except Exception:
             self.close()
             raise
@@ -355,9 +381,19 @@ class BasicMCJob:
 
     # -- lifecycle
     def close(self):
-        if getattr(self, "_h", None) is not None and self._h.value:
+        if getattr(self, "_m", None) is not None and self._m.value:
+            L.lib().klb_multi_destroy(self._m)
+            self._m, self._h, self._shards = None, C.c_void_p(), []
+        elif getattr(self, "_h", None) is not None and self._h.value:
             L.lib().klb_job_destroy(self._h)
             self._h = C.c_void_p()
+
+    def _call(self, name, *args):
+        """klb_multi_<name> when the job is sharded over devices, klb_job_<name> otherwise"""
+        lib = L.lib()
+        if self._m:
+            return L.check(getattr(lib, "klb_multi_" + name)(self._m, *args))
+        return L.check(getattr(lib, "klb_job_" + name)(self._h, *args))
 
     def __del__(self):
         try:
@@ -368,7 +404,7 @@ class BasicMCJob:
     # -- reference API
     def run(self):
         """run(job)        src/jobs/BasicMCJob.jl:212-244"""
-        L.check(L.lib().klb_job_run(self._h))
+        self._call("run")
         self.count = self.range.npoststeps
         if self.outopts["destination"] == "iostream":
             # the samples are produced on the device; the CSV files of the reference's iostream destination are
@@ -378,17 +414,19 @@ class BasicMCJob:
         return self
 
     def run_async(self):
-        L.check(L.lib().klb_job_run_async(self._h))
+        self._call("run_async")
         self.count = self.range.npoststeps
 
     def sync(self):
-        L.check(L.lib().klb_job_sync(self._h))
+        self._call("sync")
 
     def run_host(self, x0=None, outputs=None, nslices=0):
         """reset(job, x0); run(job); output(job) in one pipelined call (klb_job_run_host): the chains go through in
         `nslices` slices on their own streams so that host->device copies, kernels and device->host copies overlap.
         `outputs` maps field codes (klara_b200._lib.OUT_*) to writable C-contiguous numpy arrays -- ideally views of
         pinned memory (klb_host_alloc) -- that receive the fields.  Results are identical to the three separate calls."""
+        if self._m:
+            raise L.KlaraError(L.KLB_EUNSUPPORTED, "run_host drives one device; shard the host arrays and call it per job")
         outputs = outputs or {}
         arr = (L.KlbHostField * max(1, len(outputs)))()
         for i, (field, buf) in enumerate(outputs.items()):
@@ -408,32 +446,44 @@ class BasicMCJob:
     def reset(self, x=None):
         """reset(job) / reset(job, x)        src/jobs/BasicMCJob.jl:187-201"""
         if x is None:
-            L.check(L.lib().klb_job_reset(self._h))
+            self._call("reset")
         else:
             x = np.ascontiguousarray(np.atleast_2d(np.asarray(x, dtype=np.float64)))
             if x.shape != (self.nchains, self.dim):
                 raise AssertionError("reset value has shape %s, job has %s" % (x.shape, (self.nchains, self.dim)))
-            L.check(L.lib().klb_job_set_state(self._h, _ptr(x)))
+            self._call("set_state", _ptr(x))
         self.count = 0
         return self
 
     def reset_synthetic(self):
         """reset(job, x0) with the device-generated synthetic initial value (SyntheticNormal)"""
-        L.check(L.lib().klb_job_set_state_synthetic(self._h))
+        self._call("set_state_synthetic")
         self.count = 0
         return self
 
     def seek(self, t):
         """position the RNG streams: the next transition is number t + 1 (klb_job_seek)"""
-        L.check(L.lib().klb_job_seek(self._h, int(t)))
+        self._call("seek", int(t))
         return self
 
     def set_chunk(self, nt):
-        L.check(L.lib().klb_job_set_chunk(self._h, nt))
+        for h, _, _ in self._shards:
+            L.check(L.lib().klb_job_set_chunk(h, nt))
 
     def _fetch(self, field, shape, dtype=np.float64):
         out = np.empty(shape, dtype=dtype)
-        L.check(L.lib().klb_job_output(self._h, field, _ptr(out), out.nbytes))
+        self._call("output", field, _ptr(out), out.nbytes)
+        return out
+
+    def gathered(self, field, g=0):
+        """device g's copy of the closing all-gather (klb_multi_gathered_output): the final state / log-target /
+        tuner step / counters of ALL chains as that device holds them after run(job)"""
+        if not self._m:
+            raise L.KlaraError(L.KLB_ESTATE, "the job is not sharded over devices (ngpus = 1)")
+        shape, dtype = {L.OUT_STATE: ((self.nchains, self.dim), np.float64), L.OUT_STATE_LOGTARGET: ((self.nchains,), np.float64),
+                        L.OUT_TUNE_STEP: ((self.nchains,), np.float64), L.OUT_TUNE_COUNTERS: ((self.nchains, 3), np.int64)}[field]
+        out = np.empty(shape, dtype=dtype)
+        L.check(L.lib().klb_multi_gathered_output(self._m, g, field, _ptr(out), out.nbytes))
         return out
 
     def output(self):
@@ -467,16 +517,17 @@ class BasicMCJob:
     def ess(self, to_host=True):
         """ess(output(job)): effective sample size (IMSE) of every coordinate of every chain, computed on the
         device (src/stats/convergence/ess.jl:3-14).  Returns (nchains, dim), or None when to_host=False."""
-        if to_host:
-            out = np.empty((self.nchains, self.dim))
-            L.check(L.lib().klb_job_ess(self._h, _ptr(out)))
-            return out[0] if self.single else out
-        L.check(L.lib().klb_job_ess(self._h, None))
-        return None
+        out = np.empty((self.nchains, self.dim)) if to_host else None
+        for h, lo, n in self._shards:           # statistics are per chain: every shard computes its own
+            L.check(L.lib().klb_job_ess(h, _ptr(out[lo:lo + n]) if to_host else None))
+        if not to_host:
+            return None
+        return out[0] if self.single else out
 
     def _stat(self, code, per_chain=False):
         out = np.empty(self.nchains if per_chain else (self.nchains, self.dim))
-        L.check(L.lib().klb_job_stat(self._h, code, _ptr(out)))
+        for h, lo, n in self._shards:
+            L.check(L.lib().klb_job_stat(h, code, _ptr(out[lo:lo + n])))
         return out[0] if self.single else out
 
     def mean(self):
@@ -533,11 +584,11 @@ class BasicMCJob:
 
     @property
     def launches(self):
-        return L.lib().klb_job_launches(self._h)
+        return sum(L.lib().klb_job_launches(h) for h, _, _ in self._shards)
 
     @property
     def last_run_ms(self):
-        return L.lib().klb_job_last_run_ms(self._h)
+        return max(L.lib().klb_job_last_run_ms(h) for h, _, _ in self._shards)
 
     def device_ptr(self, field):
         p, nb = C.c_void_p(), C.c_int64()

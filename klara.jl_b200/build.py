@@ -32,7 +32,7 @@ HEADERS = ["klb_kernels.cuh", "klb_dense.cuh", "klb_dense_mma.cuh", "klb_hmc_ws.
 
 
 def units():
-    u = [("klb_api", "klb_api.cu", []), ("klb_aux", "klb_aux.cu", []),
+    u = [("klb_api", "klb_api.cu", []), ("klb_aux", "klb_aux.cu", []), ("klb_multi", "klb_multi.cu", []),
          ("klb_init", "klb_kernels_inst.cu", ["-DKLB_INST_INIT"]), ("klb_dense", "klb_dense_inst.cu", []),
          ("klb_dense_mma", "klb_dense_mma_inst.cu", []), ("klb_glm", "klb_glm_inst.cu", [])]
     for smp in (0, 1, 2):

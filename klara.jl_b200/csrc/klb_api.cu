@@ -161,6 +161,9 @@ static long long npoststeps(long long burnin, long long thinning, long long nste
   return nsteps <= burnin ? 0 : (nsteps - burnin - 1) / thinning + 1;
 }
 
+// for the other translation units of the library (klb_multi.cu)
+int klb_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+
 extern "C" {
 
 int klb_version(void) { return KLB_VERSION; }
@@ -892,6 +895,12 @@ int klb_job_plan(klb_job* j, klb_plan* out) {
   out->npoststeps = j->npost;
   out->transitions_done = (int64_t)j->t_global;
   out->saved = j->count;
+  return KLB_OK;
+}
+
+int klb_job_config(klb_job* j, klb_config* out) {
+  if (!j || !out) return fail(KLB_EINVAL, "null argument");
+  *out = j->cfg;
   return KLB_OK;
 }
 

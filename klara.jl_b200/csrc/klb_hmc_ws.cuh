@@ -158,6 +158,7 @@ klb_hmc_ws_kernel(const KArgs A) {
       y[2 * j] = v.x; y[2 * j + 1] = v.y;
     }
     if (lane == 0) cs->u_acc = uacc[slot];
+    __syncwarp();                                                            // lane 0's store is ordered before every lane's read below
     if (it + 1 < nt) bar_arrive(bar_empty, 64);                              // buffer may be refilled
 
     const double step = cs->step;
@@ -232,6 +233,7 @@ klb_hmc_ws_kernel(const KArgs A) {
       a_prob = a;
       accept = cs->u_acc < a;
     }
+    __syncwarp();                  // every lane has read this transition's scalars (lt_cur, step, u_acc) before lane 0 rewrites them
     if (A.counters_on || A.tuner == 2) {                                     // tuner record: lives in shared memory
       Tune tn;
       tn.step = step; tn.accepted = cs->accepted; tn.proposed = cs->proposed; tn.totproposed = cs->totproposed;

@@ -1,0 +1,173 @@
+"""Multi-GPU layer of the C ABI (klb_multi_*: one process, several devices; klb_gather_*: one process per GPU, CUDA
+IPC): chains sharded in contiguous blocks, RNG keyed by the global chain index, closing all-gather by the copy engines.
+run(job::Vector{MCJob}) = map(run, job), src/jobs/jobs.jl:212.  1 device vs N devices must be bit-identical; on a
+one-GPU box the same ordinal is listed several times, which exercises everything but the NVLink hop."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import assert_same, build_pair, synthetic_x0
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _devices(K, n):
+    have = K._lib.lib().klb_device_count()
+    return [g % have for g in range(n)]
+
+
+@pytest.mark.parametrize("sampler,target,dim,nshards", [("HMC", "iso", 1024, 3), ("MALA", "rosen", 96, 2), ("MH", "iso", 7, 4),
+                                                        ("HMC", "dense", 128, 2), ("HMC", "logit", 4, 5)])
+def test_multi_equals_single_device(K, sampler, target, dim, nshards):
+    L = K._lib
+    N = 101                                               # ragged shards
+    kw = dict(nchains=N, dim=dim, nsteps=24, burnin=7, thinning=2, step={"HMC": 0.02, "MALA": 0.002, "MH": 0.1}[sampler],
+              nleaps=5, seed=4242, sigma=np.full(dim, 0.05), tuner="accrate", period=5, target_rate=0.7)
+    one, cfg, x0, tp, sg = build_pair(K, sampler, target, **kw)
+    one.run()
+    ref = one.output()
+    tgt = one.parameter.target
+    smp, tun, rng = one.sampler, one.tuner, one.range
+    p = K.BasicContMuvParameter("p", logtarget=tgt)
+    multi = K.BasicMCJob(K.likelihood_model(p, False), smp, rng, {"p": x0}, tuner=tun,
+                         outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}, seed=4242,
+                         devices=_devices(K, nshards))
+    assert multi.ngpus == nshards
+    multi.run()
+    out = multi.output()
+    assert_same("value", out.value, ref.value)
+    assert_same("logtarget", out.logtarget, ref.logtarget)
+    assert_same("accept", out.diagnosticvalues, ref.diagnosticvalues)
+    assert_same("final state", multi.pstate_value, one.pstate_value)
+    assert_same("tune.step", multi.tune.step, one.tune.step)
+    for g in range(nshards):                              # every device holds the complete all-gather
+        assert_same("gathered state on device %d" % g, multi.gathered(L.OUT_STATE, g), one.pstate_value)
+        assert_same("gathered logtarget", multi.gathered(L.OUT_STATE_LOGTARGET, g), one.pstate_logtarget)
+        assert_same("gathered step", multi.gathered(L.OUT_TUNE_STEP, g), one.tune.step)
+        cnt = multi.gathered(L.OUT_TUNE_COUNTERS, g)
+        assert_same("gathered accepted", cnt[:, 0], one.tune.accepted)
+        assert_same("gathered totproposed", cnt[:, 2], one.tune.totproposed)
+    assert_same("ess", multi.ess(), one.ess())
+    assert_same("acceptance", multi.acceptance(), one.acceptance())
+    # reset + second run continue the same streams on every shard
+    multi.reset(); multi.run(); one.reset(); one.run()
+    assert_same("second run", multi.output().value, one.output().value)
+    multi.close()
+
+
+def test_multi_real_devices_when_present(K):
+    """two (or more) physical devices: the closing all-gather crosses NVLink; skipped on a one-GPU box"""
+    L = K._lib
+    have = L.lib().klb_device_count()
+    if have < 2:
+        pytest.skip("one device")
+    N, d = 4096, 1024
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    mk = lambda **kw: K.BasicMCJob(K.likelihood_model(p, False), K.HMC(0.05, 10), K.BasicMCRange(nsteps=20, burnin=10),  # noqa: E731
+                                   {"p": K.SyntheticNormal(N, d)}, outopts={"monitor": ["logtarget"], "diagnostics": ["accept"]},
+                                   seed=77, **kw)
+    one, multi = mk(), mk(ngpus=0)
+    assert multi.ngpus == have
+    one.run(); multi.run()
+    assert_same("logtarget", multi.output().logtarget, one.output().logtarget)
+    for g in range(have):
+        assert_same("gathered state on device %d" % g, multi.gathered(L.OUT_STATE, g), one.pstate_value)
+
+
+def test_synthetic_state_and_seek(K, O):
+    """klb_job_set_state_synthetic = the Philox initial value of SURVEY 8d (a function of the global chain index);
+    klb_job_seek repositions the streams"""
+    N, d = 37, 130
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    mk = lambda v0, **kw: K.BasicMCJob(K.likelihood_model(p, False), K.HMC(0.05, 4), K.BasicMCRange(nsteps=9, burnin=2), {"p": v0},  # noqa: E731
+                                       outopts={"monitor": ["value"]}, seed=99, **kw)
+    a = mk(K.SyntheticNormal(N, d), chain_offset=1000)
+    assert_same("x0", a.pstate_value, synthetic_x0(99, N, d, 1000))
+    b = mk(synthetic_x0(99, N, d, 1000), chain_offset=1000)
+    a.run(); b.run()
+    assert_same("run from the synthetic state", a.output().value, b.output().value)
+    first = a.output().value
+    a.reset_synthetic(); a.seek(0); a.run()
+    assert_same("seek(0) replays the run", a.output().value, first)
+    a.reset_synthetic(); a.seek(500); a.run()
+    assert not np.array_equal(a.output().value, first)
+    cfg = O.make_config(O.HMC, O.ISO, N, d, 9, 2, step=0.05, nleaps=4, monitor=1, seed=99, chain_offset=1000, t0=500,
+                        nv=a.plan().nv, nthreads=O.max_threads())
+    assert_same("seek(500) == oracle at t0 = 500", a.output().value, O.run(cfg, synthetic_x0(99, N, d, 1000))["value"])
+    odd = K.BasicMCJob(K.likelihood_model(p, False), K.MH(np.full(7, 0.3)), K.BasicMCRange(nsteps=3), {"p": K.SyntheticNormal(5, 7)}, seed=3)
+    assert_same("odd dim", odd.pstate_value, synthetic_x0(3, 5, 7))
+
+
+def test_device_peaks_are_plausible(K):
+    fp64, dmma = K.device_peak("fp64"), K.device_peak("dmma")
+    assert 5e12 < fp64 < 4e13, fp64                       # B200: 148 SMs x 64 lanes x ~1.9 GHz = 1.8e13 results/s
+    assert 1e13 < dmma < 1.5e14, dmma
+
+
+def _ipc_worker(rank, world, N, d, conn, ret):
+    sys.path.insert(0, ROOT)
+    import klara_b200 as K
+    L = K._lib
+    lib = L.lib()
+    dev = rank % lib.klb_device_count()
+    lo, hi = K.distributed.shard_range(N, rank, world)
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    job = K.BasicMCJob(K.likelihood_model(p, False), K.HMC(0.05, 5), K.BasicMCRange(nsteps=12, burnin=4),
+                       {"p": K.SyntheticNormal(hi - lo, d)}, outopts={"monitor": ["logtarget"]}, seed=2024, device=dev,
+                       chain_offset=lo)
+    g = C.c_void_p()
+    L.check(lib.klb_gather_create(job._h, world, rank, N, 0, C.byref(g)))
+    h = C.create_string_buffer(L.GATHER_HANDLE_BYTES)
+    L.check(lib.klb_gather_handle(g, h))
+    conn.send(h.raw)                                      # "all-gather" of the handles through the parent
+    allh = conn.recv()
+    L.check(lib.klb_gather_connect(g, C.create_string_buffer(allh, len(allh))))
+    job.run_async()
+    L.check(lib.klb_gather_push_async(g))
+    L.check(lib.klb_gather_sync(g))
+    conn.send(b"pushed")                                  # inter-process barrier: every rank has pushed
+    conn.recv()
+    full = np.empty((N, d))
+    L.check(lib.klb_gather_output(g, L.OUT_STATE, full.ctypes.data_as(C.c_void_p), full.nbytes))
+    ret.put((rank, full))
+    conn.recv()                                           # keep the buffers alive until every rank has read
+    lib.klb_gather_destroy(g)
+    job.close()
+
+
+def test_gather_between_processes_over_cuda_ipc(K):
+    """one process per GPU (the torchrun layout of bench.py): IPC handles exchanged by the caller, every rank ends up
+    with every chain's final state"""
+    import multiprocessing as mp
+    N, d, world = 64, 1024, 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    pipes = [ctx.Pipe() for _ in range(world)]
+    procs = [ctx.Process(target=_ipc_worker, args=(r, world, N, d, pipes[r][1], ret)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    try:
+        handles = b"".join(pipes[r][0].recv() for r in range(world))
+        for r in range(world):
+            pipes[r][0].send(handles)
+        for r in range(world):
+            assert pipes[r][0].recv() == b"pushed"
+        for r in range(world):
+            pipes[r][0].send(b"go")
+        got = dict(ret.get(timeout=120) for _ in range(world))
+        for r in range(world):
+            pipes[r][0].send(b"done")
+    finally:
+        for pr in procs:
+            pr.join(timeout=60)
+    assert all(pr.exitcode == 0 for pr in procs)
+    p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
+    one = K.BasicMCJob(K.likelihood_model(p, False), K.HMC(0.05, 5), K.BasicMCRange(nsteps=12, burnin=4),
+                       {"p": K.SyntheticNormal(N, d)}, outopts={"monitor": ["logtarget"]}, seed=2024)
+    one.run()
+    for r in range(world):
+        assert_same("rank %d holds the whole all-gather" % r, got[r], one.pstate_value)
