@@ -357,6 +357,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # -------- effective sample size of the stored chains, on the device
     job.reset(); job.run()
+    L.check(lib.klb_job_ess(job._h, None))             # first call allocates the result buffer
     torch.cuda.synchronize()
     tq = time.perf_counter()
     L.check(lib.klb_job_ess(job._h, None))
@@ -406,7 +407,14 @@ def run_gpu(args, rank, world, local_rank):
     for b in (x0_pin, st_pin, lt_pin, ac_pin):
         b.free()
     del state_t, ess_t, full_state, words, w, gathered_t
-    fp64_peak = K.device_peak("fp64", local_rank)
+    # fp64 issue-rate roofline: one warp instruction per 2 cycles per scheduler = 64 results per cycle and SM
+    # (tools/fp64_pipe_test.cu measured 2.005 cycles per instruction, profiles/r1_summary.md), at the part's maximum SM
+    # clock.  A stream of independent DFMA timed with CUDA events (klb_device_peak) lands ~8 % below it (all-DFMA load),
+    # so the nominal-at-max-clock figure is the stricter denominator; both are printed under `peaks`.
+    fp64_stream = K.device_peak("fp64", local_rank)
+    sm_mhz_max = (clocks or {}).get("sm_max_mhz") or 1965.0
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp64_peak = max(fp64_stream, sms * 64 * sm_mhz_max * 1e6)
     dmma_peak = K.device_peak("dmma", local_rank)
     hbm_peak, peak_src = measured_peaks()
     configs = None
@@ -444,7 +452,8 @@ def run_gpu(args, rank, world, local_rank):
                          "frac": fp64_achieved / fp64_peak,
                          "flop_definition": "one fp64 result per lane and DADD / DMUL / DFMA instruction (an FMA counts 1): the pipe issues one "
                                             "warp instruction per 2 cycles per scheduler whatever the kind, so this is the issue-rate roofline",
-                         "peak_source": "measured live: klb_device_peak(KLB_PEAK_FP64), a stream of independent DFMA on this device",
+                         "peak_source": "SMs x 64 fp64 lanes x clocks.max.sm (issue rate confirmed by microbenchmark, profiles/r1_summary.md); the "
+                                        "live-measured stream of independent DFMA (klb_device_peak) is under `peaks`",
                          "traffic": None if not traffic else traffic["dram_bytes_per_launch"] * nloc / traffic["nchains"],
                          "traffic_source": traffic_src,
                          "kernel": "klb_hmc_ws_kernel<TgtIso, NV=16> (warp-specialised: 4 consumer + 4 producer warps per CTA)",
@@ -471,7 +480,8 @@ def run_gpu(args, rank, world, local_rank):
                             "sum over chains of the coordinate-mean ESS / device time of one run"},
             "parity": parity,
             "configs": configs,
-            "peaks": {"fp64_results_per_s": fp64_peak, "dmma_flop_per_s": dmma_peak, "hbm_gbs": hbm_peak},
+            "peaks": {"fp64_results_per_s": fp64_peak, "fp64_stream_measured_results_per_s": fp64_stream,
+                      "dmma_flop_per_s": dmma_peak, "hbm_gbs": hbm_peak},
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
         }

@@ -66,6 +66,8 @@ extern "C" {
  * Per-chain step AND per-chain number of leapfrog steps, nleaps = max(1, round(λ/step)).  Elementwise and
  * logistic-regression targets (the dense-precision kernels advance their chains in lockstep tiles). */
 #define KLB_TUNER_DUAL_AVERAGING 2
+#define KLB_SCORE_LOGISTIC 0
+#define KLB_SCORE_ERF 1
 
 /* arithmetic: 0 = every product and sum rounded separately, in the reference's evaluation order
  * ((0.5*step)*g first, then the addition: src/samplers/samplers.jl:130-133); 1 = a*b+c contracted
@@ -122,7 +124,7 @@ typedef struct {
   double step;            /* HMC leapstep / MALA driftstep (> 0); unused by MH */
   int32_t nleaps;         /* HMC (> 0) */
   double target_rate;     /* AcceptanceRateMCTuner.targetrate in (0,1) */
-  double score_k;         /* steepness of logistic_rate_score (default 7) */
+  double score_k;         /* steepness k of the score function (defaults: 7 logistic, 3 erf) */
   int64_t period;         /* tuner period (> 0, default 100) */
   int32_t verbose;        /* tuner.verbose: switches the acceptance counters on (iterate/HMC.jl:129-133) */
   uint32_t monitor;       /* KLB_MONITOR_* */
@@ -132,7 +134,8 @@ typedef struct {
   int64_t chain_offset;   /* global index of this job's first chain (RNG streams use global indices,
                              so results do not depend on how chains are sharded over GPUs) */
   int32_t device;         /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t score;          /* AcceptanceRateMCTuner.score: KLB_SCORE_LOGISTIC (logistic_rate_score, 2/(1+exp(-k x))) or
+                             KLB_SCORE_ERF (erf_rate_score, erf(k x)+1); k = score_k   AcceptanceRateMCTuner.jl:9,17 */
   /* DualAveragingMCTuner only (target_rate, period, verbose above are shared with the other tuners) */
   int64_t da_nadapt;      /* nadapt > 0: transitions during which the step adapts */
   int64_t da_t0;          /* t0 > 0 (default 10) */

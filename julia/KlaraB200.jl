@@ -19,7 +19,8 @@ module KlaraB200
 using LinearAlgebra: dot
 import Statistics: mean      # Klara adds methods to mean (src/stats/mean.jl:7-11); so does the shim
 
-export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, DenseGaussian, BayesLogit, Hyperparameter, Data, DualAveragingMCTuner, run_host, ess, mcvar, mcse, iact, acceptance, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
+export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, DenseGaussian, BayesLogit, Hyperparameter, Data, DualAveragingMCTuner, run_host, GenericModel,
+       SyntheticNormal, seek!, gathered, logistic_rate_score, erf_rate_score, ess, mcvar, mcse, iact, acceptance, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
        BasicMCRange, VanillaMCTuner, AcceptanceRateMCTuner, BasicMCJob, run, reset, output
 
 const LIB = get(ENV, "KLARA_B200_LIB", "libklara_b200.so")
@@ -35,7 +36,10 @@ gradient(t::ShiftedIsoGaussian) = z -> -2 .* (z .- t.mu)
 struct Rosenbrock <: Target; a::Float64; b::Float64; scale::Float64; end
 Rosenbrock() = Rosenbrock(1.0, 100.0, 0.05)
 # -z'Cz, -2Cz with a symmetric precision matrix (doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9)
-struct DenseGaussian <: Target; C::Matrix{Float64}; end
+# DenseGaussian() is bound by BasicMCJob from the model's Hyperparameter(:C) vertex (v[1] of the reference's closures,
+# doc/examples/BivariateNormal/MALA/function/analytical.jl:4-21)
+mutable struct DenseGaussian <: Target; C::Matrix{Float64}; end
+DenseGaussian() = DenseGaussian(zeros(0, 0))
 (t::DenseGaussian)(z::Vector{Float64}) = -dot(z, t.C*z)
 gradient(t::DenseGaussian) = z -> -2 .* (t.C*z)
 # Bayesian logistic regression, N(0, λI) prior: the closures of doc/examples/swiss/HMC/noadaptation/analytical.jl:11-20.
@@ -52,9 +56,14 @@ const Data = Hyperparameter
 
 struct BasicContMuvParameter; key::Symbol; logtarget::Target; end
 BasicContMuvParameter(key::Symbol; logtarget::Target, gradlogtarget=nothing, nkeys::Int=0) = BasicContMuvParameter(key, logtarget)
+# GenericModel(vs; isindexed=false): vertices kept in the given order (src/models/GenericModel.jl:94-119); the job only
+# uses the graph to find the parameter and the other vertices' values in vertex order
 struct GenericModel; vertices::Vector{Any}; end
+GenericModel(v::Vector; isindexed::Bool=true, isdirected::Bool=true) = GenericModel(Any[v...])
 likelihood_model(p::BasicContMuvParameter, isindexed::Bool=true) = GenericModel(Any[p])
-likelihood_model(v::Vector; isindexed::Bool=true) = GenericModel(Any[v...])
+likelihood_model(v::Vector; isindexed::Bool=true, isdirected::Bool=true) = GenericModel(Any[v...])
+# initial value generated on the device from the job's Philox streams (seed, global chain, transition 0)
+struct SyntheticNormal; dim::Int; nchains::Int; end
 
 struct MH; sigma::Vector{Float64}; end
 struct MALA; driftstep::Float64; MALA(s=1.0) = (@assert s > 0 "Drift step is not positive"; new(s)); end
@@ -75,8 +84,14 @@ function BasicMCRange(; burnin::Int=0, thinning::Int=1, nsteps::Int=100)
 end
 struct VanillaMCTuner; period::Int; verbose::Bool; end
 VanillaMCTuner(; period::Int=100, verbose::Bool=false) = VanillaMCTuner(period, verbose)
-struct AcceptanceRateMCTuner; targetrate::Float64; k::Float64; period::Int; verbose::Bool; end
-AcceptanceRateMCTuner(rate; k=7.0, period::Int=100, verbose::Bool=false) = AcceptanceRateMCTuner(rate, k, period, verbose)
+logistic_rate_score(x::Real, k::Real=7.) = 2/(1+exp(-k*x))          # src/tuners/AcceptanceRateMCTuner.jl:9
+erf_rate_score(x::Real, k::Real=3.) = ccall((:erf, "libm"), Float64, (Float64,), k*x)+1   # src/tuners/AcceptanceRateMCTuner.jl:17
+struct AcceptanceRateMCTuner; targetrate::Float64; score::Int32; k::Float64; period::Int; verbose::Bool; end
+function AcceptanceRateMCTuner(rate; score::Function=logistic_rate_score, k=nothing, period::Int=100, verbose::Bool=false)
+  score === logistic_rate_score || score === erf_rate_score || error("score must be logistic_rate_score or erf_rate_score")
+  iserf = score === erf_rate_score
+  AcceptanceRateMCTuner(rate, iserf ? 1 : 0, k === nothing ? (iserf ? 3.0 : 7.0) : k, period, verbose)
+end
 # src/tuners/DualAveragingMCTuner.jl:53-93 (HMC only; per-chain step and nleaps = max(1, round(λ/step)))
 struct DualAveragingMCTuner
   targetrate::Float64; nadapt::Int; ε0bar::Float64; h0bar::Float64; γ::Float64; t0::Int; κ::Float64; period::Int; verbose::Bool
@@ -92,7 +107,7 @@ struct KlbConfig
   step::Float64; nleaps::Int32
   target_rate::Float64; score_k::Float64; period::Int64
   verbose::Int32; monitor::UInt32; diagnostics::UInt32; destination::Int32
-  seed::UInt64; chain_offset::Int64; device::Int32; reserved::Int32
+  seed::UInt64; chain_offset::Int64; device::Int32; score::Int32
   da_nadapt::Int64; da_t0::Int64; da_eps0bar::Float64; da_h0bar::Float64; da_gamma::Float64; da_kappa::Float64
 end
 struct KlbHostField; field::Int32; reserved::Int32; host_dst::Ptr{Cvoid}; nbytes::Int64; end
@@ -100,22 +115,35 @@ struct KlbHostField; field::Int32; reserved::Int32; host_dst::Ptr{Cvoid}; nbytes
 lasterror() = unsafe_string(ccall((:klb_last_error, LIB), Cstring, ()))
 check(rc::Cint) = rc == 0 ? nothing : error("klara_b200 error $rc: $(lasterror())")
 
+# handle: klb_job, or klb_multi when the chains are sharded over `ngpus` devices of this process (multi = true)
 mutable struct BasicMCJob
   handle::Ptr{Cvoid}; nchains::Int; dim::Int; range::BasicMCRange; monitor::Vector{Symbol}; diagnostics::Vector{Symbol}
+  multi::Bool
 end
+sym(job::BasicMCJob, name::String) = Symbol(job.multi ? "klb_multi_" : "klb_job_", name)
 
 function BasicMCJob(model::GenericModel, sampler, range::BasicMCRange, v0::Dict;
                     tuner=VanillaMCTuner(), outopts::Dict=Dict{Symbol,Any}(), seed::Integer=0,
-                    arith::Symbol=:reference, device::Integer=0, chain_offset::Integer=0)
+                    arith::Symbol=:reference, device::Integer=0, chain_offset::Integer=0, ngpus::Integer=1)
   pidx = findfirst(v -> v isa BasicContMuvParameter, model.vertices)
   p = model.vertices[pidx]::BasicContMuvParameter
   if length(model.vertices) > 1       # hyper-parameters / data reach the target in vertex order (BasicContMuvParameter.jl:497-501)
     vals = [v0[v.key] for (i, v) in enumerate(model.vertices) if i != pidx]
-    t = p.logtarget::BayesLogit
-    t.lambda, t.X, t.y = Float64(vals[1]), Matrix{Float64}(vals[2]), Vector{Float64}(vals[3])
+    t = p.logtarget
+    if t isa BayesLogit
+      t.lambda, t.X, t.y = Float64(vals[1]), Matrix{Float64}(vals[2]), Vector{Float64}(vals[3])
+    elseif t isa DenseGaussian
+      t.C = Matrix{Float64}(vals[1])                                    # v[1] = the Hyperparameter(:C) vertex
+    else
+      error("target $(typeof(t)) takes no hyper-parameters")
+    end
   end
-  x0 = v0[p.key]; x0 = x0 isa Vector ? reshape(Float64.(x0), :, 1) : Matrix{Float64}(x0)   # d x nchains
-  d, n = size(x0)
+  x0 = v0[p.key]
+  synthetic = x0 isa SyntheticNormal
+  if !synthetic
+    x0 = x0 isa Vector ? reshape(Float64.(x0), :, 1) : Matrix{Float64}(x0)   # d x nchains
+  end
+  d, n = synthetic ? (x0.dim, x0.nchains) : size(x0)
   monitor = get(outopts, :monitor, [:value]); diags = get(outopts, :diagnostics, Symbol[])
   dest = get(outopts, :destination, :nstate)
   mon = UInt32(sum(Dict(:value=>1, :logtarget=>2, :gradlogtarget=>4)[m] for m in monitor; init=0))
@@ -127,45 +155,63 @@ function BasicMCJob(model::GenericModel, sampler, range::BasicMCRange, v0::Dict;
                   sampler isa HMC ? sampler.nleaps : 1,
                   (tuner isa AcceptanceRateMCTuner || da) ? tuner.targetrate : 0.5,
                   tuner isa AcceptanceRateMCTuner ? tuner.k : 7.0, tuner.period, tuner.verbose,
-                  mon, (:accept in diags) ? 1 : 0, dest == :none ? 1 : 0, seed, chain_offset, device, 0,
+                  mon, (:accept in diags) ? 1 : 0, dest == :none ? 1 : 0, seed, chain_offset, device,
+                  tuner isa AcceptanceRateMCTuner ? tuner.score : 0,
                   da ? tuner.nadapt : 0, da ? tuner.t0 : 10, da ? tuner.ε0bar : 1.0, da ? tuner.h0bar : 0.0,
                   da ? tuner.γ : 0.05, da ? tuner.κ : 0.75)
   h = Ref{Ptr{Cvoid}}(C_NULL)
-  check(ccall((:klb_job_create, LIB), Cint, (Ref{KlbConfig}, Ref{Ptr{Cvoid}}), cfg, h))
-  job = BasicMCJob(h[], n, d, range, monitor, diags)
-  finalizer(j -> ccall((:klb_job_destroy, LIB), Cvoid, (Ptr{Cvoid},), j.handle), job)
-  t = p.logtarget
-  t isa ShiftedIsoGaussian && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 0, t.mu, d))
-  t isa Rosenbrock && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 3, [t.a, t.b, t.scale], 3))
-  t isa DenseGaussian && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 1, t.C, d*d))
-  if t isa BayesLogit      # X travels row-major (row i = observation i): Julia's column-major X' is exactly that
-    Xt = Matrix{Float64}(t.X')
-    check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 6, [t.lambda], 1))
-    check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 4, Xt, length(Xt)))
-    check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 5, t.y, length(t.y)))
+  multi = ngpus != 1                   # ngpus = 0: every visible device (klb_multi_create); chains in contiguous blocks
+  if multi
+    check(ccall((:klb_multi_create, LIB), Cint, (Ref{KlbConfig}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}), cfg, ngpus, C_NULL, h))
+  else
+    check(ccall((:klb_job_create, LIB), Cint, (Ref{KlbConfig}, Ref{Ptr{Cvoid}}), cfg, h))
   end
-  sampler isa MH && check(ccall((:klb_job_set_target_f64, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, 2, sampler.sigma, d))
-  GC.@preserve x0 check(ccall((:klb_job_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x0))   # initialize!
+  job = BasicMCJob(h[], n, d, range, monitor, diags, multi)
+  finalizer(j -> j.multi ? ccall((:klb_multi_destroy, LIB), Cvoid, (Ptr{Cvoid},), j.handle) :
+                           ccall((:klb_job_destroy, LIB), Cvoid, (Ptr{Cvoid},), j.handle), job)
+  settarget(which, a) = check(ccall((sym(job, "set_target_f64"), LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64), job.handle, which, a, length(a)))
+  t = p.logtarget
+  t isa ShiftedIsoGaussian && settarget(0, t.mu)
+  t isa Rosenbrock && settarget(3, [t.a, t.b, t.scale])
+  t isa DenseGaussian && settarget(1, t.C)
+  if t isa BayesLogit      # X travels row-major (row i = observation i): Julia's column-major X' is exactly that
+    settarget(6, [t.lambda]); settarget(4, Matrix{Float64}(t.X')); settarget(5, t.y)
+  end
+  sampler isa MH && settarget(2, sampler.sigma)
+  if synthetic                                                                                   # initialize!
+    check(ccall((sym(job, "set_state_synthetic"), LIB), Cint, (Ptr{Cvoid},), job.handle))
+  else
+    GC.@preserve x0 check(ccall((sym(job, "set_state"), LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x0))
+  end
   job
 end
 
-run(job::BasicMCJob) = (check(ccall((:klb_job_run, LIB), Cint, (Ptr{Cvoid},), job.handle)); job)
+run(job::BasicMCJob) = (check(ccall((sym(job, "run"), LIB), Cint, (Ptr{Cvoid},), job.handle)); job)
+# position the RNG streams: the next transition is number t + 1 (klb_job_seek / klb_multi_seek)
+seek!(job::BasicMCJob, t::Integer) = check(ccall((sym(job, "seek"), LIB), Cint, (Ptr{Cvoid}, UInt64), job.handle, t))
+# device g's copy of the closing all-gather of a sharded job: final states (d x nchains) of ALL chains
+function gathered(job::BasicMCJob, g::Integer=0)
+  a = Array{Float64}(undef, job.dim, job.nchains)
+  GC.@preserve a check(ccall((:klb_multi_gathered_output, LIB), Cint, (Ptr{Cvoid}, Int32, Cint, Ptr{Cvoid}, Int64), job.handle, g, 4, a, sizeof(a)))
+  a
+end
 run(jobs::Vector{BasicMCJob}) = map(run, jobs)
 # reset(job, x0); run(job); output fields, in ONE pipelined call (klb_job_run_host): chain slices on their own streams,
 # host->device copies, kernels and device->host copies overlap.  `outputs` maps KLB_OUT_* codes to preallocated Arrays.
 function run_host(job::BasicMCJob, x0::Union{Matrix{Float64},Nothing}, outputs::Dict{Int,<:Array}; nslices::Integer=0)
+  job.multi && error("run_host drives one device")
   f = [KlbHostField(Int32(k), 0, pointer(a), sizeof(a)) for (k, a) in outputs]
   GC.@preserve x0 outputs f check(ccall((:klb_job_run_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{KlbHostField}, Int32, Int32),
                                         job.handle, x0 === nothing ? C_NULL : x0, f, length(f), nslices))
   job
 end
-reset(job::BasicMCJob) = check(ccall((:klb_job_reset, LIB), Cint, (Ptr{Cvoid},), job.handle))
+reset(job::BasicMCJob) = check(ccall((sym(job, "reset"), LIB), Cint, (Ptr{Cvoid},), job.handle))
 function reset(job::BasicMCJob, x::Matrix{Float64})
-  GC.@preserve x check(ccall((:klb_job_set_state, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x))
+  GC.@preserve x check(ccall((sym(job, "set_state"), LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, x))
 end
 
 function fetch!(job::BasicMCJob, field::Integer, a::Array)
-  GC.@preserve a check(ccall((:klb_job_output, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), job.handle, field, a, sizeof(a)))
+  GC.@preserve a check(ccall((sym(job, "output"), LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Int64), job.handle, field, a, sizeof(a)))
   a
 end
 
@@ -181,6 +227,7 @@ end
 # ess(output(job)): effective sample size (IMSE) per coordinate and chain, computed on the device
 # (src/stats/convergence/ess.jl:3-14)
 function ess(job::BasicMCJob)
+  job.multi && error("statistics of a sharded job: ask every shard (klb_multi_job + klb_job_ess)")
   e = Array{Float64}(undef, job.dim, job.nchains)
   GC.@preserve e check(ccall((:klb_job_ess, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), job.handle, e))
   e
@@ -190,6 +237,7 @@ end
 #   mean (src/stats/mean.jl:7-11), mcvar(:iid | :imse) (src/stats/variance/mcvar.jl:5,75-105),
 #   iact (src/stats/convergence/iact.jl:3-5), acceptance (src/stats/acceptance.jl:3-14,28-34)
 function stat(job::BasicMCJob, code::Integer, perchain::Bool=false)
+  job.multi && error("statistics of a sharded job: ask every shard (klb_multi_job + klb_job_stat)")
   r = perchain ? Array{Float64}(undef, job.nchains) : Array{Float64}(undef, job.dim, job.nchains)
   GC.@preserve r check(ccall((:klb_job_stat, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), job.handle, code, r))
   r

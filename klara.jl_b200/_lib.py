@@ -16,6 +16,7 @@ KLB_OK, KLB_EINVAL, KLB_ECUDA, KLB_ENOTFINITE, KLB_ESTATE, KLB_EUNSUPPORTED, KLB
 SAMPLER_MH, SAMPLER_MALA, SAMPLER_HMC = 0, 1, 2
 TARGET_ISO, TARGET_SHIFTED_ISO, TARGET_DENSE, TARGET_ROSENBROCK, TARGET_LOGIT = 0, 1, 2, 3, 4
 TUNER_VANILLA, TUNER_ACCEPTANCE_RATE, TUNER_DUAL_AVERAGING = 0, 1, 2
+SCORE_LOGISTIC, SCORE_ERF = 0, 1
 ARITH_REFERENCE, ARITH_FMA = 0, 1
 MONITOR_VALUE, MONITOR_LOGTARGET, MONITOR_GRADLOGTARGET = 1, 2, 4
 DIAG_ACCEPT = 1
@@ -37,7 +38,7 @@ class KlbConfig(C.Structure):
         ("step", C.c_double), ("nleaps", C.c_int32),
         ("target_rate", C.c_double), ("score_k", C.c_double), ("period", C.c_int64),
         ("verbose", C.c_int32), ("monitor", C.c_uint32), ("diagnostics", C.c_uint32), ("destination", C.c_int32),
-        ("seed", C.c_uint64), ("chain_offset", C.c_int64), ("device", C.c_int32), ("reserved", C.c_int32),
+        ("seed", C.c_uint64), ("chain_offset", C.c_int64), ("device", C.c_int32), ("score", C.c_int32),
         ("da_nadapt", C.c_int64), ("da_t0", C.c_int64), ("da_eps0bar", C.c_double), ("da_h0bar", C.c_double),
         ("da_gamma", C.c_double), ("da_kappa", C.c_double),
     ]

@@ -27,7 +27,7 @@ from .targets import Target
 
 __all__ = ["SyntheticNormal", "device_peak", "BasicContMuvParameter", "Hyperparameter", "Data", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
            "VanillaMCTuner", "AcceptanceRateMCTuner", "DualAveragingMCTuner", "BasicMCTune", "DualAveragingMCTune", "BasicMCJob", "run", "reset", "output",
-           "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "ess", "mean", "mcvar", "mcse", "iact",
+           "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "erf_rate_score", "ess", "mean", "mcvar", "mcse", "iact",
            "acceptance"]
 
 
@@ -40,6 +40,11 @@ def logistic(x, l=1., k=1., x0=0., y0=0.):
 def logistic_rate_score(x, k=7.):
     """src/tuners/AcceptanceRateMCTuner.jl:9"""
     return logistic(x, 2., k, 0., 0.)
+
+
+def erf_rate_score(x, k=3.):
+    """erf(k*x)+1        src/tuners/AcceptanceRateMCTuner.jl:17"""
+    return math.erf(k * x) + 1
 
 
 # ----------------------------------------------------------------------------- parameter / model
@@ -83,18 +88,39 @@ class Data(Hyperparameter):
 
 
 class GenericModel:
-    """The graph is only used to locate the parameter vertex (src/jobs/BasicMCJob.jl:50)."""
+    """GenericModel(vs, ds=[]; isdirected=true, isindexed=true)        src/models/GenericModel.jl:94-119
 
-    def __init__(self, vertices):
-        self.vertices = list(vertices)
+    isindexed=true: the vertices already carry their positions (`index`, 1-based) and are stored sorted by it;
+    isindexed=false: they are stored in the given order and numbered 1..n.  The job only uses the graph to locate
+    the parameter and to collect the states of the other vertices in vertex order (src/jobs/BasicMCJob.jl:50-51);
+    dependences are kept as given (graph algorithms are outside the hot path)."""
+
+    def __init__(self, vertices, dependences=None, isdirected=True, isindexed=True):
+        vs = list(vertices)
+        if isindexed:
+            idx = [v.index for v in vs]
+            if sorted(idx) != list(range(1, len(vs) + 1)):
+                raise AssertionError("isindexed=true needs vertices indexed 1..%d, got %s (pass isindexed=false to "
+                                     "number them in the given order)" % (len(vs), idx))
+            vs.sort(key=lambda v: v.index)
+        else:
+            for i, v in enumerate(vs):
+                v.index = i + 1
+        self.isdirected = bool(isdirected)
+        self.vertices = vs
+        self.edges = list(dependences) if dependences is not None else []
         self.ofkey = {v.key: i for i, v in enumerate(self.vertices)}
 
 
-def likelihood_model(vertices, isindexed=True):
-    """likelihood_model(p, false)        src/models/generators.jl:5-18"""
+def likelihood_model(vertices, isindexed=True, isdirected=True):
+    """likelihood_model(vs; isdirected, isindexed) / likelihood_model(v, isindexed)        src/models/generators.jl:5-18:
+    every non-parameter vertex points at every parameter"""
     if not isinstance(vertices, (list, tuple)):
-        vertices = [vertices]
-    return GenericModel(vertices)
+        return GenericModel([vertices], isindexed=isindexed)
+    m = GenericModel(vertices, isdirected=isdirected, isindexed=isindexed)
+    params = [v for v in m.vertices if isinstance(v, BasicContMuvParameter)]
+    m.edges = [(u.key, p.key) for p in params for u in m.vertices if not isinstance(u, BasicContMuvParameter)]
+    return m
 
 
 class SyntheticNormal:
@@ -175,15 +201,19 @@ class VanillaMCTuner:
 
 class AcceptanceRateMCTuner:
     """AcceptanceRateMCTuner(targetrate; score=logistic_rate_score, period=100, verbose=false)
-    (src/tuners/AcceptanceRateMCTuner.jl:25-44).  `score` must be logistic_rate_score (optionally
-    with another steepness via `k`): the device evaluates 2/(1+exp(-k*(rate-target)))."""
+    (src/tuners/AcceptanceRateMCTuner.jl:25-44).  `score` is one of the reference's two score functions,
+    logistic_rate_score (2/(1+exp(-k*x)), k = 7) or erf_rate_score (erf(k*x)+1, k = 3), optionally with another
+    steepness `k`; tune! multiplies the step by score(rate - targetrate) (:46).  Arbitrary host closures cannot run
+    inside the kernels."""
     code = L.TUNER_ACCEPTANCE_RATE
 
-    def __init__(self, targetrate, score=logistic_rate_score, period=100, verbose=False, k=7.):
+    def __init__(self, targetrate, score=logistic_rate_score, period=100, verbose=False, k=None):
         assert 0 < targetrate < 1, "Target acceptance rate should be between 0 and 1"
         assert period > 0, "Tuning period should be positive"
-        if score is not logistic_rate_score:
-            raise TypeError("only logistic_rate_score is available on the device")
+        if score is not logistic_rate_score and score is not erf_rate_score:
+            raise TypeError("score must be logistic_rate_score or erf_rate_score (the two the device evaluates)")
+        self.score_code = L.SCORE_ERF if score is erf_rate_score else L.SCORE_LOGISTIC
+        k = (3. if score is erf_rate_score else 7.) if k is None else k
         self.targetrate, self.score, self.k = float(targetrate), score, float(k)
         self.period, self.verbose = int(period), bool(verbose)
 
@@ -329,6 +359,7 @@ class BasicMCJob:
         cfg.nleaps = getattr(sampler, "nleaps", 1)
         cfg.target_rate = getattr(tuner, "targetrate", 0.5)
         cfg.score_k = getattr(tuner, "k", 7.0)
+        cfg.score = getattr(tuner, "score_code", L.SCORE_LOGISTIC)
         cfg.period, cfg.verbose = tuner.period, int(tuner.verbose)
         cfg.monitor = sum(_MONITOR_BITS[m] for m in set(oo["monitor"]))
         cfg.diagnostics = L.DIAG_ACCEPT if "accept" in oo["diagnostics"] else 0

@@ -217,7 +217,7 @@ static void fill_args(const klb_job* j, KArgs& A) {
   // for MH only when verbose (iterate/MH.jl:73-75)
   A.counters_on = (c.sampler == KLB_SAMPLER_MH) ? (c.verbose != 0)
                                                 : ((c.tuner == KLB_TUNER_ACCEPTANCE_RATE) || c.verbose != 0);
-  A.target_rate = c.target_rate; A.score_k = c.score_k;
+  A.target_rate = c.target_rate; A.score_k = c.score_k; A.score = c.score;
   A.seed = c.seed; A.chain_offset = (unsigned long long)c.chain_offset;
   A.tune_da = j->tune_da; A.da_nadapt = c.da_nadapt; A.da_t0 = c.da_t0; A.da_gamma = c.da_gamma; A.da_kappa = c.da_kappa;
 }
@@ -286,6 +286,8 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if (c.period <= 0) return fail(KLB_EINVAL, "Adaptation period should be positive");
   if (c.tuner == KLB_TUNER_ACCEPTANCE_RATE && !(c.target_rate > 0 && c.target_rate < 1))
     return fail(KLB_EINVAL, "Target acceptance rate should be between 0 and 1");
+  if (c.tuner == KLB_TUNER_ACCEPTANCE_RATE && c.score != KLB_SCORE_LOGISTIC && c.score != KLB_SCORE_ERF)
+    return fail(KLB_EINVAL, "unknown score function %d", c.score);
   if ((c.monitor & KLB_MONITOR_GRADLOGTARGET) && c.sampler == KLB_SAMPLER_MH)
     return fail(KLB_EINVAL, "MH does not evaluate gradlogtarget; it cannot be monitored");
   if (c.monitor & ~7u) return fail(KLB_EINVAL, "unknown monitor bits");

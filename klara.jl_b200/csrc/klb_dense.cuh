@@ -129,6 +129,8 @@ klb_dense_kernel(const DArgs D) {
   }
   __syncthreads();
   dense_matvec<MC>(gc, Cm, xs, d, i0, active);   // gradient cache of the starting point (= uptogradlogtarget!)
+  __syncthreads();   // every thread has read xs before the first MALA / MH proposal overwrites it (racecheck, round 2:
+                     // the later transitions are separated by the barrier that closes a transition, the first was not)
 
   const bool saving = (A.out_value != nullptr) || (A.out_lt != nullptr) || (A.out_grad != nullptr) ||
                       (A.out_accept != nullptr);

@@ -50,7 +50,41 @@ struct Glm {
 #pragma unroll
     for (int j = 0; j < DP; ++j) g[j] = 0.0;
     const int n = (int)G.ndata;
-    for (int i = 0; i < n; ++i) {
+    // Two data rows per trip.  Everything a row needs before it touches the accumulators -- Xp_i, exp, log, the
+    // division -- is independent of the other row, and with exp / log inlined ptxas interleaves the two dependent
+    // chains (one row at a time the fp64 pipe sat at 29 %: stall_wait 2.5 per issue, profiles/r1_summary.md, column L).
+    // The accumulators (a, sl, g[j]) still take row i before row i + 1: the oracle's order, bit for bit.
+    int i = 0;
+    for (; i + 1 < n; i += 2) {
+      const double* row = Xs + (size_t)i * DP;
+      double xr[2][DP];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int j = 0; j < DP; j += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(row + r * DP + j);
+          xr[r][j] = v.x; xr[r][j + 1] = v.y;
+        }
+      double xp[2] = {0.0, 0.0};
+#pragma unroll
+      for (int j = 0; j < DP; ++j)
+        if (j < d) { xp[0] = __fma_rn(xr[0][j], x[j], xp[0]); xp[1] = __fma_rn(xr[1][j], x[j], xp[1]); }   // Xp = v[2]*p
+      const double y0 = ys[i], y1 = ys[i + 1];
+      if (WANT_LT) {
+        const double l0 = klb_log_inline(__dadd_rn(1.0, klb_exp_inline(xp[0], tab)), tab);
+        const double l1 = klb_log_inline(__dadd_rn(1.0, klb_exp_inline(xp[1], tab)), tab);
+        a = __fma_rn(xp[0], y0, a); a = __fma_rn(xp[1], y1, a);             // dot(Xp, v[3])
+        sl = __dadd_rn(sl, l0); sl = __dadd_rn(sl, l1);                     // sum(log.(1+exp.(Xp)))
+      }
+      if (WANT_G) {
+        const double r0 = __dsub_rn(y0, __ddiv_rn(1.0, __dadd_rn(1.0, klb_exp_inline(-xp[0], tab))));
+        const double r1 = __dsub_rn(y1, __ddiv_rn(1.0, __dadd_rn(1.0, klb_exp_inline(-xp[1], tab))));
+#pragma unroll
+        for (int j = 0; j < DP; ++j)
+          if (j < d) { g[j] = __fma_rn(xr[0][j], r0, g[j]); g[j] = __fma_rn(xr[1][j], r1, g[j]); }   // v[2]'*r
+      }
+    }
+    for (; i < n; ++i) {                                                    // odd row count: the last row alone
       const double* row = Xs + (size_t)i * DP;
       double xr[DP];
 #pragma unroll
@@ -61,17 +95,17 @@ struct Glm {
       double xp = 0.0;
 #pragma unroll
       for (int j = 0; j < DP; ++j)
-        if (j < d) xp = __fma_rn(xr[j], x[j], xp);                          // Xp = v[2]*p
+        if (j < d) xp = __fma_rn(xr[j], x[j], xp);
       const double yi = ys[i];
       if (WANT_LT) {
-        a = __fma_rn(xp, yi, a);                                            // dot(Xp, v[3])
-        sl = __dadd_rn(sl, klb_log(__dadd_rn(1.0, klb_exp(xp, tab)), tab)); // sum(log.(1+exp.(Xp)))
+        a = __fma_rn(xp, yi, a);
+        sl = __dadd_rn(sl, klb_log(__dadd_rn(1.0, klb_exp(xp, tab)), tab));
       }
       if (WANT_G) {
         const double r = __dsub_rn(yi, __ddiv_rn(1.0, __dadd_rn(1.0, klb_exp(-xp, tab))));
 #pragma unroll
         for (int j = 0; j < DP; ++j)
-          if (j < d) g[j] = __fma_rn(xr[j], r, g[j]);                       // v[2]'*r
+          if (j < d) g[j] = __fma_rn(xr[j], r, g[j]);
       }
     }
     if (WANT_LT) {

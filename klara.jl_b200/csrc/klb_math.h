@@ -219,8 +219,10 @@ KLB_HD double klb_accept_uniform(const klb_stream* s) {
 
 #define KLB_EXP_SHIFT 0x1.8p52
 
-/* exp(x); tab = pointer to a copy of KLB_TAB.  |error| < 0.51 ulp (tests/test_math.py). */
-KLB_HD_NOINLINE double klb_exp(double x, const uint64_t* tab) {
+/* exp(x); tab = pointer to a copy of KLB_TAB.  |error| < 0.51 ulp (tests/test_math.py).
+ * klb_exp_inline is the body; klb_exp the out-of-line call most kernels use (instruction-cache footprint).  The
+ * thread-per-chain kernels (klb_glm.cuh) inline it so that the exp chains of two data rows interleave. */
+KLB_HD double klb_exp_inline(double x, const uint64_t* tab) {
   if (!(x == x)) return x;
   if (x > 709.782712893384) return klb_u2d(0x7FF0000000000000ULL);
   if (x < -745.2) return 0.0;
@@ -254,8 +256,10 @@ KLB_HD_NOINLINE double klb_exp(double x, const uint64_t* tab) {
   }
 }
 
+KLB_HD_NOINLINE double klb_exp(double x, const uint64_t* tab) { return klb_exp_inline(x, tab); }
+
 /* log(x); error < 1 ulp, except < 2 ulp for x in (0.99, 1) (tests/test_math.py) */
-KLB_HD_NOINLINE double klb_log(double x, const uint64_t* tab) {
+KLB_HD double klb_log_inline(double x, const uint64_t* tab) {
   uint64_t ix = klb_d2u(x);
   int64_t kadj = 0;
   if (ix - 0x0010000000000000ULL >= 0x7FE0000000000000ULL) {
@@ -288,6 +292,80 @@ KLB_HD_NOINLINE double klb_log(double x, const uint64_t* tab) {
   double p = klb_fma(r2, q, klb_fma(r, -0.25, 1.0 / 3.0));
   double y = klb_fma(klb_mul(r, r2), p, klb_fma(r2, -0.5, lo));
   return klb_add(y, hi);
+}
+
+KLB_HD_NOINLINE double klb_log(double x, const uint64_t* tab) { return klb_log_inline(x, tab); }
+
+/* ---------------------------------------------------------------------- erf
+ * erf(x) for erf_rate_score(x, k) = erf(k*x)+1 (src/tuners/AcceptanceRateMCTuner.jl:17), the other score function of
+ * AcceptanceRateMCTuner.  It runs once per tuning period and chain, so it is written for exactness, not speed:
+ *   |x| <= 4.5  Maclaurin series  erf(x) = 2/sqrt(pi) sum_n (-1)^n x^(2n+1) / (n! (2n+1))  in double-double
+ *               arithmetic (error-free two-sum / fma two-product): the cancellation (terms up to e^(x^2) ~ 6e8) costs
+ *               30 of the 106 bits, the result is the correctly rounded double in all but ~1e-8 of the cases;
+ *   4.5 < |x| < 6  1 - erfc(x), erfc by its continued fraction with klb_exp (erfc < 2e-10: a relative error of
+ *               1e-14 in it is 1e-24 in the result);
+ *   |x| >= 6    +-1 (erfc(6) = 2.2e-17 < 2^-54).
+ * Only IEEE add / mul / fma / div: identical bits on host and device (tests/test_oracle_kat.py pins it to the
+ * reference's known-answer values and to mpmath). */
+typedef struct { double hi, lo; } klb_dd;
+KLB_HD klb_dd klb_dd_fast2sum(double a, double b) {          /* |a| >= |b| */
+  klb_dd r; r.hi = klb_add(a, b); r.lo = klb_sub(b, klb_sub(r.hi, a)); return r;
+}
+KLB_HD klb_dd klb_dd_2sum(double a, double b) {
+  klb_dd r; r.hi = klb_add(a, b);
+  double bb = klb_sub(r.hi, a);
+  r.lo = klb_add(klb_sub(a, klb_sub(r.hi, bb)), klb_sub(b, bb));
+  return r;
+}
+KLB_HD klb_dd klb_dd_add(klb_dd a, klb_dd b) {
+  klb_dd s = klb_dd_2sum(a.hi, b.hi);
+  return klb_dd_fast2sum(s.hi, klb_add(s.lo, klb_add(a.lo, b.lo)));
+}
+KLB_HD klb_dd klb_dd_mul(klb_dd a, klb_dd b) {
+  double p = klb_mul(a.hi, b.hi);
+  double e = klb_fma(a.hi, b.hi, -p);
+  e = klb_fma(a.hi, b.lo, e);
+  e = klb_fma(a.lo, b.hi, e);
+  return klb_dd_fast2sum(p, e);
+}
+KLB_HD klb_dd klb_dd_div_d(klb_dd a, double d) {             /* a / d, d an exactly representable small integer */
+  double q1 = klb_div(a.hi, d);
+  double r = klb_add(klb_fma(-q1, d, a.hi), a.lo);
+  double q2 = klb_div(r, d);
+  return klb_dd_fast2sum(q1, q2);
+}
+KLB_HD_NOINLINE double klb_erf(double x, const uint64_t* tab) {
+  if (!(x == x)) return x;
+  const double ax = x < 0 ? -x : x;
+  if (ax >= 6.0) return x < 0 ? -1.0 : 1.0;
+  if (ax > 4.5) {
+    /* erfc(ax) = exp(-ax^2) / (ax sqrt(pi)) * 1/(1 + u/(1 + 2u/(1 + 3u/(1 + ...)))),  u = 1/(2 ax^2); evaluated bottom-up */
+    const double u = klb_div(0.5, klb_mul(ax, ax));
+    double f = 1.0;
+    for (int n = 60; n >= 1; --n) f = klb_add(1.0, klb_div(klb_mul(klb_i2d(n), u), f));
+    /* exp(-ax^2) with the rounding error of ax^2 carried: ax^2 = p + e exactly, exp(-(p+e)) = exp(-p) (1 - e) */
+    const double pp = klb_mul(ax, ax), ee = klb_fma(ax, ax, -pp);
+    double ex = klb_exp(-pp, tab);
+    ex = klb_fma(-ex, ee, ex);
+    const double erfc = klb_div(ex, klb_mul(klb_mul(ax, 1.7724538509055160273 /* sqrt(pi) */), f));
+    const double r = klb_sub(1.0, erfc);
+    return x < 0 ? -r : r;
+  }
+  klb_dd x2; x2.hi = klb_mul(x, x); x2.lo = klb_fma(x, x, -x2.hi);
+  klb_dd term; term.hi = x; term.lo = 0.0;                   /* x^(2n+1) / n! */
+  klb_dd sum = term;
+  for (int n = 1; n < 200; ++n) {
+    term = klb_dd_div_d(klb_dd_mul(term, x2), klb_i2d(n));
+    klb_dd t = klb_dd_div_d(term, klb_i2d(2 * n + 1));
+    if (n & 1) { t.hi = -t.hi; t.lo = -t.lo; }
+    sum = klb_dd_add(sum, t);
+    const double at = t.hi < 0 ? -t.hi : t.hi, as = sum.hi < 0 ? -sum.hi : sum.hi;
+    if (at <= klb_mul(as, 0x1p-110)) break;
+  }
+  /* 2/sqrt(pi) = 1.1283791670955125738961589031215451716881... as a double-double */
+  klb_dd c; c.hi = 1.1283791670955126; c.lo = 1.533545961316588e-17;
+  sum = klb_dd_mul(sum, c);
+  return klb_add(sum.hi, sum.lo);
 }
 
 /* ------------------------------------------------- ziggurat standard normal */

@@ -77,12 +77,32 @@ class Rosenbrock(Target):
 
 
 class DenseGaussian(Target):
-    """-z'Cz, gradient -2Cz with a dense precision matrix C
-    (doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9)."""
-    code = L.TARGET_DENSE
+    """-z'Cz, gradient -2Cz with a dense precision matrix C: the closures of
+    doc/examples/BivariateNormal/MALA/function/analytical.jl:4-21,
 
-    def __init__(self, C):
-        self.C = np.ascontiguousarray(C, dtype=np.float64)
+        logtarget     = (p, v) -> -dot(p, v[1]*p)
+        gradlogtarget = (p, v) -> -2*v[1]*p            nkeys = 2,  model = GenericModel([C, p], isindexed=false)
+
+    where `v` holds the values of ALL model vertices in vertex order (BasicContMuvParameter.jl:497-501: `nkeys` is
+    only tested for > 0), so v[1] is the state of the `Hyperparameter(:C)` vertex.  `DenseGaussian(C)` carries the
+    matrix itself; `DenseGaussian()` is bound by BasicMCJob from v0[:C] like the reference does."""
+    code = L.TARGET_DENSE
+    nkeys = 2
+
+    def __init__(self, C=None):
+        self.C = None
+        if C is not None:
+            self.bind([C])
+
+    def bind(self, values):
+        """values = [C]: the states of the model's other vertices, in vertex order"""
+        if len(values) != 1:
+            raise AssertionError("DenseGaussian reads one hyper-parameter (the precision matrix), the model supplies %d" % len(values))
+        C = np.ascontiguousarray(values[0], dtype=np.float64)
+        if C.ndim != 2 or C.shape[0] != C.shape[1]:
+            raise AssertionError("the precision matrix must be square")
+        self.C = C
+        return self
 
     def __call__(self, z):
         z = np.asarray(z, dtype=np.float64)
@@ -92,6 +112,11 @@ class DenseGaussian(Target):
         return -2 * (self.C @ np.asarray(z, dtype=np.float64))
 
     def params(self, dim):
+        if self.C is None:
+            raise AssertionError("DenseGaussian has no precision matrix: pass C or give v0 a value for the model's "
+                                 "Hyperparameter vertex")
+        if self.C.shape[0] != dim:
+            raise AssertionError("C is %d x %d, parameter has %d entries" % (self.C.shape + (dim,)))
         return [(L.PARAM_C, self.C.reshape(-1))]
 
 

@@ -73,6 +73,7 @@ typedef struct {
   uint32_t monitor;                           /* bit0 value, bit1 logtarget, bit2 gradlogtarget */
   uint32_t diagnostics;                       /* bit0 accept */
   uint64_t seed, chain_offset, t0;
+  int32_t score;                              /* AcceptanceRateMCTuner score: 0 logistic_rate_score, 1 erf_rate_score */
   int32_t nv;                                 /* reduction geometry: double2 units per lane (1,2,4,8,16,64);
                                                  0 = sequential order (one thread per chain: the data-dependent
                                                  targets, klb_glm.cuh) */
@@ -113,8 +114,11 @@ double orc_logistic(double x, double l, double k, double x0, double y0) {
   return l / (1 + klb_exp(-k * (x - x0), KLB_TAB)) + y0;
 }
 double orc_logistic_rate_score(double x, double k) { return orc_logistic(x, 2., k, 0., 0.); }
-/* erf(k*x)+1 -- libm erf; host-only (the device library implements the logistic score) */
-double orc_erf_rate_score(double x, double k) { return erf(k * x) + 1; }
+/* erf(k*x)+1                                               src/tuners/AcceptanceRateMCTuner.jl:17
+ * klb_erf: double-double series shared with the device (identical bits); pinned to the reference's known-answer
+ * values and to mpmath in tests/test_oracle_kat.py */
+double orc_erf_rate_score(double x, double k) { return klb_erf(k * x, KLB_TAB) + 1; }
+double orc_erf(double x) { return klb_erf(x, KLB_TAB); }
 
 double orc_exp(double x) { return klb_exp(x, KLB_TAB); }
 double orc_log(double x) { return klb_log(x, KLB_TAB); }
@@ -350,7 +354,9 @@ static void orc_reset_burnin(orc_tune* t) {
   t->accepted = 0; t->proposed = 0; t->rate = NAN;
 }
 static void orc_tune_step(orc_tune* t, const orc_config* c) {
-  t->step *= orc_logistic_rate_score(t->rate - c->target_rate, c->score_k);
+  /* tune!: tune.step *= tuner.score(tune.rate - tuner.targetrate)   AcceptanceRateMCTuner.jl:46 */
+  t->step *= c->score == 1 ? orc_erf_rate_score(t->rate - c->target_rate, c->score_k)
+                           : orc_logistic_rate_score(t->rate - c->target_rate, c->score_k);
 }
 /* tuner_state: BasicMCTune(step, 0, 0, tuner.period); MH gets step 1.   samplers.jl:29-45 */
 void orc_tuner_state(const orc_config* c, orc_tune* t) {

@@ -26,7 +26,7 @@ class OrcConfig(C.Structure):
         ("target_rate", C.c_double), ("score_k", C.c_double), ("period", C.c_int64),
         ("verbose", C.c_int32), ("monitor", C.c_uint32), ("diagnostics", C.c_uint32),
         ("seed", C.c_uint64), ("chain_offset", C.c_uint64), ("t0", C.c_uint64),
-        ("nv", C.c_int32), ("nthreads", C.c_int32),
+        ("score", C.c_int32), ("nv", C.c_int32), ("nthreads", C.c_int32),
         ("da_nadapt", C.c_int64), ("da_t0", C.c_int64),
         ("da_eps0bar", C.c_double), ("da_h0bar", C.c_double), ("da_gamma", C.c_double), ("da_kappa", C.c_double),
         ("da", C.c_void_p),
@@ -75,6 +75,8 @@ def lib():
         L.orc_uniform.argtypes = [C.c_uint64] * 3
         L.orc_normals.restype = None
         L.orc_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p]
+        L.orc_erf.restype = dbl
+        L.orc_erf.argtypes = [dbl]
         L.orc_philox.restype = None
         L.orc_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_philox_rounds.restype = C.c_int
@@ -142,6 +144,10 @@ def log(x):
     return lib().orc_log(float(x))
 
 
+def erf(x):
+    return lib().orc_erf(float(x))
+
+
 def plan_nv(dim):
     return lib().orc_plan_nv(dim)
 
@@ -166,8 +172,9 @@ def npoststeps(burnin, thinning, nsteps):
 def make_config(sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, step=0.1, nleaps=10,
                 tuner=VANILLA, target_rate=0.574, score_k=7.0, period=100, verbose=0,
                 monitor=1, diagnostics=0, seed=0, chain_offset=0, t0=0, arith=0, nv=None, nthreads=1,
-                nadapt=1000, eps0bar=1.0, h0bar=0.0, gamma=0.05, da_t0=10, kappa=0.75):
+                nadapt=1000, eps0bar=1.0, h0bar=0.0, gamma=0.05, da_t0=10, kappa=0.75, score=0):
     cfg = OrcConfig()
+    cfg.score = score                      # AcceptanceRateMCTuner: 0 logistic_rate_score, 1 erf_rate_score
     cfg.sampler, cfg.target, cfg.tuner, cfg.arith = sampler, target, tuner, arith
     cfg.nchains, cfg.dim, cfg.nsteps, cfg.burnin, cfg.thinning = nchains, dim, nsteps, burnin, thinning
     cfg.step, cfg.nleaps = step, nleaps

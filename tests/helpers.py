@@ -50,7 +50,7 @@ def logit_data(dim, rng, ndata=200, lam=100.0):
 def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, step=0.1, nleaps=10,
                tuner="vanilla", target_rate=0.574, period=100, verbose=False, monitor=("value", "logtarget"),
                diagnostics=("accept",), seed=1234, arith="reference", chain_offset=0, x0=None, sigma=None,
-               device=0, rng_seed=0, nadapt=1000):
+               device=0, rng_seed=0, nadapt=1000, score="logistic"):
     rng = np.random.default_rng(rng_seed)
     tgt, tcode, tparams = make_target(K, target, dim, rng)
     if x0 is None:
@@ -65,7 +65,8 @@ def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, s
     da_kw = dict(nadapt=nadapt, eps0bar=1.0, h0bar=0.0, gamma=0.05, t0=10, kappa=0.75)
     tun = K.VanillaMCTuner(period=period, verbose=verbose) if tuner == "vanilla" else \
         K.DualAveragingMCTuner(target_rate, period=period, verbose=verbose, **da_kw) if tuner == "dualavg" else \
-        K.AcceptanceRateMCTuner(target_rate, period=period, verbose=verbose)
+        K.AcceptanceRateMCTuner(target_rate, period=period, verbose=verbose,
+                                score=K.erf_rate_score if score == "erf" else K.logistic_rate_score)
     p = K.BasicContMuvParameter("p", logtarget=tgt)
     model = K.likelihood_model(p, False)
     rng_ = K.BasicMCRange(nsteps=nsteps, burnin=burnin, thinning=thinning)
@@ -74,10 +75,11 @@ def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, s
                        chain_offset=chain_offset, device=device)
     mon = sum({"value": 1, "logtarget": 2, "gradlogtarget": 4}[m] for m in monitor)
     cfg = O.make_config(SAMPLERS[sampler], tcode, nchains, dim, nsteps, burnin, thinning, step, nleaps,
-                        {"vanilla": O.VANILLA, "accrate": O.ACCRATE, "dualavg": O.DUALAVG}[tuner], target_rate, 7.0,
+                        {"vanilla": O.VANILLA, "accrate": O.ACCRATE, "dualavg": O.DUALAVG}[tuner], target_rate,
+                        3.0 if score == "erf" else 7.0,
                         period, int(verbose), mon, 1 if "accept" in diagnostics else 0, seed, chain_offset, 0,
                         1 if arith == "fma" else 0, job.plan().nv, O.max_threads(), nadapt=nadapt, eps0bar=1.0, h0bar=0.0,
-                        gamma=0.05, da_t0=10, kappa=0.75)
+                        gamma=0.05, da_t0=10, kappa=0.75, score=1 if score == "erf" else 0)
     return job, cfg, x0, tparams, sigma
 
 

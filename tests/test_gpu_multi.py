@@ -150,12 +150,16 @@ def test_gather_between_processes_over_cuda_ipc(K):
     procs = [ctx.Process(target=_ipc_worker, args=(r, world, N, d, pipes[r][1], ret)) for r in range(world)]
     for pr in procs:
         pr.start()
+
+    def recv(r):                                          # a worker that died must fail the test, not hang it
+        assert pipes[r][0].poll(180), "rank %d did not answer (exit code %s)" % (r, procs[r].exitcode)
+        return pipes[r][0].recv()
     try:
-        handles = b"".join(pipes[r][0].recv() for r in range(world))
+        handles = b"".join(recv(r) for r in range(world))
         for r in range(world):
             pipes[r][0].send(handles)
         for r in range(world):
-            assert pipes[r][0].recv() == b"pushed"
+            assert recv(r) == b"pushed"
         for r in range(world):
             pipes[r][0].send(b"go")
         got = dict(ret.get(timeout=120) for _ in range(world))
@@ -164,6 +168,8 @@ def test_gather_between_processes_over_cuda_ipc(K):
     finally:
         for pr in procs:
             pr.join(timeout=60)
+            if pr.is_alive():
+                pr.kill()
     assert all(pr.exitcode == 0 for pr in procs)
     p = K.BasicContMuvParameter("p", logtarget=K.IsoGaussian())
     one = K.BasicMCJob(K.likelihood_model(p, False), K.HMC(0.05, 5), K.BasicMCRange(nsteps=12, burnin=4),

@@ -130,6 +130,25 @@ def test_dense_bivariate_normal_example(K, O):
     assert abs(cov[0, 0] - 0.5) < 0.08 and abs(cov[0, 1] - 0.4) < 0.08 and abs(chain.value.mean()) < 0.1
 
 
+def test_dense_bivariate_normal_example_through_the_hyperparameter_vertex(K, O):
+    """the same example as the reference writes it: C = Hyperparameter(:C), closures of (p, v) with v[1] = C,
+    nkeys = 2, model = GenericModel([C, p], isindexed=false), v0 = Dict(:C => inv(...), :p => [1.25, 3.11])"""
+    C = np.linalg.inv(np.array([[1.0, 0.8], [0.8, 1.0]]))
+    C = (C + C.T) / 2
+    d = K.DenseGaussian()
+    p = K.BasicContMuvParameter("p", logtarget=d, gradlogtarget=d.gradient, nkeys=2)
+    model = K.GenericModel([K.Hyperparameter("C"), p], isindexed=False)
+    job = K.BasicMCJob(model, K.MALA(0.3), K.BasicMCRange(nsteps=400, burnin=100), {"C": C, "p": [1.25, 3.11]},
+                       outopts={"monitor": ["value", "logtarget", "gradlogtarget"], "diagnostics": ["accept"]}, seed=7)
+    K.run(job)
+    chain = K.output(job)
+    cfg = O.make_config(O.MALA, O.DENSE, 1, 2, 400, 100, step=0.3, monitor=7, diagnostics=1, seed=7, nv=job.plan().nv)
+    ref = O.run(cfg, np.array([[1.25, 3.11]]), C.reshape(-1))
+    assert_same("value", chain.value, ref["value"][0])
+    assert_same("gradlogtarget", chain.gradlogtarget, ref["gradlogtarget"][0])
+    assert_same("accept", chain.diagnosticvalues, ref["accept"][0])
+
+
 def test_dense_mma_and_dfma_kernels_agree(K, monkeypatch):
     """HMC on the dense target: the tensor-pipe kernel (DMMA, default for dim 64/128/256/512) and the DFMA
     register-tile kernel (KLB_DENSE_MMA=0) produce the same bits -- both follow the increasing-j fma chain"""
@@ -181,6 +200,20 @@ def test_acceptance_rate_tuner_bit_exact(K, sampler, step):
     assert (tn.totproposed == 225).all()       # period*(1 + floor(burnin/period)) = 25*9
     assert (tn.proposed == 60).all()           # keeps counting after burn-in
     assert not np.allclose(tn.step, step)      # adapted
+
+
+@pytest.mark.parametrize("sampler,step", [("HMC", 0.12), ("MALA", 0.4)])
+def test_acceptance_rate_tuner_erf_score_bit_exact(K, sampler, step):
+    """AcceptanceRateMCTuner(targetrate, score=erf_rate_score): step *= erf(3*(rate - target)) + 1
+    (src/tuners/AcceptanceRateMCTuner.jl:17,46); klb_erf is the same double-double series on both sides"""
+    job, cfg, x0, tp, sg = build_pair(K, sampler, "iso", nchains=33, dim=40, nsteps=130, burnin=100, step=step, nleaps=4,
+                                      seed=17, tuner="accrate", target_rate=0.65, period=10, score="erf")
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    assert len(np.unique(job.tune.step)) > 10 and (job.tune.step != step).all()
+    logi, *_ = build_pair(K, sampler, "iso", nchains=33, dim=40, nsteps=130, burnin=100, step=step, nleaps=4,
+                          seed=17, tuner="accrate", target_rate=0.65, period=10)
+    logi.run()
+    assert not np.array_equal(logi.tune.step, job.tune.step)       # the two score functions really differ
 
 
 def test_verbose_vanilla_counters(K):

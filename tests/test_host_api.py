@@ -198,3 +198,68 @@ def test_new_surface_validation_without_a_device(K):
     with pytest.raises(TypeError, match="takes no hyper-parameters"):
         K.BasicMCJob(K.likelihood_model([K.Hyperparameter("λ"), iso], isindexed=False), K.HMC(0.1, 3),
                      K.BasicMCRange(nsteps=5), {"λ": 1.0, "p": x0})
+
+
+def test_generic_model_indexing(K):
+    """GenericModel(vs; isindexed) (src/models/GenericModel.jl:94-119): isindexed=false numbers the vertices in the
+    given order; isindexed=true stores them sorted by their own index"""
+    C, p = K.Hyperparameter("C"), K.BasicContMuvParameter("p", logtarget=K.DenseGaussian())
+    m = K.GenericModel([C, p], isindexed=False)
+    assert [v.key for v in m.vertices] == ["C", "p"] and [v.index for v in m.vertices] == [1, 2] and m.ofkey == {"C": 0, "p": 1}
+    a, b = K.Hyperparameter("a", 2), K.BasicContMuvParameter("b", logtarget=K.IsoGaussian(), index=1)
+    m = K.GenericModel([a, b])
+    assert [v.key for v in m.vertices] == ["b", "a"]
+    with pytest.raises(AssertionError, match="isindexed"):
+        K.GenericModel([K.Hyperparameter("u"), K.Hyperparameter("v")])
+    lm = K.likelihood_model([K.Hyperparameter("λ"), K.Data("X"), b], isindexed=False)
+    assert lm.edges == [("λ", "b"), ("X", "b")]                  # every non-parameter vertex points at the parameter
+
+
+def test_dense_gaussian_binds_the_hyperparameter_vertex(K):
+    """doc/examples/BivariateNormal/MALA/function/analytical.jl:4-21: v[1] = the state of Hyperparameter(:C)"""
+    L = K._lib
+    C = np.linalg.inv(np.array([[1.0, 0.8], [0.8, 1.0]]))
+    C = (C + C.T) / 2
+    d = K.DenseGaussian()
+    p = K.BasicContMuvParameter("p", logtarget=d, gradlogtarget=d.gradient, nkeys=2)
+    model = K.GenericModel([K.Hyperparameter("C"), p], isindexed=False)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(K.KlaraError) as ei:
+            K.BasicMCJob(model, K.MALA(0.3), K.BasicMCRange(nsteps=100, burnin=10), {"C": C, "p": [1.25, 3.11]})
+        assert ei.value.code == L.KLB_ECUDA
+    else:
+        d.bind([C])
+    z = np.array([1.25, 3.11])
+    assert d(z) == pytest.approx(-z @ C @ z, rel=1e-15) and np.allclose(d.gradient(z), -2 * C @ z, rtol=1e-15)
+    with pytest.raises(AssertionError, match="no precision matrix"):
+        K.DenseGaussian().params(2)
+    with pytest.raises(AssertionError, match="one hyper-parameter"):
+        K.DenseGaussian().bind([C, C])
+
+
+def test_erf_rate_score_kat(K):
+    """test/AcceptanceRateMCTuner.jl:13-14"""
+    assert K.erf_rate_score(-0.1) == 0.6713732405408726
+    assert K.erf_rate_score(0.93, 2) == 1.9914724883356396
+
+
+def test_julia_shim_config_struct_matches_header():
+    """julia/KlaraB200.jl cannot be executed here (no Julia): at least its hand-mirrored KlbConfig must list the header's
+    fields in the header's order with the matching widths"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "klara_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {\n  uint32_t struct_size"):hdr.index("} klb_config;")]
+    cfields = []
+    for line in body.splitlines():
+        line = line.split("/*")[0].strip()
+        m = re.match(r"(uint32_t|int32_t|int64_t|uint64_t|double)\s+([^;]+);", line)
+        if m:
+            cfields += [(n.strip(), m.group(1)) for n in m.group(2).split(",")]
+    jl = open(os.path.join(root, "julia", "KlaraB200.jl")).read()
+    jbody = jl[jl.index("struct KlbConfig"):]
+    jbody = jbody[:jbody.index("\nend")]
+    jfields = re.findall(r"(\w+)::(UInt32|Int32|Int64|UInt64|Float64)", jbody)
+    ctype = {"UInt32": "uint32_t", "Int32": "int32_t", "Int64": "int64_t", "UInt64": "uint64_t", "Float64": "double"}
+    assert [(n, ctype[t]) for n, t in jfields] == cfields

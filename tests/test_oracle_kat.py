@@ -75,6 +75,22 @@ def test_range_npoststeps(O, K):
         assert O.npoststeps(b, t, n) == len(range(b + 1, n + 1, t)) == K.BasicMCRange(burnin=b, thinning=t, nsteps=n).npoststeps
 
 
+def test_klb_erf_is_correctly_rounded_almost_everywhere(O):
+    """klb_erf (double-double series, shared by the oracle and the kernels) against mpmath: <= 0.5 ulp (+ 1e-6) on a
+    dense sample of [-6.5, 6.5] and of tiny arguments; it reproduces the reference's erf_rate_score known answers
+    (test_erf_rate_score_kat) and libm's erf wherever libm itself is correctly rounded"""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.uniform(-6.5, 6.5, 1500), rng.uniform(-1, 1, 1500), 10.0 ** rng.uniform(-300, 0, 200)])
+    for x in xs:
+        t = mp.erf(mp.mpf(float(x)))
+        e = mp.floor(mp.log(abs(t), 2))
+        assert float(abs(mp.mpf(O.erf(x)) - t) / mp.mpf(2) ** (e - 52)) < 0.5 + 1e-6
+    assert O.erf(0.0) == 0.0 and O.erf(7.0) == 1.0 and O.erf(-7.0) == -1.0 and O.erf(math.inf) == 1.0 and math.isnan(O.erf(math.nan))
+    assert sum(O.erf(x) != math.erf(x) for x in xs) < len(xs) // 8
+
+
 # ---- primitives -----------------------------------------------------------------------------
 def test_philox_random123_kat(O):
     """Philox4x32 round function + key schedule: the 10-round known-answer vectors of Random123 (kat_vectors)"""
