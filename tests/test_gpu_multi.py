@@ -177,3 +177,30 @@ def test_gather_between_processes_over_cuda_ipc(K):
     one.run()
     for r in range(world):
         assert_same("rank %d holds the whole all-gather" % r, got[r], one.pstate_value)
+
+
+def test_gibbs_driver_matches_oracle(K, O):
+    """BasicGibbsJob as a caller of the hot path (src/jobs/BasicGibbsJob.jl:185-231): every sweep runs each block's
+    BasicMCJob (one launch), saves the dependent variables' states, resets the dpjobs.  Two blocks (HMC + tuned MALA)
+    and a transformation of both, against oracle/gibbs.py bit for bit."""
+    from oracle import gibbs as OG
+    N = 19
+    kw1 = dict(nchains=N, dim=130, nsteps=3, burnin=0, step=0.05, nleaps=4, seed=11, monitor=("value",), diagnostics=())
+    kw2 = dict(nchains=N, dim=6, nsteps=5, burnin=5 - 1, step=0.3, seed=12, tuner="accrate", period=2, target_rate=0.6,
+               monitor=("value",), diagnostics=())
+    j1, c1, x1, tp1, sg1 = build_pair(K, "HMC", "iso", **kw1)
+    j2, c2, x2, tp2, sg2 = build_pair(K, "MALA", "shifted", **kw2)
+    a = K.BasicContMuvParameter("a", logtarget=j1.parameter.target)
+    b = K.BasicContMuvParameter("b", logtarget=j2.parameter.target)
+    tr = lambda v: np.concatenate([v["a"][:, :2] + v["b"][:, :2], v["a"].sum(1, keepdims=True)], axis=1)  # noqa: E731
+    model = K.GenericModel([a, K.Transformation("s", tr), b], isindexed=False)
+    job = K.BasicGibbsJob(model, {"a": j1, "b": j2}, K.BasicMCRange(nsteps=9, burnin=3, thinning=2), {"a": x1, "b": x2})
+    job.run()
+    got = job.output_dict()
+    ref = OG.run_gibbs({"a": dict(cfg=c1, x0=x1, tparams=tp1), "b": dict(cfg=c2, x0=x2, tparams=tp2)}, {"s": tr},
+                       ["a", "s", "b"], 9, 3, 2)
+    assert got["a"].value.shape == (N, 3, 130) and got["s"].value.shape == (N, 3, 3)
+    for k in ("a", "s", "b"):
+        assert_same("gibbs " + k, got[k].value, ref[k])
+    # the transformation saw the states of the SAME sweep: a was already updated, b not yet
+    assert not np.array_equal(got["a"].value[:, 0], got["a"].value[:, 1])

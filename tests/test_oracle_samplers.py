@@ -217,3 +217,19 @@ def test_stats_follow_the_reference_estimators(O):
     vals = np.cumsum(acc[:, :, None] * rng.normal(size=(4, 50, 3)), axis=1)
     expect = [(1 + sum((vals[c, t] != vals[c, t - 1]).any() for t in range(1, 50))) / 50 for c in range(4)]
     assert np.array_equal(O.acceptance(value=vals), np.array(expect))
+
+
+def test_gibbs_oracle_is_run_plus_reset_per_sweep(O):
+    """oracle/gibbs.py (BasicGibbsJob.jl:185-231): with a tuner that never adapts, S sweeps of an n-step dpjob are one
+    S*n-step chain (state and RNG counter persist across reset(dpjob)), saved once per post-burn-in sweep"""
+    from oracle import gibbs as OG
+    cfg = O.make_config(O.HMC, O.ISO, 4, 10, 3, step=0.1, nleaps=3, monitor=1, seed=5)
+    x0 = np.stack([O.normals(5, c, 0, 10) for c in range(4)])
+    out = OG.run_gibbs({"a": dict(cfg=cfg, x0=x0)}, {"twice": lambda v: 2 * v["a"]}, ["a", "twice"], 6, 2, 2)
+    long = O.run(O.make_config(O.HMC, O.ISO, 4, 10, 18, step=0.1, nleaps=3, monitor=1, seed=5), x0)
+    assert np.array_equal(out["a"][:, 0], long["value"][:, 8]) and np.array_equal(out["a"][:, 1], long["value"][:, 14])
+    assert np.array_equal(out["twice"], 2 * out["a"])
+    # with the AcceptanceRate tuner the record restarts every sweep: the step never drifts beyond one sweep's tuning
+    cfg = O.make_config(O.MALA, O.ISO, 4, 10, 4, burnin=4 - 1, step=0.5, tuner=O.ACCRATE, period=2, target_rate=0.5, monitor=1, seed=6)
+    out2 = OG.run_gibbs({"a": dict(cfg=cfg, x0=x0)}, {}, ["a"], 5, 0, 1)
+    assert out2["a"].shape == (4, 5, 10)

@@ -2,7 +2,10 @@ import time, numpy as np, klara_b200 as K, sys
 sys.path.insert(0, "tests/golden")
 import make_golden as G
 X, y, lam = G.logit_data(4)
+ONLY = sys.argv[1] if len(sys.argv) > 1 else None
 for smp, name in ((K.HMC(0.05, 10), "HMC"), (K.MALA(0.02), "MALA"), (K.MH(np.full(4, 0.1)), "MH")):
+    if ONLY and name != ONLY:
+        continue
     N = 148 * 64 * 16
     x0 = np.random.default_rng(0).normal(size=(N, 4)) * 0.3
     p = K.BasicContMuvParameter("p", logtarget=K.BayesLogit(X, y, lam))
