@@ -333,8 +333,8 @@ int klb_host_alloc(void** p, int64_t nbytes);
 int klb_host_free(void* p);
 
 /* Device self-tests used by the parity suite (run on the GPU, results copied to host):
- * n standard normals of stream (seed, chain, t) / op(x[i]) with op 0 = exp, 1 = log / the
- * accept uniform / the canonical dot product. */
+ * n standard normals of stream (seed, chain, t) / op(x[i]) with op 0 = exp, 1 = log, 2 = erf, 3 = the shared-divisor
+ * division of the MALA kernels on pairs (x[2k] / x[2k+1], written to both slots) / the accept uniform. */
 int klb_debug_normals(int device, uint64_t seed, uint64_t chain, uint64_t t, int64_t n, double* host_out);
 int klb_debug_math(int device, int op, int64_t n, const double* host_in, double* host_out);
 int klb_debug_uniform(int device, uint64_t seed, uint64_t chain, uint64_t t, double* host_out);

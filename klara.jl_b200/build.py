@@ -124,8 +124,16 @@ def build(force=False, jobs=None, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     jobs = jobs or min(8, os.cpu_count() or 1)
     objs = []
+    # experiments: KLB_VARIANT_UNITS="klb_chain_0_0,klb_chain_1_0" recompiles only those units for the variant and
+    # links the default build's objects for the rest
+    only = [u for u in os.environ.get("KLB_VARIANT_UNITS", "").split(",") if u] if VARIANT else []
     with cf.ThreadPoolExecutor(max_workers=jobs) as ex:
-        futs = [ex.submit(compile_one, n, s, d, force) for n, s, d in units()]
+        futs = []
+        for n, s, d in units():
+            if only and n not in only:
+                objs.append(os.path.join(OBJROOT, "default", n + ".o"))
+                continue
+            futs.append(ex.submit(compile_one, n, s, d, force))
         for f in futs:
             obj, err = f.result()
             objs.append(obj)

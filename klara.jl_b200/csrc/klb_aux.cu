@@ -48,8 +48,12 @@ __global__ void klb_debug_math_kernel(const uint64_t* gtab, int op, long long n,
   __shared__ uint64_t tab[KLB_TAB_LEN];
   for (int i = threadIdx.x; i < KLB_TAB_LEN; i += blockDim.x) tab[i] = gtab[i];
   __syncthreads();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] = op == 0 ? klb_exp(in[i], tab) : klb_log(in[i], tab);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (op == 0) out[i] = klb_exp(in[i], tab);
+    else if (op == 1) out[i] = klb_log(in[i], tab);
+    else if (op == 2) out[i] = klb_erf(in[i], tab);
+    else { const DivBy by(in[i | 1]); out[i] = by(in[i & ~1ll]); }            // op 3: pairs (a, b) -> a / b through DivBy, twice
+  }
 }
 void klb_launch_debug_math(const uint64_t* tab, int op, long long n, const double* in, double* out, cudaStream_t s) {
   klb_debug_math_kernel<<<148, 256, 0, s>>>(tab, op, n, in, out);
@@ -187,18 +191,13 @@ klb_ess_tile_kernel(const double* __restrict__ value, long long ld, long long np
       double acc[8], w[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) { acc[q] = 0.0; w[q] = (L + q < n) ? z[(L + q) * TC] : 0.0; }
-      // the window z[t+L .. t+L+7] lives in w[(t + q) & 7]: eight steps of t per trip, so the slot indices are
-      // compile-time constants and the window never moves between registers (the rolled loop spent 14 MOVs per
-      // 8 DFMA on shifting it).  Beyond the end of the series the window holds zeros, which add nothing: same sums.
-      for (int t0 = 0; t0 + L < n; t0 += 8) {
+      for (int t = 0; t + L < n; ++t) {
+        const double zt = z[t * TC];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int t = t0 + u;
-          const double zt = (t < n) ? z[t * TC] : 0.0;
+        for (int q = 0; q < 8; ++q) acc[q] = __fma_rn(zt, w[q], acc[q]);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = __fma_rn(zt, w[(u + q) & 7], acc[q]);
-          w[u] = (t + L + 8 < n) ? z[(t + L + 8) * TC] : 0.0;
-        }
+        for (int q = 0; q < 7; ++q) w[q] = w[q + 1];
+        w[7] = (t + L + 8 < n) ? z[(t + L + 8) * TC] : 0.0;
       }
       if (L == 0) s0 = acc[0];
 #pragma unroll

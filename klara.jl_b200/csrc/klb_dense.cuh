@@ -234,13 +234,14 @@ klb_dense_kernel(const DArgs D) {
       for (int r = 0; r < MC; ++r) {
         const double step = S.step[r];
         const double h = __dmul_rn(0.5, step), sq = __dsqrt_rn(step), hinv = __ddiv_rn(0.5, step);
+        const DivBy by_step(step);
         const double ga = __dmul_rn(-2.0, gc[r][0]), gb = __dmul_rn(-2.0, gc[r][1]);
         mu[r][0] = Ar<FMA>::ma(h, ga, x[r][0]); mu[r][1] = Ar<FMA>::ma(h, gb, x[r][1]);
         const double ya = Ar<FMA>::ma(sq, y[r][0], mu[r][0]), yb = Ar<FMA>::ma(sq, y[r][1], mu[r][1]);
         y[r][0] = ya; y[r][1] = yb;
         const double da = __dsub_rn(mu[r][0], ya), db = __dsub_rn(mu[r][1], yb);
-        const double ea = FMA ? __dmul_rn(__dmul_rn(da, hinv), da) : __dmul_rn(0.5, __ddiv_rn(__dmul_rn(da, da), step));
-        const double eb = FMA ? __dmul_rn(__dmul_rn(db, hinv), db) : __dmul_rn(0.5, __ddiv_rn(__dmul_rn(db, db), step));
+        const double ea = FMA ? __dmul_rn(__dmul_rn(da, hinv), da) : __dmul_rn(0.5, by_step(__dmul_rn(da, da)));
+        const double eb = FMA ? __dmul_rn(__dmul_rn(db, hinv), db) : __dmul_rn(0.5, by_step(__dmul_rn(db, db)));
         if (active) {
           xs[(size_t)i0 * MC + r] = ya; xs[(size_t)(i0 + 1) * MC + r] = yb;       // proposal positions
           sc[(size_t)i0 * MC + r] = ea; sc[(size_t)(i0 + 1) * MC + r] = eb;
@@ -263,11 +264,12 @@ klb_dense_kernel(const DArgs D) {
       for (int r = 0; r < MC; ++r) {
         const double step = S.step[r];
         const double h = __dmul_rn(0.5, step), hinv = __ddiv_rn(0.5, step);
+        const DivBy by_step(step);
         const double ga = __dmul_rn(-2.0, acc[r][0]), gb = __dmul_rn(-2.0, acc[r][1]);
         const double ma = Ar<FMA>::ma(h, ga, y[r][0]), mb = Ar<FMA>::ma(h, gb, y[r][1]);        // mu' = y + (h g(y))
         const double da = __dsub_rn(ma, x[r][0]), db = __dsub_rn(mb, x[r][1]);
-        const double ea = FMA ? __dmul_rn(__dmul_rn(da, hinv), da) : __dmul_rn(0.5, __ddiv_rn(__dmul_rn(da, da), step));
-        const double eb = FMA ? __dmul_rn(__dmul_rn(db, hinv), db) : __dmul_rn(0.5, __ddiv_rn(__dmul_rn(db, db), step));
+        const double ea = FMA ? __dmul_rn(__dmul_rn(da, hinv), da) : __dmul_rn(0.5, by_step(__dmul_rn(da, da)));
+        const double eb = FMA ? __dmul_rn(__dmul_rn(db, hinv), db) : __dmul_rn(0.5, by_step(__dmul_rn(db, db)));
         if (active) { sc[(size_t)i0 * MC + r] = ea; sc[(size_t)(i0 + 1) * MC + r] = eb; }
       }
       __syncthreads();

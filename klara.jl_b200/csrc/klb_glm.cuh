@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
       // ---------------------------------------------------------------- MALA
       const double sq = __dsqrt_rn(step);
       const double hinv = __ddiv_rn(0.5, step);
+      const DivBy by_step(step);
       double mu[DP];
       double e1 = 0.0, e2 = 0.0;
 #pragma unroll
@@ -261,10 +262,10 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
       for (int j = 0; j < DP; ++j) {
         if (j < d) {
           const double df = __dsub_rn(mu[j], xs[j]);
-          e1 = __dadd_rn(e1, FMA ? __dmul_rn(__dmul_rn(df, hinv), df) : __dmul_rn(0.5, __ddiv_rn(__dmul_rn(df, df), step)));
+          e1 = __dadd_rn(e1, FMA ? __dmul_rn(__dmul_rn(df, hinv), df) : __dmul_rn(0.5, by_step(__dmul_rn(df, df))));
           const double m2 = Ar<FMA>::ma(h, gs[j], xs[j]);
           const double db = __dsub_rn(m2, x[j]);
-          e2 = __dadd_rn(e2, FMA ? __dmul_rn(__dmul_rn(db, hinv), db) : __dmul_rn(0.5, __ddiv_rn(__dmul_rn(db, db), step)));
+          e2 = __dadd_rn(e2, FMA ? __dmul_rn(__dmul_rn(db, hinv), db) : __dmul_rn(0.5, by_step(__dmul_rn(db, db))));
         }
       }
       ratio = __dsub_rn(lt_new, lt_cur);

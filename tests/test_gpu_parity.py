@@ -669,3 +669,30 @@ def test_random_configurations_bit_exact(K, k, cfgd):
     every field, the final state and the tuner records against the oracle, bit for bit"""
     job, cfg, x0, tp, sg = build_pair(K, rng_seed=k, **cfgd)
     compare_run(job, cfg, x0, tp, sg)
+
+
+def test_device_erf_and_shared_divisor_division(K, O):
+    """klb_erf on the device == the oracle's (same double-double series); DivBy (the MALA kernels' division by the drift
+    step with the reciprocal refinement hoisted) == IEEE division, bit for bit, on random and on extreme operands"""
+    rng = np.random.default_rng(9)
+    xs = np.concatenate([rng.uniform(-6.5, 6.5, 20000), np.array([0.0, -0.0, 4.5, 4.500001, 6.0, -6.0, 7.0, np.inf, -np.inf, np.nan, 1e-300])])
+    out = np.empty_like(xs)
+    K._lib.check(K._lib.lib().klb_debug_math(0, 2, xs.size, _ptr(xs), _ptr(out)))
+    assert_same("erf", out, np.array([O.erf(x) for x in xs]))
+    n = 1 << 20
+    a = np.concatenate([rng.uniform(0, 4, n) ** 2, 10.0 ** rng.uniform(-320, 308, n), rng.normal(size=n)])
+    b = np.concatenate([10.0 ** rng.uniform(-4, 1, n), 10.0 ** rng.uniform(-320, 308, n), rng.uniform(1e-3, 2, n)])
+    edge = np.array([0.0, -0.0, 5e-324, 2.2250738585072014e-308, 1e-292, 1e-291, 1.7976931348623157e308, np.inf, -np.inf, np.nan, 1.0, 3.0])
+    ea, eb = np.meshgrid(edge, edge)
+    a, b = np.concatenate([a, ea.ravel()]), np.concatenate([b, eb.ravel()])
+    # significands of all ones / divisors just below a power of two: the classic hard cases of reciprocal-based division
+    hard = np.nextafter(2.0 ** rng.integers(-30, 30, 4096).astype(np.float64), 0)
+    a, b = np.concatenate([a, rng.uniform(0.5, 2, 4096), hard]), np.concatenate([b, hard, rng.uniform(0.5, 2, 4096)])
+    pairs = np.empty(2 * a.size)
+    pairs[0::2], pairs[1::2] = a, b
+    out = np.empty_like(pairs)
+    K._lib.check(K._lib.lib().klb_debug_math(0, 3, pairs.size, _ptr(pairs), _ptr(out)))
+    with np.errstate(all="ignore"):
+        want = a / b
+    assert_same("shared-divisor division", out[0::2], want)
+    assert_same("shared-divisor division (second slot)", out[1::2], want)

@@ -1,5 +1,9 @@
-import time, numpy as np, klara_b200 as K, sys
-sys.path.insert(0, "tests/golden")
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import klara_b200 as K
 import make_golden as G
 X, y, lam = G.logit_data(4)
 ONLY = sys.argv[1] if len(sys.argv) > 1 else None
