@@ -233,3 +233,34 @@ def test_gibbs_oracle_is_run_plus_reset_per_sweep(O):
     cfg = O.make_config(O.MALA, O.ISO, 4, 10, 4, burnin=4 - 1, step=0.5, tuner=O.ACCRATE, period=2, target_rate=0.5, monitor=1, seed=6)
     out2 = OG.run_gibbs({"a": dict(cfg=cfg, x0=x0)}, {}, ["a"], 5, 0, 1)
     assert out2["a"].shape == (4, 5, 10)
+
+
+def test_tuned_samplers_hit_their_target_rate_and_the_posterior(O):
+    """semantic check of the tuner branches that no reference KAT pins: after burn-in the acceptance rate
+    sits near the tuner's target and the chain samples exp(-z.z) = N(0, I/2) -- an error shared by the oracle and the
+    kernels (which agree bit for bit) would show up here"""
+    d, n = 10, 64
+    x0 = np.stack([O.normals(3, c, 0, d) for c in range(n)]) * 0.7
+    # MALA + AcceptanceRateMCTuner(0.574), both score functions
+    for score in (0, 1):
+        cfg = O.make_config(O.MALA, O.ISO, n, d, 3000, burnin=2000, step=0.05, tuner=O.ACCRATE, target_rate=0.574,
+                            score_k=3.0 if score else 7.0, period=100, monitor=1, diagnostics=1, seed=21, nthreads=O.max_threads(),
+                            score=score)
+        r = O.run(cfg, x0)
+        assert abs(r["accept"].mean() - 0.574) < 0.08, r["accept"].mean()
+        v = r["value"].reshape(-1, d)
+        assert abs(v.mean()) < 0.03 and abs(v.var() - 0.5) < 0.05
+        assert (r["tune"]["step"] != 0.05).all() and (r["tune"]["totproposed"] == 2100).all()
+    # HMC + AcceptanceRateMCTuner(0.8)
+    cfg = O.make_config(O.HMC, O.ISO, n, d, 1500, burnin=1000, step=0.6, nleaps=5, tuner=O.ACCRATE, target_rate=0.8,
+                        period=50, monitor=1, diagnostics=1, seed=22, nthreads=O.max_threads())
+    r = O.run(cfg, x0)
+    assert abs(r["accept"].mean() - 0.8) < 0.1, r["accept"].mean()
+    assert abs(r["value"].reshape(-1, d).var() - 0.5) < 0.05
+    # HMC + DualAveragingMCTuner(0.65): adapts for nadapt transitions, then freezes the averaged step
+    cfg = O.make_config(O.HMC, O.ISO, n, d, 1500, burnin=1000, step=0.1, nleaps=10, tuner=O.DUALAVG, target_rate=0.65,
+                        monitor=1, diagnostics=1, seed=23, nthreads=O.max_threads(), nadapt=1000)
+    r = O.run(cfg, x0)
+    assert abs(r["accept"].mean() - 0.65) < 0.12, r["accept"].mean()
+    assert abs(r["value"].reshape(-1, d).var() - 0.5) < 0.06
+    assert (r["tune"]["step"] == r["da"]["epsbar"]).all() and (r["da"]["count"] == 1500).all()
