@@ -105,6 +105,10 @@ extern "C" {
 #define KLB_OUT_TUNE_COUNTERS 7  /* int64   3 x nchains        accepted, proposed, totproposed */
 #define KLB_OUT_TUNE_RATE 8      /* double  nchains            sstate.tune.rate (NaN after reset_burnin!) */
 #define KLB_OUT_ESS 9            /* double  dim x nchains      filled by klb_job_ess (device_ptr only after that call) */
+#define KLB_OUT_TUNE_RATES 11    /* double  nperiods x nchains  verbose tuners only: the acceptance rate of every burn-in period of
+                                                               every chain -- what the reference prints per period (iterate/HMC.jl:
+                                                               211-221, MALA.jl:138-148, MH.jl:126-139); nperiods = burnin / period
+                                                               (nadapt / period for DualAveragingMCTuner); NaN = period not closed */
 #define KLB_OUT_TUNE_DA 10       /* double  8 x nchains        DualAveragingMCTune: λ, μ, εbar, hbar, hweight, εweight,
                                                                nleaps of the last transition, sstate.count */
 

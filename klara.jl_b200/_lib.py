@@ -23,7 +23,7 @@ DIAG_ACCEPT = 1
 DEST_NSTATE, DEST_NONE = 0, 1
 PARAM_MU, PARAM_C, PARAM_SIGMA, PARAM_ROSEN, PARAM_LOGIT_X, PARAM_LOGIT_Y, PARAM_LOGIT_LAMBDA = 0, 1, 2, 3, 4, 5, 6
 (OUT_VALUE, OUT_LOGTARGET, OUT_GRADLOGTARGET, OUT_ACCEPT, OUT_STATE, OUT_STATE_LOGTARGET,
- OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS, OUT_TUNE_DA) = range(11)
+ OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS, OUT_TUNE_DA, OUT_TUNE_RATES) = range(12)
 PEAK_FP64, PEAK_DMMA = 0, 1
 GATHER_HANDLE_BYTES = 128
 (STAT_MEAN, STAT_MCVAR_IID, STAT_MCVAR_IMSE, STAT_ESS, STAT_IACT, STAT_ACCEPTANCE, STAT_ACCEPTANCE_VALUE) = range(7)

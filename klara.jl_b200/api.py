@@ -437,12 +437,44 @@ class BasicMCJob:
         """run(job)        src/jobs/BasicMCJob.jl:212-244"""
         self._call("run")
         self.count = self.range.npoststeps
+        if self.tuner.verbose:
+            self._print_burnin_report()
         if self.outopts["destination"] == "iostream":
             # the samples are produced on the device; the CSV files of the reference's iostream destination are
             # written from the fetched NState when the run ends (README.md:117-146)
             from .iostream import write_job_output
             self.iostream = write_job_output(self, self._fetch_nstate())
         return self
+
+    @property
+    def burnin_rates(self):
+        """(nchains, nperiods): the acceptance rate of every burn-in period of every chain, recorded by the kernels of
+        a job with a verbose tuner -- the numbers the reference prints per period (iterate/HMC.jl:211-221,
+        iterate/MALA.jl:138-148, iterate/MH.jl:126-139).  NaN where a period did not close."""
+        if not self.tuner.verbose:
+            raise L.KlaraError(L.KLB_ESTATE, "burn-in rates are recorded for verbose tuners only")
+        horizon = self.tuner.nadapt if isinstance(self.tuner, DualAveragingMCTuner) else self.range.burnin
+        nper = horizon // self.tuner.period
+        if nper == 0:
+            return np.empty((self.nchains, 0))
+        return self._fetch(L.OUT_TUNE_RATES, (self.nchains, nper))
+
+    def _print_burnin_report(self, file=None):
+        """println("Burnin iteration ", fmt_iter(totproposed), " of ", burnin, ": ", fmt_perc(100*rate), " % acceptance rate")
+        once per period: fmt_iter = %<ndigits(burnin)>d, fmt_perc = %6.2f (src/format.jl, BasicMCJob.jl:90-101).  One
+        chain prints the reference's line; a batch prints the mean over chains with the range."""
+        rates = self.burnin_rates
+        horizon = self.tuner.nadapt if isinstance(self.tuner, DualAveragingMCTuner) else self.range.burnin
+        nd = len(str(horizon))
+        for k in range(rates.shape[1]):
+            r = rates[:, k]
+            if np.isnan(r).all():
+                continue
+            line = "Burnin iteration %*d of %d: %6.2f %% acceptance rate" % (nd, (k + 1) * self.tuner.period, horizon,
+                                                                           100 * float(np.nanmean(r)))
+            if self.nchains > 1:
+                line += " (mean of %d chains, %.2f .. %.2f)" % (self.nchains, 100 * np.nanmin(r), 100 * np.nanmax(r))
+            print(line, file=file)
 
     def run_async(self):
         self._call("run_async")

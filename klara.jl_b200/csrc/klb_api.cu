@@ -81,6 +81,8 @@ struct klb_job {
   long long* tune_cnt;
   double* tune_rate;
   double* tune_da;  // DualAveragingMCTuner: 8 doubles per chain
+  double* tune_rates;   // verbose tuners: nperiods burn-in acceptance rates per chain (chain-major), else null
+  long long nperiods;
   bool da, constructed;   // constructed: the first klb_job_set_state (= BasicMCJob constructor) has happened
   double* out_value;
   double* out_lt;
@@ -179,6 +181,7 @@ static void free_job(klb_job* j) {
   if (!j) return;
   cudaSetDevice(j->cfg.device);
   cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate); cudaFree(j->tune_da);
+  cudaFree(j->tune_rates);
   cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
   cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess); cudaFree(j->accrate);
   cudaFree(j->gX); cudaFree(j->gy);
@@ -219,6 +222,7 @@ static void fill_args(const klb_job* j, KArgs& A) {
                                                 : ((c.tuner == KLB_TUNER_ACCEPTANCE_RATE) || c.verbose != 0);
   A.target_rate = c.target_rate; A.score_k = c.score_k; A.score = c.score;
   A.seed = c.seed; A.chain_offset = (unsigned long long)c.chain_offset;
+  A.out_rate = j->tune_rates; A.nperiods = j->nperiods;
   A.tune_da = j->tune_da; A.da_nadapt = c.da_nadapt; A.da_t0 = c.da_t0; A.da_gamma = c.da_gamma; A.da_kappa = c.da_kappa;
 }
 
@@ -334,6 +338,13 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   CKJ(cudaMalloc(&j->tune_rate, N * sizeof(double)));
   j->da = c.tuner == KLB_TUNER_DUAL_AVERAGING;
   if (j->da) CKJ(cudaMalloc(&j->tune_da, 8 * N * sizeof(double)));
+  // verbose: one rate per chain and burn-in period (the reference prints them: iterate/HMC.jl:211-221, iterate/MH.jl:126-139);
+  // dual averaging reports while count <= nadapt, every `period` proposals
+  j->nperiods = c.verbose ? (j->da ? c.da_nadapt : c.burnin) / c.period : 0;
+  if (j->nperiods > 0 && (size_t)j->nperiods * N * sizeof(double) <= ((size_t)1 << 32)) {
+    CKJ(cudaMalloc(&j->tune_rates, (size_t)j->nperiods * N * sizeof(double)));
+    CKJ(cudaMemset(j->tune_rates, 0xff, (size_t)j->nperiods * N * sizeof(double)));   // NaN until a period closes
+  } else j->nperiods = 0;
   CKJ(cudaMalloc(&j->mu, pad * sizeof(double)));
   CKJ(cudaMalloc(&j->sigma, pad * sizeof(double)));
   CKJ(cudaMemset(j->mu, 0, pad * sizeof(double)));
@@ -450,7 +461,8 @@ static void slice_args(const klb_job* j, KArgs& A, long long c0, long long nc) {
   const long long ld = j->ld, P = j->npost;
   A.state += c0 * ld; A.lt += c0;
   A.tune_step += c0; A.tune_cnt += 3 * c0; A.tune_rate += c0;
-  if (A.tune_da) A.tune_da += 8 * c0;              // DualAveragingMCTune record: indexed by the slice-local chain id
+  if (A.tune_da) A.tune_da += 8 * c0;
+  if (A.out_rate) A.out_rate += c0 * j->nperiods;              // DualAveragingMCTune record: indexed by the slice-local chain id
   if (A.out_value) A.out_value += c0 * P * ld;
   if (A.out_lt) A.out_lt += c0 * P;
   if (A.out_grad) A.out_grad += c0 * P * ld;
@@ -523,6 +535,7 @@ static void fill_tune_slice(klb_job* j, size_t c0, size_t nc, cudaStream_t s) {
   const double step0 = tune_step0(j);
   klb_launch_fill_tune(j->tune_step + c0, j->tune_cnt + 3 * c0, j->tune_rate + c0, (long long)nc, step0, j->cfg.period, s);
   j->launches += 1;
+  if (j->tune_rates) cudaMemsetAsync(j->tune_rates + c0 * (size_t)j->nperiods, 0xff, nc * (size_t)j->nperiods * sizeof(double), s);
   if (j->da) {
     klb_launch_fill_da(j->tune_da + 8 * c0, (long long)nc, (double)j->cfg.nleaps * j->cfg.step,
                        klb_log(10 * step0, KLB_TAB), j->cfg.da_eps0bar, j->cfg.da_h0bar, s);
@@ -792,6 +805,7 @@ static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols) 
     case KLB_OUT_TUNE_RATE: *p = j->tune_rate; *nb = N * 8; break;
     case KLB_OUT_ESS: *p = j->ess; *nb = N * d * 8; break;
     case KLB_OUT_TUNE_DA: *p = j->tune_da; *nb = 8 * N * 8; break;
+    case KLB_OUT_TUNE_RATES: *p = j->tune_rates; *nb = (size_t)j->nperiods * N * 8; break;
     default: return fail(KLB_EINVAL, "unknown field %d", field);
   }
   if (!*p) return fail(KLB_ESTATE, "field %d is not monitored by this job", field);

@@ -380,7 +380,7 @@ klb_dense_mma_kernel(const DArgs D) {
       Tune tn;
       tn.step = S.step[r]; tn.accepted = S.accepted[r]; tn.proposed = S.proposed[r]; tn.totproposed = S.totproposed[r];
       tn.rate = S.rate[r];
-      tuner_block<2>(A, tn, tab);
+      tuner_block<2>(A, tn, tab, c0 + r);
       S.step[r] = tn.step; S.accepted[r] = tn.accepted; S.proposed[r] = tn.proposed; S.totproposed[r] = tn.totproposed;
       S.rate[r] = tn.rate;
     }

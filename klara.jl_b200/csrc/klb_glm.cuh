@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
 
     if (A.counters_on) { tn.proposed += 1; if (accept) tn.accepted += 1; }
     if (SAMPLER == 2 && A.tuner == 2) da_block<false>(A, c, tn, nl, a_prob, tab, true);
-    else tuner_block<SAMPLER>(A, tn, tab);
+    else tuner_block<SAMPLER>(A, tn, tab, c);
     if (accept) {
 #pragma unroll
       for (int j = 0; j < DP; ++j) { x[j] = xs[j]; if (SAMPLER != 0) g[j] = gs[j]; }

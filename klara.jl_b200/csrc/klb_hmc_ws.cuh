@@ -240,7 +240,7 @@ klb_hmc_ws_kernel(const KArgs A) {
       tn.rate = cs->rate;
       if (A.counters_on) { tn.proposed += 1; if (accept) tn.accepted += 1; }
       if (A.tuner == 2) da_block<true>(A, c, tn, nl, a_prob, tab, lane == 0);
-      else tuner_block<2>(A, tn, tab);
+      else tuner_block<2>(A, tn, tab, c);
       __syncwarp();
       if (lane == 0) {
         cs->step = tn.step; cs->accepted = tn.accepted; cs->proposed = tn.proposed; cs->totproposed = tn.totproposed;

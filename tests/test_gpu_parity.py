@@ -696,3 +696,34 @@ def test_device_erf_and_shared_divisor_division(K, O):
         want = a / b
     assert_same("shared-divisor division", out[0::2], want)
     assert_same("shared-divisor division (second slot)", out[1::2], want)
+
+
+def test_verbose_tuner_records_and_prints_the_burnin_rates(K, O, capsys):
+    """verbose tuners: the per-period burn-in acceptance rates the reference prints (iterate/HMC.jl:211-221,
+    iterate/MH.jl:126-139) are recorded by the kernels (KLB_OUT_TUNE_RATES) and printed by run() in the reference's
+    format; rate of period k = accepted / period of transitions k*period+1 .. (k+1)*period, from the accept flags"""
+    for sampler, tuner, kw in (("HMC", "accrate", dict(step=0.08, nleaps=4)), ("MALA", "vanilla", dict(step=0.2)),
+                               ("MH", "vanilla", dict(sigma=np.full(24, 0.3)))):
+        job, cfg, x0, tp, sg = build_pair(K, sampler, "iso", nchains=7, dim=24, nsteps=70, burnin=0, seed=3, tuner=tuner,
+                                          period=10, verbose=True, **kw)
+        # burnin = 0 saves every transition: re-run the same chains with a burn-in of 45 and compare the records
+        job.run()
+        acc = job.output().diagnosticvalues
+        capsys.readouterr()
+        jb, cfgb, *_ = build_pair(K, sampler, "iso", nchains=7, dim=24, nsteps=70, burnin=45, seed=3, tuner=tuner,
+                                  period=10, verbose=True, **kw)
+        jb.run()
+        text = capsys.readouterr().out.strip().splitlines()
+        rates = jb.burnin_rates
+        assert rates.shape == (7, 4) and len(text) == 4
+        if tuner == "vanilla":          # no adaptation: the burn-in chain equals the head of the all-saved chain
+            want = acc[:, :40].reshape(7, 4, 10).mean(-1)
+            assert_same("burn-in rates", rates, want)
+        assert text[0].startswith("Burnin iteration 10 of 45: ") and text[0].split(": ")[1].startswith("%6.2f" % (100 * rates[:, 0].mean()))
+        assert " % acceptance rate" in text[3] and text[3].startswith("Burnin iteration 40 of 45")
+    single, *_ = build_pair(K, "MH", "iso", nchains=1, dim=2, nsteps=30, burnin=20, seed=4, period=10, verbose=True,
+                            sigma=np.ones(2), x0=np.array([[5.1, -0.9]]))
+    single.run()
+    out = capsys.readouterr().out.strip().splitlines()
+    r = single.burnin_rates[0]
+    assert out == ["Burnin iteration %2d of 20: %6.2f %% acceptance rate" % (10 * (k + 1), 100 * r[k]) for k in range(2)]
