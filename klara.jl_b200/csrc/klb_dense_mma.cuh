@@ -52,9 +52,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
   } while (!ok);
 }
+// Release of a stage by a consumer warp: an arrive on the EMPTY barrier of CTA `cta` of the cluster.  Default semantics
+// (.release at CTA scope), the form CUTLASS's ClusterBarrier::arrive uses for consumer_release: the warp's fragment loads
+// have returned before it gets here (their values fed the DMMAs above), so nothing needs flushing.  Round 1 wrote
+// `.release.cluster`, which ptxas expands to MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of every
+// arrive: 20 % of the kernel's stall samples (`stall_membar` 2.6 per issue, profiles/r2_kernel_metrics.csv column D).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* b, unsigned cta) {
   asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-               "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(b)), "r"(cta) : "memory");
+               "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(b)), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, unsigned bytes, uint64_t* bar,
                                                    unsigned short mask) {
