@@ -190,8 +190,9 @@ class BasicMCRange:
 
 class VanillaMCTuner:
     """VanillaMCTuner(; period=100, verbose=false)        src/tuners/VanillaMCTuner.jl:6-16
-    `verbose` switches the acceptance counters on (iterate/HMC.jl:129-133); the per-period
-    println of the reference is not reproduced (the loop runs inside one kernel launch)."""
+    `verbose` switches the acceptance counters on (iterate/HMC.jl:129-133); the kernels record the acceptance rate
+    of every burn-in period (BasicMCJob.burnin_rates) and run() prints the reference's per-period lines when the
+    launch returns."""
     code = L.TUNER_VANILLA
 
     def __init__(self, period=100, verbose=False):
