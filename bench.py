@@ -240,7 +240,7 @@ def run_gpu(args, rank, world, local_rank):
     state_t = _view(torch, sp, (nloc, DIM), "f8", dev)
 
     # -------- the closing all-gather
-    gather, gathered_t, nccl = None, None, None
+    gather, gathered_t, nccl, gather_note = None, None, None, None
     if world > 1 and args.gather == "p2p":
         g = C.c_void_p()
         L.check(lib.klb_gather_create(job._h, world, rank, NCHAINS, 0, C.byref(g)))
@@ -250,12 +250,21 @@ def run_gpu(args, rank, world, local_rank):
         allh = torch.empty(world * L.GATHER_HANDLE_BYTES, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allh, mine)         # plumbing: the IPC handles travel over NCCL
         raw = bytes(allh.cpu().numpy())
-        L.check(lib.klb_gather_connect(g, C.create_string_buffer(raw, len(raw))))
-        gp, gnb = C.c_void_p(), C.c_int64()
-        L.check(lib.klb_gather_device_ptr(g, L.OUT_STATE, C.byref(gp), C.byref(gnb)))
-        gathered_t = _view(torch, gp.value, (NCHAINS, DIM), "f8", dev)
-        gather = g
-    elif world > 1:
+        ok = torch.ones(1, device=dev)
+        try:
+            L.check(lib.klb_gather_connect(g, C.create_string_buffer(raw, len(raw))))
+        except L.KlaraError as e:                       # e.g. CUDA IPC not permitted between these processes
+            ok.zero_()
+            gather_note = str(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # every rank takes the same path
+        if float(ok) > 0:
+            gp, gnb = C.c_void_p(), C.c_int64()
+            L.check(lib.klb_gather_device_ptr(g, L.OUT_STATE, C.byref(gp), C.byref(gnb)))
+            gathered_t = _view(torch, gp.value, (NCHAINS, DIM), "f8", dev)
+            gather = g
+        else:
+            lib.klb_gather_destroy(g)
+    if world > 1 and gather is None:
         # NCCL all-gather of a snapshot of the final states on its own stream (round 1's path: SM-based kernel)
         nccl = {"out": torch.empty((NCHAINS, DIM), dtype=torch.float64, device=dev), "snap": torch.empty_like(state_t),
                 "stream": torch.cuda.Stream(device=dev), "done": torch.cuda.Event()}
@@ -450,7 +459,8 @@ def run_gpu(args, rank, world, local_rank):
                        "rng": "Philox4x32-7 counter streams + 256-layer ziggurat (DESIGN.md section 3)",
                        "closing_all_gather": ("none (N=1)" if world == 1 else
                                               "copy engines, CUDA IPC peer-to-peer over NVLink (klb_gather_*)" if gather is not None
-                                              else "NCCL all_gather_into_tensor on a side stream"),
+                                              else "NCCL all_gather_into_tensor on a side stream"
+                                              + (" (peer-to-peer setup failed: %s)" % gather_note if gather_note else "")),
                        "nv": plan.nv, "regs_per_thread": plan.regs_per_thread, "blocks_per_sm": plan.blocks_per_sm,
                        "accept_rate": acc_rate, "timing": "CUDA events on the job stream, max over ranks",
                        "wall_ms_per_step": wall_ms / args.steps},
