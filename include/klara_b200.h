@@ -239,6 +239,15 @@ typedef struct {
   int64_t nbytes;    /* full size of the field, as for klb_job_output */
 } klb_host_field;
 int klb_job_run_host(klb_job* job, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices);
+/* The same call in two halves, so that several jobs (devices) can be in flight at once: _async enqueues the whole
+ * pipeline and returns; the host buffers must stay valid until _finish, which waits, reports KLB_ENOTFINITE and commits
+ * (or rolls back) the job's bookkeeping.  _wait waits and reports the same status but leaves the run pending, _abort
+ * discards it: together they let a caller commit several jobs all-or-nothing (klb_multi_run_host).  Other calls on the
+ * job are refused while a run is pending. */
+int klb_job_run_host_async(klb_job* job, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices);
+int klb_job_run_host_finish(klb_job* job);
+int klb_job_run_host_wait(klb_job* job);
+int klb_job_run_host_abort(klb_job* job);
 
 /* ess(output(job)) = ess(chain, :imse) for every coordinate of every chain (src/stats/convergence/ess.jl:3-14,
  * src/stats/variance/mcvar.jl:5,75-105), computed on the device over the monitored values; host_ess
@@ -300,6 +309,9 @@ int klb_multi_seek(klb_multi* m, uint64_t t);
 int klb_multi_run(klb_multi* m);                                        /* run on every device + closing all-gather; blocking */
 int klb_multi_run_async(klb_multi* m);
 int klb_multi_sync(klb_multi* m);
+/* klb_job_run_host for the logical job: x0 (dim x N) and the fields' host arrays are those of all N chains; every device
+ * runs its shard's pipeline concurrently (klb_job_run_host_async on each, then _finish), then the closing all-gather */
+int klb_multi_run_host(klb_multi* m, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices);
 int klb_multi_output(klb_multi* m, int field, void* host_dst, int64_t nbytes);   /* output(job): shards concatenated */
 int klb_multi_gathered(klb_multi* m, int32_t g, int field, void** dev_ptr, int64_t* nbytes);  /* device g's copy of the all-gather */
 int klb_multi_gathered_output(klb_multi* m, int32_t g, int field, void* host_dst, int64_t nbytes);

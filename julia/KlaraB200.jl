@@ -199,9 +199,8 @@ run(jobs::Vector{BasicMCJob}) = map(run, jobs)
 # reset(job, x0); run(job); output fields, in ONE pipelined call (klb_job_run_host): chain slices on their own streams,
 # host->device copies, kernels and device->host copies overlap.  `outputs` maps KLB_OUT_* codes to preallocated Arrays.
 function run_host(job::BasicMCJob, x0::Union{Matrix{Float64},Nothing}, outputs::Dict{Int,<:Array}; nslices::Integer=0)
-  job.multi && error("run_host drives one device")
   f = [KlbHostField(Int32(k), 0, pointer(a), sizeof(a)) for (k, a) in outputs]
-  GC.@preserve x0 outputs f check(ccall((:klb_job_run_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{KlbHostField}, Int32, Int32),
+  GC.@preserve x0 outputs f check(ccall((sym(job, "run_host"), LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{KlbHostField}, Int32, Int32),
                                         job.handle, x0 === nothing ? C_NULL : x0, f, length(f), nslices))
   job
 end

@@ -77,6 +77,10 @@ SYMBOLS = [
     ("klb_job_run_async", _int, [_vp]),
     ("klb_job_sync", _int, [_vp]),
     ("klb_job_run_host", _int, [_vp, _vp, C.POINTER(KlbHostField), C.c_int32, C.c_int32]),
+    ("klb_job_run_host_async", _int, [_vp, _vp, C.POINTER(KlbHostField), C.c_int32, C.c_int32]),
+    ("klb_job_run_host_finish", _int, [_vp]),
+    ("klb_job_run_host_wait", _int, [_vp]),
+    ("klb_job_run_host_abort", _int, [_vp]),
     ("klb_job_set_chunk", _int, [_vp, _i64]),
     ("klb_job_reset", _int, [_vp]),
     ("klb_job_output", _int, [_vp, _int, _vp, _i64]),
@@ -100,6 +104,7 @@ SYMBOLS = [
     ("klb_multi_run", _int, [_vp]),
     ("klb_multi_run_async", _int, [_vp]),
     ("klb_multi_sync", _int, [_vp]),
+    ("klb_multi_run_host", _int, [_vp, _vp, C.POINTER(KlbHostField), C.c_int32, C.c_int32]),
     ("klb_multi_output", _int, [_vp, _int, _vp, _i64]),
     ("klb_multi_gathered", _int, [_vp, C.c_int32, _int, C.POINTER(_vp), C.POINTER(_i64)]),
     ("klb_multi_gathered_output", _int, [_vp, C.c_int32, _int, _vp, _i64]),

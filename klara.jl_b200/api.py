@@ -489,8 +489,6 @@ class BasicMCJob:
         `nslices` slices on their own streams so that host->device copies, kernels and device->host copies overlap.
         `outputs` maps field codes (klara_b200._lib.OUT_*) to writable C-contiguous numpy arrays -- ideally views of
         pinned memory (klb_host_alloc) -- that receive the fields.  Results are identical to the three separate calls."""
-        if self._m:
-            raise L.KlaraError(L.KLB_EUNSUPPORTED, "run_host drives one device; shard the host arrays and call it per job")
         outputs = outputs or {}
         arr = (L.KlbHostField * max(1, len(outputs)))()
         for i, (field, buf) in enumerate(outputs.items()):
@@ -503,7 +501,10 @@ class BasicMCJob:
             if x0.shape != (self.nchains, self.dim):
                 raise AssertionError("initial value has shape %s, job has %s" % (x0.shape, (self.nchains, self.dim)))
             xp = _ptr(x0)
-        L.check(L.lib().klb_job_run_host(self._h, xp, arr, len(outputs), nslices))
+        if self._m:                                 # every device runs its shard's pipeline concurrently
+            L.check(L.lib().klb_multi_run_host(self._m, xp, arr, len(outputs), nslices))
+        else:
+            L.check(L.lib().klb_job_run_host(self._h, xp, arr, len(outputs), nslices))
         self.count = self.range.npoststeps
         return self
 

@@ -115,6 +115,9 @@ struct klb_job {
   int regs, bps;
   bool timed;
   // klb_job_run_host: chain slices pipelined over their own streams (H2D | kernels | D2H overlap)
+  // a pipelined run enqueued by klb_job_run_host_async and not yet finished
+  bool host_pending, host_had_x0, host_was_constructed;
+  unsigned long long* flag_host;   // pinned: the finiteness flag comes back asynchronously
   cudaStream_t sl_stream[KLB_MAX_SLICES];
   cudaEvent_t sl_done[KLB_MAX_SLICES];
   int nsl_streams;
@@ -182,6 +185,7 @@ static void free_job(klb_job* j) {
   cudaSetDevice(j->cfg.device);
   cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate); cudaFree(j->tune_da);
   cudaFree(j->tune_rates);
+  if (j->flag_host) cudaFreeHost(j->flag_host);
   cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
   cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess); cudaFree(j->accrate);
   cudaFree(j->gX); cudaFree(j->gy);
@@ -352,6 +356,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   CKJ(cudaMalloc(&j->tab, sizeof(KLB_TAB)));
   CKJ(cudaMemcpy(j->tab, KLB_TAB, sizeof(KLB_TAB), cudaMemcpyHostToDevice));
   CKJ(cudaMalloc(&j->flag, sizeof(unsigned long long)));
+  CKJ(cudaHostAlloc((void**)&j->flag_host, sizeof(unsigned long long), cudaHostAllocDefault));
   if (c.destination == KLB_DEST_NSTATE) {      // initialize_output, src/jobs/jobs.jl:188-210
     if (c.monitor & KLB_MONITOR_VALUE) CKJ(cudaMalloc(&j->out_value, N * P * d * sizeof(double)));
     if (j->out_value && (c.dim & 1)) CKJ(cudaMemset(j->out_value, 0, N * P * d * sizeof(double)));
@@ -590,6 +595,7 @@ static int init_state(klb_job* j) {
 
 int klb_job_set_state(klb_job* j, const double* x0) {
   if (!j || !x0) return fail(KLB_EINVAL, "null argument");
+  if (j->host_pending) return fail(KLB_ESTATE, "a pipelined run is pending: call klb_job_run_host_finish first");
   { int rc = da_refuses_reset(j); if (rc) return rc; }
   CK(cudaSetDevice(j->cfg.device));
   CK(cudaMemcpy2DAsync(j->state, (size_t)j->ld * 8, x0, (size_t)j->cfg.dim * 8, (size_t)j->cfg.dim * 8,
@@ -599,6 +605,7 @@ int klb_job_set_state(klb_job* j, const double* x0) {
 
 int klb_job_set_state_device(klb_job* j, const double* x0_dev) {
   if (!j || !x0_dev) return fail(KLB_EINVAL, "null argument");
+  if (j->host_pending) return fail(KLB_ESTATE, "a pipelined run is pending: call klb_job_run_host_finish first");
   { int rc = da_refuses_reset(j); if (rc) return rc; }
   CK(cudaSetDevice(j->cfg.device));
   if (x0_dev != j->state)   // x0_dev is a dense dim x nchains matrix
@@ -610,6 +617,7 @@ int klb_job_set_state_device(klb_job* j, const double* x0_dev) {
 // x0 = the synthetic initial value of the benchmark configurations, generated on the device (header)
 int klb_job_set_state_synthetic(klb_job* j) {
   if (!j) return fail(KLB_EINVAL, "null argument");
+  if (j->host_pending) return fail(KLB_ESTATE, "a pipelined run is pending: call klb_job_run_host_finish first");
   { int rc = da_refuses_reset(j); if (rc) return rc; }
   CK(cudaSetDevice(j->cfg.device));
   klb_launch_synth_state(j->tab, j->cfg.seed, (uint64_t)j->cfg.chain_offset, j->cfg.nchains, (int)j->cfg.dim, j->ld,
@@ -639,6 +647,7 @@ int klb_job_set_chunk(klb_job* j, int64_t nt) {
 
 int klb_job_run_async(klb_job* j) {
   if (!j) return fail(KLB_EINVAL, "null argument");
+  if (j->host_pending) return fail(KLB_ESTATE, "a pipelined run is pending: call klb_job_run_host_finish first");
   if (!j->have_state) return fail(KLB_ESTATE, "klb_job_set_state must succeed before klb_job_run");
   const klb_config& c = j->cfg;
   // a second run without reset would write past column npoststeps of the NState (a BoundsError in the reference)
@@ -671,8 +680,11 @@ int klb_job_run(klb_job* j) {
 static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols);
 
 // set_state + run + output in one pipelined call (header: klb_job_run_host)
-int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices) {
+int klb_job_run_host_finish(klb_job* j);
+// enqueue half of klb_job_run_host (header: klb_job_run_host_async)
+int klb_job_run_host_async(klb_job* j, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices) {
   if (!j || (nfields > 0 && !fields) || nfields < 0) return fail(KLB_EINVAL, "null argument");
+  if (j->host_pending) return fail(KLB_ESTATE, "a pipelined run is pending: call klb_job_run_host_finish first");
   const klb_config& c = j->cfg;
   CK(cudaSetDevice(c.device));
   if (!x0 && !j->have_state) return fail(KLB_ESTATE, "no initial value: pass x0 or call klb_job_set_state first");
@@ -752,29 +764,65 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
     CKR(cudaEventRecord(j->sl_done[q], st));
     if (rc == KLB_OK) CKR(cudaStreamWaitEvent(j->stream, j->sl_done[q], 0));
   }
-  unsigned long long f = none;
+  *j->flag_host = none;
   if (rc == KLB_OK) {
     CKR(cudaEventRecord(j->ev1, j->stream));
-    if (x0) CKR(cudaMemcpyAsync(&f, j->flag, sizeof f, cudaMemcpyDeviceToHost, j->stream));
+    if (x0) CKR(cudaMemcpyAsync(j->flag_host, j->flag, sizeof(unsigned long long), cudaMemcpyDeviceToHost, j->stream));
   }
 #undef CKR
-  {                                                // idle streams before ANY return: host buffers are the caller's
+  if (rc != KLB_OK) {                              // a failed enqueue: idle the streams (host buffers are the caller's), roll back
     char keep[sizeof g_err];
     memcpy(keep, g_err, sizeof keep);
-    const int rs = sync_all(j);
-    if (rc != KLB_OK) memcpy(g_err, keep, sizeof keep); else rc = rs;
-  }
-  if (rc == KLB_OK && f != none)
-    rc = fail(KLB_ENOTFINITE, "Log-target%s not finite: initial value out of support (chain %llu)",
-              c.sampler != KLB_SAMPLER_MH ? " or its gradient" : "", f - 1);
-  if (rc != KLB_OK) {                              // roll back: the state buffers hold a discarded run
-    j->have_state = false;
-    j->count = 0;
-    j->constructed = was_constructed;
-    j->timed = false;
+    sync_all(j);
+    memcpy(g_err, keep, sizeof keep);
+    j->have_state = false; j->count = 0; j->constructed = was_constructed; j->timed = false;
     return rc;
   }
-  j->t_global += (unsigned long long)c.nsteps;
+  j->host_pending = true; j->host_had_x0 = x0 != nullptr; j->host_was_constructed = was_constructed;
+  return KLB_OK;
+}
+
+// wait for the slices and look at the finiteness flag; the run stays pending (several jobs can be inspected before any
+// of them is committed: klb_multi_run_host is all-or-nothing)
+int klb_job_run_host_wait(klb_job* j) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  if (!j->host_pending) return fail(KLB_ESTATE, "no pipelined run is pending");
+  const klb_config& c = j->cfg;
+  const unsigned long long none = std::numeric_limits<unsigned long long>::max();
+  int rc = sync_all(j);                            // idle streams: host buffers are the caller's
+  if (rc == KLB_OK && j->host_had_x0 && *j->flag_host != none)
+    rc = fail(KLB_ENOTFINITE, "Log-target%s not finite: initial value out of support (chain %llu)",
+              c.sampler != KLB_SAMPLER_MH ? " or its gradient" : "", *j->flag_host - 1);
+  return rc;
+}
+
+static void host_rollback(klb_job* j) {            // the state buffers hold a discarded run
+  j->host_pending = false;
+  j->have_state = false;
+  j->count = 0;
+  j->constructed = j->host_was_constructed;
+  j->timed = false;
+}
+
+// discard a pending run (as if its start had been rejected)
+int klb_job_run_host_abort(klb_job* j) {
+  if (!j) return fail(KLB_EINVAL, "null argument");
+  if (!j->host_pending) return fail(KLB_ESTATE, "no pipelined run is pending");
+  char keep[sizeof g_err];
+  memcpy(keep, g_err, sizeof keep);
+  sync_all(j);
+  memcpy(g_err, keep, sizeof keep);
+  host_rollback(j);
+  return KLB_OK;
+}
+
+// second half: wait, then commit the job's bookkeeping -- or roll it back when the run failed
+int klb_job_run_host_finish(klb_job* j) {
+  const int rc = klb_job_run_host_wait(j);
+  if (rc == KLB_EINVAL || (rc == KLB_ESTATE && !(j && j->host_pending))) return rc;
+  if (rc != KLB_OK) { host_rollback(j); return rc; }
+  j->host_pending = false;
+  j->t_global += (unsigned long long)j->cfg.nsteps;
   j->count = j->npost;
   j->timed = true;
   j->constructed = true;
@@ -782,8 +830,14 @@ int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields,
   return KLB_OK;
 }
 
+int klb_job_run_host(klb_job* j, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices) {
+  const int rc = klb_job_run_host_async(j, x0, fields, nfields, nslices);
+  return rc ? rc : klb_job_run_host_finish(j);
+}
+
 int klb_job_reset(klb_job* j) {
   if (!j) return fail(KLB_EINVAL, "null argument");
+  if (j->host_pending) return fail(KLB_ESTATE, "a pipelined run is pending: call klb_job_run_host_finish first");
   { int rc = da_refuses_reset(j); if (rc) return rc; }
   CK(cudaSetDevice(j->cfg.device));
   return reset_tune(j);
@@ -814,6 +868,7 @@ static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols) 
 
 int klb_job_output(klb_job* j, int field, void* host_dst, int64_t nbytes) {
   if (!j || !host_dst) return fail(KLB_EINVAL, "null argument");
+  if (j->host_pending) return fail(KLB_ESTATE, "a pipelined run is pending: call klb_job_run_host_finish first");
   void* p; size_t nb, cols;
   int rc = field_ptr(j, field, &p, &nb, &cols);
   if (rc) return rc;

@@ -356,6 +356,40 @@ int klb_multi_run(klb_multi* m) {
   return rc ? rc : klb_multi_sync(m);
 }
 
+// reset(job, x0); run(job); output(job) from / to the host arrays of the logical job: every field is chain-major, so a
+// shard's part of a host array starts at lo * (bytes per chain); all devices' pipelines are enqueued before any is awaited
+int klb_multi_run_host(klb_multi* m, const double* x0, const klb_host_field* fields, int32_t nfields, int32_t nslices) {
+  if (!m || (nfields > 0 && !fields) || nfields < 0 || nfields > 32) return mfail(KLB_EINVAL, "bad argument");
+  int rc = KLB_OK, started = 0;
+  for (int g = 0; g < m->ngpus && rc == KLB_OK; ++g) {
+    klb_host_field f[32];
+    for (int q = 0; q < nfields; ++q) {
+      if (fields[q].nbytes % m->ntotal) return mfail(KLB_EINVAL, "field %d: %lld bytes is not a multiple of the chain count", fields[q].field, (long long)fields[q].nbytes);
+      const int64_t per = fields[q].nbytes / m->ntotal;
+      f[q] = fields[q];
+      f[q].host_dst = (char*)fields[q].host_dst + m->lo[g] * per;
+      f[q].nbytes = m->n[g] * per;
+    }
+    rc = klb_job_run_host_async(m->job[g], x0 ? x0 + m->lo[g] * m->dim : nullptr, f, nfields, nslices);
+    if (rc == KLB_OK) ++started;
+  }
+  char keep[512] = "";
+  if (rc != KLB_OK) snprintf(keep, sizeof keep, "%s", klb_last_error());
+  for (int g = 0; g < started; ++g) {               // every started pipeline is awaited, whatever happened elsewhere
+    const int r2 = klb_job_run_host_wait(m->job[g]);
+    if (rc == KLB_OK && r2 != KLB_OK) { rc = r2; snprintf(keep, sizeof keep, "%s", klb_last_error()); }
+  }
+  // all or nothing: the shards of one logical job keep the same transition counter
+  for (int g = 0; g < started; ++g) {
+    if (rc == KLB_OK) klb_job_run_host_finish(m->job[g]);
+    else klb_job_run_host_abort(m->job[g]);
+  }
+  if (rc != KLB_OK) return klb_set_error(rc, keep);
+  for (klb_gather* e : m->end) { int r3 = klb_gather_push_async(e); if (r3) return r3; }
+  for (klb_gather* e : m->end) { int r3 = klb_gather_sync(e); if (r3) return r3; }
+  return KLB_OK;
+}
+
 // output(job): every field is chain-major, so the logical job's array is the concatenation of the shards
 int klb_multi_output(klb_multi* m, int field, void* host_dst, int64_t nbytes) {
   if (!m || !host_dst) return mfail(KLB_EINVAL, "null argument");

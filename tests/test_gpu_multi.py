@@ -204,3 +204,46 @@ def test_gibbs_driver_matches_oracle(K, O):
         assert_same("gibbs " + k, got[k].value, ref[k])
     # the transformation saw the states of the SAME sweep: a was already updated, b not yet
     assert not np.array_equal(got["a"].value[:, 0], got["a"].value[:, 1])
+
+
+def test_run_host_in_two_halves_and_over_devices(K):
+    """klb_job_run_host_async / _finish (other calls are refused while a run is pending) and klb_multi_run_host (every
+    device runs its shard's pipeline concurrently): same bits as set_state + run + output on one device"""
+    L = K._lib
+    lib = L.lib()
+    N, d = 203, 130
+    kw = dict(nchains=N, dim=d, nsteps=24, burnin=7, thinning=2, step=0.05, nleaps=5, seed=314, tuner="accrate", period=5, target_rate=0.7)
+    ref_job, cfg, x0, tp, sg = build_pair(K, "HMC", "shifted", **kw)
+    ref_job.run()
+    ref = ref_job.output()
+    job, *_ = build_pair(K, "HMC", "shifted", **kw)
+    val, st = np.empty_like(ref.value), np.empty((N, d))
+    arr = (L.KlbHostField * 2)()
+    for i, (fld, buf) in enumerate(((L.OUT_VALUE, val), (L.OUT_STATE, st))):
+        arr[i].field, arr[i].host_dst, arr[i].nbytes = fld, buf.ctypes.data, buf.nbytes
+    L.check(lib.klb_job_run_host_async(job._h, x0.ctypes.data_as(C.c_void_p), arr, 2, 5))
+    assert lib.klb_job_run(job._h) == L.KLB_ESTATE and lib.klb_job_reset(job._h) == L.KLB_ESTATE
+    assert lib.klb_job_run_host_async(job._h, None, arr, 2, 5) == L.KLB_ESTATE
+    L.check(lib.klb_job_run_host_finish(job._h))
+    assert lib.klb_job_run_host_finish(job._h) == L.KLB_ESTATE
+    assert_same("value", val, ref.value)
+    assert_same("state", st, ref_job.pstate_value)
+    # the logical job over four shards (ragged: 203 chains)
+    p = K.BasicContMuvParameter("p", logtarget=ref_job.parameter.target)
+    multi = K.BasicMCJob(K.likelihood_model(p, False), ref_job.sampler, ref_job.range, {"p": x0[::-1].copy()}, tuner=ref_job.tuner,
+                         outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}, seed=314, devices=_devices(K, 4))
+    bufs = {L.OUT_VALUE: np.empty_like(ref.value), L.OUT_ACCEPT: np.empty_like(ref.diagnosticvalues), L.OUT_STATE: np.empty((N, d)),
+            L.OUT_TUNE_STEP: np.empty(N)}
+    multi.run_host(x0, bufs, 3)
+    assert_same("multi value", bufs[L.OUT_VALUE], ref.value)
+    assert_same("multi accept", bufs[L.OUT_ACCEPT], ref.diagnosticvalues)
+    assert_same("multi state", bufs[L.OUT_STATE], ref_job.pstate_value)
+    assert_same("multi step", bufs[L.OUT_TUNE_STEP], ref_job.tune.step)
+    assert_same("gathered after run_host", multi.gathered(L.OUT_STATE, 3), ref_job.pstate_value)
+    bad = x0.copy()
+    bad[150, 3] = np.nan
+    with pytest.raises(K.KlaraError) as ei:
+        multi.run_host(bad, {}, 2)
+    assert ei.value.code == L.KLB_ENOTFINITE and "chain 150" in str(ei.value)
+    multi.run_host(x0, bufs, 2)                          # the job is usable again
+    assert_same("multi value after a rejected start", bufs[L.OUT_VALUE], ref.value)
