@@ -245,5 +245,9 @@ def test_run_host_in_two_halves_and_over_devices(K):
     with pytest.raises(K.KlaraError) as ei:
         multi.run_host(bad, {}, 2)
     assert ei.value.code == L.KLB_ENOTFINITE and "chain 150" in str(ei.value)
-    multi.run_host(x0, bufs, 2)                          # the job is usable again
-    assert_same("multi value after a rejected start", bufs[L.OUT_VALUE], ref.value)
+    assert all(K._lib.lib().klb_job_plan(h, C.byref(pl)) == 0 and pl.transitions_done == 24
+               for h, _, _ in multi._shards for pl in [L.KlbPlan()])       # no shard kept the rejected run
+    multi.run_host(x0, bufs, 2)                          # the job is usable again: transitions 25..48 of the same streams
+    ref_job.reset(x0)
+    ref_job.run()
+    assert_same("multi value after a rejected start", bufs[L.OUT_VALUE], ref_job.output().value)
