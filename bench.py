@@ -417,7 +417,9 @@ def run_gpu(args, rank, world, local_rank):
     # -------- free the C3 job, then the other BASELINE configurations at their stated sizes
     if gather is not None:
         barrier()
-        lib.klb_gather_destroy(gather)
+        L.check(lib.klb_gather_disconnect(gather))      # every rank unmaps its peers' buffers ...
+        barrier()
+        lib.klb_gather_destroy(gather)                  # ... before any rank frees its own
     job.close()
     for b in (x0_pin, st_pin, lt_pin, ac_pin):
         b.free()

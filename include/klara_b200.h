@@ -335,6 +335,7 @@ int klb_gather_sync(klb_gather* g);
 int klb_gather_join(klb_gather* g);   /* the job's stream waits for the last push (for device-side timing) */
 int klb_gather_device_ptr(klb_gather* g, int field, void** dev_ptr, int64_t* nbytes);
 int klb_gather_output(klb_gather* g, int field, void* host_dst, int64_t nbytes);
+int klb_gather_disconnect(klb_gather* g);   /* unmap the peers' buffers; then (after the caller's barrier) klb_gather_destroy */
 void klb_gather_destroy(klb_gather* g);
 
 /* Measured throughput of one device for the roofline denominators that MEASURED_PEAKS.json does not hold:

@@ -118,6 +118,7 @@ SYMBOLS = [
     ("klb_gather_join", _int, [_vp]),
     ("klb_gather_device_ptr", _int, [_vp, _int, C.POINTER(_vp), C.POINTER(_i64)]),
     ("klb_gather_output", _int, [_vp, _int, _vp, _i64]),
+    ("klb_gather_disconnect", _int, [_vp]),
     ("klb_gather_destroy", None, [_vp]),
     ("klb_device_peak", _int, [_int, _int, C.POINTER(_dbl)]),
     ("klb_host_alloc", _int, [C.POINTER(_vp), _i64]),

@@ -228,12 +228,22 @@ int klb_gather_output(klb_gather* g, int field, void* host_dst, int64_t nbytes) 
   return KLB_OK;
 }
 
+// unmap the other ranks' buffers.  An exporting process should keep its buffer allocated until the importers have closed
+// it: one-process-per-GPU callers disconnect, meet at their own barrier, then destroy.
+int klb_gather_disconnect(klb_gather* g) {
+  if (!g) return mfail(KLB_EINVAL, "null argument");
+  MCK(cudaSetDevice(g->device));
+  if (g->copy) MCK(cudaStreamSynchronize(g->copy));
+  for (int r = 0; r < g->world; ++r)
+    if (g->opened[r] && g->peer[r]) { cudaIpcCloseMemHandle(g->peer[r]); g->peer[r] = nullptr; g->opened[r] = false; }
+  g->connected = g->world == 1;
+  return KLB_OK;
+}
+
 void klb_gather_destroy(klb_gather* g) {
   if (!g) return;
+  klb_gather_disconnect(g);
   cudaSetDevice(g->device);
-  if (g->copy) cudaStreamSynchronize(g->copy);
-  for (int r = 0; r < g->world; ++r)
-    if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
   cudaFree(g->mine);
   if (g->ran) cudaEventDestroy(g->ran);
   if (g->pushed) cudaEventDestroy(g->pushed);

@@ -134,7 +134,8 @@ def _ipc_worker(rank, world, N, d, conn, ret):
     full = np.empty((N, d))
     L.check(lib.klb_gather_output(g, L.OUT_STATE, full.ctypes.data_as(C.c_void_p), full.nbytes))
     ret.put((rank, full))
-    conn.recv()                                           # keep the buffers alive until every rank has read
+    L.check(lib.klb_gather_disconnect(g))
+    conn.recv()                                           # every rank has unmapped its peers before any buffer is freed
     lib.klb_gather_destroy(g)
     job.close()
 
