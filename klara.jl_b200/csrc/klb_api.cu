@@ -25,8 +25,8 @@ int klb_chain_1_1(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
 int klb_chain_2_0(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
 int klb_chain_2_1(const KArgs*, int, int, int, int, int*, int*, cudaStream_t);
 // warp-specialised HMC kernels, klb_hmc_ws_inst.cu
-int klb_hmc_ws_0(const KArgs*, int target, int nv, int full, int* regs, int* bps, cudaStream_t);
-int klb_hmc_ws_1(const KArgs*, int target, int nv, int full, int* regs, int* bps, cudaStream_t);
+int klb_hmc_ws_0(const KArgs*, int target, int gw, int nv, int full, int* regs, int* bps, cudaStream_t);
+int klb_hmc_ws_1(const KArgs*, int target, int gw, int nv, int full, int* regs, int* bps, cudaStream_t);
 // klb_kernels_inst.cu (-DKLB_INST_INIT) / klb_aux.cu
 int klb_launch_init(const KArgs& A, int target, int W, int NV, int fma, int check_grad, unsigned long long* flag,
                     cudaStream_t s);
@@ -123,17 +123,20 @@ struct klb_job {
   int nsl_streams;
 };
 
-// HMC with one warp per chain and 8 or 16 units per lane (dim 257..1024) runs the warp-specialised kernel
-// (klb_hmc_ws.cuh) unless KLB_HMC_WS=0 (experiments: the fused single-role kernel of klb_kernels.cuh).
+// HMC with one warp per chain and 8 or 16 units per lane (dim 257..1024), or four warps per chain (dim 1025..4096), runs
+// the warp-specialised kernel (klb_hmc_ws.cuh) unless KLB_HMC_WS=0 (experiments: the fused single-role kernel of
+// klb_kernels.cuh; KLB_HMC_WS=1: only the one-warp geometries).
 static bool use_hmc_ws(int sampler, int gw, int gnv) {
   const char* env = getenv("KLB_HMC_WS");
-  return sampler == KLB_SAMPLER_HMC && gw == 1 && (gnv == 8 || gnv == 16) && !(env && env[0] == '0');
+  if (sampler != KLB_SAMPLER_HMC || (env && env[0] == '0')) return false;
+  if (gw == 4) return gnv == 16 && !(env && env[0] == '1');
+  return gw == 1 && (gnv == 8 || gnv == 16);
 }
 
 static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int gw, int gnv, int full, int* regs, int* bps,
                           cudaStream_t s) {
   if (use_hmc_ws(sampler, gw, gnv))
-    return fma ? klb_hmc_ws_1(A, target, gnv, full, regs, bps, s) : klb_hmc_ws_0(A, target, gnv, full, regs, bps, s);
+    return fma ? klb_hmc_ws_1(A, target, gw, gnv, full, regs, bps, s) : klb_hmc_ws_0(A, target, gw, gnv, full, regs, bps, s);
   switch (sampler * 2 + (fma ? 1 : 0)) {
     case 0: return klb_chain_0_0(A, target, gw, gnv, full, regs, bps, s);
     case 1: return klb_chain_0_1(A, target, gw, gnv, full, regs, bps, s);
@@ -254,16 +257,13 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     return fail(KLB_EINVAL, "unknown target %d", c.target);
   if (c.target == KLB_TARGET_LOGIT && c.dim > KLB_GLM_MAXD)
     return fail(KLB_EUNSUPPORTED, "the logistic-regression kernels hold one chain per thread: dim <= %d", KLB_GLM_MAXD);
-  if (c.target == KLB_TARGET_DENSE && ((c.dim & 1) || c.dim > KLB_DENSE_MAXD))
-    return fail(KLB_EUNSUPPORTED, "the dense-precision kernels need an even dim <= %d", KLB_DENSE_MAXD);
+  if (c.target == KLB_TARGET_DENSE && c.dim > KLB_DENSE_MAXD)
+    return fail(KLB_EUNSUPPORTED, "the dense-precision kernels need dim <= %d", KLB_DENSE_MAXD);
   if (c.tuner != KLB_TUNER_VANILLA && c.tuner != KLB_TUNER_ACCEPTANCE_RATE && c.tuner != KLB_TUNER_DUAL_AVERAGING)
     return fail(KLB_EINVAL, "unknown tuner %d", c.tuner);
   if (c.tuner == KLB_TUNER_DUAL_AVERAGING) {
     if (c.sampler != KLB_SAMPLER_HMC)
       return fail(KLB_EINVAL, "DualAveragingMCTuner tunes HMC (and NUTS) only; MALA / MH have no tuner_state method for it");
-    if (c.target == KLB_TARGET_DENSE)
-      return fail(KLB_EUNSUPPORTED, "DualAveragingMCTuner gives every chain its own number of leapfrog steps; the "
-                                    "dense-precision kernels advance their chains in lockstep tiles");
     // DualAveragingMCTuner asserts (src/tuners/DualAveragingMCTuner.jl:76-80)
     if (!(c.target_rate > 0 && c.target_rate < 1)) return fail(KLB_EINVAL, "Target acceptance rate should be between 0 and 1");
     if (c.da_nadapt <= 0) return fail(KLB_EINVAL, "Number of adaptation steps should be positive");
@@ -365,18 +365,23 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     if (c.diagnostics & KLB_DIAG_ACCEPT) CKJ(cudaMalloc(&j->out_accept, N * P));
   }
   j->dense = c.target == KLB_TARGET_DENSE;
-  if (j->dense) CKJ(cudaMalloc(&j->Cm, d * d * sizeof(double)));
+  if (j->dense) {                        // rows padded to the even length of the state columns (zero pad column)
+    CKJ(cudaMalloc(&j->Cm, (size_t)c.dim * d * sizeof(double)));
+    CKJ(cudaMemset(j->Cm, 0, (size_t)c.dim * d * sizeof(double)));
+  }
   j->glm = c.target == KLB_TARGET_LOGIT;
   j->lambda = 100.0;                               // v0 of the swiss examples; KLB_PARAM_LOGIT_LAMBDA overrides
   for (j->gdp = 2; j->gdp < c.dim; j->gdp *= 2) {}
   {
     const char* env = getenv("KLB_DENSE_MMA");     // KLB_DENSE_MMA=0 forces the DFMA register-tile kernel (experiments)
+    // (DualAveragingMCTuner: chains of a tile run different numbers of leapfrog steps; the DFMA tile kernel masks them,
+    // the cluster pipeline of the tensor-pipe kernel wants every CTA to run the same number of matrix products)
     j->dense_mma = j->dense && c.sampler == KLB_SAMPLER_HMC && !(env && env[0] == '0') &&
-                   (c.dim == 64 || c.dim == 128 || c.dim == 256 || c.dim == 512);
+                   c.tuner != KLB_TUNER_DUAL_AVERAGING && (c.dim == 64 || c.dim == 128 || c.dim == 256 || c.dim == 512);
   }
   if (j->glm ? klb_glm_attrs(c.sampler, c.arith, j->gdp, 0, &j->regs, &j->bps) != 0
       : j->dense_mma ? klb_dense_mma_attrs(c.arith, (int)c.dim, &j->regs, &j->bps) != 0
-      : j->dense ? klb_dense_attrs(c.sampler, c.arith, (int)c.dim, &j->regs, &j->bps) != 0
+      : j->dense ? klb_dense_attrs(c.sampler, c.arith, c.tuner == KLB_TUNER_DUAL_AVERAGING, (int)c.dim, &j->regs, &j->bps) != 0
                : chain_dispatch(c.sampler, c.arith, nullptr, c.target, gw, gnv, c.dim == 64ll * gw * gnv, &j->regs, &j->bps, j->stream) != 0) {
     cudaGetLastError();
     free_job(j);
@@ -422,7 +427,8 @@ int klb_job_set_target_f64(klb_job* j, int which, const double* host, int64_t n)
           if (memcmp(&host[a * d + b], &host[b * d + a], sizeof(double)) != 0)
             return fail(KLB_EINVAL, "C must be exactly symmetric (C[%lld][%lld] != C[%lld][%lld])", (long long)a,
                         (long long)b, (long long)b, (long long)a);
-      CK(cudaMemcpy(j->Cm, host, n * sizeof(double), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy2D(j->Cm, (size_t)j->ld * sizeof(double), host, (size_t)d * sizeof(double), (size_t)d * sizeof(double), (size_t)d,
+                      cudaMemcpyHostToDevice));
       j->have_C = true;
       return KLB_OK;
     }

@@ -21,6 +21,11 @@
 
 #define KLB_DENSE_THREADS 256
 #define KLB_DENSE_MAXD 512  /* 2 elements per thread */
+// Odd dim: rows of C on the device and the per-element arrays in shared memory are padded to the even length
+// dl = dim + 1.  The pad column of C is zero, the pad element of every chain is +0.0 and never moves (its momentum /
+// proposal noise is 0, not a draw; (C z)_pad = 0), and the canonical reductions skip it (i + 1 < dim), so every sum
+// has exactly the oracle's addends.
+__host__ __device__ __forceinline__ int klb_dense_dl(int d) { return (d + 1) & ~1; }
 
 template <int MC>
 struct DenseShared {
@@ -28,6 +33,9 @@ struct DenseShared {
   long long accepted[MC], proposed[MC], totproposed[MC];
   double rate[MC];
   int accept[MC];
+  // DualAveragingMCTuner: the chain's leapfrog count of this transition and a = min(1, exp(ratio))
+  int nl[MC];
+  double aprob[MC];
 };
 
 // canonical reduction of one chain's addends by one warp.  MODE 0: dot product sum of a[i]*b[i]
@@ -62,13 +70,14 @@ __device__ __forceinline__ double dense_reduce(const double* a, const double* b,
 template <int MC>
 __device__ __forceinline__ void dense_matvec(double (&acc)[MC][2], const double* __restrict__ Cm, const double* xs,
                                              int d, int i0, bool active) {
+  const int dl = klb_dense_dl(d);
 #pragma unroll
   for (int r = 0; r < MC; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
   if (!active) return;
   const double* col = Cm + i0;
 #pragma unroll 4
   for (int j = 0; j < d; ++j) {
-    const double2 c = __ldg(reinterpret_cast<const double2*>(col + (size_t)j * d));
+    const double2 c = __ldg(reinterpret_cast<const double2*>(col + (size_t)j * dl));
     const double2* xj = reinterpret_cast<const double2*>(xs + (size_t)j * MC);
 #pragma unroll
     for (int r2 = 0; r2 < MC / 2; ++r2) {
@@ -83,28 +92,34 @@ __device__ __forceinline__ void dense_matvec(double (&acc)[MC][2], const double*
 
 struct DArgs {
   KArgs k;
-  const double* Cm;  // d x d, row-major, symmetric
+  const double* Cm;  // d rows of dl = klb_dense_dl(d) values, row-major, symmetric
   int nv;            // canonical reduction units per lane for this dim
 };
 
-template <int SAMPLER, int MC, bool FMA>
+// DA (HMC with DualAveragingMCTuner): every chain has its own step AND its own number of leapfrog steps
+// (iterate/HMC.jl:142-144).  The CTA runs max(nl) steps; a chain that has done its nl steps stops moving (its updates
+// are predicated off; the matrix-vector product of the tile recomputes the same C x for it), so each chain sees exactly
+// its own trajectory.
+template <int SAMPLER, int MC, bool FMA, bool DA = false>
 __global__ void __launch_bounds__(KLB_DENSE_THREADS)
 klb_dense_kernel(const DArgs D) {
+  static_assert(!DA || SAMPLER == 2, "DualAveragingMCTuner tunes HMC");
   const KArgs& A = D.k;
   extern __shared__ __align__(16) unsigned char dsm[];
-  const int d = (int)A.dim;
-  // dynamic shared memory: tab | xs[d*MC] | sc[d*MC] | sc2[d*MC] | DenseShared
+  const int d = (int)A.dim, dl = klb_dense_dl(d);
+  // dynamic shared memory: tab | xs[dl*MC] | sc[dl*MC] | sc2[dl*MC] | DenseShared
   uint64_t* tab = reinterpret_cast<uint64_t*>(dsm);
   double* xs = reinterpret_cast<double*>(dsm + ((KLB_TAB_LEN * 8 + 15) & ~15));
-  double* sc = xs + (size_t)d * MC;
-  double* sc2 = sc + (size_t)d * MC;
-  DenseShared<MC>& S = *reinterpret_cast<DenseShared<MC>*>(sc2 + (size_t)d * MC);
+  double* sc = xs + (size_t)dl * MC;
+  double* sc2 = sc + (size_t)dl * MC;
+  DenseShared<MC>& S = *reinterpret_cast<DenseShared<MC>*>(sc2 + (size_t)dl * MC);
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   for (int i = t; i < KLB_TAB_LEN; i += blockDim.x) tab[i] = A.tab[i];
   const long long c0 = (long long)blockIdx.x * MC;
   const int i0 = 2 * t;
-  const bool active = i0 < d;                     // d is even for this kernel family
+  const bool active = i0 < d;                     // this thread owns elements i0 and (unless it is the pad) i0 + 1
+  const bool pad_b = i0 + 1 >= d;
   const double* Cm = D.Cm;
 
   // per-chain scalars
@@ -117,6 +132,7 @@ klb_dense_kernel(const DArgs D) {
     S.proposed[t] = live ? A.tune_cnt[3 * c + 1] : 0;
     S.totproposed[t] = live ? A.tune_cnt[3 * c + 2] : 0;
     S.rate[t] = live ? A.tune_rate[c] : 0.0;
+    if (DA) S.nl[t] = live ? da_nleaps(A, c, S.step[t]) : 0;
   }
   // positions -> registers and shared memory; chains beyond nchains are padded with zeros
   double x[MC][2], gc[MC][2];   // current position, cached raw C x of the current position
@@ -155,7 +171,8 @@ klb_dense_kernel(const DArgs D) {
         klb_stream_draw(&st, (unsigned)t, KLB_TAG_NORMAL, 0u, &w0, &w1);
         double a, b;
         if (!klb_zig_fast(w0, tab, &a)) a = klb_normal_from_word(w0, (unsigned)i0, &st, tab);
-        if (!klb_zig_fast(w1, tab, &b)) b = klb_normal_from_word(w1, (unsigned)i0 + 1u, &st, tab);
+        if (pad_b) b = 0.0;
+        else if (!klb_zig_fast(w1, tab, &b)) b = klb_normal_from_word(w1, (unsigned)i0 + 1u, &st, tab);
         y[r][0] = a; y[r][1] = b;
       }
     }
@@ -175,10 +192,17 @@ klb_dense_kernel(const DArgs D) {
       // leapfrog: the cached gradient of the current point opens the first step
 #pragma unroll
       for (int r = 0; r < MC; ++r) { acc[r][0] = gc[r][0]; acc[r][1] = gc[r][1]; }
-      for (int s = 1; s <= A.nleaps; ++s) {
+      int nlmax = A.nleaps;
+      if (DA) {
+        nlmax = 0;
+#pragma unroll
+        for (int r = 0; r < MC; ++r) nlmax = max(nlmax, S.nl[r]);
+      }
+      for (int s = 1; s <= nlmax; ++s) {
         __syncthreads();                       // xs readers of the previous matvec / reduction are done
 #pragma unroll
         for (int r = 0; r < MC; ++r) {
+          if (DA && s > S.nl[r]) continue;     // this chain's trajectory is complete
           const double step = S.step[r];
           const double h = __dmul_rn(0.5, step);
           const double ga = __dmul_rn(-2.0, acc[r][0]), gb = __dmul_rn(-2.0, acc[r][1]);
@@ -192,6 +216,7 @@ klb_dense_kernel(const DArgs D) {
         dense_matvec<MC>(acc, Cm, xs, d, i0, active);            // g = -2 C x
 #pragma unroll
         for (int r = 0; r < MC; ++r) {
+          if (DA && s > S.nl[r]) continue;
           const double h = __dmul_rn(0.5, S.step[r]);
           y[r][0] = Ar<FMA>::ma(h, __dmul_rn(-2.0, acc[r][0]), y[r][0]);
           y[r][1] = Ar<FMA>::ma(h, __dmul_rn(-2.0, acc[r][1]), y[r][1]);
@@ -217,14 +242,17 @@ klb_dense_kernel(const DArgs D) {
           const double ratio = __dsub_rn(newh, oldh);
           const klb_stream st = klb_stream_make(A.seed, A.chain_offset + (unsigned long long)c, tglob);
           bool acc_ = false;
+          double a_prob = 1.0;
           if (ratio >= 0.0) acc_ = true;
           else {
             const double ex = klb_exp(ratio, tab);
             const double a = (ex != ex) ? ex : (ex < 1.0 ? ex : 1.0);
+            a_prob = a;
             acc_ = klb_accept_uniform(&st) < a;
           }
           S.lt_new[r] = lt_new;
           S.accept[r] = (acc_ && c < A.nchains) ? 1 : 0;
+          if (DA) S.aprob[r] = a_prob;
         }
       }
     } else if (SAMPLER == 1) {
@@ -323,7 +351,12 @@ klb_dense_kernel(const DArgs D) {
       Tune tn;
       tn.step = S.step[r]; tn.accepted = S.accepted[r]; tn.proposed = S.proposed[r]; tn.totproposed = S.totproposed[r];
       tn.rate = S.rate[r];
-      tuner_block<SAMPLER>(A, tn, tab, c0 + r);
+      if (DA) {
+        if (c0 + r < A.nchains) {
+          da_block<false>(A, c0 + r, tn, S.nl[r], S.aprob[r], tab, true);
+          S.nl[r] = da_nleaps(A, c0 + r, tn.step);                 // of the next transition
+        }
+      } else tuner_block<SAMPLER>(A, tn, tab, c0 + r);
       S.step[r] = tn.step; S.accepted[r] = tn.accepted; S.proposed[r] = tn.proposed; S.totproposed[r] = tn.totproposed;
       S.rate[r] = tn.rate;
     }
@@ -383,9 +416,9 @@ __global__ void __launch_bounds__(KLB_DENSE_THREADS)
 klb_dense_init_kernel(const DArgs D, int check_grad, unsigned long long* flag) {
   const KArgs& A = D.k;
   extern __shared__ __align__(16) unsigned char dsm[];
-  const int d = (int)A.dim;
+  const int d = (int)A.dim, dl = klb_dense_dl(d);
   double* xs = reinterpret_cast<double*>(dsm);
-  double* sc2 = xs + (size_t)d * MC;
+  double* sc2 = xs + (size_t)dl * MC;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const long long c0 = (long long)blockIdx.x * MC;
   const int i0 = 2 * t;
@@ -421,4 +454,4 @@ klb_dense_init_kernel(const DArgs D, int check_grad, unsigned long long* flag) {
 #define KLB_DENSE_MC 8
 int klb_dense_launch(const DArgs& D, int sampler, int fma, cudaStream_t s);
 int klb_dense_init(const DArgs& D, int fma, int check_grad, unsigned long long* flag, cudaStream_t s);
-int klb_dense_attrs(int sampler, int fma, int dim, int* regs, int* bps);
+int klb_dense_attrs(int sampler, int fma, int da, int dim, int* regs, int* bps);

@@ -2,13 +2,13 @@
 #include "klb_dense.cuh"
 
 static size_t chain_smem(int d) {
-  return ((KLB_TAB_LEN * 8 + 15) & ~15) + 3 * (size_t)d * KLB_DENSE_MC * 8 + sizeof(DenseShared<KLB_DENSE_MC>);
+  return ((KLB_TAB_LEN * 8 + 15) & ~15) + 3 * (size_t)klb_dense_dl(d) * KLB_DENSE_MC * 8 + sizeof(DenseShared<KLB_DENSE_MC>);
 }
-static size_t init_smem(int d) { return 2 * (size_t)d * KLB_DENSE_MC * 8; }
+static size_t init_smem(int d) { return 2 * (size_t)klb_dense_dl(d) * KLB_DENSE_MC * 8; }
 
-template <int S, bool F>
+template <int S, bool F, bool DA = false>
 static int go(const DArgs* D, int dim, int* regs, int* bps, cudaStream_t st) {
-  auto kern = klb_dense_kernel<S, KLB_DENSE_MC, F>;
+  auto kern = klb_dense_kernel<S, KLB_DENSE_MC, F, DA>;
   const size_t sm = chain_smem(D ? (int)D->k.dim : dim);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return -2;
   if (D) {
@@ -22,7 +22,11 @@ static int go(const DArgs* D, int dim, int* regs, int* bps, cudaStream_t st) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(bps, kern, KLB_DENSE_THREADS, sm) != cudaSuccess) return -2;
   return 0;
 }
-static int dispatch(const DArgs* D, int sampler, int fma, int dim, int* regs, int* bps, cudaStream_t st) {
+static int dispatch(const DArgs* D, int sampler, int fma, int da, int dim, int* regs, int* bps, cudaStream_t st) {
+  if (da) {                                     // DualAveragingMCTuner: HMC only (checked by klb_job_create)
+    if (sampler != 2) return -1;
+    return fma ? go<2, true, true>(D, dim, regs, bps, st) : go<2, false, true>(D, dim, regs, bps, st);
+  }
   switch (sampler * 2 + (fma ? 1 : 0)) {
     case 0: return go<0, false>(D, dim, regs, bps, st);
     case 1: return go<0, true>(D, dim, regs, bps, st);
@@ -34,10 +38,10 @@ static int dispatch(const DArgs* D, int sampler, int fma, int dim, int* regs, in
   return -1;
 }
 int klb_dense_launch(const DArgs& D, int sampler, int fma, cudaStream_t s) {
-  return dispatch(&D, sampler, fma, 0, nullptr, nullptr, s);
+  return dispatch(&D, sampler, fma, D.k.tuner == 2, 0, nullptr, nullptr, s);
 }
-int klb_dense_attrs(int sampler, int fma, int dim, int* regs, int* bps) {
-  return dispatch(nullptr, sampler, fma, dim, regs, bps, 0);
+int klb_dense_attrs(int sampler, int fma, int da, int dim, int* regs, int* bps) {
+  return dispatch(nullptr, sampler, fma, da, dim, regs, bps, 0);
 }
 int klb_dense_init(const DArgs& D, int fma, int check_grad, unsigned long long* flag, cudaStream_t s) {
   const size_t sm = init_smem((int)D.k.dim);

@@ -1,4 +1,5 @@
-// klb_hmc_ws.cuh -- warp-specialised HMC chain kernel (one chain per consumer warp, dim 257..1024).
+// klb_hmc_ws.cuh -- warp-specialised HMC chain kernel (W = 1: one chain per consumer warp, dim 257..1024;
+// W = 4: one chain per consumer warpgroup, dim 1025..4096).
 //
 // The fused kernel of klb_kernels.cuh leaves the fp64 pipe ~58 % busy: every warp alternates between an
 // fp64-dense leapfrog phase and integer / latency-bound phases (Philox + ziggurat, the slow-path pass, the
@@ -14,6 +15,12 @@
 // integer instructions run in between (measured cost and ceiling: profiles/r1_summary.md, fp64 pipe microbenchmarks).
 // The counter-based RNG makes this legal: a draw depends on (seed, chain, transition) only.
 // Results are bit-identical to klb_chain_kernel (same per-element operations, same reduction order).
+//
+// W = 4 (one chain per CTA): consumer w owns the units j*4 + w of the chain and is fed by producer w, exactly like a W = 1
+// pair; the four consumers meet once per transition at the exchange of the lane accumulators (team_allsum, named barrier
+// over the 128 consumer threads, double-buffered).  After it every consumer holds the same three sums, so each evaluates
+// the Metropolis test and the tuner for itself on its own copy of the chain's scalars -- no broadcast, no second barrier
+// (the dual-averaging record lives in global memory: there the four read, meet, and consumer 0 writes).
 #pragma once
 #include <type_traits>
 #include "klb_kernels.cuh"
@@ -82,15 +89,19 @@ struct WsChain {          // per consumer: the chain's scalars between trajector
   long long accepted, proposed, totproposed, count, thin;
 };
 
-template <class T, int NV, bool FMA, bool FULL>
+#define KLB_WS_BAR_TEAM 9   /* W = 4: the four consumers of a chain */
+extern __shared__ __align__(16) unsigned char klb_ws_dyn[];   // W = 4: the momentum stages (4 x NV x 32 double2 = 32 KB at NV = 16)
+
+template <class T, int NV, int W, bool FMA, bool FULL>
 __global__ void __launch_bounds__(256, 2)
 klb_hmc_ws_kernel(const KArgs A) {
-  constexpr int W = 1;
+  static_assert(W == 1 || W == 4, "one chain per consumer warp or per consumer warpgroup");
   __shared__ WsChain wchain[4];
   __shared__ __align__(16) uint64_t tab[KLB_TAB_LEN + 512];   // + the sign-flipped ziggurat pairs (zig_build9)
-  __shared__ double2 zstage[4][NV * 32];
+  __shared__ double2 zstage[W == 1 ? 4 : 1][W == 1 ? NV * 32 : 1];
   __shared__ unsigned short zqueue[4][KLB_QCAP];
   __shared__ double uacc[4];
+  __shared__ double red[W == 1 ? 1 : 2][W == 1 ? 1 : 3 * 4 * 32];   // W = 4: exchange of the lane accumulators, by transition parity
   for (int i = threadIdx.x; i < KLB_TAB_LEN; i += blockDim.x) tab[i] = A.tab[i];
   __syncthreads();
   zig_build9(tab);
@@ -104,10 +115,11 @@ klb_hmc_ws_kernel(const KArgs A) {
 #endif
   // which warp-id range the producers take makes no measurable difference (profiles/r1_summary.md)
   const bool producer = KLB_WS_PRODUCER_LOW ? (warp < 4) : (warp >= 4);
-  const long long c = (long long)blockIdx.x * 4 + slot;
+  const int w = (W == 1) ? 0 : slot;               // warp within the chain's team
+  const long long c = (W == 1) ? (long long)blockIdx.x * 4 + slot : (long long)blockIdx.x;
   const bool live = c < A.nchains;                 // a dead slot retires its consumer AND its producer
   const int d = (int)A.dim;
-  double2* const zbuf = zstage[slot];
+  double2* const zbuf = (W == 1) ? zstage[W == 1 ? slot : 0] : reinterpret_cast<double2*>(klb_ws_dyn) + slot * (NV * 32);
   const int bar_full = 1 + slot, bar_empty = 5 + slot;
 
   if (producer) {
@@ -118,7 +130,7 @@ klb_hmc_ws_kernel(const KArgs A) {
                                             A.t0 + 1ull + (unsigned long long)it);
       if (it > 0) bar_sync(bar_empty, 64);         // the consumer has taken the previous transition's draws
 #if KLB_WS_EXP != 2      // timing experiment 2: producers idle (consumer-bound time; results meaningless)
-      randn_stage<NV, W, FULL, true>(st, d, 0, lane, tab, zbuf, zqueue[slot]);
+      randn_stage<NV, W, FULL, true>(st, d, w, lane, tab, zbuf, zqueue[slot]);
 #endif
       if (lane == 0) uacc[slot] = klb_accept_uniform(&st);
       bar_arrive(bar_full, 64);
@@ -130,11 +142,12 @@ klb_hmc_ws_kernel(const KArgs A) {
   if (!live) return;
   double* const xcol = A.state + c * A.ld;
   double x[2 * NV];
-  load_chain<NV, W, FULL>(x, xcol, d, 0, lane);
+  load_chain<NV, W, FULL>(x, xcol, d, w, lane);
   // Per-chain scalars that are only touched between trajectories (log-target, tuner record, output cursor, the
   // accept uniform) are parked in shared memory, so that during the leapfrog loop the registers hold x, p and
   // enough temporaries for the software-pipelined step (iso_leap_step).  Every lane of the warp computes the same
-  // values, so lane 0 alone writes them back.
+  // values, so lane 0 alone writes them back (W = 4: every consumer keeps its own, identical, copy).
+  const bool writer = lane == 0 && w == 0;                                     // of the chain's records in global memory
   volatile WsChain* const cs = &wchain[slot];
   if (lane == 0) {
     cs->lt_cur = A.lt[c];
@@ -164,20 +177,29 @@ klb_hmc_ws_kernel(const KArgs A) {
     const double step = cs->step;
     const double h = __dmul_rn(0.5, step);
     const int nl = (A.tuner == 2) ? da_nleaps(A, c, step) : A.nleaps;         // DualAveragingMCTuner: per chain
-    double k0lane;
+    double k0lane;                                                           // W = 4: the warp's one accumulator
     {
-      double a0[4] = {};
+      double a0[4 / W] = {};
 #pragma unroll
       for (int j = 0; j < NV; ++j) {                                         // old kinetic energy
-        a0[j & 3] = dotacc(y[2 * j], y[2 * j], a0[j & 3]);
-        a0[j & 3] = dotacc(y[2 * j + 1], y[2 * j + 1], a0[j & 3]);
+        const int q = AccIdx<W>::local(j);
+        a0[q] = dotacc(y[2 * j], y[2 * j], a0[q]);
+        a0[q] = dotacc(y[2 * j + 1], y[2 * j + 1], a0[q]);
       }
-      k0lane = __dadd_rn(__dadd_rn(a0[0], a0[1]), __dadd_rn(a0[2], a0[3]));  // the lane value of team_allsum
+      if (W == 1) k0lane = __dadd_rn(__dadd_rn(a0[0], a0[1 % (4 / W)]), __dadd_rn(a0[2 % (4 / W)], a0[3 % (4 / W)]));  // the lane value of team_allsum
+      else {
+        // One accumulator = one chain of 2 NV dependent fma.  Left in a register, the compiler sinks the whole chain below
+        // the leapfrog loop and keeps the untouched momenta alive for it (+34 registers; the hand-pipelined step then
+        // collapses to one temporary).  The volatile store of the team exchange pins it here.  Nobody reads this half of
+        // `red` any more: see the note at the exchange.
+        k0lane = a0[0];
+        *static_cast<volatile double*>(&red[W == 1 ? 0 : (it & 1)][(W == 1 ? 0 : w) * 32 + lane]) = k0lane;
+      }
     }
     // leapfrog! (src/samplers/samplers.jl:122-134): see klb_chain_kernel for the exact-rewrite notes
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const int i = Geo<NV, W>::elem(j, 0, lane);
+      const int i = Geo<NV, W>::elem(j, w, lane);
       T::template kick<FMA, false>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
     }
 #if KLB_WS_EXP == 1      // timing experiment 1: consumers skip the inner leapfrog steps (producer-bound time)
@@ -191,33 +213,59 @@ klb_hmc_ws_kernel(const KArgs A) {
       }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        const int i = Geo<NV, W>::elem(j, 0, lane);
+        const int i = Geo<NV, W>::elem(j, w, lane);
         x[2 * j] = Ar<FMA>::ma(step, y[2 * j], x[2 * j]);
         x[2 * j + 1] = Ar<FMA>::ma(step, y[2 * j + 1], x[2 * j + 1]);
         T::template kick<FMA, true>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
       }
     }
-    double acc[2][4] = {};
+    double acc[2][4 / W] = {};
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const int i = Geo<NV, W>::elem(j, 0, lane);
+      const int i = Geo<NV, W>::elem(j, w, lane);
+      const int q = AccIdx<W>::local(j);
       x[2 * j] = Ar<FMA>::ma(step, y[2 * j], x[2 * j]);
       x[2 * j + 1] = Ar<FMA>::ma(step, y[2 * j + 1], x[2 * j + 1]);
       T::template kick<FMA, false>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
-      acc[0][j & 3] = T::template lt_acc<FMA>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], acc[0][j & 3]);
-      acc[1][j & 3] = dotacc(y[2 * j], y[2 * j], acc[1][j & 3]);
-      acc[1][j & 3] = dotacc(y[2 * j + 1], y[2 * j + 1], acc[1][j & 3]);
+      acc[0][q] = T::template lt_acc<FMA>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], acc[0][q]);
+      acc[1][q] = dotacc(y[2 * j], y[2 * j], acc[1][q]);
+      acc[1][q] = dotacc(y[2 * j + 1], y[2 * j + 1], acc[1][q]);
     }
-    // canonical reduction (team_allsum, W = 1) of (old kinetic energy, log-target sum, new kinetic energy)
-    double sums[3] = {k0lane, __dadd_rn(__dadd_rn(acc[0][0], acc[0][1]), __dadd_rn(acc[0][2], acc[0][3])),
-                      __dadd_rn(__dadd_rn(acc[1][0], acc[1][1]), __dadd_rn(acc[1][2], acc[1][3]))};
+    // canonical reduction (team_allsum) of (old kinetic energy, log-target sum, new kinetic energy)
+    double sums[3];
+    if (W == 1) {
+      constexpr int M = 4 / W;
+      sums[0] = k0lane;
+      sums[1] = __dadd_rn(__dadd_rn(acc[0][0], acc[0][1 % M]), __dadd_rn(acc[0][2 % M], acc[0][3 % M]));
+      sums[2] = __dadd_rn(__dadd_rn(acc[1][0], acc[1][1 % M]), __dadd_rn(acc[1][2 % M], acc[1][3 % M]));
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      double t[3];
+      for (int o = 16; o >= 1; o >>= 1) {
+        double t[3];
 #pragma unroll
-      for (int v = 0; v < 3; ++v) t[v] = __shfl_xor_sync(0xffffffffu, sums[v], o);
+        for (int v = 0; v < 3; ++v) t[v] = __shfl_xor_sync(0xffffffffu, sums[v], o);
 #pragma unroll
-      for (int v = 0; v < 3; ++v) sums[v] = __dadd_rn(sums[v], t[v]);
+        for (int v = 0; v < 3; ++v) sums[v] = __dadd_rn(sums[v], t[v]);
+      }
+    } else {
+      // a consumer that is a transition ahead writes the other half of `red`; it cannot get two ahead, because the
+      // barrier of the transition in between needs the slowest consumer, which by then has read this half
+      // team_allsum<3, 4> with the first value already in place: accumulator q of value v sits at red[(4 v + q) * 32 + lane]
+      double* const rb = red[W == 1 ? 0 : (it & 1)];
+      rb[(4 + w) * 32 + lane] = acc[0][0];
+      rb[(8 + w) * 32 + lane] = acc[1][0];
+      bar_sync(KLB_WS_BAR_TEAM, 128);
+#pragma unroll
+      for (int v = 0; v < 3; ++v)
+        sums[v] = __dadd_rn(__dadd_rn(rb[(4 * v) * 32 + lane], rb[(4 * v + 1) * 32 + lane]),
+                            __dadd_rn(rb[(4 * v + 2) * 32 + lane], rb[(4 * v + 3) * 32 + lane]));
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        double t[3];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) t[v] = __shfl_xor_sync(0xffffffffu, sums[v], o);
+#pragma unroll
+        for (int v = 0; v < 3; ++v) sums[v] = __dadd_rn(sums[v], t[v]);
+      }
     }
     const double lt_new = T::lt_fin(A, sums[1]);
     double lt_cur = cs->lt_cur;
@@ -239,7 +287,7 @@ klb_hmc_ws_kernel(const KArgs A) {
       tn.step = step; tn.accepted = cs->accepted; tn.proposed = cs->proposed; tn.totproposed = cs->totproposed;
       tn.rate = cs->rate;
       if (A.counters_on) { tn.proposed += 1; if (accept) tn.accepted += 1; }
-      if (A.tuner == 2) da_block<true>(A, c, tn, nl, a_prob, tab, lane == 0);
+      if (A.tuner == 2) da_block<true, (W == 1 ? 0 : KLB_WS_BAR_TEAM)>(A, c, tn, nl, a_prob, tab, writer);
       else tuner_block<2>(A, tn, tab, c);
       __syncwarp();
       if (lane == 0) {
@@ -248,11 +296,11 @@ klb_hmc_ws_kernel(const KArgs A) {
       }
     }
     if (accept) {
-      store_chain<NV, W, FULL>(x, xcol, d, 0, lane);
+      store_chain<NV, W, FULL>(x, xcol, d, w, lane);
       lt_cur = lt_new;
       if (lane == 0) cs->lt_cur = lt_new;
     } else {
-      load_chain<NV, W, FULL>(x, xcol, d, 0, lane);
+      load_chain<NV, W, FULL>(x, xcol, d, w, lane);
     }
     if (A.i0 + it > A.burnin) {                                              // in(i, postrange) -> save
       const long long thin = cs->thin, count = cs->count;
@@ -260,19 +308,19 @@ klb_hmc_ws_kernel(const KArgs A) {
       if (thin == 0) {
         if (saving) {
           const long long col = c * A.npost + count;
-          if (A.out_value) store_chain<NV, W, FULL>(x, A.out_value + col * A.ld, d, 0, lane);
+          if (A.out_value) store_chain<NV, W, FULL>(x, A.out_value + col * A.ld, d, w, lane);
           if (A.out_grad) {
             double gbuf[2 * NV];
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-              const int i = Geo<NV, W>::elem(j, 0, lane);
+              const int i = Geo<NV, W>::elem(j, w, lane);
               T::template grad<FMA>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], gbuf[2 * j], gbuf[2 * j + 1]);
               if (!valid<FULL>(i + 1, d)) gbuf[2 * j + 1] = 0.0;
               if (!valid<FULL>(i, d)) gbuf[2 * j] = 0.0;
             }
-            store_chain<NV, W, FULL>(gbuf, A.out_grad + col * A.ld, d, 0, lane);
+            store_chain<NV, W, FULL>(gbuf, A.out_grad + col * A.ld, d, w, lane);
           }
-          if (lane == 0) {
+          if (writer) {
             if (A.out_lt) A.out_lt[col] = lt_cur;
             if (A.out_accept) A.out_accept[col] = accept ? 1 : 0;
           }
@@ -283,7 +331,7 @@ klb_hmc_ws_kernel(const KArgs A) {
     }
     __syncwarp();
   }
-  if (lane == 0) {
+  if (writer) {
     A.lt[c] = cs->lt_cur;
     A.tune_step[c] = cs->step;
     A.tune_cnt[3 * c] = cs->accepted; A.tune_cnt[3 * c + 1] = cs->proposed; A.tune_cnt[3 * c + 2] = cs->totproposed;

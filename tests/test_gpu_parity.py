@@ -95,7 +95,7 @@ def test_other_targets_bit_exact(K, sampler, target):
 
 
 @pytest.mark.parametrize("arith", ["reference", "fma"])
-@pytest.mark.parametrize("dim", [2, 64, 128, 130, 256, 512])
+@pytest.mark.parametrize("dim", [1, 2, 3, 7, 64, 65, 128, 130, 255, 256, 511, 512])
 @pytest.mark.parametrize("sampler", ["HMC", "MALA", "MH"])
 def test_dense_precision_target_bit_exact(K, sampler, dim, arith):
     """-z'Cz, -2Cz with C = inv(AR(1) covariance): the matrix-vector kernels (klb_dense.cuh) against the oracle;
@@ -572,15 +572,46 @@ def test_run_host_dual_averaging_slices(K, O, target, dim):
     assert_same("after a rejected start", job.output().value, orc["value"])
 
 
+# ------------------------------------------------------------------ HMC, four consumer warps per chain (dim 1025..4096)
+@pytest.mark.parametrize("arith", ["reference", "fma"])
+@pytest.mark.parametrize("target,dim,tuner", [("iso", 4096, "accrate"), ("iso", 1025, "vanilla"), ("shifted", 2050, "accrate"),
+                                              ("rosen", 3000, "vanilla"), ("iso", 3001, "vanilla"), ("rosen", 4096, "dualavg"), ("shifted", 1536, "dualavg")])
+def test_hmc_team_kernel_bit_exact(K, target, dim, tuner, arith):
+    """klb_hmc_ws_kernel<W = 4>: one chain per consumer warpgroup, masked and full dims, every tuner, every output
+    (value, logtarget, gradient, accept flags), thinning, the verbose rate records      iterate/HMC.jl:124-248"""
+    step = {"iso": 0.5 / np.sqrt(dim), "shifted": 0.5 / np.sqrt(dim), "rosen": 0.004}[target]
+    job, cfg, x0, tp, sg = build_pair(K, "HMC", target, nchains=11, dim=dim, nsteps=36, burnin=12, thinning=3, step=step,
+                                      nleaps=6, seed=8128 + dim, arith=arith, tuner=tuner, target_rate=0.7, nadapt=20,
+                                      period=4, verbose=True, monitor=("value", "logtarget", "gradlogtarget"))
+    assert job.plan().warps_per_block == 8
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    assert 0.05 < out.diagnosticvalues.mean() <= 1.0
+    # the same chains through the fused 4-warp-team kernel of klb_kernels.cuh (KLB_HMC_WS=1 keeps only the one-warp
+    # warp-specialised geometries): bit-identical by construction
+    os.environ["KLB_HMC_WS"] = "1"
+    try:
+        job2, *_ = build_pair(K, "HMC", target, nchains=11, dim=dim, nsteps=36, burnin=12, thinning=3, step=step,
+                              nleaps=6, seed=8128 + dim, arith=arith, tuner=tuner, target_rate=0.7, nadapt=20,
+                              period=4, verbose=True, monitor=("value", "logtarget", "gradlogtarget"))
+        job2.run()
+        out2 = job2.output()
+    finally:
+        del os.environ["KLB_HMC_WS"]
+    assert np.array_equal(out.value, out2.value) and np.array_equal(out.logtarget, out2.logtarget)
+    assert np.array_equal(job.pstate_value, job2.pstate_value)
+
+
 # ------------------------------------------------------------------ DualAveragingMCTuner (HMC)
 @pytest.mark.parametrize("arith", ["reference", "fma"])
 @pytest.mark.parametrize("target,dim", [("iso", 1024), ("iso", 700), ("iso", 64), ("iso", 7), ("iso", 2048),
-                                        ("shifted", 100), ("rosen", 96), ("logit", 4)])
+                                        ("shifted", 100), ("rosen", 96), ("logit", 4), ("dense", 30), ("dense", 64),
+                                        ("dense", 129), ("dense", 2)])
 def test_dual_averaging_hmc_bit_exact(K, target, dim, arith):
     """DualAveragingMCTuner (src/tuners/DualAveragingMCTuner.jl:95-101, iterate/HMC.jl:125-127,142-144,225-248):
     per-chain step and per-chain nleaps = max(1, round(λ/step)); adaptation for nadapt transitions, then step = εbar.
-    Warp-specialised kernel (dim 1024, 700), fused kernel, 4-warp teams (2048), thread-per-chain (logit)."""
-    step = {"iso": 0.8 / np.sqrt(dim), "shifted": 0.08, "rosen": 0.01, "logit": 0.02}[target]
+    Warp-specialised kernel (dim 1024, 700), fused kernel, 4-warp teams (2048), thread-per-chain (logit), and the
+    dense-precision tile kernel, where the chains of a CTA tile stop after their own number of steps."""
+    step = {"iso": 0.8 / np.sqrt(dim), "shifted": 0.08, "rosen": 0.01, "logit": 0.02, "dense": 0.05}[target]
     job, cfg, x0, tp, sg = build_pair(K, "HMC", target, nchains=37, dim=dim, nsteps=70, burnin=20, thinning=2, step=step,
                                       nleaps=40 if target == "iso" else 6, seed=2718, arith=arith, tuner="dualavg", target_rate=0.651, nadapt=45,
                                       verbose=(dim % 2 == 0), period=10)
@@ -619,12 +650,9 @@ def test_dual_averaging_chunks_shards_and_reset_rule(K, O):
     assert (tn.step == 1.0).all() and np.allclose(tn.mu, np.log(10.0), rtol=1e-15) and (tn.lam == 8 * 0.05).all()
     t_ref, d_ref = O.da_state(cfg, first=False)
     assert_same("reset mu", tn.mu, d_ref["mu"][:24])
-    # dual averaging is an HMC tuner; dense targets are refused
+    # dual averaging is an HMC tuner
     with pytest.raises(K.KlaraError):
         build_pair(K, "MALA", "iso", nchains=4, dim=8, nsteps=5, tuner="dualavg")
-    with pytest.raises(K.KlaraError) as ei:
-        build_pair(K, "HMC", "dense", nchains=4, dim=8, nsteps=5, tuner="dualavg")
-    assert ei.value.code == L.KLB_EUNSUPPORTED
 
 
 # ------------------------------------------------------------------ randomized sweep
@@ -637,13 +665,13 @@ def _random_configs(n, seed):
         if target == "logit":
             dim = int(rng.integers(1, 17))
         elif target == "dense":
-            dim = int(2 * rng.integers(1, 70))
+            dim = int(rng.integers(1, 140))
         else:
             dim = int(rng.choice([rng.integers(1, 64), rng.integers(64, 600), rng.integers(600, 1400), rng.integers(1400, 4097)]))
             if target == "rosen":
                 dim += dim & 1
         tuner = rng.choice(["vanilla", "accrate", "dualavg"])
-        if tuner == "dualavg" and (sampler != "HMC" or target == "dense"):
+        if tuner == "dualavg" and sampler != "HMC":
             continue
         if tuner == "accrate" and sampler == "MH":
             tuner = "vanilla"

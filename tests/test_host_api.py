@@ -170,10 +170,10 @@ def test_new_surface_validation_without_a_device(K):
     with pytest.raises(K.KlaraError) as ei:                     # no tuner_state method for MALA + dual averaging
         K.BasicMCJob(K.likelihood_model(iso, False), K.MALA(0.1), K.BasicMCRange(nsteps=5), {"p": x0}, tuner=t)
     assert ei.value.code == L.KLB_EINVAL and "HMC" in str(ei.value)
-    dense = K.BasicContMuvParameter("p", logtarget=K.DenseGaussian(np.eye(8)))
-    with pytest.raises(K.KlaraError) as ei:
-        K.BasicMCJob(K.likelihood_model(dense, False), K.HMC(0.1, 3), K.BasicMCRange(nsteps=5), {"p": x0}, tuner=t)
-    assert ei.value.code == L.KLB_EUNSUPPORTED
+    dense = K.BasicContMuvParameter("p", logtarget=K.DenseGaussian(np.eye(513)))
+    with pytest.raises(K.KlaraError) as ei:                     # the dense-precision kernels hold 2 elements per thread
+        K.BasicMCJob(K.likelihood_model(dense, False), K.HMC(0.1, 3), K.BasicMCRange(nsteps=5), {"p": np.zeros((3, 513))})
+    assert ei.value.code == L.KLB_EUNSUPPORTED and "dim <= 512" in str(ei.value)
     logit = K.BasicContMuvParameter("p", logtarget=K.BayesLogit(np.ones((5, 17)), np.ones(5), 1.0))
     with pytest.raises(K.KlaraError) as ei:
         K.BasicMCJob(K.likelihood_model(logit, False), K.HMC(0.1, 3), K.BasicMCRange(nsteps=5), {"p": np.zeros(17)})

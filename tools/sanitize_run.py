@@ -18,7 +18,8 @@ CASES = [
     ("ws-hmc iso 1024 (warp-specialised producer/consumer, named barriers)", "HMC", "iso", dict(nchains=10, dim=1024, nsteps=5, burnin=2, step=0.05, nleaps=4)),
     ("ws-hmc iso 700 (masked)", "HMC", "iso", dict(nchains=6, dim=700, nsteps=4, burnin=1, step=0.05, nleaps=3)),
     ("ws-hmc dual averaging", "HMC", "iso", dict(nchains=6, dim=1024, nsteps=5, burnin=1, step=0.03, nleaps=3, tuner="dualavg", nadapt=3)),
-    ("fused hmc 4-warp teams 2048", "HMC", "iso", dict(nchains=3, dim=2048, nsteps=3, burnin=1, step=0.03, nleaps=3)),
+    ("ws-hmc 4 consumer warps per chain 2048 (team barrier, double-buffered exchange)", "HMC", "iso", dict(nchains=3, dim=2048, nsteps=5, burnin=1, step=0.03, nleaps=3)),
+    ("ws-hmc 4 consumer warps per chain 3000 rosen, dual averaging", "HMC", "rosen", dict(nchains=3, dim=3000, nsteps=5, burnin=1, step=0.004, nleaps=3, tuner="dualavg", nadapt=3)),
     ("fused hmc 64", "HMC", "shifted", dict(nchains=9, dim=64, nsteps=6, burnin=2, step=0.1, nleaps=3)),
     ("mala rosen 256 + tuner", "MALA", "rosen", dict(nchains=9, dim=256, nsteps=12, burnin=8, step=0.01, tuner="accrate", period=4)),
     ("mh iso 1024", "MH", "iso", dict(nchains=5, dim=1024, nsteps=6, burnin=2, sigma=np.full(1024, 0.02))),
