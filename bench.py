@@ -19,7 +19,7 @@ Besides the timed legs the run VERIFIES itself (`parity`): a fresh run from the 
 is compared, on a chain subset, with the CPU oracle (accept/reject sequence, log-targets, values, final
 state: bit for bit), at N > 1 chains of the OTHER ranks' shards are recomputed on rank 0 and compared with
 the all-gathered result (G-invariance), and a checksum of all final states is printed that must be the same
-for every N.  `configs` carries the other BASELINE.json configurations (C2, C4, C5, MH) at their stated sizes.
+for every N.  `configs` carries the other BASELINE.json configurations (C2, C4, C5, MH) at their stated sizes and HMC at dim 4096.
 
 Prints ONE JSON line (rank 0).
 """
@@ -560,7 +560,7 @@ def verify(args, torch, K, L, job, nloc, lo, world, full_state, dev):
 
 
 def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak, dmma_peak, hbm_peak):
-    """BASELINE.json configs C2, C4, C5 and the MH sampler at the C3 size: device-resident runs, chains sharded over
+    """BASELINE.json configs C2, C4, C5, the MH sampler at the C3 size and HMC at dim 4096: device-resident runs, chains sharded over
     the ranks like C3, CUDA-event time of the run kernels (max over ranks), each with its own roofline figures."""
     idx = np.arange(512)
     Cm = np.linalg.inv(0.8 ** np.abs(idx[:, None] - idx[None, :]))
@@ -574,6 +574,8 @@ def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak,
          K.MALA(0.01), K.Rosenbrock(1.0, 100.0, 0.05), 32768, 256, 2000, 1000, K.AcceptanceRateMCTuner(0.574), "transitions/s", 1),
         ("MH", "MH(sigma = 0.02), -z.z, 65536 x 1024, nsteps 200 / burnin 100", K.MH(np.full(1024, 0.02)), K.IsoGaussian(),
          65536, 1024, 200, 100, None, "transitions/s", 1),
+        ("HMC4096", "HMC(0.025, 10), -z.z, 16384 x 4096, nsteps 200 / burnin 100 (one chain per CTA: 4 consumer + 4 producer warps)",
+         K.HMC(0.025, 10), K.IsoGaussian(), 16384, 4096, 200, 100, None, "leapfrog-steps/s", 10),
     ]
     out = {}
     for name, workload, smp, tgt, N, d, nsteps, burnin, tuner, unit, per in specs:
@@ -603,6 +605,10 @@ def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak,
             ent["roofline"] = {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": dmma_peak / 1e12, "unit": "TFLOP/s",
                                "frac": flop / (ms * 1e-3) / dmma_peak, "kernel": "klb_dense_mma_kernel (DMMA m8n8k4 + cluster TMA multicast)",
                                "peak_source": "measured live: klb_device_peak(KLB_PEAK_DMMA), independent mma.sync.m8n8k4.f64"}
+        elif name == "HMC4096":
+            res = nloc * nsteps * per * 5 * d                                  # the 5 d fp64 operations of a leapfrog step, as for C3
+            ent["roofline"] = {"bound": "fp64_issue", "achieved": res / (ms * 1e-3) / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                               "frac": res / (ms * 1e-3) / fp64_peak, "kernel": "klb_hmc_ws_kernel<TgtIso, 16, W = 4>"}
         else:
             # algorithmic un-fused fp64 operations per transition: MALA iso 19 d, MALA Rosenbrock 25 d, MH 4 d
             ops = {"C2": 19, "C5": 25, "MH": 4}[name] * d

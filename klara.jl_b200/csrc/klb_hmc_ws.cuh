@@ -58,7 +58,7 @@ __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.
 #endif
 template <bool FMA, int NE>
 __device__ __forceinline__ void iso_leap_step(double (&x)[NE], double (&y)[NE], double step, double c) {
-  constexpr int B = KLB_WS_BLK;
+  constexpr int B = KLB_WS_BLK > 0 ? KLB_WS_BLK : 1;   // (KLB_WS_BLK = 0 never gets here)
 #pragma unroll
   for (int b = 0; b < NE; b += B) {
     if (FMA) {
@@ -84,6 +84,60 @@ __device__ __forceinline__ void iso_leap_step(double (&x)[NE], double (&y)[NE], 
   }
 }
 
+// The same for the shifted target, gradient -2 (x - mu): x += step p; v = x - mu; p += 2 (c v), c = -2h.  (h (-2 v) and
+// (-2h) v are the same real product, rounded once: scaling by 2 is exact.)  Without the blocking ptxas serialises the
+// NV = 16 loop onto one temporary (tools/sass_depdist.py: 89 % of its fp64 instructions at distance 1).  mu comes from
+// L1 (read-only path), one 16-byte load per unit and leapfrog step.  The caller passes `mu` plus a zero it has just read
+// from shared memory through a volatile pointer: with a loop-invariant address ptxas hoists all 2 NV values of mu out of
+// the leapfrog loop, spills them (LDL in the loop) and the step collapses onto one temporary all the same.
+template <bool FMA, int NV, int W>
+__device__ __forceinline__ void shifted_leap_step(const double* __restrict__ mu, double (&x)[2 * NV], double (&y)[2 * NV],
+                                                  double step, double c, int w, int lane) {
+  constexpr int B = (KLB_WS_BLK >= 2 && KLB_WS_BLK % 2 == 0) ? KLB_WS_BLK : 4;
+#pragma unroll
+  for (int b = 0; b < 2 * NV; b += B) {
+    double m[B];
+#pragma unroll
+    for (int k = 0; k < B; k += 2) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(mu + Geo<NV, W>::elem((b + k) / 2, w, lane)));   // padded: always in range
+      m[k] = v.x; m[k + 1] = v.y;
+    }
+    if (FMA) {
+#pragma unroll
+      for (int k = 0; k < B; ++k) x[b + k] = __fma_rn(step, y[b + k], x[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) m[k] = __dsub_rn(x[b + k], m[k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) y[b + k] = __fma_rn(c, m[k], y[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) y[b + k] = __fma_rn(c, m[k], y[b + k]);
+    } else {
+      double t[B];
+#pragma unroll
+      for (int k = 0; k < B; ++k) t[k] = __dmul_rn(step, y[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) x[b + k] = __dadd_rn(t[k], x[b + k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) m[k] = __dsub_rn(x[b + k], m[k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) t[k] = __dmul_rn(c, m[k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) y[b + k] = __dadd_rn(y[b + k], t[k]);
+#pragma unroll
+      for (int k = 0; k < B; ++k) y[b + k] = __dadd_rn(y[b + k], t[k]);
+    }
+  }
+}
+
+// What the targets read of the argument block.  For the shifted target `mu` carries a zero offset read through a volatile
+// pointer, a different read for each phase of a transition (opening half-kick | inner steps | closing step and log-target):
+// otherwise the loads of mu -- invariant over the transitions, the same addresses in every phase -- are hoisted / merged
+// into 2 NV values that stay live (or get spilled) through the leapfrog loop.
+struct WsArgs {
+  const double* mu;
+  double ra, rb, rscale;
+};
+
 struct WsChain {          // per consumer: the chain's scalars between trajectories
   double lt_cur, step, rate, u_acc;
   long long accepted, proposed, totproposed, count, thin;
@@ -101,6 +155,8 @@ klb_hmc_ws_kernel(const KArgs A) {
   __shared__ double2 zstage[W == 1 ? 4 : 1][W == 1 ? NV * 32 : 1];
   __shared__ unsigned short zqueue[4][KLB_QCAP];
   __shared__ double uacc[4];
+  __shared__ int ws_zero;                                      // see shifted_leap_step
+  if (threadIdx.x == 0) ws_zero = 0;
   __shared__ double red[W == 1 ? 1 : 2][W == 1 ? 1 : 3 * 4 * 32];   // W = 4: exchange of the lane accumulators, by transition parity
   for (int i = threadIdx.x; i < KLB_TAB_LEN; i += blockDim.x) tab[i] = A.tab[i];
   __syncthreads();
@@ -196,11 +252,13 @@ klb_hmc_ws_kernel(const KArgs A) {
         *static_cast<volatile double*>(&red[W == 1 ? 0 : (it & 1)][(W == 1 ? 0 : w) * 32 + lane]) = k0lane;
       }
     }
+    constexpr bool kOpaqueMu = std::is_same<T, TgtShifted>::value && NV == 16;
+    const WsArgs B0 = {A.mu + (kOpaqueMu ? *static_cast<volatile int*>(&ws_zero) : 0), A.ra, A.rb, A.rscale};
     // leapfrog! (src/samplers/samplers.jl:122-134): see klb_chain_kernel for the exact-rewrite notes
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int i = Geo<NV, W>::elem(j, w, lane);
-      T::template kick<FMA, false>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
+      T::template kick<FMA, false>(B0, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
     }
 #if KLB_WS_EXP == 1      // timing experiment 1: consumers skip the inner leapfrog steps (producer-bound time)
     for (int s = nl; s < nl; ++s) {
@@ -211,14 +269,19 @@ klb_hmc_ws_kernel(const KArgs A) {
         iso_leap_step<FMA, 2 * NV>(x, y, step, __dmul_rn(-2.0, h));
         continue;
       }
+      if (KLB_WS_BLK > 0 && NV == 16 && std::is_same<T, TgtShifted>::value) {
+        shifted_leap_step<FMA, NV, W>(A.mu + *static_cast<volatile int*>(&ws_zero), x, y, step, __dmul_rn(-2.0, h), w, lane);
+        continue;
+      }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const int i = Geo<NV, W>::elem(j, w, lane);
         x[2 * j] = Ar<FMA>::ma(step, y[2 * j], x[2 * j]);
         x[2 * j + 1] = Ar<FMA>::ma(step, y[2 * j + 1], x[2 * j + 1]);
-        T::template kick<FMA, true>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
+        T::template kick<FMA, true>(B0, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
       }
     }
+    const WsArgs B1 = {A.mu + (kOpaqueMu ? *static_cast<volatile int*>(&ws_zero) : 0), A.ra, A.rb, A.rscale};
     double acc[2][4 / W] = {};
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -226,8 +289,8 @@ klb_hmc_ws_kernel(const KArgs A) {
       const int q = AccIdx<W>::local(j);
       x[2 * j] = Ar<FMA>::ma(step, y[2 * j], x[2 * j]);
       x[2 * j + 1] = Ar<FMA>::ma(step, y[2 * j + 1], x[2 * j + 1]);
-      T::template kick<FMA, false>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
-      acc[0][q] = T::template lt_acc<FMA>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], acc[0][q]);
+      T::template kick<FMA, false>(B1, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], h, y[2 * j], y[2 * j + 1]);
+      acc[0][q] = T::template lt_acc<FMA>(B1, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], acc[0][q]);
       acc[1][q] = dotacc(y[2 * j], y[2 * j], acc[1][q]);
       acc[1][q] = dotacc(y[2 * j + 1], y[2 * j + 1], acc[1][q]);
     }
@@ -267,7 +330,7 @@ klb_hmc_ws_kernel(const KArgs A) {
         for (int v = 0; v < 3; ++v) sums[v] = __dadd_rn(sums[v], t[v]);
       }
     }
-    const double lt_new = T::lt_fin(A, sums[1]);
+    const double lt_new = T::lt_fin(B1, sums[1]);
     double lt_cur = cs->lt_cur;
     const double oldh = __dsub_rn(lt_cur, __dmul_rn(0.5, sums[0]));          // hamiltonian()
     const double newh = __dsub_rn(lt_new, __dmul_rn(0.5, sums[2]));
@@ -314,7 +377,7 @@ klb_hmc_ws_kernel(const KArgs A) {
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
               const int i = Geo<NV, W>::elem(j, w, lane);
-              T::template grad<FMA>(A, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], gbuf[2 * j], gbuf[2 * j + 1]);
+              T::template grad<FMA>(B1, i, valid<FULL>(i, d), valid<FULL>(i + 1, d), x[2 * j], x[2 * j + 1], gbuf[2 * j], gbuf[2 * j + 1]);
               if (!valid<FULL>(i + 1, d)) gbuf[2 * j + 1] = 0.0;
               if (!valid<FULL>(i, d)) gbuf[2 * j] = 0.0;
             }

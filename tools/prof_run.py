@@ -31,6 +31,8 @@ def _target():
         idx = np.arange(a.dim)
         C = np.linalg.inv(0.8 ** np.abs(idx[:, None] - idx[None, :]))
         return K.DenseGaussian((C + C.T) / 2)
+    if a.target == "shifted":
+        return K.ShiftedIsoGaussian(np.random.default_rng(5).standard_normal(a.dim))
     return {"iso": K.IsoGaussian(), "rosen": K.Rosenbrock()}[a.target]
 
 
