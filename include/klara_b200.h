@@ -51,7 +51,7 @@ extern "C" {
  * BasicContMuvParameter, src/variables/parameters/BasicContMuvParameter.jl:174-201) */
 #define KLB_TARGET_ISO 0        /* -z.z, -2z                        README.md:153-155 */
 #define KLB_TARGET_SHIFTED_ISO 1 /* -(z-mu).(z-mu), -2(z-mu)        test/BasicContMuvParameter.jl:539-563 */
-#define KLB_TARGET_DENSE 2      /* -z'Cz, -2Cz   doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9 */
+#define KLB_TARGET_DENSE 2      /* -z'Cz, -2Cz   doc/examples/BivariateNormal/MALA/function/analytical.jl:8-9 (dim <= 512) */
 #define KLB_TARGET_ROSENBROCK 3 /* -scale*sum_k [b(x_2k+1 - x_2k^2)^2 + (a - x_2k)^2]  (this repo) */
 #define KLB_TARGET_LOGIT 4      /* Bayesian logistic regression, N(0, lambda I) prior, hyper-parameters [lambda, X, y]:
                                    dot(Xp,y) - sum(log.(1+exp.(Xp))) - 0.5*(dot(p,p)/lambda + d*log(2*pi*lambda)),
@@ -63,8 +63,8 @@ extern "C" {
 #define KLB_TUNER_ACCEPTANCE_RATE 1
 /* DualAveragingMCTuner(targetrate, nadapt; ε0bar, h0bar, γ, t0, κ, period, verbose) for HMC:
  * src/tuners/DualAveragingMCTuner.jl:53-101, src/samplers/HMC.jl:124-133,192-223, iterate/HMC.jl:125-127,142-144,225-248.
- * Per-chain step AND per-chain number of leapfrog steps, nleaps = max(1, round(λ/step)).  Elementwise and
- * logistic-regression targets (the dense-precision kernels advance their chains in lockstep tiles). */
+ * Per-chain step AND per-chain number of leapfrog steps, nleaps = max(1, round(λ/step)), with every target (the
+ * dense-precision tile kernel runs the longest trajectory of a tile and masks the chains that have finished theirs). */
 #define KLB_TUNER_DUAL_AVERAGING 2
 #define KLB_SCORE_LOGISTIC 0
 #define KLB_SCORE_ERF 1
