@@ -58,7 +58,7 @@
 
 #include "../klara.jl_b200/csrc/klb_math.h"
 
-enum { ORC_MH = 0, ORC_MALA = 1, ORC_HMC = 2 };
+enum { ORC_MH = 0, ORC_MALA = 1, ORC_HMC = 2, ORC_NUTS = 3 };
 enum { ORC_ISO = 0, ORC_SHIFTED = 1, ORC_DENSE = 2, ORC_ROSEN = 3, ORC_LOGIT = 4 };
 enum { ORC_VANILLA = 0, ORC_ACCRATE = 1, ORC_DUALAVG = 2 };
 
@@ -83,6 +83,9 @@ typedef struct {
   int64_t da_nadapt, da_t0;
   double da_eps0bar, da_h0bar, da_gamma, da_kappa;
   double* da;                                 /* per chain, in/out: the DualAveragingMCTune fields below (8 doubles) */
+  /* NUTS(leapstep; maxδ, maxndoublings)   src/samplers/NUTS.jl:228-241; step above = leapstep */
+  int32_t nuts_maxdelta, nuts_maxndoublings;
+  uint8_t* nuts_ndoublings;                   /* out, npost x nchains: the :ndoublings diagnostic (diagnostics bit1); may be NULL */
 } orc_config;
 
 /* DualAveragingMCTune minus the BasicMCTune part (src/tuners/DualAveragingMCTuner.jl:1-13); sstate.count rides along */
@@ -92,7 +95,7 @@ typedef struct { double lambda, mu, epsbar, hbar, hweight, epsweight, nleaps, co
 typedef struct { double step; int64_t accepted, proposed, totproposed; double rate; } orc_tune;
 
 /* one chain's BasicContMuvParameterState (src/states/ParameterStates/BasicContMuvParameterState.jl:62-97) */
-typedef struct { double* value; double logtarget; double* gradlogtarget; int accept; } orc_pstate;
+typedef struct { double* value; double logtarget; double* gradlogtarget; int accept; int ndoublings; } orc_pstate;
 
 typedef struct {
   const orc_config* cfg;
@@ -136,6 +139,14 @@ double orc_uniform(uint64_t seed, uint64_t chain, uint64_t t) {
   return klb_accept_uniform(&s);
 }
 /* units per lane the library uses for `dim` (klb_job_plan().nv): 1,2,4,8,16 for dim <= 1024, 64 up to 4096 */
+/* uniform number q of transition t: slot q of KLB_TAG_ACCEPT (q = 0 is the accept uniform of HMC / MALA / MH; NUTS draws
+ * q = 0, 1, 2, ... in the order the reference calls rand()) */
+double orc_uniform_seq(uint64_t seed, uint64_t chain, uint64_t t, uint32_t q) {
+  klb_stream st = klb_stream_make(seed, chain, t);
+  uint64_t w0, w1;
+  klb_stream_draw(&st, q, KLB_TAG_ACCEPT, 0u, &w0, &w1);
+  return klb_u01(w0);
+}
 int orc_plan_nv(int64_t dim) {
   int nv = 1;
   while (64 * (int64_t)nv < dim && nv < 16) nv *= 2;
@@ -365,6 +376,7 @@ void orc_tuner_state(const orc_config* c, orc_tune* t) {
 }
 static int orc_counters_on(const orc_config* c) {
   if (c->sampler == ORC_MH) return c->verbose != 0;                    /* iterate/MH.jl:73-75 */
+  if (c->sampler == ORC_NUTS) return c->verbose != 0;                  /* iterate/NUTS.jl:238-240 */
   return (c->tuner == ORC_VANILLA && c->verbose) || c->tuner == ORC_ACCRATE ||
          (c->tuner == ORC_DUALAVG && c->verbose);                      /* iterate/HMC.jl:129-133 */
 }
@@ -383,7 +395,7 @@ static int orc_counters_on(const orc_config* c) {
 void orc_da_state(const orc_config* c, orc_tune* t, orc_da* d, int first) {
   t->step = first ? c->step : 1.;
   t->accepted = 0; t->proposed = 0; t->totproposed = c->period; t->rate = NAN;
-  d->lambda = (double)c->nleaps * c->step;
+  d->lambda = (c->sampler == ORC_NUTS) ? NAN : (double)c->nleaps * c->step;      /* NUTS: λ=NaN   NUTS.jl:260-269 */
   d->epsbar = c->da_eps0bar; d->hbar = c->da_h0bar;
   d->hweight = NAN; d->epsweight = NAN; d->nleaps = 0.;
   d->mu = klb_log(10 * t->step, KLB_TAB);
@@ -486,6 +498,97 @@ static void orc_iterate_hmc(const orc_model* M, orc_pstate* ps, orc_sstate* ss, 
   if (c->tuner == ORC_DUALAVG) orc_da_block(c, tune, da, a); else orc_tuner_block(c, tune);
 }
 
+/* ---- NUTS, multivariate                src/samplers/iterate/NUTS.jl:230-457, src/samplers/NUTS.jl:514-628, :781-927
+ * The reference constructs its sampler state as MuvNUTSState(pstate, pstate, pstate, pstate, ...) (NUTS.jl:198-225): the
+ * plus end, the minus end, the proposal and the second-subtree proposal are ONE mutable object, every leaf of build_tree!
+ * returns sstate.pstateprime / sstate.momentumprime for all of them (:533-539) and every level keeps n', s' in the one
+ * shared sstate (:541-549).  Resolving that aliasing by Julia's reference semantics (oracle/nuts_alias.py holds the
+ * statement-by-statement model and tests/test_oracle_nuts.py checks the two against each other) leaves:
+ *   - one moving point E (sp below) that every leaf advances in place by one leapfrog step of size v*step;
+ *   - one running momentum (momentumprime); each direction owns a pristine copy of the initial momentum until it is first
+ *     used: the first leaf of a doubling in a direction that has not been used reads that copy, afterwards that end (at
+ *     j >= 1 both ends, :541-549) IS momentumprime;
+ *   - uturn(E.value - E.value, ...) = (0 < 0) never fires; the rand() of an inner node only decides a self-copy, but is
+ *     consumed; an inner node returns n' = 2 n'(second half), s' = s'(second half) (the first half's n' lived in the
+ *     same field), a' and na' do add up (they are locals, :879-880);
+ *   - job.pstate takes E's value, gradient and log-target whenever `s' && rand() < n'/n` (iterate/NUTS.jl:355-375).
+ * Uniforms are consumed in order from the transition's stream: slot q of KLB_TAG_ACCEPT, q = 0 the slice variable, then
+ * per doubling the direction (rand(Bool) := uniform < 0.5 -> +1), the inner nodes in post-order, the acceptance test. */
+static double orc_sequ(const klb_stream* st, uint32_t* q) {
+  uint64_t w0, w1;
+  klb_stream_draw(st, (*q)++, KLB_TAG_ACCEPT, 0u, &w0, &w1);
+  return klb_u01(w0);
+}
+#define ORC_NUTS_MAXLEVELS 16
+static void orc_nuts_tree(const orc_model* M, orc_sstate* ss, double step_v, int j, double u, double oldh,
+                          const klb_stream* st, uint32_t* q, int64_t* n_out, int* s_out, double* a_out, int64_t* na_out) {
+  const orc_config* c = M->cfg;
+  double saved_a[ORC_NUTS_MAXLEVELS + 1]; int64_t saved_na[ORC_NUTS_MAXLEVELS + 1];
+  for (uint64_t leaf = 0;; ++leaf) {
+    orc_leapfrog(M, &ss->sp, ss->momentum, step_v, ss->scratch);                       /* NUTS.jl:527 */
+    orc_logtarget(M, &ss->sp, ss->scratch);
+    const double hprime = orc_hamiltonian(M, ss->sp.logtarget, ss->momentum, ss->scratch);
+    int64_t n = (u <= hprime) ? 1 : 0;                                                 /* :532 */
+    const int s = u < (double)c->nuts_maxdelta + hprime;                               /* :533 */
+    const double e = klb_exp(hprime - oldh, KLB_TAB);
+    double a = (e != e) ? e : (e < 1. ? e : 1.);                                       /* min(1, exp(H' - H0))   :818 */
+    int64_t na = 1;
+    int k = 1, descend = 0;
+    while (k <= j) {
+      if ((leaf >> (k - 1)) & 1u) {                 /* the block just finished was a second half   :580-603 */
+        (void)orc_sequ(st, q);
+        n = 2 * n;
+        a = saved_a[k] + a; na = saved_na[k] + na;
+        ++k;
+      } else if (s) {                               /* a first half that did not stop: on to the second */
+        saved_a[k] = a; saved_na[k] = na;
+        descend = 1;
+        break;
+      } else ++k;                                   /* a first half that stopped is returned as it is */
+    }
+    if (!descend) { *n_out = n; *s_out = s; *a_out = a; *na_out = na; return; }
+  }
+}
+static void orc_iterate_nuts(const orc_model* M, orc_pstate* ps, orc_sstate* ss, orc_tune* tune, orc_da* da,
+                             const klb_stream* st) {
+  const orc_config* c = M->cfg;
+  if (c->tuner == ORC_DUALAVG) da->count += 1;                                         /* iterate/NUTS.jl:234-236 */
+  if (c->verbose) tune->proposed += 1;                                                 /* :238-240 */
+  orc_randn(M, st, ss->z);                                                             /* momentum[:] = randn(size) */
+  const double oldh = orc_hamiltonian(M, ps->logtarget, ss->z, ss->scratch);
+  memcpy(ss->sp.value, ps->value, M->dp * sizeof(double));                             /* E = copies of job.pstate   :246-251 */
+  memcpy(ss->sp.gradlogtarget, ps->gradlogtarget, M->dp * sizeof(double));
+  int aliased_plus = 0, aliased_minus = 0, j = 0, s = 1, update = 0;
+  int64_t n = 1, na = 1;
+  double a = NAN;
+  uint32_t q = 0;
+  const double u = klb_log(orc_sequ(st, &q), KLB_TAB) + oldh;                          /* :261 */
+  while (s && j < c->nuts_maxndoublings) {
+    const int v = (orc_sequ(st, &q) < 0.5) ? 1 : -1;                                   /* rand(Bool) ? 1 : -1   :264 */
+    if (!(v == 1 ? aliased_plus : aliased_minus)) memcpy(ss->momentum, ss->z, M->dp * sizeof(double));
+    int64_t nprime; int sprime;
+    orc_nuts_tree(M, ss, (double)v * tune->step, j, u, oldh, st, &q, &nprime, &sprime, &a, &na);
+    if (v == 1) aliased_plus = 1; else aliased_minus = 1;
+    if (j >= 1) aliased_plus = aliased_minus = 1;
+    if (sprime && orc_sequ(st, &q) < (double)nprime / (double)n) {                     /* :355-375 */
+      memcpy(ps->value, ss->sp.value, M->dp * sizeof(double));
+      memcpy(ps->gradlogtarget, ss->sp.gradlogtarget, M->dp * sizeof(double));
+      ps->logtarget = ss->sp.logtarget;
+      update = 1;
+    }
+    j += 1; n += nprime; s = sprime;                                                   /* :377-381 */
+  }
+  ps->accept = update; ps->ndoublings = j;                                             /* :384-399 */
+  if (c->verbose && update) tune->accepted += 1;                                       /* :402-404 */
+  if (c->tuner == ORC_DUALAVG) {                                                       /* :424-447 */
+    da->nleaps = (double)na;
+    if (da->count <= (double)c->da_nadapt) orc_da_tune(tune, da, c, a / (double)na); else tune->step = da->epsbar;
+    if (c->verbose && tune->totproposed <= c->burnin && tune->proposed % c->period == 0) { orc_rate(tune); orc_reset_burnin(tune); }
+  } else if (c->verbose) {                                                             /* :406-423 */
+    if (tune->totproposed <= c->burnin && tune->proposed % c->period == 0) { orc_rate(tune); orc_reset_burnin(tune); }
+  }
+}
+
 static void orc_iterate_mala(const orc_model* M, orc_pstate* ps, orc_sstate* ss, orc_tune* tune,
                              const klb_stream* st) {
   const orc_config* c = M->cfg;
@@ -571,6 +674,7 @@ static void orc_save(const orc_model* M, const orc_pstate* ps, const orc_output*
   if ((c->monitor & 2u) && o->logtarget) o->logtarget[col] = ps->logtarget;
   if ((c->monitor & 4u) && o->grad) memcpy(o->grad + col * M->d, ps->gradlogtarget, M->d * sizeof(double));
   if ((c->diagnostics & 1u) && o->accept) o->accept[col] = (uint8_t)ps->accept;
+  if ((c->diagnostics & 2u) && c->nuts_ndoublings) c->nuts_ndoublings[col] = (uint8_t)ps->ndoublings;
 }
 
 int64_t orc_npoststeps(int64_t burnin, int64_t thinning, int64_t nsteps) {
@@ -605,7 +709,7 @@ int orc_run(const orc_config* cfg, const double* tparams, const double* sigma,
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nth)
   for (int64_t c = 0; c < N; ++c) {
     double* buf = calloc(9 * dp, sizeof(double));
-    orc_pstate ps = {buf, 0., buf + dp, 0};
+    orc_pstate ps = {buf, 0., buf + dp, 0, 0};
     orc_sstate ss; ss.sp.value = buf + 2 * dp; ss.sp.gradlogtarget = buf + 3 * dp; ss.sp.logtarget = NAN; ss.sp.accept = 0;
     ss.momentum = buf + 4 * dp; ss.z = buf + 5 * dp; ss.scratch = buf + 6 * dp;
     memcpy(ps.value, x + c * d, d * sizeof(double));
@@ -628,6 +732,7 @@ int orc_run(const orc_config* cfg, const double* tparams, const double* sigma,
       klb_stream st = klb_stream_make(cfg->seed, cfg->chain_offset + (uint64_t)c, cfg->t0 + (uint64_t)i);
       switch (cfg->sampler) {                                          /* BasicMCJob.jl:224 */
         case ORC_HMC: orc_iterate_hmc(&M, &ps, &ss, &tn, &da, &st); break;
+        case ORC_NUTS: orc_iterate_nuts(&M, &ps, &ss, &tn, &da, &st); break;
         case ORC_MALA: orc_iterate_mala(&M, &ps, &ss, &tn, &st); break;
         default: orc_iterate_mh(&M, &ps, &ss, &tn, &st); break;
       }

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "libklb_oracle.so")
 
-MH, MALA, HMC = 0, 1, 2
+MH, MALA, HMC, NUTS = 0, 1, 2, 3
 ISO, SHIFTED, DENSE, ROSEN, LOGIT = 0, 1, 2, 3, 4
 VANILLA, ACCRATE, DUALAVG = 0, 1, 2
 
@@ -30,6 +30,7 @@ class OrcConfig(C.Structure):
         ("da_nadapt", C.c_int64), ("da_t0", C.c_int64),
         ("da_eps0bar", C.c_double), ("da_h0bar", C.c_double), ("da_gamma", C.c_double), ("da_kappa", C.c_double),
         ("da", C.c_void_p),
+        ("nuts_maxdelta", C.c_int32), ("nuts_maxndoublings", C.c_int32), ("nuts_ndoublings", C.c_void_p),
     ]
 
 
@@ -172,8 +173,10 @@ def npoststeps(burnin, thinning, nsteps):
 def make_config(sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, step=0.1, nleaps=10,
                 tuner=VANILLA, target_rate=0.574, score_k=7.0, period=100, verbose=0,
                 monitor=1, diagnostics=0, seed=0, chain_offset=0, t0=0, arith=0, nv=None, nthreads=1,
-                nadapt=1000, eps0bar=1.0, h0bar=0.0, gamma=0.05, da_t0=10, kappa=0.75, score=0):
+                nadapt=1000, eps0bar=1.0, h0bar=0.0, gamma=0.05, da_t0=10, kappa=0.75, score=0, maxdelta=1000,
+                maxndoublings=5):
     cfg = OrcConfig()
+    cfg.nuts_maxdelta, cfg.nuts_maxndoublings, cfg.nuts_ndoublings = maxdelta, maxndoublings, None
     cfg.score = score                      # AcceptanceRateMCTuner: 0 logistic_rate_score, 1 erf_rate_score
     cfg.sampler, cfg.target, cfg.tuner, cfg.arith = sampler, target, tuner, arith
     cfg.nchains, cfg.dim, cfg.nsteps, cfg.burnin, cfg.thinning = nchains, dim, nsteps, burnin, thinning
@@ -245,13 +248,24 @@ def run(cfg, x0, tparams=None, sigma=None, tune=None, logtarget=None, da=None):
     ol = np.zeros((N, npost)) if cfg.monitor & 2 else None
     og = np.zeros((N, npost, d)) if cfg.monitor & 4 else None
     oa = np.zeros((N, npost), dtype=np.uint8) if cfg.diagnostics & 1 else None
+    ond = np.zeros((N, npost), dtype=np.uint8) if (cfg.diagnostics & 2 and cfg.sampler == NUTS) else None
+    cfg.nuts_ndoublings = None if ond is None else ond.ctypes.data
     rc = lib().orc_run(C.byref(cfg), _ptr(tp), _ptr(sg), _ptr(x), _ptr(lt), _ptr(tune), int(initialized),
                        _ptr(ov), _ptr(ol), _ptr(og), _ptr(oa))
     if rc:
         raise ValueError("oracle: initial log-target/gradient not finite in chain %d" % (-rc - 1))
     cfg.da = None
+    cfg.nuts_ndoublings = None
     return {"x": x, "logtarget_state": lt, "tune": tune, "da": da, "value": ov, "logtarget": ol,
-            "gradlogtarget": og, "accept": oa, "npost": npost}
+            "gradlogtarget": og, "accept": oa, "ndoublings": ond, "npost": npost}
+
+
+def uniform_seq(seed, chain, t, q):
+    """uniform number q of (seed, chain, transition t): what NUTS consumes in order (q = 0: the accept uniform)"""
+    f = lib().orc_uniform_seq
+    f.restype = C.c_double
+    f.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32]
+    return f(seed, chain, t, q)
 
 
 def max_threads():
