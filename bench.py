@@ -576,6 +576,8 @@ def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak,
          65536, 1024, 200, 100, None, "transitions/s", 1),
         ("HMC4096", "HMC(0.025, 10), -z.z, 16384 x 4096, nsteps 200 / burnin 100 (one chain per CTA: 4 consumer + 4 producer warps)",
          K.HMC(0.025, 10), K.IsoGaussian(), 16384, 4096, 200, 100, None, "leapfrog-steps/s", 10),
+        ("NUTS", "NUTS(0.05; maxndoublings 5), -z.z, 65536 x 1024, nsteps 40 / burnin 20 (the reference's multivariate transition: 2^j leapfrog "
+                 "steps per doubling, no U-turn stop)", K.NUTS(0.05), K.IsoGaussian(), 65536, 1024, 40, 20, None, "leapfrog-steps/s", 31),
     ]
     out = {}
     for name, workload, smp, tgt, N, d, nsteps, burnin, tuner, unit, per in specs:
@@ -583,8 +585,8 @@ def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak,
         p = K.BasicContMuvParameter("p", logtarget=tgt)
         job = K.BasicMCJob(K.likelihood_model(p, False), smp, K.BasicMCRange(nsteps=nsteps, burnin=burnin),
                            {"p": K.SyntheticNormal(hi - lo, d)}, tuner=tuner,
-                           outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}, seed=SEED, arith=args.arith,
-                           device=local_rank, chain_offset=lo)
+                           outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept", "ndoublings"] if name == "NUTS" else ["accept"]},
+                           seed=SEED, arith=args.arith, device=local_rank, chain_offset=lo)
         job.run()
         ms = []
         for _ in range(2):
@@ -592,6 +594,9 @@ def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak,
             job.run()
             ms.append(job.last_run_ms)
         acc = float(job.acceptance().mean())
+        if name == "NUTS":                                                     # leapfrog steps per transition: 2^ndoublings - 1, from the diagnostic
+            nd = job._fetch(L.OUT_NDOUBLINGS, (hi - lo, nsteps - burnin), np.uint8).astype(np.int64)
+            per = float(allmax([float((2 ** nd - 1).mean())])[0])
         job.close()
         ms = allmax([float(np.mean(ms))])[0]
         nloc, npost = hi - lo, nsteps - burnin
@@ -605,6 +610,11 @@ def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak,
             ent["roofline"] = {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": dmma_peak / 1e12, "unit": "TFLOP/s",
                                "frac": flop / (ms * 1e-3) / dmma_peak, "kernel": "klb_dense_mma_kernel (DMMA m8n8k4 + cluster TMA multicast)",
                                "peak_source": "measured live: klb_device_peak(KLB_PEAK_DMMA), independent mma.sync.m8n8k4.f64"}
+        elif name == "NUTS":
+            res = nloc * nsteps * per * 8 * d                                  # 8 d fp64 operations per leaf (two half-kicks, the move, log-target, kinetic energy)
+            ent["roofline"] = {"bound": "fp64_issue", "achieved": res / (ms * 1e-3) / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+                               "frac": res / (ms * 1e-3) / fp64_peak, "kernel": "klb_nuts_kernel<TgtIso, 16, 1>",
+                               "leapfrog_steps_per_transition": per}
         elif name == "HMC4096":
             res = nloc * nsteps * per * 5 * d                                  # the 5 d fp64 operations of a leapfrog step, as for C3
             ent["roofline"] = {"bound": "fp64_issue", "achieved": res / (ms * 1e-3) / 1e12, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",

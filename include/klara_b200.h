@@ -46,6 +46,9 @@ extern "C" {
 #define KLB_SAMPLER_MH 0
 #define KLB_SAMPLER_MALA 1
 #define KLB_SAMPLER_HMC 2
+#define KLB_SAMPLER_NUTS 3   /* NUTS(leapstep; maxδ, maxndoublings), src/samplers/NUTS.jl:228-241, iterate/NUTS.jl:230-457: the
+                                 multivariate transition as the reference computes it; elementwise
+                                 targets; VanillaMCTuner or DualAveragingMCTuner */
 
 /* target descriptors (device-resident replacements of the logtarget / gradlogtarget closures of
  * BasicContMuvParameter, src/variables/parameters/BasicContMuvParameter.jl:174-201) */
@@ -80,6 +83,7 @@ extern "C" {
 #define KLB_MONITOR_LOGTARGET 2u
 #define KLB_MONITOR_GRADLOGTARGET 4u
 #define KLB_DIAG_ACCEPT 1u
+#define KLB_DIAG_NDOUBLINGS 2u /* NUTS: the :ndoublings diagnostic (src/samplers/NUTS.jl:285, iterate/NUTS.jl:389-391) */
 
 /* outopts[:destination]: :nstate (device-resident buffer) or :none */
 #define KLB_DEST_NSTATE 0
@@ -109,6 +113,7 @@ extern "C" {
                                                                every chain -- what the reference prints per period (iterate/HMC.jl:
                                                                211-221, MALA.jl:138-148, MH.jl:126-139); nperiods = burnin / period
                                                                (nadapt / period for DualAveragingMCTuner); NaN = period not closed */
+#define KLB_OUT_NDOUBLINGS 12    /* uint8   npost x nchains    NUTS: doublings of the stored transitions (KLB_DIAG_NDOUBLINGS) */
 #define KLB_OUT_TUNE_DA 10       /* double  8 x nchains        DualAveragingMCTune: λ, μ, εbar, hbar, hweight, εweight,
                                                                nleaps of the last transition, sstate.count */
 
@@ -147,6 +152,9 @@ typedef struct {
   double da_h0bar;        /* h0bar (default 0) */
   double da_gamma;        /* γ (default 0.05) */
   double da_kappa;        /* κ (default 0.75) */
+  /* NUTS only (step above = leapstep) */
+  int32_t nuts_maxdelta;       /* maxδ > 0 (default 1000) */
+  int32_t nuts_maxndoublings;  /* maxndoublings in 1..10 (default 5) */
 } klb_config;
 
 /* geometry the library chose for a job (needed by the oracle to reproduce the reduction order) */

@@ -20,7 +20,7 @@ using LinearAlgebra: dot
 import Statistics: mean      # Klara adds methods to mean (src/stats/mean.jl:7-11); so does the shim
 
 export IsoGaussian, ShiftedIsoGaussian, Rosenbrock, DenseGaussian, BayesLogit, Hyperparameter, Data, DualAveragingMCTuner, run_host, GenericModel,
-       SyntheticNormal, seek!, gathered, logistic_rate_score, erf_rate_score, ess, mcvar, mcse, iact, acceptance, BasicContMuvParameter, likelihood_model, MH, MALA, HMC,
+       SyntheticNormal, seek!, gathered, logistic_rate_score, erf_rate_score, ess, mcvar, mcse, iact, acceptance, BasicContMuvParameter, likelihood_model, MH, MALA, HMC, NUTS,
        BasicMCRange, VanillaMCTuner, AcceptanceRateMCTuner, BasicMCJob, run, reset, output
 
 const LIB = get(ENV, "KLARA_B200_LIB", "libklara_b200.so")
@@ -75,6 +75,16 @@ struct HMC
     new(leapstep, nleaps)
   end
 end
+# src/samplers/NUTS.jl:228-241 (the multivariate transition as the reference computes it; Vanilla or DualAveraging tuner)
+struct NUTS
+  leapstep::Float64; maxδ::Int; maxndoublings::Int
+  function NUTS(leapstep=0.1; maxδ::Integer=1000, maxndoublings::Integer=5)
+    @assert leapstep > 0 "Leapfrog step is not positive"
+    @assert maxδ > 0 "maxδ is not positive"
+    @assert maxndoublings > 0 "Maximum number of doublings is not positive"
+    new(leapstep, maxδ, maxndoublings)
+  end
+end
 struct BasicMCRange; burnin::Int; thinning::Int; nsteps::Int; npoststeps::Int; end
 function BasicMCRange(; burnin::Int=0, thinning::Int=1, nsteps::Int=100)
   @assert burnin >= 0 "Number of burn-in iterations should be non-negative"
@@ -109,6 +119,7 @@ struct KlbConfig
   verbose::Int32; monitor::UInt32; diagnostics::UInt32; destination::Int32
   seed::UInt64; chain_offset::Int64; device::Int32; score::Int32
   da_nadapt::Int64; da_t0::Int64; da_eps0bar::Float64; da_h0bar::Float64; da_gamma::Float64; da_kappa::Float64
+  nuts_maxdelta::Int32; nuts_maxndoublings::Int32
 end
 struct KlbHostField; field::Int32; reserved::Int32; host_dst::Ptr{Cvoid}; nbytes::Int64; end
 
@@ -147,18 +158,19 @@ function BasicMCJob(model::GenericModel, sampler, range::BasicMCRange, v0::Dict;
   monitor = get(outopts, :monitor, [:value]); diags = get(outopts, :diagnostics, Symbol[])
   dest = get(outopts, :destination, :nstate)
   mon = UInt32(sum(Dict(:value=>1, :logtarget=>2, :gradlogtarget=>4)[m] for m in monitor; init=0))
-  smp = sampler isa MH ? 0 : sampler isa MALA ? 1 : 2
+  smp = sampler isa MH ? 0 : sampler isa MALA ? 1 : sampler isa NUTS ? 3 : 2
   da = tuner isa DualAveragingMCTuner
   cfg = KlbConfig(sizeof(KlbConfig), smp, code(p.logtarget), tunercode(tuner),
                   arith == :fma ? 1 : 0, n, d, range.nsteps, range.burnin, range.thinning,
-                  sampler isa HMC ? sampler.leapstep : sampler isa MALA ? sampler.driftstep : 1.0,
+                  (sampler isa HMC || sampler isa NUTS) ? sampler.leapstep : sampler isa MALA ? sampler.driftstep : 1.0,
                   sampler isa HMC ? sampler.nleaps : 1,
                   (tuner isa AcceptanceRateMCTuner || da) ? tuner.targetrate : 0.5,
                   tuner isa AcceptanceRateMCTuner ? tuner.k : 7.0, tuner.period, tuner.verbose,
-                  mon, (:accept in diags) ? 1 : 0, dest == :none ? 1 : 0, seed, chain_offset, device,
+                  mon, ((:accept in diags) ? 1 : 0) | ((:ndoublings in diags) ? 2 : 0), dest == :none ? 1 : 0, seed, chain_offset, device,
                   tuner isa AcceptanceRateMCTuner ? tuner.score : 0,
                   da ? tuner.nadapt : 0, da ? tuner.t0 : 10, da ? tuner.ε0bar : 1.0, da ? tuner.h0bar : 0.0,
-                  da ? tuner.γ : 0.05, da ? tuner.κ : 0.75)
+                  da ? tuner.γ : 0.05, da ? tuner.κ : 0.75,
+                  sampler isa NUTS ? sampler.maxδ : 0, sampler isa NUTS ? sampler.maxndoublings : 0)
   h = Ref{Ptr{Cvoid}}(C_NULL)
   multi = ngpus != 1                   # ngpus = 0: every visible device (klb_multi_create); chains in contiguous blocks
   if multi

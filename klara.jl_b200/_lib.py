@@ -13,17 +13,17 @@ LIB_PATH = os.environ.get("KLB_LIB_PATH") or os.path.join(HERE, "lib", "libklara
 
 # error codes / enums (mirror include/klara_b200.h)
 KLB_OK, KLB_EINVAL, KLB_ECUDA, KLB_ENOTFINITE, KLB_ESTATE, KLB_EUNSUPPORTED, KLB_ENOMEM = 0, -1, -2, -3, -4, -5, -6
-SAMPLER_MH, SAMPLER_MALA, SAMPLER_HMC = 0, 1, 2
+SAMPLER_MH, SAMPLER_MALA, SAMPLER_HMC, SAMPLER_NUTS = 0, 1, 2, 3
 TARGET_ISO, TARGET_SHIFTED_ISO, TARGET_DENSE, TARGET_ROSENBROCK, TARGET_LOGIT = 0, 1, 2, 3, 4
 TUNER_VANILLA, TUNER_ACCEPTANCE_RATE, TUNER_DUAL_AVERAGING = 0, 1, 2
 SCORE_LOGISTIC, SCORE_ERF = 0, 1
 ARITH_REFERENCE, ARITH_FMA = 0, 1
 MONITOR_VALUE, MONITOR_LOGTARGET, MONITOR_GRADLOGTARGET = 1, 2, 4
-DIAG_ACCEPT = 1
+DIAG_ACCEPT, DIAG_NDOUBLINGS = 1, 2
 DEST_NSTATE, DEST_NONE = 0, 1
 PARAM_MU, PARAM_C, PARAM_SIGMA, PARAM_ROSEN, PARAM_LOGIT_X, PARAM_LOGIT_Y, PARAM_LOGIT_LAMBDA = 0, 1, 2, 3, 4, 5, 6
 (OUT_VALUE, OUT_LOGTARGET, OUT_GRADLOGTARGET, OUT_ACCEPT, OUT_STATE, OUT_STATE_LOGTARGET,
- OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS, OUT_TUNE_DA, OUT_TUNE_RATES) = range(12)
+ OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS, OUT_TUNE_DA, OUT_TUNE_RATES, OUT_NDOUBLINGS) = range(13)
 PEAK_FP64, PEAK_DMMA = 0, 1
 GATHER_HANDLE_BYTES = 128
 (STAT_MEAN, STAT_MCVAR_IID, STAT_MCVAR_IMSE, STAT_ESS, STAT_IACT, STAT_ACCEPTANCE, STAT_ACCEPTANCE_VALUE) = range(7)
@@ -41,6 +41,7 @@ class KlbConfig(C.Structure):
         ("seed", C.c_uint64), ("chain_offset", C.c_int64), ("device", C.c_int32), ("score", C.c_int32),
         ("da_nadapt", C.c_int64), ("da_t0", C.c_int64), ("da_eps0bar", C.c_double), ("da_h0bar", C.c_double),
         ("da_gamma", C.c_double), ("da_kappa", C.c_double),
+        ("nuts_maxdelta", C.c_int32), ("nuts_maxndoublings", C.c_int32),
     ]
 
 

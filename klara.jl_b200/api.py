@@ -25,7 +25,7 @@ import numpy as np
 from . import _lib as L
 from .targets import Target
 
-__all__ = ["SyntheticNormal", "device_peak", "BasicContMuvParameter", "Hyperparameter", "Data", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "BasicMCRange",
+__all__ = ["SyntheticNormal", "device_peak", "BasicContMuvParameter", "Hyperparameter", "Data", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "NUTS", "BasicMCRange",
            "VanillaMCTuner", "AcceptanceRateMCTuner", "DualAveragingMCTuner", "BasicMCTune", "DualAveragingMCTune", "BasicMCJob", "run", "reset", "output",
            "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "erf_rate_score", "ess", "mean", "mcvar", "mcse", "iact",
            "acceptance"]
@@ -172,6 +172,21 @@ class HMC:
         assert nleaps > 0, "Number of leapfrog steps is not positive"
         self.leapstep = float(leapstep)
         self.nleaps = int(nleaps)
+
+
+class NUTS:
+    """NUTS(leapstep=0.1; maxδ=1000, maxndoublings=5)        src/samplers/NUTS.jl:228-241
+    The multivariate transition as the reference computes it (its four tree states are one object, NUTS.jl:198-225;
+    DESIGN.md section 6b), with VanillaMCTuner or DualAveragingMCTuner; diagnostics :accept and :ndoublings."""
+    code = L.SAMPLER_NUTS
+
+    def __init__(self, leapstep=0.1, maxdelta=1000, maxndoublings=5):
+        assert leapstep > 0, "Leapfrog step is not positive"
+        assert maxdelta > 0, "maxδ is not positive"
+        assert maxndoublings > 0, "Maximum number of doublings is not positive"
+        self.leapstep = float(leapstep)
+        self.maxdelta = int(maxdelta)
+        self.maxndoublings = int(maxndoublings)
 
 
 # ----------------------------------------------------------------------------- range / tuners
@@ -326,7 +341,7 @@ class BasicMCJob:
             if m not in _MONITOR_BITS:
                 raise KeyError("cannot monitor %r on the device path" % (m,))
         for dg in oo["diagnostics"]:
-            if dg != "accept":
+            if dg != "accept" and not (dg == "ndoublings" and isinstance(sampler, NUTS)):
                 raise KeyError("unknown diagnostic %r" % (dg,))
         self.outopts = oo
 
@@ -363,7 +378,9 @@ class BasicMCJob:
         cfg.score = getattr(tuner, "score_code", L.SCORE_LOGISTIC)
         cfg.period, cfg.verbose = tuner.period, int(tuner.verbose)
         cfg.monitor = sum(_MONITOR_BITS[m] for m in set(oo["monitor"]))
-        cfg.diagnostics = L.DIAG_ACCEPT if "accept" in oo["diagnostics"] else 0
+        cfg.diagnostics = (L.DIAG_ACCEPT if "accept" in oo["diagnostics"] else 0) | \
+            (L.DIAG_NDOUBLINGS if "ndoublings" in oo["diagnostics"] else 0)
+        cfg.nuts_maxdelta, cfg.nuts_maxndoublings = getattr(sampler, "maxdelta", 0), getattr(sampler, "maxndoublings", 0)
         cfg.destination = L.DEST_NONE if oo["destination"] == "none" else L.DEST_NSTATE
         cfg.seed, cfg.chain_offset, cfg.device = seed, chain_offset, device
         cfg.da_nadapt, cfg.da_t0 = getattr(tuner, "nadapt", 0), getattr(tuner, "t0", 10)
@@ -447,6 +464,13 @@ class BasicMCJob:
             self.iostream = write_job_output(self, self._fetch_nstate())
         return self
 
+    def _report_horizon(self):
+        """transitions over which a verbose tuner reports: nadapt for DualAveragingMCTuner with HMC (iterate/HMC.jl:225-248),
+        burnin otherwise -- NUTS keeps the burn-in condition with either tuner (iterate/NUTS.jl:406-447)"""
+        if isinstance(self.tuner, DualAveragingMCTuner) and not isinstance(self.sampler, NUTS):
+            return self.tuner.nadapt
+        return self.range.burnin
+
     @property
     def burnin_rates(self):
         """(nchains, nperiods): the acceptance rate of every burn-in period of every chain, recorded by the kernels of
@@ -454,8 +478,7 @@ class BasicMCJob:
         iterate/MALA.jl:138-148, iterate/MH.jl:126-139).  NaN where a period did not close."""
         if not self.tuner.verbose:
             raise L.KlaraError(L.KLB_ESTATE, "burn-in rates are recorded for verbose tuners only")
-        horizon = self.tuner.nadapt if isinstance(self.tuner, DualAveragingMCTuner) else self.range.burnin
-        nper = horizon // self.tuner.period
+        nper = self._report_horizon() // self.tuner.period
         if nper == 0:
             return np.empty((self.nchains, 0))
         return self._fetch(L.OUT_TUNE_RATES, (self.nchains, nper))
@@ -465,7 +488,7 @@ class BasicMCJob:
         once per period: fmt_iter = %<ndigits(burnin)>d, fmt_perc = %6.2f (src/format.jl, BasicMCJob.jl:90-101).  One
         chain prints the reference's line; a batch prints the mean over chains with the range."""
         rates = self.burnin_rates
-        horizon = self.tuner.nadapt if isinstance(self.tuner, DualAveragingMCTuner) else self.range.burnin
+        horizon = self._report_horizon()
         nd = len(str(horizon))
         for k in range(rates.shape[1]):
             r = rates[:, k]
@@ -569,9 +592,13 @@ class BasicMCJob:
             ns.logtarget = self._fetch(L.OUT_LOGTARGET, (N, P))
         if "gradlogtarget" in mon:
             ns.gradlogtarget = self._fetch(L.OUT_GRADLOGTARGET, (N, P, d))
-        if "accept" in self.outopts["diagnostics"]:
-            ns.diagnostickeys = ["accept"]
-            ns.diagnosticvalues = self._fetch(L.OUT_ACCEPT, (N, P), np.uint8)
+        diag = [k for k in self.outopts["diagnostics"]]
+        if diag:
+            # one diagnostic: (nchains, npost); several (NUTS: accept, ndoublings): (nchains, nkeys, npost), the reference's
+            # nkeys x npost matrix per chain, in the order of outopts[:diagnostics]
+            vals = [self._fetch({"accept": L.OUT_ACCEPT, "ndoublings": L.OUT_NDOUBLINGS}[k], (N, P), np.uint8) for k in diag]
+            ns.diagnostickeys = diag
+            ns.diagnosticvalues = vals[0] if len(vals) == 1 else np.stack(vals, axis=1)
         if self.single:
             for f in ("value", "logtarget", "gradlogtarget", "diagnosticvalues"):
                 a = getattr(ns, f)

@@ -28,7 +28,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-fmad=false",                      # never contract a*b+c behind our back: fma is always explicit
          "-Xcompiler", "-fPIC,-ffp-contract=off,-O2"] + os.environ.get("KLB_EXTRA_FLAGS", "").split()
 
-HEADERS = ["klb_kernels.cuh", "klb_dense.cuh", "klb_dense_mma.cuh", "klb_hmc_ws.cuh", "klb_glm.cuh", "klb_math.h", "klb_tables.h", "../../include/klara_b200.h"]
+HEADERS = ["klb_kernels.cuh", "klb_dense.cuh", "klb_dense_mma.cuh", "klb_hmc_ws.cuh", "klb_nuts.cuh", "klb_glm.cuh", "klb_math.h", "klb_tables.h", "../../include/klara_b200.h"]
 
 
 def units():
@@ -41,6 +41,7 @@ def units():
                       ["-DKLB_INST_SAMPLER=%d" % smp, "-DKLB_INST_FMA=%d" % fma]))
     for fma in (0, 1):
         u.append(("klb_hmc_ws_%d" % fma, "klb_hmc_ws_inst.cu", ["-DKLB_INST_FMA=%d" % fma]))
+        u.append(("klb_nuts_%d" % fma, "klb_nuts_inst.cu", ["-DKLB_INST_FMA=%d" % fma]))
     return u
 
 

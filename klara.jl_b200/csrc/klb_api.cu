@@ -15,6 +15,7 @@
 #include "klb_kernels.cuh"
 #include "klb_dense.cuh"
 #include "klb_dense_mma.cuh"
+#include "klb_nuts.cuh"
 #include "klb_glm.cuh"
 
 // per-(sampler, arithmetic) dispatchers, klb_kernels_inst.cu
@@ -88,6 +89,7 @@ struct klb_job {
   double* out_lt;
   double* out_grad;
   unsigned char* out_accept;
+  unsigned char* out_ndoublings;   // NUTS, KLB_DIAG_NDOUBLINGS
   double* mu;
   double* sigma;
   double* Cm;       // dense precision matrix (d x d), KLB_TARGET_DENSE only
@@ -133,8 +135,14 @@ static bool use_hmc_ws(int sampler, int gw, int gnv) {
   return gw == 1 && (gnv == 8 || gnv == 16);
 }
 
+// NUTS kernels, klb_nuts_inst.cu
+int klb_nuts_0(const KArgs*, int target, int W, int NV, int* regs, int* bps, cudaStream_t);
+int klb_nuts_1(const KArgs*, int target, int W, int NV, int* regs, int* bps, cudaStream_t);
+
 static int chain_dispatch(int sampler, int fma, const KArgs* A, int target, int gw, int gnv, int full, int* regs, int* bps,
                           cudaStream_t s) {
+  if (sampler == KLB_SAMPLER_NUTS)
+    return fma ? klb_nuts_1(A, target, gw, gnv, regs, bps, s) : klb_nuts_0(A, target, gw, gnv, regs, bps, s);
   if (use_hmc_ws(sampler, gw, gnv))
     return fma ? klb_hmc_ws_1(A, target, gw, gnv, full, regs, bps, s) : klb_hmc_ws_0(A, target, gw, gnv, full, regs, bps, s);
   switch (sampler * 2 + (fma ? 1 : 0)) {
@@ -189,7 +197,7 @@ static void free_job(klb_job* j) {
   cudaFree(j->state); cudaFree(j->lt); cudaFree(j->tune_step); cudaFree(j->tune_cnt); cudaFree(j->tune_rate); cudaFree(j->tune_da);
   cudaFree(j->tune_rates);
   if (j->flag_host) cudaFreeHost(j->flag_host);
-  cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept);
+  cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept); cudaFree(j->out_ndoublings);
   cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess); cudaFree(j->accrate);
   cudaFree(j->gX); cudaFree(j->gy);
   for (int q = 0; q < 5; ++q) if (q != KLB_STAT_ESS) cudaFree(j->stat[q]);
@@ -218,6 +226,7 @@ static void fill_args(const klb_job* j, KArgs& A) {
   A.state = j->state; A.lt = j->lt;
   A.tune_step = j->tune_step; A.tune_cnt = j->tune_cnt; A.tune_rate = j->tune_rate;
   A.out_value = j->out_value; A.out_lt = j->out_lt; A.out_grad = j->out_grad; A.out_accept = j->out_accept;
+  A.out_ndoublings = j->out_ndoublings; A.nuts_maxdelta = c.nuts_maxdelta; A.nuts_maxndoublings = c.nuts_maxndoublings;
   A.mu = j->mu; A.sigma = j->sigma; A.tab = j->tab;
   A.ra = j->rosen[0]; A.rb = j->rosen[1]; A.rscale = j->rosen[2];
   A.nchains = c.nchains; A.dim = c.dim; A.ld = j->ld;
@@ -225,8 +234,9 @@ static void fill_args(const klb_job* j, KArgs& A) {
   A.nleaps = c.nleaps; A.tuner = c.tuner;
   // counters advance for AcceptanceRateMCTuner or a verbose tuner (iterate/HMC.jl:129-133);
   // for MH only when verbose (iterate/MH.jl:73-75)
-  A.counters_on = (c.sampler == KLB_SAMPLER_MH) ? (c.verbose != 0)
-                                                : ((c.tuner == KLB_TUNER_ACCEPTANCE_RATE) || c.verbose != 0);
+  // and for NUTS (iterate/NUTS.jl:238-240)
+  A.counters_on = (c.sampler == KLB_SAMPLER_MH || c.sampler == KLB_SAMPLER_NUTS)
+                      ? (c.verbose != 0) : ((c.tuner == KLB_TUNER_ACCEPTANCE_RATE) || c.verbose != 0);
   A.target_rate = c.target_rate; A.score_k = c.score_k; A.score = c.score;
   A.seed = c.seed; A.chain_offset = (unsigned long long)c.chain_offset;
   A.out_rate = j->tune_rates; A.nperiods = j->nperiods;
@@ -251,7 +261,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if (cfg->struct_size != sizeof(klb_config))
     return fail(KLB_EINVAL, "klb_config.struct_size = %u, library expects %zu", cfg->struct_size, sizeof(klb_config));
   const klb_config& c = *cfg;
-  if (c.sampler < 0 || c.sampler > 2) return fail(KLB_EINVAL, "unknown sampler %d", c.sampler);
+  if (c.sampler < 0 || c.sampler > 3) return fail(KLB_EINVAL, "unknown sampler %d", c.sampler);
   if (c.target != KLB_TARGET_ISO && c.target != KLB_TARGET_SHIFTED_ISO && c.target != KLB_TARGET_ROSENBROCK &&
       c.target != KLB_TARGET_DENSE && c.target != KLB_TARGET_LOGIT)
     return fail(KLB_EINVAL, "unknown target %d", c.target);
@@ -262,7 +272,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if (c.tuner != KLB_TUNER_VANILLA && c.tuner != KLB_TUNER_ACCEPTANCE_RATE && c.tuner != KLB_TUNER_DUAL_AVERAGING)
     return fail(KLB_EINVAL, "unknown tuner %d", c.tuner);
   if (c.tuner == KLB_TUNER_DUAL_AVERAGING) {
-    if (c.sampler != KLB_SAMPLER_HMC)
+    if (c.sampler != KLB_SAMPLER_HMC && c.sampler != KLB_SAMPLER_NUTS)
       return fail(KLB_EINVAL, "DualAveragingMCTuner tunes HMC (and NUTS) only; MALA / MH have no tuner_state method for it");
     // DualAveragingMCTuner asserts (src/tuners/DualAveragingMCTuner.jl:76-80)
     if (!(c.target_rate > 0 && c.target_rate < 1)) return fail(KLB_EINVAL, "Target acceptance rate should be between 0 and 1");
@@ -290,6 +300,17 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     if (c.nleaps <= 0) return fail(KLB_EINVAL, "Number of leapfrog steps is not positive");
   }
   if (c.sampler == KLB_SAMPLER_MALA && !(c.step > 0)) return fail(KLB_EINVAL, "Drift step is not positive");
+  if (c.sampler == KLB_SAMPLER_NUTS) {                                 // NUTS.jl:233-237
+    if (!(c.step > 0)) return fail(KLB_EINVAL, "Leapfrog step is not positive");
+    if (c.nuts_maxdelta <= 0) return fail(KLB_EINVAL, "maxδ is not positive");
+    if (c.nuts_maxndoublings <= 0) return fail(KLB_EINVAL, "Maximum number of doublings is not positive");
+    if (c.nuts_maxndoublings > KLB_NUTS_MAXLEVELS)
+      return fail(KLB_EUNSUPPORTED, "maxndoublings <= %d (2^maxndoublings - 1 leapfrog steps per transition)", KLB_NUTS_MAXLEVELS);
+    if (c.tuner == KLB_TUNER_ACCEPTANCE_RATE)
+      return fail(KLB_EINVAL, "NUTS has sampler states for VanillaMCTuner and DualAveragingMCTuner only (src/samplers/NUTS.jl:271-345)");
+    if (c.target != KLB_TARGET_ISO && c.target != KLB_TARGET_SHIFTED_ISO && c.target != KLB_TARGET_ROSENBROCK)
+      return fail(KLB_EUNSUPPORTED, "the NUTS kernels cover the elementwise targets (iso, shifted iso, Rosenbrock)");
+  }
   // tuner asserts (VanillaMCTuner.jl:10-13, AcceptanceRateMCTuner.jl:31-35)
   if (c.period <= 0) return fail(KLB_EINVAL, "Adaptation period should be positive");
   if (c.tuner == KLB_TUNER_ACCEPTANCE_RATE && !(c.target_rate > 0 && c.target_rate < 1))
@@ -299,7 +320,9 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if ((c.monitor & KLB_MONITOR_GRADLOGTARGET) && c.sampler == KLB_SAMPLER_MH)
     return fail(KLB_EINVAL, "MH does not evaluate gradlogtarget; it cannot be monitored");
   if (c.monitor & ~7u) return fail(KLB_EINVAL, "unknown monitor bits");
-  if (c.diagnostics & ~1u) return fail(KLB_EINVAL, "unknown diagnostics bits");
+  if (c.diagnostics & ~3u) return fail(KLB_EINVAL, "unknown diagnostics bits");
+  if ((c.diagnostics & KLB_DIAG_NDOUBLINGS) && c.sampler != KLB_SAMPLER_NUTS)
+    return fail(KLB_EINVAL, ":ndoublings is a diagnostic of NUTS");
   if (c.destination != KLB_DEST_NSTATE && c.destination != KLB_DEST_NONE) return fail(KLB_EINVAL, "unknown destination");
   if (c.chain_offset < 0 || (unsigned long long)c.chain_offset + (unsigned long long)c.nchains > 0xFFFFFFFFull)
     return fail(KLB_EINVAL, "global chain indices must fit 32 bits");
@@ -344,7 +367,8 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if (j->da) CKJ(cudaMalloc(&j->tune_da, 8 * N * sizeof(double)));
   // verbose: one rate per chain and burn-in period (the reference prints them: iterate/HMC.jl:211-221, iterate/MH.jl:126-139);
   // dual averaging reports while count <= nadapt, every `period` proposals
-  j->nperiods = c.verbose ? (j->da ? c.da_nadapt : c.burnin) / c.period : 0;
+  // (NUTS: the burn-in condition holds for both tuners, iterate/NUTS.jl:406-447)
+  j->nperiods = c.verbose ? ((j->da && c.sampler != KLB_SAMPLER_NUTS) ? c.da_nadapt : c.burnin) / c.period : 0;
   if (j->nperiods > 0 && (size_t)j->nperiods * N * sizeof(double) <= ((size_t)1 << 32)) {
     CKJ(cudaMalloc(&j->tune_rates, (size_t)j->nperiods * N * sizeof(double)));
     CKJ(cudaMemset(j->tune_rates, 0xff, (size_t)j->nperiods * N * sizeof(double)));   // NaN until a period closes
@@ -363,6 +387,7 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     if (c.monitor & KLB_MONITOR_LOGTARGET) CKJ(cudaMalloc(&j->out_lt, N * P * sizeof(double)));
     if (c.monitor & KLB_MONITOR_GRADLOGTARGET) CKJ(cudaMalloc(&j->out_grad, N * P * d * sizeof(double)));
     if (c.diagnostics & KLB_DIAG_ACCEPT) CKJ(cudaMalloc(&j->out_accept, N * P));
+    if (c.diagnostics & KLB_DIAG_NDOUBLINGS) CKJ(cudaMalloc(&j->out_ndoublings, N * P));
   }
   j->dense = c.target == KLB_TARGET_DENSE;
   if (j->dense) {                        // rows padded to the even length of the state columns (zero pad column)
@@ -478,6 +503,7 @@ static void slice_args(const klb_job* j, KArgs& A, long long c0, long long nc) {
   if (A.out_lt) A.out_lt += c0 * P;
   if (A.out_grad) A.out_grad += c0 * P * ld;
   if (A.out_accept) A.out_accept += c0 * P;
+  if (A.out_ndoublings) A.out_ndoublings += c0 * P;
   A.nchains = nc;
   A.chain_offset += (unsigned long long)c0;
 }
@@ -548,7 +574,9 @@ static void fill_tune_slice(klb_job* j, size_t c0, size_t nc, cudaStream_t s) {
   j->launches += 1;
   if (j->tune_rates) cudaMemsetAsync(j->tune_rates + c0 * (size_t)j->nperiods, 0xff, nc * (size_t)j->nperiods * sizeof(double), s);
   if (j->da) {
-    klb_launch_fill_da(j->tune_da + 8 * c0, (long long)nc, (double)j->cfg.nleaps * j->cfg.step,
+    klb_launch_fill_da(j->tune_da + 8 * c0, (long long)nc,
+                       j->cfg.sampler == KLB_SAMPLER_NUTS ? klb_u2d(0x7FF8000000000000ULL)       // λ = NaN   NUTS.jl:260-269
+                                                          : (double)j->cfg.nleaps * j->cfg.step,
                        klb_log(10 * step0, KLB_TAB), j->cfg.da_eps0bar, j->cfg.da_h0bar, s);
     j->launches += 1;
   }
@@ -858,6 +886,7 @@ static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols) 
     case KLB_OUT_LOGTARGET: *p = j->out_lt; *nb = N * P * 8; break;
     case KLB_OUT_GRADLOGTARGET: *p = j->out_grad; *nb = N * P * d * 8; *cols = N * P; break;
     case KLB_OUT_ACCEPT: *p = j->out_accept; *nb = N * P; break;
+    case KLB_OUT_NDOUBLINGS: *p = j->out_ndoublings; *nb = N * P; break;
     case KLB_OUT_STATE: *p = j->state; *nb = N * d * 8; *cols = N; break;
     case KLB_OUT_STATE_LOGTARGET: *p = j->lt; *nb = N * 8; break;
     case KLB_OUT_TUNE_STEP: *p = j->tune_step; *nb = N * 8; break;

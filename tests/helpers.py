@@ -4,7 +4,7 @@ import numpy as np
 
 from oracle import oracle as O
 
-SAMPLERS = {"MH": O.MH, "MALA": O.MALA, "HMC": O.HMC}
+SAMPLERS = {"MH": O.MH, "MALA": O.MALA, "HMC": O.HMC, "NUTS": O.NUTS}
 
 
 def synthetic_x0(seed, nchains, dim, chain_offset=0):
@@ -50,7 +50,7 @@ def logit_data(dim, rng, ndata=200, lam=100.0):
 def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, step=0.1, nleaps=10,
                tuner="vanilla", target_rate=0.574, period=100, verbose=False, monitor=("value", "logtarget"),
                diagnostics=("accept",), seed=1234, arith="reference", chain_offset=0, x0=None, sigma=None,
-               device=0, rng_seed=0, nadapt=1000, score="logistic"):
+               device=0, rng_seed=0, nadapt=1000, score="logistic", maxdelta=1000, maxndoublings=5):
     rng = np.random.default_rng(rng_seed)
     tgt, tcode, tparams = make_target(K, target, dim, rng)
     if x0 is None:
@@ -60,6 +60,8 @@ def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, s
         smp = K.MH(sigma)
     elif sampler == "MALA":
         smp = K.MALA(step)
+    elif sampler == "NUTS":
+        smp = K.NUTS(step, maxdelta=maxdelta, maxndoublings=maxndoublings)
     else:
         smp = K.HMC(step, nleaps)
     da_kw = dict(nadapt=nadapt, eps0bar=1.0, h0bar=0.0, gamma=0.05, t0=10, kappa=0.75)
@@ -77,9 +79,11 @@ def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, s
     cfg = O.make_config(SAMPLERS[sampler], tcode, nchains, dim, nsteps, burnin, thinning, step, nleaps,
                         {"vanilla": O.VANILLA, "accrate": O.ACCRATE, "dualavg": O.DUALAVG}[tuner], target_rate,
                         3.0 if score == "erf" else 7.0,
-                        period, int(verbose), mon, 1 if "accept" in diagnostics else 0, seed, chain_offset, 0,
+                        period, int(verbose), mon, (1 if "accept" in diagnostics else 0) | (2 if "ndoublings" in diagnostics else 0),
+                        seed, chain_offset, 0,
                         1 if arith == "fma" else 0, job.plan().nv, O.max_threads(), nadapt=nadapt, eps0bar=1.0, h0bar=0.0,
-                        gamma=0.05, da_t0=10, kappa=0.75, score=1 if score == "erf" else 0)
+                        gamma=0.05, da_t0=10, kappa=0.75, score=1 if score == "erf" else 0, maxdelta=maxdelta,
+                        maxndoublings=maxndoublings)
     return job, cfg, x0, tparams, sigma
 
 
@@ -109,8 +113,14 @@ def compare_run(job, cfg, x0, tparams, sigma, t0=0):
         assert_same("logtarget", out.logtarget, ref["logtarget"])
     if cfg.monitor & 4:
         assert_same("gradlogtarget", out.gradlogtarget, ref["gradlogtarget"])
-    if cfg.diagnostics & 1:
+    if cfg.diagnostics == 1:
         assert_same("accept", out.diagnosticvalues, ref["accept"])
+    elif cfg.diagnostics == 2:
+        assert_same("ndoublings", out.diagnosticvalues, ref["ndoublings"])
+    elif cfg.diagnostics == 3:                       # (nchains, nkeys, npost) in the order of outopts[:diagnostics]
+        keys = list(out.diagnostickeys)
+        assert_same("accept", out.diagnosticvalues[..., keys.index("accept"), :], ref["accept"])
+        assert_same("ndoublings", out.diagnosticvalues[..., keys.index("ndoublings"), :], ref["ndoublings"])
     assert_same("final state", job.pstate_value, ref["x"])
     assert_same("final logtarget", job.pstate_logtarget, ref["logtarget_state"])
     tn = job.tune

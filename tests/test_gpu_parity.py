@@ -755,3 +755,68 @@ def test_verbose_tuner_records_and_prints_the_burnin_rates(K, O, capsys):
     out = capsys.readouterr().out.strip().splitlines()
     r = single.burnin_rates[0]
     assert out == ["Burnin iteration %2d of 20: %6.2f %% acceptance rate" % (10 * (k + 1), 100 * r[k]) for k in range(2)]
+
+
+# ------------------------------------------------------------------ NUTS
+@pytest.mark.parametrize("arith", ["reference", "fma"])
+@pytest.mark.parametrize("target,dim,tuner,maxnd,maxdelta", [
+    ("iso", 7, "vanilla", 5, 1000), ("iso", 64, "dualavg", 4, 1000), ("shifted", 100, "vanilla", 6, 1000),
+    ("rosen", 96, "dualavg", 5, 1000), ("iso", 250, "vanilla", 3, 1000), ("shifted", 512, "dualavg", 4, 1000),
+    ("iso", 1024, "vanilla", 4, 1000), ("rosen", 1000, "vanilla", 3, 1000), ("iso", 1500, "dualavg", 3, 1000),
+    ("shifted", 4096, "vanilla", 2, 1000), ("iso", 33, "vanilla", 7, 2), ("iso", 2, "dualavg", 10, 1)])
+def test_nuts_bit_exact(K, target, dim, tuner, maxnd, maxdelta, arith):
+    """NUTS as the reference computes it (iterate/NUTS.jl:230-457, NUTS.jl:514-628, :781-927; the resolved aliasing of
+    DESIGN.md 6b): every geometry, both tuners, trees that stop early (small maxδ, large steps), both diagnostics"""
+    step = {"iso": 0.9 / np.sqrt(dim) ** 0.5, "shifted": 0.9 / np.sqrt(dim) ** 0.5, "rosen": 0.01}[target]
+    if maxdelta < 10:
+        step *= 3
+    job, cfg, x0, tp, sg = build_pair(K, "NUTS", target, nchains=19, dim=dim, nsteps=40, burnin=12, thinning=2, step=step,
+                                      seed=31337 + dim, arith=arith, tuner=tuner, target_rate=0.7, nadapt=25, period=5,
+                                      verbose=(dim % 2 == 0), monitor=("value", "logtarget", "gradlogtarget"),
+                                      diagnostics=("accept", "ndoublings"), maxdelta=maxdelta, maxndoublings=maxnd)
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    nd = ref["ndoublings"]
+    assert nd.min() >= 1 and nd.max() <= maxnd
+    if maxdelta < 10:
+        assert nd.min() < maxnd                        # some trees stopped before the last doubling
+
+
+def test_nuts_chunks_shards_and_run_host(K, O):
+    """one launch per transition == one launch; 2 shards == 1 job; the pipelined host call == the three calls"""
+    kw = dict(nchains=26, dim=130, nsteps=30, burnin=8, step=0.25, seed=77, tuner="dualavg", target_rate=0.65, nadapt=20,
+              period=4, verbose=True, diagnostics=("accept", "ndoublings"), maxndoublings=4)
+    whole, cfg, x0, tp, sg = build_pair(K, "NUTS", "iso", **kw)
+    out, ref = compare_run(whole, cfg, x0, tp, sg)
+    step, *_ = build_pair(K, "NUTS", "iso", **kw)
+    step.set_chunk(1)
+    step.run()
+    assert_same("chunked value", step.output().value, out.value)
+    assert_same("chunked diagnostics", step.output().diagnosticvalues, out.diagnosticvalues)
+    a, *_ = build_pair(K, "NUTS", "iso", **dict(kw, nchains=10, x0=x0[:10]))
+    b, *_ = build_pair(K, "NUTS", "iso", **dict(kw, nchains=16, x0=x0[10:], chain_offset=10))
+    a.run(); b.run()
+    assert_same("sharded value", np.concatenate([a.output().value, b.output().value]), out.value)
+    assert_same("sharded steps", np.concatenate([a.tune.step, b.tune.step]), whole.tune.step)
+    host, *_ = build_pair(K, "NUTS", "iso", **kw)
+    val = np.empty_like(out.value)
+    nd = np.empty((26, out.value.shape[1]), dtype=np.uint8)
+    host.run_host(x0, {K._lib.OUT_VALUE: val, K._lib.OUT_NDOUBLINGS: nd}, 3)
+    assert_same("run_host value", val, out.value)
+    assert_same("run_host ndoublings", nd, ref["ndoublings"])
+
+
+def test_nuts_validation(K):
+    L = K._lib
+    with pytest.raises(AssertionError, match="maxδ is not positive"):                         # NUTS.jl:235
+        K.NUTS(0.1, maxdelta=0)
+    with pytest.raises(K.KlaraError) as ei:                                                    # no sampler_state method
+        build_pair(K, "NUTS", "iso", nchains=3, dim=8, nsteps=5, tuner="accrate")
+    assert ei.value.code == L.KLB_EINVAL
+    with pytest.raises(K.KlaraError) as ei:
+        build_pair(K, "NUTS", "dense", nchains=3, dim=8, nsteps=5)
+    assert ei.value.code == L.KLB_EUNSUPPORTED
+    with pytest.raises(K.KlaraError) as ei:
+        build_pair(K, "NUTS", "iso", nchains=3, dim=8, nsteps=5, maxndoublings=11)
+    assert ei.value.code == L.KLB_EUNSUPPORTED
+    with pytest.raises(KeyError):
+        build_pair(K, "HMC", "iso", nchains=3, dim=8, nsteps=5, diagnostics=("ndoublings",))

@@ -35,7 +35,7 @@ def test_config_struct_matches_header(K):
             if decl:
                 names += [n.strip() for n in decl.split(None, 1)[1].split(",")]
         assert names == [f[0] for f in cls._fields_], struct
-    assert C.sizeof(K._lib.KlbConfig) == 192
+    assert C.sizeof(K._lib.KlbConfig) == 200
 
 
 def test_enums_match_header(K):
@@ -50,7 +50,9 @@ def test_enums_match_header(K):
                   ("PARAM_LOGIT_LAMBDA", "KLB_PARAM_LOGIT_LAMBDA"), ("OUT_TUNE_DA", "KLB_OUT_TUNE_DA"),
                   ("KLB_ENOTFINITE", "KLB_ENOTFINITE"), ("KLB_ECUDA", "KLB_ECUDA"), ("OUT_VALUE", "KLB_OUT_VALUE"),
                   ("OUT_TUNE_RATE", "KLB_OUT_TUNE_RATE"), ("PARAM_SIGMA", "KLB_PARAM_SIGMA"),
-                  ("MONITOR_GRADLOGTARGET", "KLB_MONITOR_GRADLOGTARGET"), ("DEST_NONE", "KLB_DEST_NONE")]:
+                  ("MONITOR_GRADLOGTARGET", "KLB_MONITOR_GRADLOGTARGET"), ("DEST_NONE", "KLB_DEST_NONE"),
+                  ("SAMPLER_NUTS", "KLB_SAMPLER_NUTS"), ("DIAG_NDOUBLINGS", "KLB_DIAG_NDOUBLINGS"),
+                  ("OUT_NDOUBLINGS", "KLB_OUT_NDOUBLINGS"), ("OUT_TUNE_RATES", "KLB_OUT_TUNE_RATES")]:
         assert getattr(L, py) == int(defs[c]), (py, c)
 
 
@@ -72,6 +74,12 @@ def test_constructor_asserts_follow_the_reference(K):
     with pytest.raises(AssertionError, match="between 0 and 1"):                      # AcceptanceRateMCTuner.jl:31
         K.AcceptanceRateMCTuner(1.0)
     assert K.HMC().leapstep == 0.1 and K.HMC().nleaps == 10 and K.MALA().driftstep == 1.0   # defaults HMC.jl:100, MALA.jl:70
+    with pytest.raises(AssertionError, match="Leapfrog step is not positive"):       # NUTS.jl:234
+        K.NUTS(0.0)
+    with pytest.raises(AssertionError, match="Maximum number of doublings is not positive"):   # NUTS.jl:236
+        K.NUTS(0.1, maxndoublings=0)
+    n = K.NUTS()
+    assert (n.leapstep, n.maxdelta, n.maxndoublings) == (0.1, 1000, 5)               # NUTS.jl:241
     r = K.BasicMCRange(nsteps=10000, burnin=1000)
     assert r.npoststeps == 9000 and r.postrange[0] == 1001
     assert K.VanillaMCTuner().period == 100 and not K.VanillaMCTuner().verbose

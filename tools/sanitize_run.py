@@ -28,6 +28,14 @@ CASES = [
     ("dense DFMA tile mala 30", "MALA", "dense", dict(nchains=11, dim=30, nsteps=4, burnin=1, step=0.02)),
     ("glm hmc", "HMC", "logit", dict(nchains=70, dim=4, nsteps=4, burnin=1, step=0.02, nleaps=3)),
 ]
+CASES += [
+    ("nuts iso 2048, four warps per chain, dual averaging (team barrier between the reads and the writer's stores)", "NUTS", "iso",
+     dict(nchains=5, dim=2048, nsteps=6, burnin=2, step=0.1, tuner="dualavg", nadapt=4, period=2, verbose=True,
+          diagnostics=("accept", "ndoublings"), maxndoublings=3)),
+    ("nuts shifted 100", "NUTS", "shifted", dict(nchains=5, dim=100, nsteps=6, burnin=2, step=0.2, diagnostics=("accept", "ndoublings"), maxndoublings=4)),
+    ("nuts rosen 1000, dual averaging", "NUTS", "rosen", dict(nchains=5, dim=1000, nsteps=6, burnin=2, step=0.02, tuner="dualavg", nadapt=4,
+                                                         diagnostics=("accept", "ndoublings"), maxndoublings=3)),
+]
 for name, smp, tgt, kw in CASES:
     job, cfg, x0, tp, sg = build_pair(K, smp, tgt, seed=31, **kw)
     compare_run(job, cfg, x0, tp, sg)
