@@ -797,12 +797,17 @@ def test_nuts_chunks_shards_and_run_host(K, O):
     a.run(); b.run()
     assert_same("sharded value", np.concatenate([a.output().value, b.output().value]), out.value)
     assert_same("sharded steps", np.concatenate([a.tune.step, b.tune.step]), whole.tune.step)
-    host, *_ = build_pair(K, "NUTS", "iso", **kw)
-    val = np.empty_like(out.value)
-    nd = np.empty((26, out.value.shape[1]), dtype=np.uint8)
+    # run_host = reset(job, x0) + run + output; with the vanilla tuner (a reset dual-averaging job restarts from step = 1,
+    # NUTS.jl:320-325, so it would not retrace the constructor's run)
+    kv = dict(kw, tuner="vanilla")
+    plain, cfgv, _, _, _ = build_pair(K, "NUTS", "iso", **kv)
+    outv, refv = compare_run(plain, cfgv, x0, tp, sg)
+    host, *_ = build_pair(K, "NUTS", "iso", **kv)
+    val = np.empty_like(outv.value)
+    nd = np.empty((26, outv.value.shape[1]), dtype=np.uint8)
     host.run_host(x0, {K._lib.OUT_VALUE: val, K._lib.OUT_NDOUBLINGS: nd}, 3)
-    assert_same("run_host value", val, out.value)
-    assert_same("run_host ndoublings", nd, ref["ndoublings"])
+    assert_same("run_host value", val, outv.value)
+    assert_same("run_host ndoublings", nd, refv["ndoublings"])
 
 
 def test_nuts_validation(K):
