@@ -232,7 +232,8 @@ function output(job::BasicMCJob)
   (value = :value in job.monitor ? fetch!(job, 0, Array{Float64}(undef, job.dim, P, job.nchains)) : nothing,
    logtarget = :logtarget in job.monitor ? fetch!(job, 1, Array{Float64}(undef, P, job.nchains)) : nothing,
    gradlogtarget = :gradlogtarget in job.monitor ? fetch!(job, 2, Array{Float64}(undef, job.dim, P, job.nchains)) : nothing,
-   accept = :accept in job.diagnostics ? fetch!(job, 3, Array{UInt8}(undef, P, job.nchains)) .!= 0 : nothing)
+   accept = :accept in job.diagnostics ? fetch!(job, 3, Array{UInt8}(undef, P, job.nchains)) .!= 0 : nothing,
+   ndoublings = :ndoublings in job.diagnostics ? Int.(fetch!(job, 12, Array{UInt8}(undef, P, job.nchains))) : nothing)   # NUTS
 end
 
 # ess(output(job)): effective sample size (IMSE) per coordinate and chain, computed on the device

@@ -31,8 +31,11 @@ CASES = {
     "hmc_logit_d4": ("HMC", "logit", 6, 4, 60, dict(burnin=20, step=0.03, nleaps=10, monitor=7, diagnostics=1, seed=41), {}),
     "mala_logit_d3_accrate": ("MALA", "logit", 5, 3, 150, dict(burnin=100, step=0.01, tuner=O.ACCRATE, target_rate=0.574, period=25, monitor=3, diagnostics=1, seed=42), {}),
     "mh_logit_d4_fma": ("MH", "logit", 4, 4, 120, dict(burnin=40, thinning=2, monitor=3, diagnostics=1, seed=43, arith=1), {"sigma": [0.1, 0.15, 0.2, 0.1]}),
+    # NUTS as the reference computes it; cross-checked against oracle/nuts_alias.py instead of the twin
+    "nuts_iso_d70": ("NUTS", "iso", 4, 70, 30, dict(burnin=10, step=0.15, monitor=3, diagnostics=3, seed=1729, maxndoublings=4), {}),
+    "nuts_shifted_d9_delta2": ("NUTS", "shifted", 5, 9, 40, dict(burnin=0, step=1.1, monitor=3, diagnostics=3, seed=1730, maxndoublings=6, maxdelta=2), {}),
 }
-SAMPLERS = {"MH": O.MH, "MALA": O.MALA, "HMC": O.HMC}
+SAMPLERS = {"MH": O.MH, "MALA": O.MALA, "HMC": O.HMC, "NUTS": O.NUTS}
 TARGETS = {"iso": O.ISO, "shifted": O.SHIFTED, "rosen": O.ROSEN, "logit": O.LOGIT}
 
 
@@ -76,13 +79,64 @@ def twin_crosscheck(name, cfg, x0, tparams, sigma, r):
     return w
 
 
+def nuts_crosscheck(name, cfg, x0, tparams, r):
+    """every transition of every chain against the resolved state machine of oracle/nuts_alias.py (which
+    tests/test_oracle_nuts.py pins to the aliasing-faithful model of the reference code), teacher-forced"""
+    from oracle import nuts_alias as NA
+    smp, tgt, n, d, nsteps, kw, extra = CASES[name]
+    target = NA.Target(tparams if tgt == "shifted" else None)
+
+    class Draws:
+        def __init__(self, chain, t):
+            self.chain, self.t, self.q = chain, t, 0
+
+        def randn(self, dd):
+            return O.normals(cfg.seed, self.chain, self.t, dd)
+
+        def rand(self):
+            self.q += 1
+            return O.uniform_seq(cfg.seed, self.chain, self.t, self.q - 1)
+
+        def randbool(self):
+            return self.rand() < 0.5
+
+    def fresh(x):
+        ps = NA.PState(d)
+        ps.value = np.array(x, dtype=float)
+        target.gradlogtarget(ps)
+        target.logtarget(ps)
+        return dict(value=ps.value, gradlogtarget=ps.gradlogtarget, logtarget=ps.logtarget)
+
+    assert kw.get("burnin", 0) == 0 or kw.get("thinning", 1) == 1
+    b = kw.get("burnin", 0)
+    full = O.run(O.make_config(O.NUTS, TARGETS[tgt], n, d, nsteps, **dict(kw, burnin=0)), x0, tparams)   # every transition
+    agree = 0
+    for c in range(n):
+        st = fresh(x0[c])
+        for it in range(nsteps):
+            upd, j, _, _ = NA.simple_transition(st, kw["step"], target, kw.get("maxdelta", 1000), kw["maxndoublings"], Draws(c, it + 1))
+            ok = upd == bool(full["accept"][c, it]) and j == int(full["ndoublings"][c, it]) and \
+                np.allclose(st["value"], full["value"][c, it], rtol=1e-9, atol=1e-12)
+            agree += ok
+            st = fresh(full["value"][c, it])
+    assert agree >= 0.97 * n * nsteps, (name, agree)
+    assert np.array_equal(full["value"][:, b:], r["value"])
+    return {"transitions": n * nsteps, "agree": int(agree)}
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name in CASES:
+        if only and name not in only:
+            continue
         cfg, x0, tparams, sigma = build(name)
         r = O.run(cfg, x0, tparams, sigma)
-        print(name, "twin:", twin_crosscheck(name, cfg, x0, tparams, sigma, r))
+        if CASES[name][0] == "NUTS":
+            print(name, "state machine:", nuts_crosscheck(name, cfg, x0, tparams, r))
+        else:
+            print(name, "twin:", twin_crosscheck(name, cfg, x0, tparams, sigma, r))
         out = {"x0": x0, "x": r["x"], "logtarget_state": r["logtarget_state"], "tune": r["tune"]}
-        for k in ("value", "logtarget", "gradlogtarget", "accept"):
+        for k in ("value", "logtarget", "gradlogtarget", "accept", "ndoublings"):
             if r[k] is not None:
                 out[k] = r[k]
         if tparams is not None:

@@ -21,12 +21,13 @@ def _devices(K, n):
 
 
 @pytest.mark.parametrize("sampler,target,dim,nshards", [("HMC", "iso", 1024, 3), ("MALA", "rosen", 96, 2), ("MH", "iso", 7, 4),
-                                                        ("HMC", "dense", 128, 2), ("HMC", "logit", 4, 5)])
+                                                        ("HMC", "dense", 128, 2), ("HMC", "logit", 4, 5), ("NUTS", "shifted", 130, 3)])
 def test_multi_equals_single_device(K, sampler, target, dim, nshards):
     L = K._lib
     N = 101                                               # ragged shards
-    kw = dict(nchains=N, dim=dim, nsteps=24, burnin=7, thinning=2, step={"HMC": 0.02, "MALA": 0.002, "MH": 0.1}[sampler],
-              nleaps=5, seed=4242, sigma=np.full(dim, 0.05), tuner="accrate", period=5, target_rate=0.7)
+    kw = dict(nchains=N, dim=dim, nsteps=24, burnin=7, thinning=2, step={"HMC": 0.02, "MALA": 0.002, "MH": 0.1, "NUTS": 0.1}[sampler],
+              nleaps=5, seed=4242, sigma=np.full(dim, 0.05), tuner="dualavg" if sampler == "NUTS" else "accrate", period=5,
+              target_rate=0.7, nadapt=15, maxndoublings=3)
     one, cfg, x0, tp, sg = build_pair(K, sampler, target, **kw)
     one.run()
     ref = one.output()
