@@ -582,23 +582,39 @@ def other_configs(args, torch, K, L, rank, world, local_rank, allmax, fp64_peak,
     out = {}
     for name, workload, smp, tgt, N, d, nsteps, burnin, tuner, unit, per in specs:
         lo, hi = K.distributed.shard_range(N, rank, world)
-        p = K.BasicContMuvParameter("p", logtarget=tgt)
-        job = K.BasicMCJob(K.likelihood_model(p, False), smp, K.BasicMCRange(nsteps=nsteps, burnin=burnin),
-                           {"p": K.SyntheticNormal(hi - lo, d)}, tuner=tuner,
-                           outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept", "ndoublings"] if name == "NUTS" else ["accept"]},
-                           seed=SEED, arith=args.arith, device=local_rank, chain_offset=lo)
-        job.run()
-        ms = []
-        for _ in range(2):
-            job.reset()
+        # A secondary configuration must never take the headline line down with it: its failure is recorded under its
+        # name.  The collectives below run on every rank whatever happened, so the ranks stay in step.
+        job, err, ms, acc, per_loc = None, None, [float("nan")], float("nan"), float(per)
+        try:
+            p = K.BasicContMuvParameter("p", logtarget=tgt)
+            job = K.BasicMCJob(K.likelihood_model(p, False), smp, K.BasicMCRange(nsteps=nsteps, burnin=burnin),
+                               {"p": K.SyntheticNormal(hi - lo, d)}, tuner=tuner,
+                               outopts={"monitor": ["value", "logtarget"], "diagnostics": ["accept", "ndoublings"] if name == "NUTS" else ["accept"]},
+                               seed=SEED, arith=args.arith, device=local_rank, chain_offset=lo)
             job.run()
-            ms.append(job.last_run_ms)
-        acc = float(job.acceptance().mean())
-        if name == "NUTS":                                                     # leapfrog steps per transition: 2^ndoublings - 1, from the diagnostic
-            nd = job._fetch(L.OUT_NDOUBLINGS, (hi - lo, nsteps - burnin), np.uint8).astype(np.int64)
-            per = float(allmax([float((2 ** nd - 1).mean())])[0])
-        job.close()
-        ms = allmax([float(np.mean(ms))])[0]
+            ms = []
+            for _ in range(2):
+                job.reset()
+                job.run()
+                ms.append(job.last_run_ms)
+            acc = float(job.acceptance().mean())
+            if name == "NUTS":                                                 # leapfrog steps per transition: 2^ndoublings - 1, from the diagnostic
+                nd = job._fetch(L.OUT_NDOUBLINGS, (hi - lo, nsteps - burnin), np.uint8).astype(np.int64)
+                per_loc = float((2 ** nd - 1).mean())
+        except Exception as e:                                                 # noqa: BLE001  (recorded, not swallowed)
+            err = "%s: %s" % (type(e).__name__, e)
+        finally:
+            if job is not None:
+                try:
+                    job.close()
+                except Exception:                                              # noqa: BLE001
+                    pass
+        failed = allmax([0.0 if err is None else 1.0])[0] > 0
+        per = float(allmax([per_loc])[0])
+        ms = allmax([float(np.mean(ms)) if err is None else 0.0])[0]
+        if failed:
+            out[name] = {"workload": workload, "error": err or "failed on another rank"}
+            continue
         nloc, npost = hi - lo, nsteps - burnin
         rate = N * nsteps * per / (ms * 1e-3)
         bytes_launch = nloc * (nsteps * 16 * d + npost * (8 * d + 9))          # SURVEY.md 8d contract bytes, this rank
