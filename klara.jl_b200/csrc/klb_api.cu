@@ -308,8 +308,9 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
       return fail(KLB_EUNSUPPORTED, "maxndoublings <= %d (2^maxndoublings - 1 leapfrog steps per transition)", KLB_NUTS_MAXLEVELS);
     if (c.tuner == KLB_TUNER_ACCEPTANCE_RATE)
       return fail(KLB_EINVAL, "NUTS has sampler states for VanillaMCTuner and DualAveragingMCTuner only (src/samplers/NUTS.jl:271-345)");
-    if (c.target != KLB_TARGET_ISO && c.target != KLB_TARGET_SHIFTED_ISO && c.target != KLB_TARGET_ROSENBROCK)
-      return fail(KLB_EUNSUPPORTED, "the NUTS kernels cover the elementwise targets (iso, shifted iso, Rosenbrock)");
+    if (c.target == KLB_TARGET_DENSE)
+      return fail(KLB_EUNSUPPORTED, "the NUTS kernels cover the elementwise targets (iso, shifted iso, Rosenbrock) and the "
+                                    "logistic-regression target, not the dense-precision one");
   }
   // tuner asserts (VanillaMCTuner.jl:10-13, AcceptanceRateMCTuner.jl:31-35)
   if (c.period <= 0) return fail(KLB_EINVAL, "Adaptation period should be positive");

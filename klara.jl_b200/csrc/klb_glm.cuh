@@ -23,11 +23,26 @@
 //
 // Transitions: HMC iterate/HMC.jl:124-224 + samplers.jl:101-134, MALA iterate/MALA.jl:78-152,
 // MH iterate/MH.jl:72-141 (symmetric branch); tuner block and save as in klb_kernels.cuh.
+// NUTS (SAMPLER = 3; doc/examples/swiss/NUTS/{noadaptation,dualaveraging}/analytical.jl): the reference's multivariate
+// transition as klb_nuts.cuh resolves it (one moving point, one running momentum, the pristine initial momentum for a
+// direction that has not been used yet), evaluated by the chain's one thread: the moving point
+// carries its gradient (the cached pstate.gradlogtarget of the reference's one shared state object), so a leaf costs ONE
+// pass over the data (gradient and log-target of the new point share X*p).
 #pragma once
 #include "klb_kernels.cuh"
 
 #define KLB_GLM_MAXD 16
 #define KLB_GLM_THREADS 64
+#ifndef KLB_NUTS_MAXLEVELS
+#define KLB_NUTS_MAXLEVELS 10
+#endif
+
+// uniform number q of the transition: slot q of KLB_TAG_ACCEPT, consumed in the order the reference calls rand()
+__device__ __forceinline__ double glm_seq_uniform(const klb_stream& st, unsigned& q) {
+  uint64_t w0, w1;
+  klb_stream_draw(&st, q++, KLB_TAG_ACCEPT, 0u, &w0, &w1);
+  return klb_u01(w0);
+}
 
 struct GArgs {
   KArgs k;
@@ -214,7 +229,85 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
     glm_randn<DP>(st, d, tab, z);
     const double step = tn.step;
     const double h = __dmul_rn(0.5, step);
-    if (SAMPLER == 2) {
+    int ndoub = 0;
+    long long nuts_na = 1;
+    double nuts_a = klb_u2d(0x7FF8000000000000ULL);
+    if (SAMPLER == 3) {
+      // ---------------------------------------------------------------- NUTS   iterate/NUTS.jl:230-457, NUTS.jl:514-628, :781-927
+      double y[DP];                                                            // the running momentum (momentumprime)
+      double k0 = 0.0;
+#pragma unroll
+      for (int j = 0; j < DP; ++j) { k0 = dotacc(z[j], z[j], k0); xs[j] = x[j]; gs[j] = g[j]; y[j] = z[j]; }
+      const double oldh = __dsub_rn(lt_cur, __dmul_rn(0.5, k0));               // hamiltonian(job.pstate.logtarget, momentum)   :244
+      unsigned q = 0u;
+      const double u = __dadd_rn(klb_log(glm_seq_uniform(st, q), tab), oldh);  // log(rand()) + oldhamiltonian     :261
+      bool used_plus = false, used_minus = false, y_is_initial = true, s = true;
+      long long n = 1;
+      double lt_e = lt_cur;
+      while (s && ndoub < A.nuts_maxndoublings) {
+        const bool fwd = glm_seq_uniform(st, q) < 0.5;                         // v = rand(Bool) ? 1 : -1            :264
+        if (!(fwd ? used_plus : used_minus) && !y_is_initial) {
+#pragma unroll
+          for (int j = 0; j < DP; ++j) y[j] = z[j];
+        }
+        y_is_initial = false;
+        const double step_v = fwd ? step : -step;                              // v*sstate.tune.step
+        const double hv = __dmul_rn(0.5, step_v);
+        // ---- build_tree!(..., ndoub): up to 2^ndoub leaves; the recursion is unwound after every leaf
+        double saved_a[KLB_NUTS_MAXLEVELS + 1];
+        long long saved_na[KLB_NUTS_MAXLEVELS + 1];
+        long long nprime = 0;
+        bool sprime = false;
+        for (unsigned leaf = 0u;; ++leaf) {
+#pragma unroll
+          for (int j = 0; j < DP; ++j) {                                       // leapfrog!  samplers.jl:122-134    NUTS.jl:527
+            y[j] = Ar<FMA>::ma(hv, gs[j], y[j]);
+            xs[j] = Ar<FMA>::ma(step_v, y[j], xs[j]);
+          }
+          Glm<DP, FMA>::template eval<true, true>(G, Xs, ys, tab, d, xs, lt_e, gs);   // gradlogtarget!, logtarget!(pstateprime)
+          double k1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < DP; ++j) { y[j] = Ar<FMA>::ma(hv, gs[j], y[j]); k1 = dotacc(y[j], y[j], k1); }
+          const double hprime = __dsub_rn(lt_e, __dmul_rn(0.5, k1));
+          long long nn = (u <= hprime) ? 1 : 0;                                // :532
+          const bool ss = u < __dadd_rn((double)A.nuts_maxdelta, hprime);      // :533
+          double a = 0.0;
+          if (A.tuner == 2) {                                                  // min(1, exp(H' - H0))               :818
+            const double ex = klb_exp(__dsub_rn(hprime, oldh), tab);
+            a = (ex != ex) ? ex : (ex < 1.0 ? ex : 1.0);
+          }
+          long long nna = 1;
+          bool descend = false;
+          for (int k = 1; k <= ndoub; ++k) {
+            if ((leaf >> (k - 1)) & 1u) {             // a second half is complete: its rand(), n' doubles, sums add up
+              (void)glm_seq_uniform(st, q);
+              nn = 2 * nn;
+              a = __dadd_rn(saved_a[k], a);
+              nna = saved_na[k] + nna;
+            } else if (ss) {                          // a first half that did not stop: on to its second half
+              saved_a[k] = a; saved_na[k] = nna;
+              descend = true;
+              break;
+            }                                         // a first half that stopped is returned as it is
+          }
+          if (!descend) { nprime = nn; sprime = ss; nuts_a = a; nuts_na = nna; break; }
+        }
+        if (fwd) used_plus = true; else used_minus = true;
+        if (ndoub >= 1) { used_plus = true; used_minus = true; }               // NUTS.jl:541-549 rebinds both ends
+        if (sprime) {
+          const double r = glm_seq_uniform(st, q);
+          if (r < __ddiv_rn((double)nprime, (double)n)) {                      // job.pstate <- pstateprime          :355-375
+#pragma unroll
+            for (int j = 0; j < DP; ++j) { x[j] = xs[j]; g[j] = gs[j]; }
+            lt_cur = lt_e;
+            accept = true;
+          }
+        }
+        ndoub += 1;
+        n += nprime;
+        s = sprime;                                                            // && !uturn(E - E, ...) = true       :377-381
+      }
+    } else if (SAMPLER == 2) {
       // ---------------------------------------------------------------- HMC
       double k0 = 0.0;
 #pragma unroll
@@ -282,9 +375,12 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
     }
 
     if (A.counters_on) { tn.proposed += 1; if (accept) tn.accepted += 1; }
-    if (SAMPLER == 2 && A.tuner == 2) da_block<false>(A, c, tn, nl, a_prob, tab, true);
+    if (SAMPLER == 3) {                                        // iterate/NUTS.jl:402-447: tune! is fed a/na of the last doubling
+      if (A.tuner == 2) da_block<false, 0, true>(A, c, tn, (int)nuts_na, __ddiv_rn(nuts_a, (double)nuts_na), tab, true);
+      else tuner_block<2>(A, tn, tab, c);
+    } else if (SAMPLER == 2 && A.tuner == 2) da_block<false>(A, c, tn, nl, a_prob, tab, true);
     else tuner_block<SAMPLER>(A, tn, tab, c);
-    if (accept) {
+    if (SAMPLER != 3 && accept) {                              // (NUTS moved job.pstate inside its loop)
 #pragma unroll
       for (int j = 0; j < DP; ++j) { x[j] = xs[j]; if (SAMPLER != 0) g[j] = gs[j]; }
       lt_cur = lt_new;
@@ -297,6 +393,7 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
         if (A.out_grad) glm_store<DP>(g, A.out_grad + col * A.ld, d);
         if (A.out_lt) A.out_lt[col] = lt_cur;
         if (A.out_accept) A.out_accept[col] = accept ? 1 : 0;
+        if (SAMPLER == 3 && A.out_ndoublings) A.out_ndoublings[col] = (unsigned char)ndoub;
         count += 1;
       }
       thin = (thin + 1 == A.thinning) ? 0 : thin + 1;

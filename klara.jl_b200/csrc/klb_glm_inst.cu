@@ -35,6 +35,8 @@ static int glm_any(const GArgs* G, int sampler, int fma, int dp, size_t dyn, int
     case 3: return glm_dp<1, true>(G, dp, dyn, regs, bps, s);
     case 4: return glm_dp<2, false>(G, dp, dyn, regs, bps, s);
     case 5: return glm_dp<2, true>(G, dp, dyn, regs, bps, s);
+    case 6: return glm_dp<3, false>(G, dp, dyn, regs, bps, s);   // NUTS
+    case 7: return glm_dp<3, true>(G, dp, dyn, regs, bps, s);
   }
   return -1;
 }

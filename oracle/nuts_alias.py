@@ -80,6 +80,26 @@ class Target:
         ps.gradlogtarget = -2.0 * z
 
 
+class LogitTarget:
+    """the closures of doc/examples/swiss/NUTS/*/analytical.jl:11-20, v = [lambda, X, y, p], in numpy / libm:
+    ploglikelihood = dot(Xp, y) - sum(log.(1+exp.(Xp))), plogprior = -0.5*(dot(p, p)/lambda + length(p)*log(2*pi*lambda)),
+    pgradlogtarget = X'*(y - 1./(1+exp.(-X*p))) - p/lambda;  logtarget = loglikelihood + logprior"""
+
+    def __init__(self, X, y, lam):
+        self.X, self.y, self.lam = np.asarray(X, dtype=np.float64), np.asarray(y, dtype=np.float64), float(lam)
+
+    def logtarget(self, ps):
+        p = ps.value
+        Xp = self.X @ p
+        loglik = float(np.dot(Xp, self.y)) - float(np.sum(np.log(1 + np.exp(Xp))))
+        logprior = -0.5 * (float(np.dot(p, p)) / self.lam + p.size * np.log(2 * np.pi * self.lam))
+        ps.logtarget = loglik + logprior
+
+    def gradlogtarget(self, ps):
+        p = ps.value
+        ps.gradlogtarget = self.X.T @ (self.y - 1.0 / (1 + np.exp(-(self.X @ p)))) - p / self.lam
+
+
 def hamiltonian(logtarget, momentum):                    # samplers.jl:103
     return logtarget - 0.5 * float(np.dot(momentum, momentum))
 

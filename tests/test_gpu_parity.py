@@ -781,6 +781,24 @@ def test_nuts_bit_exact(K, target, dim, tuner, maxnd, maxdelta, arith):
         assert nd.min() < maxnd                        # some trees stopped before the last doubling
 
 
+@pytest.mark.parametrize("dim,tuner,maxnd,maxdelta,step,arith", [
+    (4, "dualavg", 5, 1000, 0.15, "reference"), (4, "vanilla", 4, 1000, 0.2, "fma"), (3, "vanilla", 6, 1000, 0.1, "reference"),
+    (2, "dualavg", 3, 1000, 0.3, "fma"), (7, "dualavg", 4, 1000, 0.1, "reference"), (8, "vanilla", 5, 3, 0.3, "reference"),
+    (16, "vanilla", 3, 1000, 0.08, "fma"), (13, "dualavg", 4, 1000, 0.08, "reference")])
+def test_nuts_logit_bit_exact(K, dim, tuner, maxnd, maxdelta, step, arith):
+    """NUTS on the Bayesian logistic-regression target (doc/examples/swiss/NUTS/{noadaptation,dualaveraging}/analytical.jl):
+    klb_glm_kernel<3, DP, FMA>, one thread per chain, every padded dimension, both tuners, trees that stop early"""
+    job, cfg, x0, tp, sg = build_pair(K, "NUTS", "logit", nchains=70, dim=dim, nsteps=30, burnin=9, thinning=2, step=step,
+                                      seed=5150 + dim, arith=arith, tuner=tuner, target_rate=0.651, nadapt=20, period=5,
+                                      verbose=(dim % 2 == 0), monitor=("value", "logtarget", "gradlogtarget"),
+                                      diagnostics=("accept", "ndoublings"), maxdelta=maxdelta, maxndoublings=maxnd)
+    out, ref = compare_run(job, cfg, x0, tp, sg)
+    nd = ref["ndoublings"]
+    assert nd.min() >= 1 and nd.max() <= maxnd
+    if maxdelta < 10:
+        assert nd.min() < nd.max()                     # some trees stopped before the last doubling
+
+
 def test_nuts_chunks_shards_and_run_host(K, O):
     """one launch per transition == one launch; 2 shards == 1 job; the pipelined host call == the three calls"""
     kw = dict(nchains=26, dim=130, nsteps=30, burnin=8, step=0.25, seed=77, tuner="dualavg", target_rate=0.65, nadapt=20,

@@ -91,16 +91,26 @@ class OracleDraws:
 
 @pytest.mark.parametrize("target,dim,step,maxnd,maxdelta", [("iso", 5, 0.3, 5, 1000), ("iso", 70, 0.12, 4, 1000),
                                                             ("shifted", 9, 0.4, 6, 1000), ("iso", 3, 1.4, 5, 2),
-                                                            ("shifted", 130, 0.1, 3, 1000)])
+                                                            ("shifted", 130, 0.1, 3, 1000),
+                                                            ("logit", 4, 0.2, 5, 1000), ("logit", 7, 0.3, 5, 3)])
 def test_c_oracle_follows_the_state_machine(target, dim, step, maxnd, maxdelta):
     N, nsteps, seed = 6, 25, 424242
     rng = np.random.default_rng(dim)
     mu = rng.standard_normal(dim) if target == "shifted" else None
     x0 = rng.standard_normal((N, dim))
-    cfg = O.make_config(O.NUTS, O.SHIFTED if target == "shifted" else O.ISO, N, dim, nsteps, 0, step=step, monitor=3,
-                        diagnostics=3, seed=seed, maxdelta=maxdelta, maxndoublings=maxnd)
-    ref = O.run(cfg, x0, tparams=mu)
-    tgt = NA.Target(mu)
+    if target == "logit":                 # doc/examples/swiss/NUTS/*/analytical.jl: data-dependent target, sequential sums (nv = 0)
+        X = rng.standard_normal((200, dim))
+        X = (X - X.mean(0)) / X.std(0, ddof=1)
+        y = (rng.uniform(size=200) < 1 / (1 + np.exp(-X @ rng.standard_normal(dim)))).astype(np.float64)
+        cfg = O.make_config(O.NUTS, O.LOGIT, N, dim, nsteps, 0, step=step, monitor=3, diagnostics=3, seed=seed,
+                            maxdelta=maxdelta, maxndoublings=maxnd, nv=0)
+        ref = O.run(cfg, x0, tparams=O.logit_params(X, y, 100.0))
+        tgt = NA.LogitTarget(X, y, 100.0)
+    else:
+        cfg = O.make_config(O.NUTS, O.SHIFTED if target == "shifted" else O.ISO, N, dim, nsteps, 0, step=step, monitor=3,
+                            diagnostics=3, seed=seed, maxdelta=maxdelta, maxndoublings=maxnd)
+        ref = O.run(cfg, x0, tparams=mu)
+        tgt = NA.Target(mu)
     checked = 0
     for c in range(N):
         q = _fresh(tgt, x0[c])
