@@ -84,6 +84,8 @@ extern "C" {
 #define KLB_MONITOR_GRADLOGTARGET 4u
 #define KLB_DIAG_ACCEPT 1u
 #define KLB_DIAG_NDOUBLINGS 2u /* NUTS: the :ndoublings diagnostic (src/samplers/NUTS.jl:285, iterate/NUTS.jl:389-391) */
+#define KLB_DIAG_NUTS_A 4u     /* NUTS + DualAveragingMCTuner: :a  (src/samplers/NUTS.jl:317,344, iterate/NUTS.jl:393-395) */
+#define KLB_DIAG_NUTS_NA 8u    /* NUTS + DualAveragingMCTuner: :na (iterate/NUTS.jl:397-399) */
 
 /* outopts[:destination]: :nstate (device-resident buffer) or :none */
 #define KLB_DEST_NSTATE 0
@@ -114,6 +116,10 @@ extern "C" {
                                                                211-221, MALA.jl:138-148, MH.jl:126-139); nperiods = burnin / period
                                                                (nadapt / period for DualAveragingMCTuner); NaN = period not closed */
 #define KLB_OUT_NDOUBLINGS 12    /* uint8   npost x nchains    NUTS: doublings of the stored transitions (KLB_DIAG_NDOUBLINGS) */
+#define KLB_OUT_NUTS_A 13        /* double  npost x nchains    NUTS + dual averaging, :a: sum of min(1, exp(H' - H0)) over the leaves of
+                                                               the last doubling of the stored transitions (KLB_DIAG_NUTS_A) */
+#define KLB_OUT_NUTS_NA 14       /* int32   npost x nchains    ... and :na, the number of those leaves (KLB_DIAG_NUTS_NA); the example's
+                                                               mean(diags[:a]./diags[:na]), doc/examples/swiss/NUTS/dualaveraging/analytical.jl:50 */
 #define KLB_OUT_TUNE_DA 10       /* double  8 x nchains        DualAveragingMCTune: λ, μ, εbar, hbar, hweight, εweight,
                                                                nleaps of the last transition, sstate.count */
 

@@ -166,7 +166,7 @@ function BasicMCJob(model::GenericModel, sampler, range::BasicMCRange, v0::Dict;
                   sampler isa HMC ? sampler.nleaps : 1,
                   (tuner isa AcceptanceRateMCTuner || da) ? tuner.targetrate : 0.5,
                   tuner isa AcceptanceRateMCTuner ? tuner.k : 7.0, tuner.period, tuner.verbose,
-                  mon, ((:accept in diags) ? 1 : 0) | ((:ndoublings in diags) ? 2 : 0), dest == :none ? 1 : 0, seed, chain_offset, device,
+                  mon, ((:accept in diags) ? 1 : 0) | ((:ndoublings in diags) ? 2 : 0) | ((:a in diags) ? 4 : 0) | ((:na in diags) ? 8 : 0), dest == :none ? 1 : 0, seed, chain_offset, device,
                   tuner isa AcceptanceRateMCTuner ? tuner.score : 0,
                   da ? tuner.nadapt : 0, da ? tuner.t0 : 10, da ? tuner.ε0bar : 1.0, da ? tuner.h0bar : 0.0,
                   da ? tuner.γ : 0.05, da ? tuner.κ : 0.75,
@@ -233,7 +233,9 @@ function output(job::BasicMCJob)
    logtarget = :logtarget in job.monitor ? fetch!(job, 1, Array{Float64}(undef, P, job.nchains)) : nothing,
    gradlogtarget = :gradlogtarget in job.monitor ? fetch!(job, 2, Array{Float64}(undef, job.dim, P, job.nchains)) : nothing,
    accept = :accept in job.diagnostics ? fetch!(job, 3, Array{UInt8}(undef, P, job.nchains)) .!= 0 : nothing,
-   ndoublings = :ndoublings in job.diagnostics ? Int.(fetch!(job, 12, Array{UInt8}(undef, P, job.nchains))) : nothing)   # NUTS
+   ndoublings = :ndoublings in job.diagnostics ? Int.(fetch!(job, 12, Array{UInt8}(undef, P, job.nchains))) : nothing,   # NUTS
+   a = :a in job.diagnostics ? fetch!(job, 13, Array{Float64}(undef, P, job.nchains)) : nothing,          # NUTS + DualAveragingMCTuner
+   na = :na in job.diagnostics ? Int.(fetch!(job, 14, Array{Int32}(undef, P, job.nchains))) : nothing)
 end
 
 # ess(output(job)): effective sample size (IMSE) per coordinate and chain, computed on the device

@@ -19,11 +19,12 @@ TUNER_VANILLA, TUNER_ACCEPTANCE_RATE, TUNER_DUAL_AVERAGING = 0, 1, 2
 SCORE_LOGISTIC, SCORE_ERF = 0, 1
 ARITH_REFERENCE, ARITH_FMA = 0, 1
 MONITOR_VALUE, MONITOR_LOGTARGET, MONITOR_GRADLOGTARGET = 1, 2, 4
-DIAG_ACCEPT, DIAG_NDOUBLINGS = 1, 2
+DIAG_ACCEPT, DIAG_NDOUBLINGS, DIAG_NUTS_A, DIAG_NUTS_NA = 1, 2, 4, 8
 DEST_NSTATE, DEST_NONE = 0, 1
 PARAM_MU, PARAM_C, PARAM_SIGMA, PARAM_ROSEN, PARAM_LOGIT_X, PARAM_LOGIT_Y, PARAM_LOGIT_LAMBDA = 0, 1, 2, 3, 4, 5, 6
 (OUT_VALUE, OUT_LOGTARGET, OUT_GRADLOGTARGET, OUT_ACCEPT, OUT_STATE, OUT_STATE_LOGTARGET,
- OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS, OUT_TUNE_DA, OUT_TUNE_RATES, OUT_NDOUBLINGS) = range(13)
+ OUT_TUNE_STEP, OUT_TUNE_COUNTERS, OUT_TUNE_RATE, OUT_ESS, OUT_TUNE_DA, OUT_TUNE_RATES, OUT_NDOUBLINGS, OUT_NUTS_A,
+ OUT_NUTS_NA) = range(15)
 PEAK_FP64, PEAK_DMMA = 0, 1
 GATHER_HANDLE_BYTES = 128
 (STAT_MEAN, STAT_MCVAR_IID, STAT_MCVAR_IMSE, STAT_ESS, STAT_IACT, STAT_ACCEPTANCE, STAT_ACCEPTANCE_VALUE) = range(7)

@@ -292,6 +292,9 @@ class BasicContMuvParameterNState:
 
 
 _MONITOR_BITS = {"value": L.MONITOR_VALUE, "logtarget": L.MONITOR_LOGTARGET, "gradlogtarget": L.MONITOR_GRADLOGTARGET}
+_DIAG_BITS = {"accept": L.DIAG_ACCEPT, "ndoublings": L.DIAG_NDOUBLINGS, "a": L.DIAG_NUTS_A, "na": L.DIAG_NUTS_NA}
+_DIAG_FIELDS = {"accept": (L.OUT_ACCEPT, np.uint8), "ndoublings": (L.OUT_NDOUBLINGS, np.uint8), "a": (L.OUT_NUTS_A, np.float64),
+                "na": (L.OUT_NUTS_NA, np.int32)}
 
 
 def _ptr(a):
@@ -341,7 +344,10 @@ class BasicMCJob:
             if m not in _MONITOR_BITS:
                 raise KeyError("cannot monitor %r on the device path" % (m,))
         for dg in oo["diagnostics"]:
-            if dg != "accept" and not (dg == "ndoublings" and isinstance(sampler, NUTS)):
+            # :accept everywhere; :ndoublings for NUTS (src/samplers/NUTS.jl:285); :a and :na for NUTS with
+            # DualAveragingMCTuner (NUTS.jl:317,344)
+            nuts_da = isinstance(sampler, NUTS) and isinstance(tuner, DualAveragingMCTuner)
+            if dg != "accept" and not (dg == "ndoublings" and isinstance(sampler, NUTS)) and not (dg in ("a", "na") and nuts_da):
                 raise KeyError("unknown diagnostic %r" % (dg,))
         self.outopts = oo
 
@@ -378,8 +384,7 @@ class BasicMCJob:
         cfg.score = getattr(tuner, "score_code", L.SCORE_LOGISTIC)
         cfg.period, cfg.verbose = tuner.period, int(tuner.verbose)
         cfg.monitor = sum(_MONITOR_BITS[m] for m in set(oo["monitor"]))
-        cfg.diagnostics = (L.DIAG_ACCEPT if "accept" in oo["diagnostics"] else 0) | \
-            (L.DIAG_NDOUBLINGS if "ndoublings" in oo["diagnostics"] else 0)
+        cfg.diagnostics = sum(_DIAG_BITS[k] for k in set(oo["diagnostics"]))
         cfg.nuts_maxdelta, cfg.nuts_maxndoublings = getattr(sampler, "maxdelta", 0), getattr(sampler, "maxndoublings", 0)
         cfg.destination = L.DEST_NONE if oo["destination"] == "none" else L.DEST_NSTATE
         cfg.seed, cfg.chain_offset, cfg.device = seed, chain_offset, device
@@ -594,9 +599,10 @@ class BasicMCJob:
             ns.gradlogtarget = self._fetch(L.OUT_GRADLOGTARGET, (N, P, d))
         diag = [k for k in self.outopts["diagnostics"]]
         if diag:
-            # one diagnostic: (nchains, npost); several (NUTS: accept, ndoublings): (nchains, nkeys, npost), the reference's
-            # nkeys x npost matrix per chain, in the order of outopts[:diagnostics]
-            vals = [self._fetch({"accept": L.OUT_ACCEPT, "ndoublings": L.OUT_NDOUBLINGS}[k], (N, P), np.uint8) for k in diag]
+            # one diagnostic: (nchains, npost); several (NUTS: accept, ndoublings, a, na): (nchains, nkeys, npost), the
+            # reference's nkeys x npost matrix per chain (an Array{Any} there), in the order of outopts[:diagnostics]; numpy
+            # promotes the stack to float64 when :a is among the keys (every count is exactly representable)
+            vals = [self._fetch(_DIAG_FIELDS[k][0], (N, P), _DIAG_FIELDS[k][1]) for k in diag]
             ns.diagnostickeys = diag
             ns.diagnosticvalues = vals[0] if len(vals) == 1 else np.stack(vals, axis=1)
         if self.single:

@@ -90,6 +90,8 @@ struct klb_job {
   double* out_grad;
   unsigned char* out_accept;
   unsigned char* out_ndoublings;   // NUTS, KLB_DIAG_NDOUBLINGS
+  double* out_nuts_a;              // NUTS + DualAveragingMCTuner, KLB_DIAG_NUTS_A
+  int* out_nuts_na;                // NUTS + DualAveragingMCTuner, KLB_DIAG_NUTS_NA
   double* mu;
   double* sigma;
   double* Cm;       // dense precision matrix (d x d), KLB_TARGET_DENSE only
@@ -198,6 +200,7 @@ static void free_job(klb_job* j) {
   cudaFree(j->tune_rates);
   if (j->flag_host) cudaFreeHost(j->flag_host);
   cudaFree(j->out_value); cudaFree(j->out_lt); cudaFree(j->out_grad); cudaFree(j->out_accept); cudaFree(j->out_ndoublings);
+  cudaFree(j->out_nuts_a); cudaFree(j->out_nuts_na);
   cudaFree(j->mu); cudaFree(j->sigma); cudaFree(j->Cm); cudaFree(j->tab); cudaFree(j->flag); cudaFree(j->ess); cudaFree(j->accrate);
   cudaFree(j->gX); cudaFree(j->gy);
   for (int q = 0; q < 5; ++q) if (q != KLB_STAT_ESS) cudaFree(j->stat[q]);
@@ -226,6 +229,7 @@ static void fill_args(const klb_job* j, KArgs& A) {
   A.state = j->state; A.lt = j->lt;
   A.tune_step = j->tune_step; A.tune_cnt = j->tune_cnt; A.tune_rate = j->tune_rate;
   A.out_value = j->out_value; A.out_lt = j->out_lt; A.out_grad = j->out_grad; A.out_accept = j->out_accept;
+  A.out_nuts_a = j->out_nuts_a; A.out_nuts_na = j->out_nuts_na;
   A.out_ndoublings = j->out_ndoublings; A.nuts_maxdelta = c.nuts_maxdelta; A.nuts_maxndoublings = c.nuts_maxndoublings;
   A.mu = j->mu; A.sigma = j->sigma; A.tab = j->tab;
   A.ra = j->rosen[0]; A.rb = j->rosen[1]; A.rscale = j->rosen[2];
@@ -321,7 +325,10 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
   if ((c.monitor & KLB_MONITOR_GRADLOGTARGET) && c.sampler == KLB_SAMPLER_MH)
     return fail(KLB_EINVAL, "MH does not evaluate gradlogtarget; it cannot be monitored");
   if (c.monitor & ~7u) return fail(KLB_EINVAL, "unknown monitor bits");
-  if (c.diagnostics & ~3u) return fail(KLB_EINVAL, "unknown diagnostics bits");
+  if (c.diagnostics & ~15u) return fail(KLB_EINVAL, "unknown diagnostics bits");
+  if ((c.diagnostics & (KLB_DIAG_NUTS_A | KLB_DIAG_NUTS_NA)) &&
+      !(c.sampler == KLB_SAMPLER_NUTS && c.tuner == KLB_TUNER_DUAL_AVERAGING))
+    return fail(KLB_EINVAL, ":a and :na are diagnostics of NUTS with DualAveragingMCTuner (src/samplers/NUTS.jl:317,344)");
   if ((c.diagnostics & KLB_DIAG_NDOUBLINGS) && c.sampler != KLB_SAMPLER_NUTS)
     return fail(KLB_EINVAL, ":ndoublings is a diagnostic of NUTS");
   if (c.destination != KLB_DEST_NSTATE && c.destination != KLB_DEST_NONE) return fail(KLB_EINVAL, "unknown destination");
@@ -389,6 +396,8 @@ int klb_job_create(const klb_config* cfg, klb_job** out) {
     if (c.monitor & KLB_MONITOR_GRADLOGTARGET) CKJ(cudaMalloc(&j->out_grad, N * P * d * sizeof(double)));
     if (c.diagnostics & KLB_DIAG_ACCEPT) CKJ(cudaMalloc(&j->out_accept, N * P));
     if (c.diagnostics & KLB_DIAG_NDOUBLINGS) CKJ(cudaMalloc(&j->out_ndoublings, N * P));
+    if (c.diagnostics & KLB_DIAG_NUTS_A) CKJ(cudaMalloc(&j->out_nuts_a, N * P * sizeof(double)));
+    if (c.diagnostics & KLB_DIAG_NUTS_NA) CKJ(cudaMalloc(&j->out_nuts_na, N * P * sizeof(int)));
   }
   j->dense = c.target == KLB_TARGET_DENSE;
   if (j->dense) {                        // rows padded to the even length of the state columns (zero pad column)
@@ -505,6 +514,8 @@ static void slice_args(const klb_job* j, KArgs& A, long long c0, long long nc) {
   if (A.out_grad) A.out_grad += c0 * P * ld;
   if (A.out_accept) A.out_accept += c0 * P;
   if (A.out_ndoublings) A.out_ndoublings += c0 * P;
+  if (A.out_nuts_a) A.out_nuts_a += c0 * P;
+  if (A.out_nuts_na) A.out_nuts_na += c0 * P;
   A.nchains = nc;
   A.chain_offset += (unsigned long long)c0;
 }
@@ -888,6 +899,8 @@ static int field_ptr(klb_job* j, int field, void** p, size_t* nb, size_t* cols) 
     case KLB_OUT_GRADLOGTARGET: *p = j->out_grad; *nb = N * P * d * 8; *cols = N * P; break;
     case KLB_OUT_ACCEPT: *p = j->out_accept; *nb = N * P; break;
     case KLB_OUT_NDOUBLINGS: *p = j->out_ndoublings; *nb = N * P; break;
+    case KLB_OUT_NUTS_A: *p = j->out_nuts_a; *nb = N * P * 8; break;
+    case KLB_OUT_NUTS_NA: *p = j->out_nuts_na; *nb = N * P * 4; break;
     case KLB_OUT_STATE: *p = j->state; *nb = N * d * 8; *cols = N; break;
     case KLB_OUT_STATE_LOGTARGET: *p = j->lt; *nb = N * 8; break;
     case KLB_OUT_TUNE_STEP: *p = j->tune_step; *nb = N * 8; break;

@@ -1,6 +1,11 @@
 // klb_aux.cu -- small support kernels: tuner-record reset and the device self-tests that the
 // parity suite uses to compare the device math/RNG primitives with the oracle bit by bit.
+#include <cstdlib>
 #include "klb_kernels.cuh"
+
+#ifndef KLB_ESS_DEFAULT_VARIANT
+#define KLB_ESS_DEFAULT_VARIANT 0   /* 0: klb_ess_tile_kernel (eight lags per pass, centred tile) */
+#endif
 
 // tuner_state / reset!(tune, sampler, tuner):  (step, 0, 0, tuner.period, NaN)
 //                                              src/samplers/samplers.jl:29-45, 79-90
@@ -239,6 +244,123 @@ klb_ess_tile_kernel(const double* __restrict__ value, long long ld, long long np
   stat_store(S, c * dim + i, o_mean, o_iid, o_imse, out, o_iact);
 }
 
+// The same estimator with a window of WIN lags per pass and, with RAW, the samples left as they were staged (the
+// centring pass over the tile -- a load, a subtraction and a store per sample -- is replaced by a subtraction where a
+// sample is read: z_t = v_t - mean is the same double either way).  Why: with eight lags per pass the warp's slowest
+// lane decides how many passes run (Geyer's rule stops at the first non-positive pair, and with 100 samples the
+// estimated autocovariances are noisy: three or four passes per warp are common), and every pass reads the series
+// twice from shared memory -- the kernel was bound by the shared-memory pipe, not by HBM or the fp64 pipe.  A pass over
+// WIN lags costs the same 2 loads per step as a pass over 8.  Trips of WIN steps keep the window slots compile-time
+// constants; the trips that reach the end of the series take predicated loads (an out-of-range sample counts as 0:
+// its products are +-0 and leave the sums as they are).  Same sums in the same order as klb_ess_tile_kernel.
+template <int TC, int WIN, bool RAW>
+__global__ void __launch_bounds__(TC)
+klb_ess_win_kernel(const double* __restrict__ value, long long ld, long long npost, int dim, const KlbStatPtrs S) {
+  extern __shared__ double tile[];                              // [npost][TC]
+  const int i = blockIdx.x * TC + threadIdx.x;
+  const long long c = blockIdx.y;
+  const bool act = i < dim;
+  const double* v = value + c * npost * ld + (act ? i : 0);
+  const int n = (int)npost;
+  if (act) {
+    for (int t = 0; t < n; ++t) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(tile + t * TC + threadIdx.x);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(v + (long long)t * ld) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  if (!act) return;                                              // every thread only ever reads its own column
+  double* const z = tile + threadIdx.x;
+  double s = 0.0;
+  for (int t = 0; t < n; ++t) s = __dadd_rn(s, z[t * TC]);
+  const double qnan = klb_u2d(0x7FF8000000000000ULL);
+  double out = qnan, o_iid = qnan, o_imse = qnan, o_iact = qnan;
+  const double o_mean = n >= 1 ? __ddiv_rn(s, (double)n) : qnan;
+  if (n >= 4) {
+    const double dn = (double)n;
+    const double mu = o_mean;
+    if (!RAW)
+      for (int t = 0; t < n; ++t) z[t * TC] = __dsub_rn(z[t * TC], mu);
+#define KLB_ESS_Z(idx) (RAW ? __dsub_rn(z[(idx) * TC], mu) : z[(idx) * TC])
+    const int k = (n - 2) / 2;
+    double sumg = 0.0, gprev = 0.0, s0 = 0.0;
+    bool done = false;
+    for (int L = 0; !done && L <= 2 * k + 1; L += WIN) {
+      double acc[WIN], w[WIN];
+#pragma unroll
+      for (int q = 0; q < WIN; ++q) { acc[q] = 0.0; w[q] = (L + q < n) ? KLB_ESS_Z(L + q) : 0.0; }
+      int t = 0;
+      for (; t + L + 2 * WIN - 1 < n; t += WIN) {               // every index of the trip lies inside the series
+#pragma unroll
+        for (int h = 0; h < WIN; h += 8) {
+          double zt[8], wn[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { zt[u] = KLB_ESS_Z(t + h + u); wn[u] = KLB_ESS_Z(t + h + u + L + WIN); }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) acc[q] = __fma_rn(zt[u], w[(h + u + q) & (WIN - 1)], acc[q]);
+            w[(h + u) & (WIN - 1)] = wn[u];
+          }
+        }
+      }
+      for (; t + L < n; t += WIN) {                             // the trips that reach the end of the series
+#pragma unroll
+        for (int h = 0; h < WIN; h += 8) {
+          double zt[8], wn[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            zt[u] = (t + h + u < n) ? KLB_ESS_Z(t + h + u) : 0.0;
+            wn[u] = (t + h + u + L + WIN < n) ? KLB_ESS_Z(t + h + u + L + WIN) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+#pragma unroll
+            for (int q = 0; q < WIN; ++q) acc[q] = __fma_rn(zt[u], w[(h + u + q) & (WIN - 1)], acc[q]);
+            w[(h + u) & (WIN - 1)] = wn[u];
+          }
+        }
+      }
+#undef KLB_ESS_Z
+      if (L == 0) s0 = acc[0];
+#pragma unroll
+      for (int q = 0; q < WIN / 2; ++q) {
+        const int j = L / 2 + q;
+        if (!done && j <= k) {
+          double g = __dadd_rn(__ddiv_rn(acc[2 * q], dn), __ddiv_rn(acc[2 * q + 1], dn));
+          if (g <= 0.0) done = true;
+          else {
+            if (j > 0 && g > gprev) g = gprev;
+            sumg = __dadd_rn(sumg, g);
+            gprev = g;
+          }
+        }
+      }
+    }
+    const double iidvar = __ddiv_rn(__ddiv_rn(s0, (double)(n - 1)), dn);
+    const double acv0 = __ddiv_rn(s0, dn);
+    const double mcvar = __ddiv_rn(__dadd_rn(-acv0, __dmul_rn(2.0, sumg)), dn);
+    out = __ddiv_rn(__dmul_rn(dn, iidvar), mcvar);
+    o_iid = iidvar; o_imse = mcvar; o_iact = __ddiv_rn(mcvar, iidvar);
+  }
+  stat_store(S, c * dim + i, o_mean, o_iid, o_imse, out, o_iact);
+}
+
+template <int TC, int WIN, bool RAW>
+static bool launch_ess_win(const double* value, long long ld, long long npost, long long nchains, int dim,
+                           const KlbStatPtrs& S, cudaStream_t s) {
+  const size_t sm = (size_t)npost * TC * sizeof(double);
+  if (sm > (size_t)(100 * 1024) * TC / 128) return false;         // 2 CTAs of 128 series per SM, or 4 of 64, or 8 of 32
+  auto kern = klb_ess_win_kernel<TC, WIN, RAW>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  dim3 grid((unsigned)((dim + TC - 1) / TC), (unsigned)nchains);
+  kern<<<grid, TC, sm, s>>>(value, ld, npost, dim, S);
+  return true;
+}
+
 template <int TC>
 static bool launch_ess_tile(const double* value, long long ld, long long npost, long long nchains, int dim,
                             const KlbStatPtrs& S, cudaStream_t s) {
@@ -258,6 +380,20 @@ static bool launch_ess_tile(const double* value, long long ld, long long npost, 
 void klb_launch_stats(const double* value, long long ld, long long npost, long long nchains, int dim,
                       double* const stats[5], cudaStream_t s) {
   const KlbStatPtrs S = {stats[0], stats[1], stats[2], stats[3], stats[4]};
+  // KLB_ESS_VARIANT (experiments, tools/ess_variants.py): window of lags per pass / raw or centred tile / series per CTA
+  const char* ev = getenv("KLB_ESS_VARIANT");
+  const int variant = ev ? atoi(ev) : KLB_ESS_DEFAULT_VARIANT;
+  switch (variant) {
+    case 1: if (launch_ess_win<128, 8, true>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 2: if (launch_ess_win<128, 16, false>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 3: if (launch_ess_win<128, 16, true>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 4: if (launch_ess_win<128, 32, false>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 5: if (launch_ess_win<128, 32, true>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 6: if (launch_ess_win<64, 16, true>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 7: if (launch_ess_win<32, 16, true>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 8: if (launch_ess_win<64, 32, true>(value, ld, npost, nchains, dim, S, s)) return; break;
+    default: break;
+  }
   if (launch_ess_tile<128>(value, ld, npost, nchains, dim, S, s)) return;
   if (launch_ess_tile<64>(value, ld, npost, nchains, dim, S, s)) return;
   if (launch_ess_tile<32>(value, ld, npost, nchains, dim, S, s)) return;

@@ -394,6 +394,8 @@ __global__ void __launch_bounds__(KLB_GLM_THREADS) klb_glm_kernel(const GArgs G)
         if (A.out_lt) A.out_lt[col] = lt_cur;
         if (A.out_accept) A.out_accept[col] = accept ? 1 : 0;
         if (SAMPLER == 3 && A.out_ndoublings) A.out_ndoublings[col] = (unsigned char)ndoub;
+        if (SAMPLER == 3 && A.out_nuts_a) A.out_nuts_a[col] = nuts_a;          // :a, :na        iterate/NUTS.jl:393-399
+        if (SAMPLER == 3 && A.out_nuts_na) A.out_nuts_na[col] = (int)nuts_na;
         count += 1;
       }
       thin = (thin + 1 == A.thinning) ? 0 : thin + 1;

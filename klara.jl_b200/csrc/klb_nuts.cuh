@@ -64,7 +64,8 @@ klb_nuts_kernel(const KArgs A) {
   tn.accepted = A.tune_cnt[3 * c]; tn.proposed = A.tune_cnt[3 * c + 1]; tn.totproposed = A.tune_cnt[3 * c + 2];
   tn.rate = A.tune_rate[c];
   const bool saving = (A.out_value != nullptr) || (A.out_lt != nullptr) || (A.out_grad != nullptr) ||
-                      (A.out_accept != nullptr) || (A.out_ndoublings != nullptr);
+                      (A.out_accept != nullptr) || (A.out_ndoublings != nullptr) || (A.out_nuts_a != nullptr) ||
+                      (A.out_nuts_na != nullptr);
   long long count = A.count0;
   long long thin = (A.i0 > A.burnin) ? klb_mod(A.i0 - A.burnin - 1, A.thinning) : 0;
 
@@ -195,6 +196,8 @@ klb_nuts_kernel(const KArgs A) {
             if (A.out_lt) A.out_lt[col] = lt_cur;
             if (A.out_accept) A.out_accept[col] = update ? 1 : 0;
             if (A.out_ndoublings) A.out_ndoublings[col] = (unsigned char)j;
+            if (A.out_nuts_a) A.out_nuts_a[col] = a_sum;                        // :a, :na        iterate/NUTS.jl:393-399
+            if (A.out_nuts_na) A.out_nuts_na[col] = (int)na;
           }
         }
         count += 1;

@@ -86,6 +86,8 @@ typedef struct {
   /* NUTS(leapstep; maxδ, maxndoublings)   src/samplers/NUTS.jl:228-241; step above = leapstep */
   int32_t nuts_maxdelta, nuts_maxndoublings;
   uint8_t* nuts_ndoublings;                   /* out, npost x nchains: the :ndoublings diagnostic (diagnostics bit1); may be NULL */
+  double* nuts_a;                             /* out, npost x nchains: :a  (diagnostics bit2; NUTS + DualAveragingMCTuner, NUTS.jl:317) */
+  int32_t* nuts_na;                           /* out, npost x nchains: :na (diagnostics bit3) */
 } orc_config;
 
 /* DualAveragingMCTune minus the BasicMCTune part (src/tuners/DualAveragingMCTuner.jl:1-13); sstate.count rides along */
@@ -95,7 +97,7 @@ typedef struct { double lambda, mu, epsbar, hbar, hweight, epsweight, nleaps, co
 typedef struct { double step; int64_t accepted, proposed, totproposed; double rate; } orc_tune;
 
 /* one chain's BasicContMuvParameterState (src/states/ParameterStates/BasicContMuvParameterState.jl:62-97) */
-typedef struct { double* value; double logtarget; double* gradlogtarget; int accept; int ndoublings; } orc_pstate;
+typedef struct { double* value; double logtarget; double* gradlogtarget; int accept; int ndoublings; double nuts_a; int64_t nuts_na; } orc_pstate;
 
 typedef struct {
   const orc_config* cfg;
@@ -579,6 +581,7 @@ static void orc_iterate_nuts(const orc_model* M, orc_pstate* ps, orc_sstate* ss,
     j += 1; n += nprime; s = sprime;                                                   /* :377-381 */
   }
   ps->accept = update; ps->ndoublings = j;                                             /* :384-399 */
+  ps->nuts_a = a; ps->nuts_na = na;                                                    /* :a, :na of the LAST doubling   :393-399 */
   if (c->verbose && update) tune->accepted += 1;                                       /* :402-404 */
   if (c->tuner == ORC_DUALAVG) {                                                       /* :424-447 */
     da->nleaps = (double)na;
@@ -675,6 +678,8 @@ static void orc_save(const orc_model* M, const orc_pstate* ps, const orc_output*
   if ((c->monitor & 4u) && o->grad) memcpy(o->grad + col * M->d, ps->gradlogtarget, M->d * sizeof(double));
   if ((c->diagnostics & 1u) && o->accept) o->accept[col] = (uint8_t)ps->accept;
   if ((c->diagnostics & 2u) && c->nuts_ndoublings) c->nuts_ndoublings[col] = (uint8_t)ps->ndoublings;
+  if ((c->diagnostics & 4u) && c->nuts_a) c->nuts_a[col] = ps->nuts_a;
+  if ((c->diagnostics & 8u) && c->nuts_na) c->nuts_na[col] = (int32_t)ps->nuts_na;
 }
 
 int64_t orc_npoststeps(int64_t burnin, int64_t thinning, int64_t nsteps) {

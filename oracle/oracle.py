@@ -31,6 +31,7 @@ class OrcConfig(C.Structure):
         ("da_eps0bar", C.c_double), ("da_h0bar", C.c_double), ("da_gamma", C.c_double), ("da_kappa", C.c_double),
         ("da", C.c_void_p),
         ("nuts_maxdelta", C.c_int32), ("nuts_maxndoublings", C.c_int32), ("nuts_ndoublings", C.c_void_p),
+        ("nuts_a", C.c_void_p), ("nuts_na", C.c_void_p),
     ]
 
 
@@ -250,13 +251,19 @@ def run(cfg, x0, tparams=None, sigma=None, tune=None, logtarget=None, da=None):
     oa = np.zeros((N, npost), dtype=np.uint8) if cfg.diagnostics & 1 else None
     ond = np.zeros((N, npost), dtype=np.uint8) if (cfg.diagnostics & 2 and cfg.sampler == NUTS) else None
     cfg.nuts_ndoublings = None if ond is None else ond.ctypes.data
+    nuts_da = cfg.sampler == NUTS and cfg.tuner == DUALAVG          # :a, :na exist for that pair only (NUTS.jl:317,344)
+    ona = np.zeros((N, npost)) if (cfg.diagnostics & 4 and nuts_da) else None
+    onn = np.zeros((N, npost), dtype=np.int32) if (cfg.diagnostics & 8 and nuts_da) else None
+    cfg.nuts_a = None if ona is None else ona.ctypes.data
+    cfg.nuts_na = None if onn is None else onn.ctypes.data
     rc = lib().orc_run(C.byref(cfg), _ptr(tp), _ptr(sg), _ptr(x), _ptr(lt), _ptr(tune), int(initialized),
                        _ptr(ov), _ptr(ol), _ptr(og), _ptr(oa))
     if rc:
         raise ValueError("oracle: initial log-target/gradient not finite in chain %d" % (-rc - 1))
     cfg.da = None
     cfg.nuts_ndoublings = None
-    return {"x": x, "logtarget_state": lt, "tune": tune, "da": da, "value": ov, "logtarget": ol,
+    cfg.nuts_a = cfg.nuts_na = None
+    return {"a": ona, "na": onn, "x": x, "logtarget_state": lt, "tune": tune, "da": da, "value": ov, "logtarget": ol,
             "gradlogtarget": og, "accept": oa, "ndoublings": ond, "npost": npost}
 
 

@@ -79,7 +79,7 @@ def build_pair(K, sampler, target, nchains, dim, nsteps, burnin=0, thinning=1, s
     cfg = O.make_config(SAMPLERS[sampler], tcode, nchains, dim, nsteps, burnin, thinning, step, nleaps,
                         {"vanilla": O.VANILLA, "accrate": O.ACCRATE, "dualavg": O.DUALAVG}[tuner], target_rate,
                         3.0 if score == "erf" else 7.0,
-                        period, int(verbose), mon, (1 if "accept" in diagnostics else 0) | (2 if "ndoublings" in diagnostics else 0),
+                        period, int(verbose), mon, sum({"accept": 1, "ndoublings": 2, "a": 4, "na": 8}[k] for k in set(diagnostics)),
                         seed, chain_offset, 0,
                         1 if arith == "fma" else 0, job.plan().nv, O.max_threads(), nadapt=nadapt, eps0bar=1.0, h0bar=0.0,
                         gamma=0.05, da_t0=10, kappa=0.75, score=1 if score == "erf" else 0, maxdelta=maxdelta,
@@ -113,14 +113,12 @@ def compare_run(job, cfg, x0, tparams, sigma, t0=0):
         assert_same("logtarget", out.logtarget, ref["logtarget"])
     if cfg.monitor & 4:
         assert_same("gradlogtarget", out.gradlogtarget, ref["gradlogtarget"])
-    if cfg.diagnostics == 1:
-        assert_same("accept", out.diagnosticvalues, ref["accept"])
-    elif cfg.diagnostics == 2:
-        assert_same("ndoublings", out.diagnosticvalues, ref["ndoublings"])
-    elif cfg.diagnostics == 3:                       # (nchains, nkeys, npost) in the order of outopts[:diagnostics]
-        keys = list(out.diagnostickeys)
-        assert_same("accept", out.diagnosticvalues[..., keys.index("accept"), :], ref["accept"])
-        assert_same("ndoublings", out.diagnosticvalues[..., keys.index("ndoublings"), :], ref["ndoublings"])
+    keys = list(out.diagnostickeys)
+    if len(keys) == 1:
+        assert_same(keys[0], out.diagnosticvalues, ref[keys[0]])
+    for q, key in enumerate(keys if len(keys) > 1 else []):   # (nchains, nkeys, npost) in the order of outopts[:diagnostics]
+        got = out.diagnosticvalues[..., q, :]
+        assert_same(key, got, ref[key].astype(got.dtype))      # the stack is float64 when :a is among the keys
     assert_same("final state", job.pstate_value, ref["x"])
     assert_same("final logtarget", job.pstate_logtarget, ref["logtarget_state"])
     tn = job.tune

@@ -773,12 +773,16 @@ def test_nuts_bit_exact(K, target, dim, tuner, maxnd, maxdelta, arith):
     job, cfg, x0, tp, sg = build_pair(K, "NUTS", target, nchains=19, dim=dim, nsteps=40, burnin=12, thinning=2, step=step,
                                       seed=31337 + dim, arith=arith, tuner=tuner, target_rate=0.7, nadapt=25, period=5,
                                       verbose=(dim % 2 == 0), monitor=("value", "logtarget", "gradlogtarget"),
-                                      diagnostics=("accept", "ndoublings"), maxdelta=maxdelta, maxndoublings=maxnd)
+                                      diagnostics=("accept", "ndoublings") + (("a", "na") if tuner == "dualavg" else ()),
+                                      maxdelta=maxdelta, maxndoublings=maxnd)
     out, ref = compare_run(job, cfg, x0, tp, sg)
     nd = ref["ndoublings"]
     assert nd.min() >= 1 and nd.max() <= maxnd
     if maxdelta < 10:
         assert nd.min() < maxnd                        # some trees stopped before the last doubling
+    if tuner == "dualavg":                             # :a, :na: the leaves of the last doubling (iterate/NUTS.jl:393-399)
+        assert out.diagnostickeys == ["accept", "ndoublings", "a", "na"] and out.diagnosticvalues.dtype == np.float64
+        assert (ref["na"] >= 1).all() and (ref["na"] <= 2 ** (nd.astype(np.int64) - 1)).all()
 
 
 @pytest.mark.parametrize("dim,tuner,maxnd,maxdelta,step,arith", [
@@ -791,7 +795,8 @@ def test_nuts_logit_bit_exact(K, dim, tuner, maxnd, maxdelta, step, arith):
     job, cfg, x0, tp, sg = build_pair(K, "NUTS", "logit", nchains=70, dim=dim, nsteps=30, burnin=9, thinning=2, step=step,
                                       seed=5150 + dim, arith=arith, tuner=tuner, target_rate=0.651, nadapt=20, period=5,
                                       verbose=(dim % 2 == 0), monitor=("value", "logtarget", "gradlogtarget"),
-                                      diagnostics=("accept", "ndoublings"), maxdelta=maxdelta, maxndoublings=maxnd)
+                                      diagnostics=("accept", "ndoublings") + (("na", "a") if tuner == "dualavg" else ()),
+                                      maxdelta=maxdelta, maxndoublings=maxnd)
     out, ref = compare_run(job, cfg, x0, tp, sg)
     nd = ref["ndoublings"]
     assert nd.min() >= 1 and nd.max() <= maxnd
@@ -802,7 +807,7 @@ def test_nuts_logit_bit_exact(K, dim, tuner, maxnd, maxdelta, step, arith):
 def test_nuts_chunks_shards_and_run_host(K, O):
     """one launch per transition == one launch; 2 shards == 1 job; the pipelined host call == the three calls"""
     kw = dict(nchains=26, dim=130, nsteps=30, burnin=8, step=0.25, seed=77, tuner="dualavg", target_rate=0.65, nadapt=20,
-              period=4, verbose=True, diagnostics=("accept", "ndoublings"), maxndoublings=4)
+              period=4, verbose=True, diagnostics=("accept", "ndoublings", "a", "na"), maxndoublings=4)
     whole, cfg, x0, tp, sg = build_pair(K, "NUTS", "iso", **kw)
     out, ref = compare_run(whole, cfg, x0, tp, sg)
     step, *_ = build_pair(K, "NUTS", "iso", **kw)
@@ -815,9 +820,10 @@ def test_nuts_chunks_shards_and_run_host(K, O):
     a.run(); b.run()
     assert_same("sharded value", np.concatenate([a.output().value, b.output().value]), out.value)
     assert_same("sharded steps", np.concatenate([a.tune.step, b.tune.step]), whole.tune.step)
+    assert_same("sharded diagnostics", np.concatenate([a.output().diagnosticvalues, b.output().diagnosticvalues]), out.diagnosticvalues)
     # run_host = reset(job, x0) + run + output; with the vanilla tuner (a reset dual-averaging job restarts from step = 1,
     # NUTS.jl:320-325, so it would not retrace the constructor's run)
-    kv = dict(kw, tuner="vanilla")
+    kv = dict(kw, tuner="vanilla", diagnostics=("accept", "ndoublings"))
     plain, cfgv, _, _, _ = build_pair(K, "NUTS", "iso", **kv)
     outv, refv = compare_run(plain, cfgv, x0, tp, sg)
     host, *_ = build_pair(K, "NUTS", "iso", **kv)
@@ -826,6 +832,18 @@ def test_nuts_chunks_shards_and_run_host(K, O):
     host.run_host(x0, {K._lib.OUT_VALUE: val, K._lib.OUT_NDOUBLINGS: nd}, 3)
     assert_same("run_host value", val, outv.value)
     assert_same("run_host ndoublings", nd, refv["ndoublings"])
+    # :a / :na through the sliced pipeline: one slice == three slices (fresh dual-averaging jobs; both restart the tuner alike)
+    got = []
+    for nslices in (1, 3):
+        hj, *_ = build_pair(K, "NUTS", "iso", **kw)
+        bufs = {K._lib.OUT_NUTS_A: np.empty((26, val.shape[1])), K._lib.OUT_NUTS_NA: np.empty((26, val.shape[1]), dtype=np.int32),
+                K._lib.OUT_VALUE: np.empty_like(val)}
+        hj.run_host(x0, bufs, nslices)
+        got.append(bufs)
+        hj.close()
+    for f in got[0]:
+        assert_same("run_host field %d, 1 vs 3 slices" % f, got[1][f], got[0][f])
+    assert (got[0][K._lib.OUT_NUTS_NA] >= 1).all()
 
 
 def test_nuts_validation(K):
@@ -843,3 +861,5 @@ def test_nuts_validation(K):
     assert ei.value.code == L.KLB_EUNSUPPORTED
     with pytest.raises(KeyError):
         build_pair(K, "HMC", "iso", nchains=3, dim=8, nsteps=5, diagnostics=("ndoublings",))
+    with pytest.raises(KeyError):                                                              # :a, :na need dual averaging (NUTS.jl:317)
+        build_pair(K, "NUTS", "iso", nchains=3, dim=8, nsteps=5, diagnostics=("accept", "a"))

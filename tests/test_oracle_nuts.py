@@ -144,3 +144,38 @@ def test_nuts_oracle_samples_the_target(tuner):
     if tuner == "dualavg":
         assert np.isnan(r["da"]["lambda"]).all() and (r["da"]["count"] == 400).all()
         assert len(np.unique(r["tune"]["step"])) == N
+
+
+@pytest.mark.parametrize("target,dim,step,maxnd", [("iso", 6, 0.35, 5), ("shifted", 40, 0.2, 4), ("logit", 4, 0.3, 6)])
+def test_c_oracle_a_and_na_diagnostics(target, dim, step, maxnd):
+    """:a and :na of NUTS with DualAveragingMCTuner (src/samplers/NUTS.jl:317,344; iterate/NUTS.jl:393-399): the sum of
+    min(1, exp(H' - H0)) over the leaves of the LAST doubling and their number.  First transition of every chain (its step
+    is still the sampler's), C oracle against the state machine fed the same draws."""
+    N, seed = 48, 777
+    rng = np.random.default_rng(dim)
+    x0 = rng.standard_normal((N, dim))
+    if target == "logit":
+        X = rng.standard_normal((200, dim))
+        X = (X - X.mean(0)) / X.std(0, ddof=1)
+        y = (rng.uniform(size=200) < 1 / (1 + np.exp(-X @ rng.standard_normal(dim)))).astype(np.float64)
+        tcode, tp, tgt, nv = O.LOGIT, O.logit_params(X, y, 100.0), NA.LogitTarget(X, y, 100.0), 0
+    else:
+        mu = rng.standard_normal(dim) if target == "shifted" else None
+        tcode, tp, tgt, nv = (O.SHIFTED if mu is not None else O.ISO), mu, NA.Target(mu), None
+    cfg = O.make_config(O.NUTS, tcode, N, dim, 1, 0, step=step, tuner=O.DUALAVG, target_rate=0.65, nadapt=10, monitor=3,
+                        diagnostics=15, seed=seed, maxndoublings=maxnd, nv=nv)
+    ref = O.run(cfg, x0, tparams=tp)
+    assert ref["a"].shape == (N, 1) and ref["na"].dtype == np.int32
+    checked = 0
+    for c in range(N):
+        q = _fresh(tgt, x0[c])
+        st = dict(value=q.value, gradlogtarget=q.gradlogtarget, logtarget=q.logtarget)
+        upd, j, a, na = NA.simple_transition(st, step, tgt, 1000, maxnd, OracleDraws(seed, c, 1), da=True)
+        if upd == bool(ref["accept"][c, 0]) and j == int(ref["ndoublings"][c, 0]):
+            assert na == int(ref["na"][c, 0])
+            assert abs(a - ref["a"][c, 0]) <= 1e-9 * max(1.0, abs(a))
+            assert 1 <= na <= 2 ** (j - 1) and 0.0 <= ref["a"][c, 0] <= na
+            checked += 1
+    assert checked >= 0.95 * N
+    # the tuner was fed a/na of that doubling: tune! with count = 1        DualAveragingMCTuner.jl:95-101
+    assert np.all(ref["da"]["nleaps"] == ref["na"][:, 0])

@@ -24,7 +24,8 @@ for dim, tuner, maxnd, maxdelta, step, arith in CASES:
     job, cfg, x0, tp, sg = build_pair(K, "NUTS", "logit", nchains=70, dim=dim, nsteps=30, burnin=9, thinning=2, step=step,
                                       seed=5150 + dim, arith=arith, tuner=tuner, target_rate=0.651, nadapt=20, period=5,
                                       verbose=(dim % 2 == 0), monitor=("value", "logtarget", "gradlogtarget"),
-                                      diagnostics=("accept", "ndoublings"), maxdelta=maxdelta, maxndoublings=maxnd)
+                                      diagnostics=("accept", "ndoublings") + (("na", "a") if tuner == "dualavg" else ()),
+                                      maxdelta=maxdelta, maxndoublings=maxnd)
     try:
         out, ref = compare_run(job, cfg, x0, tp, sg)
         nd = ref["ndoublings"]
