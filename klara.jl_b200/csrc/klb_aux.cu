@@ -4,7 +4,7 @@
 #include "klb_kernels.cuh"
 
 #ifndef KLB_ESS_DEFAULT_VARIANT
-#define KLB_ESS_DEFAULT_VARIANT 0   /* 0: klb_ess_tile_kernel (eight lags per pass, centred tile) */
+#define KLB_ESS_DEFAULT_VARIANT 7   /* klb_ess_win_kernel<32, 16, true>; 0: klb_ess_tile_kernel (round 1: eight lags per pass, centred tile) */
 #endif
 
 // tuner_state / reset!(tune, sampler, tuner):  (step, 0, 0, tuner.period, NaN)
@@ -350,7 +350,7 @@ template <int TC, int WIN, bool RAW>
 static bool launch_ess_win(const double* value, long long ld, long long npost, long long nchains, int dim,
                            const KlbStatPtrs& S, cudaStream_t s) {
   const size_t sm = (size_t)npost * TC * sizeof(double);
-  if (sm > (size_t)(100 * 1024) * TC / 128) return false;         // 2 CTAs of 128 series per SM, or 4 of 64, or 8 of 32
+  if (sm > (size_t)(100 * 1024)) return false;                    // npost = 100: 2 CTAs of 128 series per SM, or 4 of 64, or 8 of 32
   auto kern = klb_ess_win_kernel<TC, WIN, RAW>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
     cudaGetLastError();
@@ -380,7 +380,12 @@ static bool launch_ess_tile(const double* value, long long ld, long long npost, 
 void klb_launch_stats(const double* value, long long ld, long long npost, long long nchains, int dim,
                       double* const stats[5], cudaStream_t s) {
   const KlbStatPtrs S = {stats[0], stats[1], stats[2], stats[3], stats[4]};
-  // KLB_ESS_VARIANT (experiments, tools/ess_variants.py): window of lags per pass / raw or centred tile / series per CTA
+  // Default: one warp per CTA (32 series), sixteen lags per pass, raw tile.  Measured on the C3 output (65 536 x 1024 series of
+  // 100 samples, one B200, tools/ess_variants.py; every variant bit-identical to the oracle): 128 series per CTA with 8 / 16 /
+  // 32 lags per pass 34.2 / 33.0 / 54.6 ms (the time follows the number of lags evaluated, wasted ones included: 32 per pass
+  // is too many), 64 series per CTA 30.5 ms, 32 series per CTA 29.1 ms: eight independent one-warp CTAs per SM overlap their
+  // load, mean and lag phases better than two CTAs of four warps that move in step.
+  // KLB_ESS_VARIANT selects the others (experiments): window of lags per pass / raw or centred tile / series per CTA.
   const char* ev = getenv("KLB_ESS_VARIANT");
   const int variant = ev ? atoi(ev) : KLB_ESS_DEFAULT_VARIANT;
   switch (variant) {
@@ -392,6 +397,9 @@ void klb_launch_stats(const double* value, long long ld, long long npost, long l
     case 6: if (launch_ess_win<64, 16, true>(value, ld, npost, nchains, dim, S, s)) return; break;
     case 7: if (launch_ess_win<32, 16, true>(value, ld, npost, nchains, dim, S, s)) return; break;
     case 8: if (launch_ess_win<64, 32, true>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 9: if (launch_ess_win<32, 8, true>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 10: if (launch_ess_win<32, 16, false>(value, ld, npost, nchains, dim, S, s)) return; break;
+    case 11: if (launch_ess_win<32, 8, false>(value, ld, npost, nchains, dim, S, s)) return; break;
     default: break;
   }
   if (launch_ess_tile<128>(value, ld, npost, nchains, dim, S, s)) return;

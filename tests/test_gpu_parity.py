@@ -468,6 +468,36 @@ def test_swiss_example_model_form(K, O):
     assert np.all(np.abs(K.mean(job) - b) < 0.5 * sd)
 
 
+def test_swiss_nuts_dual_averaging_example(K, O):
+    """doc/examples/swiss/NUTS/dualaveraging/analytical.jl as written (shorter range; synthetic stand-in for the data):
+    NUTS(0.4, maxndoublings=7) with DualAveragingMCTuner(0.651, nadapt), monitor value / logtarget / gradlogtarget,
+    diagnostics [:accept, :ndoublings, :a, :na]; the example's closing statistic mean(diags[:a]./diags[:na]) sits at the
+    tuner's target.  One chain (the reference's own shape) against the oracle, bit for bit."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as G
+    X, y, lam = G.logit_data(4)
+    t = K.BayesLogit()
+    p = K.BasicContMuvParameter("p", loglikelihood=t.loglikelihood, logprior=t.logprior, gradlogtarget=t.gradient, nkeys=4)
+    model = K.likelihood_model([K.Hyperparameter("λ"), K.Data("X"), K.Data("y"), p], isindexed=False)
+    v0 = {"λ": lam, "X": X, "y": y, "p": [5.1, -0.9, 8.2, -4.5]}
+    outopts = {"monitor": ["value", "logtarget", "gradlogtarget"], "diagnostics": ["accept", "ndoublings", "a", "na"]}
+    job = K.BasicMCJob(model, K.NUTS(0.4, maxndoublings=7), K.BasicMCRange(nsteps=300, burnin=100), v0,
+                       tuner=K.DualAveragingMCTuner(0.651, 300), outopts=outopts, seed=9)
+    K.run(job)
+    chain = K.output(job)
+    cfg = O.make_config(O.NUTS, O.LOGIT, 1, 4, 300, 100, step=0.4, tuner=O.DUALAVG, target_rate=0.651, nadapt=300, monitor=7,
+                        diagnostics=15, seed=9, maxndoublings=7, nv=0)
+    ref = O.run(cfg, np.array([v0["p"]]), O.logit_params(X, y, lam))
+    assert_same("value", chain.value, ref["value"][0])
+    assert_same("gradlogtarget", chain.gradlogtarget, ref["gradlogtarget"][0])
+    diags = dict(zip(chain.diagnostickeys, chain.diagnosticvalues))          # diagnostics(chain)
+    for k in ("accept", "ndoublings", "a", "na"):
+        assert_same(k, diags[k], ref[k][0].astype(np.float64))
+    assert abs(np.mean(diags["a"] / diags["na"]) - 0.651) < 0.08              # mean(diags[:a]./diags[:na])
+    assert_same("tuned step", np.atleast_1d(job.tune.step), ref["tune"]["step"])
+
+
 def test_logit_needs_its_data(K):
     p = K.BasicContMuvParameter("p", logtarget=K.BayesLogit())
     with pytest.raises(AssertionError, match="no data"):

@@ -38,7 +38,7 @@ def _target():
 
 p = K.BasicContMuvParameter("p", logtarget=_target())
 tuner = K.AcceptanceRateMCTuner(a.accrate) if a.accrate > 0 else K.VanillaMCTuner()
-smp = {"HMC": K.HMC(a.step, a.nleaps), "MALA": K.MALA(a.step), "MH": K.MH(np.full(a.dim, 0.02))}[a.sampler]
+smp = {"HMC": K.HMC(a.step, a.nleaps), "MALA": K.MALA(a.step), "MH": K.MH(np.full(a.dim, 0.02)), "NUTS": K.NUTS(a.step)}[a.sampler]
 oo = {"destination": "none"} if a.none else {"monitor": ["value", "logtarget"], "diagnostics": ["accept"]}
 job = K.BasicMCJob(K.likelihood_model(p, False), smp, K.BasicMCRange(nsteps=a.nsteps, burnin=a.burnin), {"p": x0},
                    tuner=tuner, outopts=oo, seed=1, arith=a.arith)
@@ -46,7 +46,7 @@ for r in range(a.reps):
     job.reset()
     job.run()
     ms = job.last_run_ms
-    lf = a.nchains * a.nsteps * (a.nleaps if a.sampler == "HMC" else 1)
-    print("rep %d: %.3f ms  %.4g %s/s" % (r, ms, lf / ms * 1e3, "leapfrog-steps" if a.sampler == "HMC" else "transitions"))
+    lf = a.nchains * a.nsteps * (a.nleaps if a.sampler == "HMC" else 31 if a.sampler == "NUTS" else 1)   # NUTS on a Gaussian: every tree runs 2^5 - 1 leaves
+    print("rep %d: %.3f ms  %.4g %s/s" % (r, ms, lf / ms * 1e3, "leapfrog-steps" if a.sampler in ("HMC", "NUTS") else "transitions"))
 if not a.none:
     print("accept rate %.3f" % job.output().diagnosticvalues.mean())

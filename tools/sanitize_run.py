@@ -36,6 +36,15 @@ CASES += [
     ("nuts rosen 1000, dual averaging", "NUTS", "rosen", dict(nchains=5, dim=1000, nsteps=6, burnin=2, step=0.02, tuner="dualavg", nadapt=4,
                                                          diagnostics=("accept", "ndoublings"), maxndoublings=3)),
 ]
+CASES += [
+    ("glm nuts (thread per chain), dual averaging, :a / :na", "NUTS", "logit",
+     dict(nchains=70, dim=4, nsteps=5, burnin=1, step=0.15, tuner="dualavg", nadapt=3, diagnostics=("accept", "ndoublings", "a", "na"), maxndoublings=3)),
+    ("glm nuts dim 13 (padded to 16), trees that stop early", "NUTS", "logit",
+     dict(nchains=40, dim=13, nsteps=4, burnin=1, step=0.3, diagnostics=("accept", "ndoublings"), maxndoublings=3, maxdelta=3)),
+]
+ONLY = os.environ.get("KLB_SANITIZE_ONLY", "")          # substring filter, e.g. KLB_SANITIZE_ONLY=nuts
+if ONLY:
+    CASES = [c for c in CASES if ONLY in c[0]]
 for name, smp, tgt, kw in CASES:
     job, cfg, x0, tp, sg = build_pair(K, smp, tgt, seed=31, **kw)
     compare_run(job, cfg, x0, tp, sg)
@@ -48,6 +57,20 @@ ref, *_ = build_pair(K, "HMC", "iso", nchains=50, dim=1024, nsteps=4, burnin=1, 
 ref.run()
 assert np.array_equal(val, ref.output().value)
 print("ok: klb_job_run_host, 4 slices", flush=True)
-# post-hoc statistics kernels
-ref.ess(); ref.mean(); ref.acceptance()
-print("ok: ess / stats / acceptance kernels", flush=True)
+# post-hoc statistics kernels: the shipping one-warp-per-CTA window kernel and the variants, series lengths that end inside a trip
+from oracle import oracle as O  # noqa: E402
+for npost, dim in ((3, 1024), (37, 130), (100, 33)):
+    sj, *_ = build_pair(K, "HMC", "iso", nchains=7, dim=dim, nsteps=npost + 2, burnin=2, step=0.1, nleaps=3, seed=8, monitor=("value",))
+    sj.run()
+    want = O.stats(sj.output().value)
+    for variant in ("", "0", "2", "6", "9", "10"):
+        if variant:
+            os.environ["KLB_ESS_VARIANT"] = variant
+        else:
+            os.environ.pop("KLB_ESS_VARIANT", None)
+        for got, key in ((sj.ess(), "ess"), (sj.mean(), "mean"), (sj.mcvar("imse"), "mcvar_imse")):
+            assert np.array_equal(got.view(np.uint64), np.ascontiguousarray(want[key]).view(np.uint64)), (npost, dim, variant, key)
+    os.environ.pop("KLB_ESS_VARIANT", None)
+    sj.acceptance()
+    sj.close()
+print("ok: ess / stats / acceptance kernels (window kernel and variants)", flush=True)
