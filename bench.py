@@ -47,6 +47,15 @@ WORKLOAD = ("C3: HMC(leapstep=0.05, nleaps=10), isotropic Gaussian logtarget -z.
 VERIFY_T = 0            # the verification run replays transitions 1 .. NSTEPS of the streams (what a fresh job does)
 
 
+def job_config(arith):
+    """`config` of the JSON line: what the workload IS.  The same dict in both arms (the reference arm runs on this arm's
+    config); what a particular run looked like goes under `details`."""
+    return {"workload": WORKLOAD, "arith": arith,
+            "l2": "inputs larger than L2 (state 512 MiB + 50 GiB of samples per step at N=1)",
+            "x0": "Philox stream (seed, global chain, transition 0)",
+            "rng": "Philox4x32-7 counter streams + 256-layer ziggurat (DESIGN.md section 3)"}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -158,10 +167,11 @@ def run_reference(args, rank):
     out = {"impl": "reference", "metric": METRIC, "value": mean_v, "unit": UNIT, "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([c["seconds"] for c in vals])),
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "note": "reference algorithm (CPU oracle = C restatement of Klara.jl's "
-                      "BasicMCJob loop; Klara.jl itself needs Julia 0.6, not installable offline) on a bounded "
-                      "chain subset, all host threads; an upper bound on Klara.jl's own allocating, dynamically "
-                      "dispatched loop"},
+           "config": job_config(args.arith),
+           "details": {"note": "reference algorithm (CPU oracle = C restatement of Klara.jl's "
+                       "BasicMCJob loop; Klara.jl itself needs Julia 0.6, not installable offline) on a bounded "
+                       "chain subset, all host threads; an upper bound on Klara.jl's own allocating, dynamically "
+                       "dispatched loop"},
            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": mean_v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": total}
@@ -455,10 +465,8 @@ def run_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "chains_per_gpu": nloc, "arith": arith,
-                       "l2": "inputs larger than L2 (state 512 MiB + 50 GiB of samples per step at N=1)",
-                       "x0": "Philox stream (seed, global chain, transition 0), generated on the device",
-                       "rng": "Philox4x32-7 counter streams + 256-layer ziggurat (DESIGN.md section 3)",
+            "config": job_config(arith),
+            "details": {"chains_per_gpu": nloc, "x0": "generated on the device (klb_job_set_state_synthetic)",
                        "closing_all_gather": ("none (N=1)" if world == 1 else
                                               "copy engines, CUDA IPC peer-to-peer over NVLink (klb_gather_*)" if gather is not None
                                               else "NCCL all_gather_into_tensor on a side stream"

@@ -27,6 +27,14 @@ def test_reference_arm_prints_one_json_line():
         assert k in d, k
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert "workload" in d["config"] and "65536 chains x 1024" in d["config"]["workload"]
+    # both arms print the SAME config dict (the reference arm runs on this arm's config): bench.job_config
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("klb_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert d["config"] == bench.job_config("reference")
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": job_config(') == 2          # the reference arm and the CUDA arm
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "chains" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

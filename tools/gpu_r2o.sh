@@ -14,6 +14,6 @@ timeout 300 python -m pytest tests/test_gpu_multi.py -m gpu -x -q | tail -2
 for n in 1 2 4 8; do grep '^{' gpurun_out/r2o_bench_n$n.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('N', d['n_gpus'], 'value %.4g'%d['value'], 'ms %.3f'%d['ms_per_step'], 'e2e %.4g'%d['e2e']['value'], 'full', d['e2e_full_output'].get('value'), 'parity', d['parity']['bit_exact'], d['parity'].get('g_invariance',{}).get('equal'), d['parity']['final_state_checksum'], d['config']['closing_all_gather'][:12])
+print('N', d['n_gpus'], 'value %.4g'%d['value'], 'ms %.3f'%d['ms_per_step'], 'e2e %.4g'%d['e2e']['value'], 'full', d['e2e_full_output'].get('value'), 'parity', d['parity']['bit_exact'], d['parity'].get('g_invariance',{}).get('equal'), d['parity']['final_state_checksum'], d.get('details', d['config'])['closing_all_gather'][:12])
 for k,v in d['configs'].items(): print('   ', k, '%.4g'%v['value'], '%.2f ms'%v['ms_per_run'], 'frac %.3f'%v['roofline']['frac'])
 "; done
