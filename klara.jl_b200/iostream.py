@@ -53,6 +53,16 @@ def _line(values):
     return ",".join(julia_float(v) for v in np.atleast_1d(values))
 
 
+# how string() prints the entries of state.diagnosticvalues (an Array{Any} in the reference): :accept is a Bool, :ndoublings and
+# :na are Ints, :a is a Float64 (src/samplers/iterate/NUTS.jl:384-399)
+_DIAG_FORMAT = {"accept": lambda v: "true" if v else "false", "ndoublings": lambda v: "%d" % int(v), "na": lambda v: "%d" % int(v),
+                "a": julia_float}
+
+
+def _diag_token(tok):
+    return 1.0 if tok == "true" else 0.0 if tok == "false" else float(tok.replace("Inf", "inf").replace("NaN", "nan"))
+
+
 class BasicContParamIOStream:
     """Writer / reader of one chain's CSV files."""
 
@@ -73,8 +83,15 @@ class BasicContParamIOStream:
         for f, path in self.names.items():
             with open(path, self.mode) as fh:
                 if f == "diagnosticvalues":
-                    for row in np.atleast_1d(diagnosticvalues):
-                        fh.write(",".join("true" if b else "false" for b in np.atleast_1d(row)) + "\n")
+                    keys = self.diagnostickeys
+                    dv = np.asarray(diagnosticvalues)
+                    if len(keys) > 1:                    # (nkeys, n) as output(job) holds it -> one line per saved state
+                        for row in dv.T:
+                            fh.write(",".join(_DIAG_FORMAT.get(k, julia_float)(v) for k, v in zip(keys, row)) + "\n")
+                    else:
+                        fmt = _DIAG_FORMAT.get(keys[0], julia_float) if keys else _DIAG_FORMAT["accept"]
+                        for row in np.atleast_1d(dv):
+                            fh.write(",".join(fmt(b) for b in np.atleast_1d(row)) + "\n")
                 else:
                     for row in data[f]:
                         fh.write(_line(row) + "\n")
@@ -85,7 +102,11 @@ class BasicContParamIOStream:
         for f, path in self.names.items():
             if f == "diagnosticvalues":
                 with open(path) as fh:
-                    out[f] = np.array([[tok == "true" for tok in ln.strip().split(",")] for ln in fh if ln.strip()])
+                    rows = [ln.strip().split(",") for ln in fh if ln.strip()]
+                if self.diagnostickeys in ([], ["accept"]):
+                    out[f] = np.array([[tok == "true" for tok in r] for r in rows])
+                else:                                    # (n, nkeys) float64: true / false read back as 1 / 0
+                    out[f] = np.array([[_diag_token(tok) for tok in r] for r in rows])
             else:
                 a = np.loadtxt(path, delimiter=",", dtype=dtype, ndmin=2)
                 out[f] = a[:, 0] if f == "logtarget" else a
@@ -96,7 +117,7 @@ def write_job_output(job, out):
     """save the fetched NState of a BasicMCJob as CSV files following outopts"""
     oo = job.outopts
     fp, sfx = oo.get("filepath", ""), oo.get("filesuffix", "csv")
-    diag = ["accept"] if "accept" in oo["diagnostics"] else []
+    diag = list(oo["diagnostics"])
     streams = []
     nchains = 1 if job.single else job.nchains
     for c in range(nchains):

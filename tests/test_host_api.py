@@ -299,3 +299,17 @@ def test_scheduling_post_pass_is_in_the_shipped_library():
                     seen[kind][1] += ((w1 >> 41) & 0xf) < 2
     assert seen["ws"][0] > 1000 and seen["ws"][1] == 0, seen
     assert seen["chain"][0] > 1000 and seen["chain"][1] > seen["chain"][0] // 2, seen
+
+
+def test_iostream_nuts_diagnostics(K, tmp_path):
+    """diagnosticvalues.csv of a NUTS + DualAveragingMCTuner job: join(state.diagnosticvalues, ',') of [:accept, :ndoublings,
+    :a, :na] = Bool, Int, Float64, Int per saved state (BasicContParamIOStream.jl:152-159, iterate/NUTS.jl:384-399)"""
+    keys = ["accept", "ndoublings", "a", "na"]
+    dv = np.array([[1, 0, 1], [5, 3, 4], [12.25, 0.5, 7.0], [16, 4, 8]], dtype=np.float64)      # (nkeys, npost) as output(job) holds it
+    st = K.BasicContParamIOStream(2, 3, ["value"], str(tmp_path), "csv", keys)
+    st.write_nstate(value=np.zeros((3, 2)), diagnosticvalues=dv)
+    assert open(os.path.join(tmp_path, "diagnosticvalues.csv")).read().splitlines() == ["true,5,12.25,16", "false,3,0.5,4", "true,4,7.0,8"]
+    assert np.array_equal(st.read()["diagnosticvalues"], dv.T)
+    one = K.BasicContParamIOStream(2, 3, [], str(tmp_path / "nd"), "csv", ["ndoublings"])
+    one.write_nstate(diagnosticvalues=np.array([5, 3, 4], dtype=np.uint8))
+    assert open(os.path.join(tmp_path, "nd", "diagnosticvalues.csv")).read().splitlines() == ["5", "3", "4"]
