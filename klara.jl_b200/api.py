@@ -28,7 +28,7 @@ from .targets import Target
 __all__ = ["SyntheticNormal", "device_peak", "BasicContMuvParameter", "Hyperparameter", "Data", "GenericModel", "likelihood_model", "MH", "MALA", "HMC", "NUTS", "BasicMCRange",
            "VanillaMCTuner", "AcceptanceRateMCTuner", "DualAveragingMCTuner", "BasicMCTune", "DualAveragingMCTune", "BasicMCJob", "run", "reset", "output",
            "BasicContMuvParameterNState", "logistic", "logistic_rate_score", "erf_rate_score", "ess", "mean", "mcvar", "mcse", "iact",
-           "acceptance"]
+           "acceptance", "diagnostics"]
 
 
 # ----------------------------------------------------------------------------- scalars
@@ -732,3 +732,15 @@ def iact(job):
 
 def acceptance(job, diagnostics=True):
     return job.acceptance(diagnostics)
+
+
+def diagnostics(nstate):
+    """diagnostics(chain): Dict(zip(diagnostickeys, rows of diagnosticvalues))        src/nstates/ParameterNStates/ParameterNStates.jl:14-15
+    key -> (npost,) array for a single chain, (nchains, npost) for a batch; e.g. the swiss NUTS example's
+    `diags = diagnostics(chain); mean(diags[:a]./diags[:na])`"""
+    keys, dv = list(nstate.diagnostickeys), nstate.diagnosticvalues
+    if not keys:
+        return {}
+    if len(keys) == 1:
+        return {keys[0]: dv}
+    return {k: dv[..., q, :] for q, k in enumerate(keys)}

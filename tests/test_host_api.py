@@ -313,3 +313,17 @@ def test_iostream_nuts_diagnostics(K, tmp_path):
     one = K.BasicContParamIOStream(2, 3, [], str(tmp_path / "nd"), "csv", ["ndoublings"])
     one.write_nstate(diagnosticvalues=np.array([5, 3, 4], dtype=np.uint8))
     assert open(os.path.join(tmp_path, "nd", "diagnosticvalues.csv")).read().splitlines() == ["5", "3", "4"]
+
+
+def test_diagnostics_dict(K):
+    """diagnostics(chain) = Dict(zip(diagnostickeys, rows of diagnosticvalues))        ParameterNStates.jl:14-15"""
+    ns = K.BasicContMuvParameterNState(2, 3)
+    assert K.diagnostics(ns) == {}
+    ns.diagnostickeys, ns.diagnosticvalues = ["accept"], np.array([1, 0, 1], dtype=np.uint8)
+    assert list(K.diagnostics(ns)) == ["accept"] and K.diagnostics(ns)["accept"].shape == (3,)
+    ns.diagnostickeys = ["accept", "ndoublings", "a", "na"]
+    ns.diagnosticvalues = np.arange(24.0).reshape(2, 4, 3)                  # (nchains, nkeys, npost)
+    d = K.diagnostics(ns)
+    assert d["a"].shape == (2, 3) and np.array_equal(d["na"][1], [21.0, 22.0, 23.0])
+    ns.diagnosticvalues = ns.diagnosticvalues[0]                            # a single chain: (nkeys, npost)
+    assert np.array_equal(K.diagnostics(ns)["ndoublings"], [3.0, 4.0, 5.0])
