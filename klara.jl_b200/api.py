@@ -289,6 +289,7 @@ class BasicContMuvParameterNState:
         self.gradlogtarget = None
         self.diagnosticvalues = None
         self.diagnostickeys = []
+        self._job = None
 
 
 _MONITOR_BITS = {"value": L.MONITOR_VALUE, "logtarget": L.MONITOR_LOGTARGET, "gradlogtarget": L.MONITOR_GRADLOGTARGET}
@@ -590,6 +591,7 @@ class BasicMCJob:
     def _fetch_nstate(self):
         N, P, d = self.nchains, self.range.npoststeps, self.dim
         ns = BasicContMuvParameterNState(d, P)
+        ns._job = self                       # mean(chain), ess(chain), acceptance(chain) find the device-resident samples through it
         mon = self.outopts["monitor"]
         if "value" in mon:
             ns.value = self._fetch(L.OUT_VALUE, (N, P, d))
@@ -709,29 +711,40 @@ def output(job):
     return job.output()
 
 
+def _job_of(x):
+    """the reference's statistics take the chain (`chain = output(job); mean(chain)`, src/stats/*.jl); here the samples live
+    on the device of the job that produced them, so the NState output(job) returned carries a reference to that job and
+    either may be passed"""
+    if isinstance(x, BasicContMuvParameterNState):
+        if getattr(x, "_job", None) is None:
+            raise TypeError("this NState did not come from output(job): device statistics need the job that holds the samples")
+        return x._job
+    return x
+
+
 def ess(job):
-    """ess(chain) for the job's monitored values, on the device"""
-    return job.ess()
+    """ess(chain) for the job's monitored values, on the device        src/stats/convergence/ess.jl:3-14"""
+    return _job_of(job).ess()
 
 
 def mean(job):
-    return job.mean()
+    return _job_of(job).mean()
 
 
 def mcvar(job, vtype="imse"):
-    return job.mcvar(vtype)
+    return _job_of(job).mcvar(vtype)
 
 
 def mcse(job, vtype="imse"):
-    return job.mcse(vtype)
+    return _job_of(job).mcse(vtype)
 
 
 def iact(job):
-    return job.iact()
+    return _job_of(job).iact()
 
 
 def acceptance(job, diagnostics=True):
-    return job.acceptance(diagnostics)
+    return _job_of(job).acceptance(diagnostics)
 
 
 def diagnostics(nstate):

@@ -327,3 +327,18 @@ def test_diagnostics_dict(K):
     assert d["a"].shape == (2, 3) and np.array_equal(d["na"][1], [21.0, 22.0, 23.0])
     ns.diagnosticvalues = ns.diagnosticvalues[0]                            # a single chain: (nkeys, npost)
     assert np.array_equal(K.diagnostics(ns)["ndoublings"], [3.0, 4.0, 5.0])
+
+
+def test_statistics_take_the_chain_or_the_job(K):
+    """mean(chain), ess(chain), acceptance(chain) as the reference's examples call them: the NState of output(job) leads back
+    to the job that holds the samples; a hand-made NState is refused"""
+    class FakeJob:
+        def mean(self): return "mean"
+        def ess(self): return "ess"
+        def acceptance(self, diagnostics=True): return ("acc", diagnostics)
+    ns = K.BasicContMuvParameterNState(2, 3)
+    with pytest.raises(TypeError, match="did not come from output"):
+        K.mean(ns)
+    ns._job = FakeJob()
+    assert K.mean(ns) == "mean" and K.ess(ns) == "ess" and K.acceptance(ns, diagnostics=False) == ("acc", False)
+    assert K.mean(FakeJob()) == "mean"
