@@ -342,3 +342,31 @@ def test_statistics_take_the_chain_or_the_job(K):
     ns._job = FakeJob()
     assert K.mean(ns) == "mean" and K.ess(ns) == "ess" and K.acceptance(ns, diagnostics=False) == ("acc", False)
     assert K.mean(FakeJob()) == "mean"
+
+
+def test_julia_shim_calls_only_exported_symbols(K):
+    """julia/KlaraB200.jl cannot be executed here: every C symbol it `ccall`s -- literal (:klb_...) or built by
+    sym(job, "name") with the klb_job_ / klb_multi_ prefix -- must be declared in the header and exported by the library"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jl = open(os.path.join(root, "julia", "KlaraB200.jl")).read()
+    hdr = open(os.path.join(root, "include", "klara_b200.h")).read()
+    declared = set(re.findall(r"\b(klb_[a-z0-9_]+)\s*\(", hdr))
+    names = set(re.findall(r"\(:(klb_[a-z0-9_]+),\s*LIB\)", jl))
+    for suffix in set(re.findall(r'sym\(job,\s*"([a-z0-9_]+)"\)', jl)):
+        names |= {"klb_job_" + suffix, "klb_multi_" + suffix}
+    assert len(names) > 15
+    lib = K._lib.lib()
+    for n in sorted(names):
+        assert n in declared, "%s is called by the Julia shim but not declared in include/klara_b200.h" % n
+        assert hasattr(lib, n), "%s is not exported by libklara_b200.so" % n
+    # the field codes the shim's output(job) passes to klb_job_output are the header's
+    outs = dict((name, int(v)) for name, v in re.findall(r"#define (KLB_OUT_[A-Z_]+) (\d+)", hdr))
+    got = {}
+    for key, code in re.findall(r"(\w+) = :\w+ in job\.\w+ \? (?:Int\.\()?fetch!\(job, (\d+),", jl):
+        got[key] = int(code)
+    want = {"value": "KLB_OUT_VALUE", "logtarget": "KLB_OUT_LOGTARGET", "gradlogtarget": "KLB_OUT_GRADLOGTARGET", "accept": "KLB_OUT_ACCEPT",
+            "ndoublings": "KLB_OUT_NDOUBLINGS", "a": "KLB_OUT_NUTS_A", "na": "KLB_OUT_NUTS_NA"}
+    assert set(got) == set(want), got
+    for key, macro in want.items():
+        assert got[key] == outs[macro], (key, got[key], macro, outs[macro])
