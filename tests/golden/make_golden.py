@@ -34,6 +34,8 @@ CASES = {
     # NUTS as the reference computes it; cross-checked against oracle/nuts_alias.py instead of the twin
     "nuts_iso_d70": ("NUTS", "iso", 4, 70, 30, dict(burnin=10, step=0.15, monitor=3, diagnostics=3, seed=1729, maxndoublings=4), {}),
     "nuts_shifted_d9_delta2": ("NUTS", "shifted", 5, 9, 40, dict(burnin=0, step=1.1, monitor=3, diagnostics=3, seed=1730, maxndoublings=6, maxdelta=2), {}),
+    # doc/examples/swiss/NUTS/noadaptation/analytical.jl on the synthetic 200 x 4 data (thread-per-chain kernel)
+    "nuts_logit_d4": ("NUTS", "logit", 6, 4, 30, dict(burnin=10, step=0.2, monitor=7, diagnostics=3, seed=1731, maxndoublings=5), {}),
 }
 SAMPLERS = {"MH": O.MH, "MALA": O.MALA, "HMC": O.HMC, "NUTS": O.NUTS}
 TARGETS = {"iso": O.ISO, "shifted": O.SHIFTED, "rosen": O.ROSEN, "logit": O.LOGIT}
@@ -84,7 +86,7 @@ def nuts_crosscheck(name, cfg, x0, tparams, r):
     tests/test_oracle_nuts.py pins to the aliasing-faithful model of the reference code), teacher-forced"""
     from oracle import nuts_alias as NA
     smp, tgt, n, d, nsteps, kw, extra = CASES[name]
-    target = NA.Target(tparams if tgt == "shifted" else None)
+    target = NA.LogitTarget(*logit_data(d)) if tgt == "logit" else NA.Target(tparams if tgt == "shifted" else None)
 
     class Draws:
         def __init__(self, chain, t):
