@@ -320,7 +320,12 @@ class BasicMCJob:
     """
 
     def __init__(self, model, sampler, mcrange, v0, tuner=None, outopts=None, pindex=None,
-                 seed=0, arith="reference", device=0, chain_offset=0, verbose=False, ngpus=1, devices=None):
+                 seed=0, arith="reference", device=0, chain_offset=0, verbose=False, ngpus=1, devices=None,
+                 resetpstate=True, check=False):
+        # resetpstate, check: accepted for the reference's signature (src/jobs/BasicMCJob.jl:107-119).  resetpstate only
+        # matters to BasicGibbsJob's reset (a draw from the parameter's prior, host-side: not on this path); the
+        # constructor's consistency checks always run here.
+        self.resetpstate, self.check = bool(resetpstate), bool(check)
         tuner = VanillaMCTuner() if tuner is None else tuner
         self.model, self.sampler, self.range, self.tuner = model, sampler, mcrange, tuner
         self.pindex = next(i for i, v in enumerate(model.vertices) if isinstance(v, BasicContMuvParameter)) \
@@ -356,8 +361,11 @@ class BasicMCJob:
         # reference passes to the closures as `v` (BasicContMuvParameter.jl:497-501; `nkeys` only tested > 0)
         others = [v for i, v in enumerate(model.vertices) if i != self.pindex]
         if others:
+            if isinstance(v0, (list, tuple)) and len(v0) == len(model.vertices):
+                v0 = {v.key: val for v, val in zip(model.vertices, v0)}        # v0::Vector: values in vertex order (BasicMCJob.jl:139-152)
             if not isinstance(v0, dict):
-                raise TypeError("a model with Hyperparameter / Data vertices needs v0 as a Dict of initial values")
+                raise TypeError("a model with Hyperparameter / Data vertices needs v0 as a Dict of initial values (or a "
+                                "list with one entry per vertex)")
             if not hasattr(self.parameter.target, "bind"):
                 raise TypeError("target %s takes no hyper-parameters" % type(self.parameter.target).__name__)
             self.parameter.target.bind([v0[v.key] for v in others])

@@ -370,3 +370,23 @@ def test_julia_shim_calls_only_exported_symbols(K):
     assert set(got) == set(want), got
     for key, macro in want.items():
         assert got[key] == outs[macro], (key, got[key], macro, outs[macro])
+
+
+def test_v0_as_a_vector_in_vertex_order(K):
+    """BasicMCJob(model, sampler, range, v0::Vector; resetpstate, check) (src/jobs/BasicMCJob.jl:139-152): the values in
+    model-vertex order bind exactly like the Dict form"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side test of the constructor's host logic")
+    C = np.linalg.inv(np.array([[1.0, 0.5], [0.5, 1.0]]))
+    C = (C + C.T) / 2
+    d = K.DenseGaussian()
+    p = K.BasicContMuvParameter("p", logtarget=d, gradlogtarget=d.gradient, nkeys=2)
+    model = K.GenericModel([K.Hyperparameter("C"), p], isindexed=False)
+    with pytest.raises(K.KlaraError) as ei:                                   # everything host-side has run when the device is missed
+        K.BasicMCJob(model, K.MALA(0.3), K.BasicMCRange(nsteps=100, burnin=10), [C, [1.25, 3.11]], resetpstate=False, check=True)
+    assert ei.value.code == K._lib.KLB_ECUDA
+    z = np.array([1.25, 3.11])
+    assert d(z) == pytest.approx(-z @ C @ z, rel=1e-15)                       # the hyper-parameter reached the target
+    with pytest.raises(TypeError, match="one entry per vertex"):
+        K.BasicMCJob(model, K.MALA(0.3), K.BasicMCRange(nsteps=100, burnin=10), [C])
