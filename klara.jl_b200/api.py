@@ -177,7 +177,8 @@ class HMC:
 class NUTS:
     """NUTS(leapstep=0.1; maxδ=1000, maxndoublings=5)        src/samplers/NUTS.jl:228-241
     The multivariate transition as the reference computes it (its four tree states are one object, NUTS.jl:198-225;
-    DESIGN.md section 6b), with VanillaMCTuner or DualAveragingMCTuner; diagnostics :accept and :ndoublings."""
+    DESIGN.md section 6b), with VanillaMCTuner or DualAveragingMCTuner, on the elementwise targets and the logistic-regression
+    target; diagnostics :accept and :ndoublings, and :a / :na with dual averaging (NUTS.jl:317)."""
     code = L.SAMPLER_NUTS
 
     def __init__(self, leapstep=0.1, maxdelta=1000, maxndoublings=5):
